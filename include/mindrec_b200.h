@@ -1,0 +1,111 @@
+/* libmindrec_b200.so — C-ABI of the B200-native MindRec embedding-and-interaction hot path.
+ *
+ * Every compute entry point has the signature MindSpore's ops.Custom(func_type="aot") binds
+ * (mindspore/ops/operations/custom_ops.py, "aot" section [upstream]):
+ *
+ *     int f(int nparam, void **params, int *ndims, int64_t **shapes,
+ *           const char **dtypes, void *stream, void *extra);
+ *
+ *   params  inputs, then outputs (workspaces are declared as trailing uint8 outputs) — DEVICE pointers
+ *   ndims / shapes / dtypes   per-param rank, extents and MindSpore dtype name ("float32","int32","int64",...)
+ *   stream  cudaStream_t the kernels are enqueued on; the call never synchronises, allocates or frees
+ *   extra   ignored (all scalars travel in small device tensors, so no attr / AotExtra C++ ABI is needed)
+ *   return  0 on success, else one of MREC_ERR_* (MindSpore raises RuntimeError); text in mrec_last_error()
+ *
+ * Persistent state (tables, optimizer moments, hash slots) is passed as INPUTS and mutated in place;
+ * such ops return a dummy int32[1] output.  Data-dependent sizes are returned as device scalars
+ * (count[1]) with outputs padded to their static maximum.
+ *
+ * The reference interface each symbol replaces is cited as /root/reference/<file>:<line>.
+ */
+#ifndef MINDREC_B200_H_
+#define MINDREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MREC_OK 0
+#define MREC_ERR_NPARAM 1    /* wrong number of params */
+#define MREC_ERR_DTYPE 2     /* dtype string mismatch */
+#define MREC_ERR_SHAPE 3     /* rank / extent mismatch */
+#define MREC_ERR_ALIGN 4     /* pointer not 16-byte aligned where vector access needs it */
+#define MREC_ERR_DIM 5       /* unsupported embedding dim */
+#define MREC_ERR_CUDA 6      /* cudaPeekAtLastError() after launch */
+#define MREC_ERR_WORKSPACE 7 /* workspace too small (see *_workspace_bytes) */
+#define MREC_ERR_NULL 8      /* null pointer for a non-empty param */
+
+#define MREC_AOT_ARGS                                                                      \
+  int nparam, void **params, int *ndims, int64_t **shapes, const char **dtypes, void *stream, \
+      void *extra
+
+/* ---- helpers (host only, not aot) ------------------------------------------------------------ */
+const char *mrec_version(void);
+const char *mrec_last_error(void);            /* thread-local text of the last non-zero return */
+unsigned long long mrec_launch_count(void);   /* kernels launched by this library in this process */
+
+/* ---- K1 gather -------------------------------------------------------------------------------
+ * Replaces nn.EmbeddingLookup / P.Gather(table, ids, 0):
+ *   models/wide_deep/src/wide_and_deep.py:277-290,300-302; models/deepfm/src/deepfm.py:217,221;
+ *   models/deep_and_cross/src/deep_and_cross.py:199; mindspore_rec/ops/embedding.py:194.
+ * Out-of-range ids -> zero row (GPU Gather) and the optional oob flag is set.
+ *   in : table[V,D] f32, ids[...] i32|i64            out: out[N*D] f32, (oob[1] i32)            */
+int mrec_gather(MREC_AOT_ARGS);
+/* gather + Mul(mask) + Reshape fused (wide_and_deep.py:303,308-309; deepfm.py:215,222,230;
+ * deep_and_cross.py:295-298):
+ *   in : table[V,D], ids[B,F], mask[B,F] f32         out: out[B,F*D] f32, (oob[1])              */
+int mrec_gather_masked(MREC_AOT_ARGS);
+/* dim-1 gather + Mul(mask) + ReduceSum(axis 1) + bias (wide_and_deep.py:300,305-306;
+ * deepfm.py:217-219):
+ *   in : table[V]|[V,1], ids[B,F], mask[B,F], bias[1] out: out[B]|[B,1] f32, (oob[1])           */
+int mrec_gather_reduce(MREC_AOT_ARGS);
+
+/* ---- K2 unique -------------------------------------------------------------------------------
+ * Replaces P.Unique (mindspore_rec/ops/embedding.py:192) and the optimizer-side RowTensor dedup
+ * (nn.Optimizer, reached from wide_and_deep.py:420-445).  Ascending order = upstream GPU kernel.
+ *   in : ids[N] i32|i64
+ *   out: uniq[N] (ids dtype, padded), inverse[N] i32, count[1] i32, perm[N] i32 (stable sort
+ *        permutation), seg_start[N+1] i32, seg_of[N] i32, workspace[mrec_unique_workspace_bytes] u8 */
+int mrec_unique(MREC_AOT_ARGS);
+/* Same, second input table_like[V,...]: only ceil(log2(V+1)) key bits are sorted; ids outside [0,V)
+ * collapse onto the value V (they form the last segment, which the optimizers skip).            */
+int mrec_unique_bounded(MREC_AOT_ARGS);
+/* First-occurrence order = upstream CPU Unique kernel (BASELINE config 1 runs device_target=CPU).
+ *   in : ids[N]   out: uniq[N], inverse[N] i32, count[1] i32, workspace[mrec_unique_first_workspace_bytes] */
+int mrec_unique_first(MREC_AOT_ARGS);
+size_t mrec_unique_workspace_bytes(int64_t n, int key_bytes);
+size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes);
+
+/* ---- K3-K5 deterministic segment-sum fused with sparse optimizers ------------------------------
+ * Replaces Gather-bprop RowTensor -> Unique -> UnsortedSegmentSum -> LazyAdam / FTRL:
+ *   wide_and_deep.py:420-430,479-492 (LazyAdam lr 3.5e-4 eps 1e-8; FTRL lr 5e-2 l1=l2=1e-8 accum 1.0);
+ *   models/wide_and_deep_multitable/src/wide_and_deep.py:525-535.
+ * g[N/div, D] holds one gradient row per `div` consecutive lookup positions (div = F for the wide
+ * logit gradient, 1 for the deep input gradient); mask[N] is the Mul(mask) bprop factor (numel 0 = none).
+ * Hyper blocks are f32[8] device tensors:
+ *   Adam : lr, beta1, beta2, eps, beta1_power, beta2_power, lr_t, 1/loss_scale
+ *   FTRL : lr, l1, l2, lr_power, 1/loss_scale, -, -, -
+ *   in : w[V,D] m[V,D] v[V,D] hyper[8] g mask uniq[N] perm[N] seg_start[N+1] seg_of[N]
+ *   out: dummy[1] i32, workspace[mrec_sparse_opt_workspace_bytes(N, D)] u8                       */
+int mrec_sparse_lazy_adam(MREC_AOT_ARGS);
+/*   in : w[V,D] accum[V,D] linear[V,D] hyper[8] g mask uniq perm seg_start seg_of   out: dummy, workspace */
+int mrec_sparse_ftrl(MREC_AOT_ARGS);
+/* Stand-alone UnsortedSegmentSum in sorted-segment order (no atomics, bit-reproducible):
+ *   in : g mask perm seg_start seg_of     out: gsum[N,D] f32 (rows >= count untouched), workspace */
+int mrec_segment_sum(MREC_AOT_ARGS);
+size_t mrec_sparse_opt_workspace_bytes(int64_t n, int dim);
+/* nn.Adam preamble: beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  in: hyper[8]  out: dummy[1] */
+int mrec_adam_begin_step(MREC_AOT_ARGS);
+/* nn.Adam dense kernel (MLP weights, Wide_b: wide_and_deep.py:405-413,435-437).
+ *   in : w m v hyper[8] g (same numel)   out: dummy[1]                                            */
+int mrec_adam_dense(MREC_AOT_ARGS);
+/* nn.FTRL dense kernel (ApplyFtrl).  in : w accum linear hyper[8] g   out: dummy[1]               */
+int mrec_ftrl_dense(MREC_AOT_ARGS);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINDREC_B200_H_ */

@@ -1,0 +1,586 @@
+// K3/K4/K5 — deterministic segment-sum fused with sparse LazyAdam / FTRL row updates; dense Adam/FTRL.
+//
+// Replaces, for the embedding backward + optimizer step of
+//   models/wide_deep/src/wide_and_deep.py:420-445,479-492  (LazyAdam deep, FTRL wide, loss_scale=sens)
+//   models/wide_and_deep_multitable/src/wide_and_deep.py:525-535
+//   models/deepfm/src/deepfm.py:272, models/deep_and_cross/src/deep_and_cross.py:342-344 (Adam)
+// the upstream chain  Gather-bprop -> RowTensor -> Unique -> UnsortedSegmentSum(atomicAdd) ->
+// FusedSparseLazyAdam / FusedSparseFtrl  (SURVEY B4-B7).
+//
+// Input is the stable sort of the lookup ids (mrec_unique: perm / seg_of / seg_start / uniq).  The
+// sorted positions are cut into fixed tiles of 32; a group of D/4 threads (one float4 column chunk
+// each) walks a tile in order, accumulating mask[p] * g[p] for each run of equal keys:
+//   * a run that starts and ends inside the tile is final: the optimizer update for its row is applied
+//     on the spot, so the summed gradient never touches HBM;
+//   * a run that crosses a tile edge writes a partial (at most 2 per tile); a second kernel, launched
+//     over tiles, lets the tile in which such a segment starts add the partials in tile order and apply
+//     the update; chains longer than kLongChain tiles (Zipf head keys, the 13 dense Criteo fields that
+//     appear once per sample) go to a third kernel that sums them with a fixed-shape CTA reduction.
+// No atomics touch floating-point data: the summation order depends only on the sorted order, so the
+// result is bit-reproducible run to run.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mrec {
+
+constexpr int kSegTile = 32;      // sorted positions per tile
+constexpr int kSegBatch = 8;      // independent row loads in flight per thread
+constexpr int kLongChain = 16;    // partial chains longer than this go to the CTA kernel
+constexpr int kSegThreads = 256;
+
+// ---- vector helpers ----
+template <typename Vec> struct VOps;
+template <> struct VOps<float4> {
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void fma(float4& a, const float4& x, float s) { f4_fma(a, x, s); }
+  static __device__ __forceinline__ void add(float4& a, const float4& x) {
+    a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+  }
+  static __device__ __forceinline__ float4 ldg(const float4* p) { return ld_stream_f4(p); }
+};
+template <> struct VOps<float> {
+  static __device__ __forceinline__ float zero() { return 0.f; }
+  static __device__ __forceinline__ void fma(float& a, const float& x, float s) { a = fmaf(x, s, a); }
+  static __device__ __forceinline__ void add(float& a, const float& x) { a += x; }
+  static __device__ __forceinline__ float ldg(const float* p) { return ld_stream_f1(p); }
+};
+
+// ---- hyper-parameter blocks (device f32 tensors, so schedules / bias-correction never sync the host)
+// Adam : [0] lr [1] beta1 [2] beta2 [3] eps [4] beta1_power [5] beta2_power [6] lr_t [7] grad_scale
+// FTRL : [0] lr [1] l1 [2] l2 [3] lr_power [4] grad_scale
+constexpr int kHyperLen = 8;
+
+__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, float b1, float b2,
+                                          float eps, float lr_t) {
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  w = w - lr_t * m / (sqrtf(v) + eps);
+}
+
+__device__ __forceinline__ void ftrl_elem(float& w, float& a, float& lin, float g, float lr, float l1,
+                                          float l2, float lr_power) {
+  const float a_new = a + g * g;
+  float pa_new, pa_old;
+  if (lr_power == -0.5f) {
+    pa_new = sqrtf(a_new);
+    pa_old = sqrtf(a);
+  } else {
+    pa_new = powf(a_new, -lr_power);
+    pa_old = powf(a, -lr_power);
+  }
+  const float sigma = (pa_new - pa_old) / lr;
+  lin = lin + g - sigma * w;
+  const float q = pa_new / lr + 2.f * l2;
+  const float sgn = lin > 0.f ? 1.f : (lin < 0.f ? -1.f : 0.f);
+  w = (fabsf(lin) > l1) ? (sgn * l1 - lin) / q : 0.f;
+  a = a_new;
+}
+
+// ---- per-segment sinks ----
+template <typename Vec, typename IdT> struct LazyAdamSink;
+template <typename IdT>
+struct LazyAdamSink<float4, IdT> {
+  float4* w; float4* m; float4* v;
+  const IdT* uniq;
+  const float* hyper;
+  int64_t vocab;
+  int cpr;
+  __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
+    const int64_t row = (int64_t)uniq[seg];
+    if ((uint64_t)row >= (uint64_t)vocab) return;  // out-of-range ids carry no row
+    const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6], sc = hyper[7];
+    const int64_t o = row * cpr + c;
+    float4 W = w[o], M = m[o], V = v[o];
+    adam_elem(W.x, M.x, V.x, gs.x * sc, b1, b2, eps, lr_t);
+    adam_elem(W.y, M.y, V.y, gs.y * sc, b1, b2, eps, lr_t);
+    adam_elem(W.z, M.z, V.z, gs.z * sc, b1, b2, eps, lr_t);
+    adam_elem(W.w, M.w, V.w, gs.w * sc, b1, b2, eps, lr_t);
+    w[o] = W; m[o] = M; v[o] = V;
+  }
+};
+template <typename IdT>
+struct LazyAdamSink<float, IdT> {
+  float* w; float* m; float* v;
+  const IdT* uniq;
+  const float* hyper;
+  int64_t vocab;
+  int cpr;
+  __device__ __forceinline__ void apply(int seg, int c, const float& gs) const {
+    const int64_t row = (int64_t)uniq[seg];
+    if ((uint64_t)row >= (uint64_t)vocab) return;
+    const int64_t o = row * cpr + c;
+    float W = w[o], M = m[o], V = v[o];
+    adam_elem(W, M, V, gs * hyper[7], hyper[1], hyper[2], hyper[3], hyper[6]);
+    w[o] = W; m[o] = M; v[o] = V;
+  }
+};
+
+template <typename Vec, typename IdT> struct FtrlSink;
+template <typename IdT>
+struct FtrlSink<float4, IdT> {
+  float4* w; float4* acc; float4* lin;
+  const IdT* uniq;
+  const float* hyper;
+  int64_t vocab;
+  int cpr;
+  __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
+    const int64_t row = (int64_t)uniq[seg];
+    if ((uint64_t)row >= (uint64_t)vocab) return;
+    const float lr = hyper[0], l1 = hyper[1], l2 = hyper[2], p = hyper[3], sc = hyper[4];
+    const int64_t o = row * cpr + c;
+    float4 W = w[o], A = acc[o], L = lin[o];
+    ftrl_elem(W.x, A.x, L.x, gs.x * sc, lr, l1, l2, p);
+    ftrl_elem(W.y, A.y, L.y, gs.y * sc, lr, l1, l2, p);
+    ftrl_elem(W.z, A.z, L.z, gs.z * sc, lr, l1, l2, p);
+    ftrl_elem(W.w, A.w, L.w, gs.w * sc, lr, l1, l2, p);
+    w[o] = W; acc[o] = A; lin[o] = L;
+  }
+};
+template <typename IdT>
+struct FtrlSink<float, IdT> {
+  float* w; float* acc; float* lin;
+  const IdT* uniq;
+  const float* hyper;
+  int64_t vocab;
+  int cpr;
+  __device__ __forceinline__ void apply(int seg, int c, const float& gs) const {
+    const int64_t row = (int64_t)uniq[seg];
+    if ((uint64_t)row >= (uint64_t)vocab) return;
+    const int64_t o = row * cpr + c;
+    float W = w[o], A = acc[o], L = lin[o];
+    ftrl_elem(W, A, L, gs * hyper[4], hyper[0], hyper[1], hyper[2], hyper[3]);
+    w[o] = W; acc[o] = A; lin[o] = L;
+  }
+};
+
+// plain segment-sum: gsum[seg] = sum
+template <typename Vec>
+struct StoreSink {
+  Vec* out;
+  int cpr;
+  __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const {
+    out[(int64_t)seg * cpr + c] = gs;
+  }
+};
+
+// ---- kernel A: walk tiles ----
+template <typename Vec, typename Sink, bool HAS_MASK>
+__global__ void __launch_bounds__(kSegThreads)
+segsum_tiles_kernel(const Vec* __restrict__ g, int cpr, int div, const float* __restrict__ mask,
+                    const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of, int64_t n,
+                    int64_t n_tiles, Vec* __restrict__ part, Sink sink) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t j = gid / cpr;
+  if (j >= n_tiles) return;
+  const int c = (int)(gid - j * cpr);
+  const int64_t pos0 = j * kSegTile;
+  const int64_t pos1 = min(n, pos0 + kSegTile);
+
+  int cur = seg_of[pos0];
+  bool enters = (pos0 > 0) && (seg_of[pos0 - 1] == cur);
+  Vec acc = VOps<Vec>::zero();
+
+  for (int64_t b0 = pos0; b0 < pos1; b0 += kSegBatch) {
+    int seg[kSegBatch];
+    int32_t p[kSegBatch];
+    Vec gv[kSegBatch];
+    float mk[kSegBatch];
+#pragma unroll
+    for (int k = 0; k < kSegBatch; ++k) {
+      const int64_t i = b0 + k;
+      seg[k] = (i < pos1) ? seg_of[i] : -1;
+      p[k] = (i < pos1) ? perm[i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kSegBatch; ++k) {
+      if (seg[k] >= 0) {
+        const int64_t grow = (div == 1) ? (int64_t)p[k] : (int64_t)(p[k] / div);
+        gv[k] = VOps<Vec>::ldg(g + grow * cpr + c);
+        mk[k] = HAS_MASK ? mask[p[k]] : 1.f;
+      } else {
+        gv[k] = VOps<Vec>::zero();
+        mk[k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kSegBatch; ++k) {
+      if (seg[k] >= 0) {
+        if (seg[k] != cur) {
+          // run [.., here) ended inside the tile
+          if (enters) part[(j * 2 + 0) * cpr + c] = acc;
+          else sink.apply(cur, c, acc);
+          cur = seg[k];
+          enters = false;
+          acc = VOps<Vec>::zero();
+        }
+        VOps<Vec>::fma(acc, gv[k], mk[k]);
+      }
+    }
+  }
+  const bool leaves = (pos1 < n) && (seg_of[pos1] == cur);
+  if (enters) part[(j * 2 + 0) * cpr + c] = acc;        // entered (and maybe also leaves): slot 0
+  else if (leaves) part[(j * 2 + 1) * cpr + c] = acc;   // starts here, continues right: slot 1
+  else sink.apply(cur, c, acc);
+}
+
+// ---- kernel B: short partial chains, one thread group per tile in which a crossing segment starts
+template <typename Vec, typename Sink>
+__global__ void __launch_bounds__(kSegThreads)
+segsum_boundary_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
+                       int64_t n, int64_t n_tiles, const Vec* __restrict__ part,
+                       int32_t* __restrict__ long_list, int32_t* __restrict__ long_count, Sink sink) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t j = gid / cpr;
+  if (j >= n_tiles) return;
+  const int c = (int)(gid - j * cpr);
+  const int64_t pos0 = j * kSegTile;
+  const int64_t pos1 = pos0 + kSegTile;
+  if (pos1 >= n) return;
+  const int s = seg_of[pos1 - 1];
+  if (seg_of[pos1] != s) return;         // nothing leaves this tile
+  if (seg_start[s] < pos0) return;       // it entered from the left: an earlier tile owns it
+  const int64_t j_last = ((int64_t)seg_start[s + 1] - 1) / kSegTile;
+  if (j_last - j > kLongChain) {
+    if (c == 0) long_list[atomicAdd(long_count, 1)] = (int32_t)j;
+    return;
+  }
+  Vec acc = part[(j * 2 + 1) * cpr + c];
+  for (int64_t jj = j + 1; jj <= j_last; ++jj) VOps<Vec>::add(acc, part[(jj * 2 + 0) * cpr + c]);
+  sink.apply(s, c, acc);
+}
+
+// ---- kernel C: long chains, one CTA per segment, fixed-shape reduction ----
+template <typename Vec, typename Sink>
+__global__ void __launch_bounds__(kSegThreads)
+segsum_long_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
+                   const Vec* __restrict__ part, const int32_t* __restrict__ long_list,
+                   const int32_t* __restrict__ long_count, Sink sink) {
+  __shared__ Vec s_part[kSegThreads];
+  const int groups = min(kSegThreads / cpr, 32);
+  const int gi = threadIdx.x / cpr;
+  const int c = threadIdx.x - gi * cpr;
+  const int n_long = *long_count;
+  for (int idx = blockIdx.x; idx < n_long; idx += gridDim.x) {
+    const int64_t j = long_list[idx];
+    const int s = seg_of[(j + 1) * kSegTile - 1];
+    const int64_t j_last = ((int64_t)seg_start[s + 1] - 1) / kSegTile;
+    const int64_t pieces = j_last - j + 1;  // piece 0 = slot 1 of tile j, piece k = slot 0 of tile j+k
+    if (gi < groups) {
+      Vec acc = VOps<Vec>::zero();
+      for (int64_t k = gi; k < pieces; k += groups) {
+        const int64_t slot = (k == 0) ? (j * 2 + 1) : ((j + k) * 2 + 0);
+        VOps<Vec>::add(acc, part[slot * cpr + c]);
+      }
+      s_part[gi * cpr + c] = acc;
+    }
+    __syncthreads();
+    if (gi == 0) {
+      Vec acc = s_part[c];
+      for (int q = 1; q < groups; ++q) VOps<Vec>::add(acc, s_part[q * cpr + c]);
+      sink.apply(s, c, acc);
+    }
+    __syncthreads();
+  }
+}
+
+struct SegWorkspace {
+  size_t off_part, off_list, off_count, total;
+};
+static SegWorkspace seg_ws(int64_t n, int dim) {
+  const int64_t n_tiles = cdiv(n > 0 ? n : 1, kSegTile);
+  SegWorkspace w;
+  size_t o = 0;
+  w.off_part = o; o = align_up(o + (size_t)n_tiles * 2 * dim * 4, 256);
+  w.off_list = o; o = align_up(o + (size_t)n_tiles * 4, 256);
+  w.off_count = o; o = align_up(o + 16, 256);
+  w.total = o;
+  return w;
+}
+size_t sparse_opt_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim).total; }
+
+template <typename Vec, typename Sink>
+static int run_segsum(const float* g, int dim, int div, const float* mask, const int32_t* perm,
+                      const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws,
+                      size_t ws_bytes, Sink sink, cudaStream_t stream) {
+  if (n == 0) return OK;
+  const int vec = sizeof(Vec) / 4;
+  const int cpr = dim / vec;
+  const SegWorkspace W = seg_ws(n, dim);
+  if (ws_bytes < W.total)
+    return fail(ERR_WORKSPACE, "sparse update: workspace %zu bytes < required %zu", ws_bytes, W.total);
+  if (reinterpret_cast<uintptr_t>(ws) % 16 != 0)
+    return fail(ERR_ALIGN, "sparse update: workspace must be 16-byte aligned");
+  char* w = reinterpret_cast<char*>(ws);
+  Vec* part = reinterpret_cast<Vec*>(w + W.off_part);
+  int32_t* long_list = reinterpret_cast<int32_t*>(w + W.off_list);
+  int32_t* long_count = reinterpret_cast<int32_t*>(w + W.off_count);
+  const int64_t n_tiles = cdiv(n, kSegTile);
+  const int64_t threads = n_tiles * cpr;
+  const int grid = (int)cdiv(threads, kSegThreads);
+  cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
+  const Vec* gv = reinterpret_cast<const Vec*>(g);
+  if (mask) {
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, Sink, true>), grid, kSegThreads, 0, stream, gv, cpr, div, mask,
+                perm, seg_of, n, n_tiles, part, sink);
+  } else {
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, Sink, false>), grid, kSegThreads, 0, stream, gv, cpr, div, mask,
+                perm, seg_of, n, n_tiles, part, sink);
+  }
+  if (n_tiles > 1) {
+    MREC_LAUNCH((segsum_boundary_kernel<Vec, Sink>), grid, kSegThreads, 0, stream, cpr, seg_of, seg_start,
+                n, n_tiles, part, long_list, long_count, sink);
+    MREC_LAUNCH((segsum_long_kernel<Vec, Sink>), kNumSMs * 2, kSegThreads, 0, stream, cpr, seg_of,
+                seg_start, part, long_list, long_count, sink);
+  }
+  return check_launch("segment_sum");
+}
+
+// ---- dense optimizers (MLP parameters, Wide_b: SURVEY a5/a7) ----
+__global__ void adam_begin_step_kernel(float* hyper) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float b1p = hyper[4] * hyper[1];
+    const float b2p = hyper[5] * hyper[2];
+    hyper[4] = b1p;
+    hyper[5] = b2p;
+    hyper[6] = hyper[0] * sqrtf(1.f - b2p) / (1.f - b1p);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                  const float* __restrict__ g, const float* __restrict__ hyper, int64_t n) {
+  const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6], sc = hyper[7];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) % 16 == 0)
+                         ? n / 4 : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 W = reinterpret_cast<float4*>(w)[i], M = reinterpret_cast<float4*>(m)[i],
+           V = reinterpret_cast<float4*>(v)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    adam_elem(W.x, M.x, V.x, G.x * sc, b1, b2, eps, lr_t);
+    adam_elem(W.y, M.y, V.y, G.y * sc, b1, b2, eps, lr_t);
+    adam_elem(W.z, M.z, V.z, G.z * sc, b1, b2, eps, lr_t);
+    adam_elem(W.w, M.w, V.w, G.w * sc, b1, b2, eps, lr_t);
+    reinterpret_cast<float4*>(w)[i] = W;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float W = w[i], M = m[i], V = v[i];
+    adam_elem(W, M, V, g[i] * sc, b1, b2, eps, lr_t);
+    w[i] = W; m[i] = M; v[i] = V;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ftrl_dense_kernel(float* __restrict__ w, float* __restrict__ acc, float* __restrict__ lin,
+                  const float* __restrict__ g, const float* __restrict__ hyper, int64_t n) {
+  const float lr = hyper[0], l1 = hyper[1], l2 = hyper[2], p = hyper[3], sc = hyper[4];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float W = w[i], A = acc[i], L = lin[i];
+    ftrl_elem(W, A, L, g[i] * sc, lr, l1, l2, p);
+    w[i] = W; acc[i] = A; lin[i] = L;
+  }
+}
+
+}  // namespace mrec
+
+using namespace mrec;
+
+MREC_API size_t mrec_sparse_opt_workspace_bytes(int64_t n, int dim) {
+  return sparse_opt_workspace_bytes(n, dim);
+}
+
+// Shared validation of (g, mask, uniq, perm, seg_start, seg_of) starting at param index `b`.
+struct SegArgs {
+  const float* g; const float* mask; const void* uniq; bool uniq64;
+  const int32_t* perm; const int32_t* seg_start; const int32_t* seg_of;
+  int64_t n; int div;
+};
+static int parse_seg_args(const Aot& a, int b, int dim, bool has_uniq, SegArgs* s, const char* who) {
+  int i = b;
+  MREC_REQUIRE(a.is_f32(i), ERR_DTYPE, "%s: grad rows must be float32", who);
+  MREC_REQUIRE(dim == 1 || a.last(i) == dim, ERR_SHAPE, "%s: grad rows must have last dim %d", who, dim);
+  const int64_t g_rows = a.numel(i) / dim;
+  s->g = a.ptr<float>(i++);
+  MREC_REQUIRE(a.is_f32(i), ERR_DTYPE, "%s: mask must be float32 (numel 0 = no mask)", who);
+  const int64_t mask_n = a.numel(i);
+  s->mask = mask_n ? a.ptr<float>(i) : nullptr;
+  i++;
+  if (has_uniq) {
+    MREC_REQUIRE(a.is_i32(i) || a.is_i64(i), ERR_DTYPE, "%s: uniq must be int32|int64", who);
+    s->uniq64 = a.is_i64(i);
+    s->uniq = a.params[i++];
+  }
+  MREC_REQUIRE(a.is_i32(i) && a.is_i32(i + 1) && a.is_i32(i + 2), ERR_DTYPE,
+               "%s: perm/seg_start/seg_of must be int32", who);
+  s->n = a.numel(i);
+  s->perm = a.ptr<int32_t>(i++);
+  MREC_REQUIRE(a.numel(i) >= s->n + 1, ERR_SHAPE, "%s: seg_start must have N+1 entries", who);
+  s->seg_start = a.ptr<int32_t>(i++);
+  MREC_REQUIRE(a.numel(i) >= s->n, ERR_SHAPE, "%s: seg_of must have N entries", who);
+  s->seg_of = a.ptr<int32_t>(i++);
+  MREC_REQUIRE(mask_n == 0 || mask_n == s->n, ERR_SHAPE, "%s: mask numel must be 0 or N", who);
+  MREC_REQUIRE(g_rows > 0 ? (s->n % g_rows == 0) : s->n == 0, ERR_SHAPE,
+               "%s: N (%lld) must be a multiple of the number of grad rows (%lld)", who, (long long)s->n,
+               (long long)g_rows);
+  s->div = g_rows > 0 ? (int)(s->n / g_rows) : 1;
+  if (dim % 4 == 0)
+    MREC_REQUIRE(reinterpret_cast<uintptr_t>(s->g) % 16 == 0, ERR_ALIGN, "%s: grad rows must be 16-B aligned", who);
+  return OK;
+}
+
+// inputs : w[V,D] m[V,D] v[V,D] hyper[8] g[N/div,D] mask[N|0] uniq[N] perm[N] seg_start[N+1] seg_of[N]
+// outputs: dummy[1] i32, workspace[bytes]
+MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_t** shapes,
+                                   const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 12);
+  MREC_REQUIRE(a.is_f32(0) && a.is_f32(1) && a.is_f32(2) && a.is_f32(3), ERR_DTYPE,
+               "mrec_sparse_lazy_adam: w/m/v/hyper must be float32");
+  MREC_REQUIRE(a.numel(3) >= kHyperLen, ERR_SHAPE, "mrec_sparse_lazy_adam: hyper needs %d floats", kHyperLen);
+  const int64_t vocab = a.dim(0, 0);
+  const int dim = a.ndims[0] >= 2 ? (int)a.dim(0, 1) : 1;
+  MREC_REQUIRE(a.numel(1) == a.numel(0) && a.numel(2) == a.numel(0), ERR_SHAPE,
+               "mrec_sparse_lazy_adam: m/v shape must equal w shape");
+  SegArgs s;
+  int rc = parse_seg_args(a, 4, dim, true, &s, "mrec_sparse_lazy_adam");
+  if (rc) return rc;
+  const size_t ws_bytes = (size_t)a.numel(11);
+  void* ws = a.params[11];
+  const float* hyper = a.ptr<float>(3);
+  if (dim % 4 == 0) {
+    MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(2, 16), ERR_ALIGN,
+                 "mrec_sparse_lazy_adam: w/m/v must be 16-byte aligned");
+    const int cpr = dim / 4;
+    MREC_REQUIRE(cpr <= kSegThreads, ERR_DIM, "mrec_sparse_lazy_adam: D too large");
+    if (s.uniq64) {
+      LazyAdamSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
+                                         (const int64_t*)s.uniq, hyper, vocab, cpr};
+      return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    }
+    LazyAdamSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
+                                       (const int32_t*)s.uniq, hyper, vocab, cpr};
+    return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  }
+  MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_lazy_adam: D too large");
+  if (s.uniq64) {
+    LazyAdamSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
+                                      (const int64_t*)s.uniq, hyper, vocab, dim};
+    return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  }
+  LazyAdamSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
+                                    (const int32_t*)s.uniq, hyper, vocab, dim};
+  return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+}
+
+// inputs : w[V,D] accum[V,D] linear[V,D] hyper[8] g[N/div,D] mask[N|0] uniq[N] perm[N] seg_start[N+1] seg_of[N]
+// outputs: dummy[1] i32, workspace[bytes]
+MREC_API int mrec_sparse_ftrl(int nparam, void** params, int* ndims, int64_t** shapes,
+                              const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 12);
+  MREC_REQUIRE(a.is_f32(0) && a.is_f32(1) && a.is_f32(2) && a.is_f32(3), ERR_DTYPE,
+               "mrec_sparse_ftrl: w/accum/linear/hyper must be float32");
+  MREC_REQUIRE(a.numel(3) >= kHyperLen, ERR_SHAPE, "mrec_sparse_ftrl: hyper needs %d floats", kHyperLen);
+  const int64_t vocab = a.dim(0, 0);
+  const int dim = a.ndims[0] >= 2 ? (int)a.dim(0, 1) : 1;
+  MREC_REQUIRE(a.numel(1) == a.numel(0) && a.numel(2) == a.numel(0), ERR_SHAPE,
+               "mrec_sparse_ftrl: accum/linear shape must equal w shape");
+  SegArgs s;
+  int rc = parse_seg_args(a, 4, dim, true, &s, "mrec_sparse_ftrl");
+  if (rc) return rc;
+  const size_t ws_bytes = (size_t)a.numel(11);
+  void* ws = a.params[11];
+  const float* hyper = a.ptr<float>(3);
+  if (dim % 4 == 0) {
+    MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(2, 16), ERR_ALIGN,
+                 "mrec_sparse_ftrl: w/accum/linear must be 16-byte aligned");
+    const int cpr = dim / 4;
+    MREC_REQUIRE(cpr <= kSegThreads, ERR_DIM, "mrec_sparse_ftrl: D too large");
+    if (s.uniq64) {
+      FtrlSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
+                                     (const int64_t*)s.uniq, hyper, vocab, cpr};
+      return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    }
+    FtrlSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
+                                   (const int32_t*)s.uniq, hyper, vocab, cpr};
+    return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  }
+  MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_ftrl: D too large");
+  if (s.uniq64) {
+    FtrlSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
+                                  (const int64_t*)s.uniq, hyper, vocab, dim};
+    return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  }
+  FtrlSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
+                                (const int32_t*)s.uniq, hyper, vocab, dim};
+  return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+}
+
+// Standalone deterministic segment-sum (the UnsortedSegmentSum of SURVEY a4, in sorted-segment order).
+// inputs : g[N/div,D] mask[N|0] perm[N] seg_start[N+1] seg_of[N] ; outputs: gsum[N,D] (rows >= U untouched),
+//          workspace[bytes]
+MREC_API int mrec_segment_sum(int nparam, void** params, int* ndims, int64_t** shapes,
+                              const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 7);
+  MREC_REQUIRE(a.is_f32(5), ERR_DTYPE, "mrec_segment_sum: gsum must be float32");
+  const int dim = a.ndims[5] >= 2 ? (int)a.last(5) : 1;
+  SegArgs s;
+  int rc = parse_seg_args(a, 0, dim, false, &s, "mrec_segment_sum");
+  if (rc) return rc;
+  MREC_REQUIRE(a.numel(5) >= s.n * dim, ERR_SHAPE, "mrec_segment_sum: gsum must be padded to [N,D]");
+  const size_t ws_bytes = (size_t)a.numel(6);
+  if (dim % 4 == 0) {
+    MREC_REQUIRE(a.aligned(5, 16), ERR_ALIGN, "mrec_segment_sum: gsum must be 16-byte aligned");
+    MREC_REQUIRE(dim / 4 <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
+    StoreSink<float4> sink{a.ptr<float4>(5), dim / 4};
+    return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
+  }
+  MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
+  StoreSink<float> sink{a.ptr<float>(5), dim};
+  return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
+}
+
+// inputs: hyper[8] ; outputs: dummy[1].  beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).
+MREC_API int mrec_adam_begin_step(int nparam, void** params, int* ndims, int64_t** shapes,
+                                  const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 2);
+  MREC_REQUIRE(a.is_f32(0) && a.numel(0) >= kHyperLen, ERR_SHAPE, "mrec_adam_begin_step: hyper must be f32[8]");
+  MREC_LAUNCH(adam_begin_step_kernel, 1, 32, 0, a.stream, a.ptr<float>(0));
+  return check_launch("adam_begin_step");
+}
+
+// inputs: w m v hyper[8] g (all same numel) ; outputs: dummy[1]
+MREC_API int mrec_adam_dense(int nparam, void** params, int* ndims, int64_t** shapes,
+                             const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 6);
+  for (int i = 0; i < 5; ++i) MREC_REQUIRE(a.is_f32(i), ERR_DTYPE, "mrec_adam_dense: param %d must be float32", i);
+  const int64_t n = a.numel(0);
+  MREC_REQUIRE(a.numel(1) == n && a.numel(2) == n && a.numel(4) == n && a.numel(3) >= kHyperLen, ERR_SHAPE,
+               "mrec_adam_dense: w/m/v/g numel mismatch");
+  if (n == 0) return OK;
+  MREC_LAUNCH(adam_dense_kernel, grid_for(cdiv(n, 1024), 8), 256, 0, a.stream, a.ptr<float>(0),
+              a.ptr<float>(1), a.ptr<float>(2), a.ptr<float>(4), a.ptr<float>(3), n);
+  return check_launch("adam_dense");
+}
+
+// inputs: w accum linear hyper[8] g ; outputs: dummy[1]
+MREC_API int mrec_ftrl_dense(int nparam, void** params, int* ndims, int64_t** shapes,
+                             const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 6);
+  for (int i = 0; i < 5; ++i) MREC_REQUIRE(a.is_f32(i), ERR_DTYPE, "mrec_ftrl_dense: param %d must be float32", i);
+  const int64_t n = a.numel(0);
+  MREC_REQUIRE(a.numel(1) == n && a.numel(2) == n && a.numel(4) == n && a.numel(3) >= kHyperLen, ERR_SHAPE,
+               "mrec_ftrl_dense: w/accum/linear/g numel mismatch");
+  if (n == 0) return OK;
+  MREC_LAUNCH(ftrl_dense_kernel, grid_for(cdiv(n, 256), 8), 256, 0, a.stream, a.ptr<float>(0),
+              a.ptr<float>(1), a.ptr<float>(2), a.ptr<float>(4), a.ptr<float>(3), n);
+  return check_launch("ftrl_dense");
+}

@@ -1,0 +1,542 @@
+// K2 — sparse-gradient / lookup dedup: stable LSD radix sort of (key, position) + unique.
+//
+// Replaces the upstream Unique kernel (thrust stable_sort_by_key + unique + scan) reached from
+//   mindspore_rec/ops/embedding.py:191-194            (HashEmbeddingLookup forward dedup)
+//   models/wide_deep/src/wide_and_deep.py:420-445     (optimizer-side RowTensor dedup)
+// and produces, in one call, everything the deterministic segment-sum needs:
+//   uniq[U]      ascending unique keys (GPU Unique order)
+//   inverse[N]   uniq[inverse[i]] == ids[i]
+//   count[1]     U (device scalar: aot outputs are statically shaped, so uniq is padded to N)
+//   perm[N]      stable sort permutation (sorted position -> original position)
+//   seg_start[N+1]  first sorted position of each segment, seg_start[U] = N
+//   seg_of[N]    segment id of each sorted position
+//
+// The sort is an 8-bit-digit LSD radix sort over only the significant key bits (a table with V rows
+// needs ceil(log2(V+1)) bits: 26 bits -> 4 passes for the 33.8 M-row Criteo table).  Each pass is
+// histogram -> column scan -> stable scatter; ranking inside a tile uses warp match-any so equal digits
+// keep their input order (stability is what makes perm's first entry of a segment the first occurrence).
+// All buffers (ping-pong keys/values, histograms) come from the caller-provided workspace: the library
+// never allocates (aot contract).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mrec {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+
+template <typename KeyT> struct UKeyOf;
+template <> struct UKeyOf<int32_t> { using type = uint32_t; static constexpr uint32_t sign = 0x80000000u; };
+template <> struct UKeyOf<int64_t> { using type = uint64_t; static constexpr uint64_t sign = 0x8000000000000000ull; };
+
+// bound > 0: keys outside [0, bound) collapse onto `bound` (they sort last and form one segment that
+// downstream kernels skip); bound == 0: full-width signed order (sign bit flipped).
+template <typename KeyT>
+__device__ __forceinline__ typename UKeyOf<KeyT>::type encode_key(KeyT k, uint64_t bound) {
+  using U = typename UKeyOf<KeyT>::type;
+  if (bound) return ((uint64_t)k < bound) ? (U)k : (U)bound;
+  return (U)k ^ UKeyOf<KeyT>::sign;
+}
+template <typename KeyT>
+__device__ __forceinline__ KeyT decode_key(typename UKeyOf<KeyT>::type u, uint64_t bound) {
+  if (bound) return (KeyT)u;
+  return (KeyT)(u ^ UKeyOf<KeyT>::sign);
+}
+
+template <typename KeyT, bool RAW>
+__device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys, int64_t i,
+                                                                uint64_t bound) {
+  using U = typename UKeyOf<KeyT>::type;
+  if (RAW) return encode_key<KeyT>(reinterpret_cast<const KeyT*>(keys)[i], bound);
+  return reinterpret_cast<const U*>(keys)[i];
+}
+
+// ---- pass kernel 1: per-block digit histogram -> hist[block][digit] ----
+template <typename KeyT, bool RAW>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, uint64_t bound,
+                  int tiles_per_block, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[RADIX];
+  for (int d = threadIdx.x; d < RADIX; d += RS_THREADS) s_hist[d] = 0;
+  __syncthreads();
+  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
+  const int64_t end = min(n, begin + (int64_t)tiles_per_block * RS_TILE);
+  for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
+    const auto k = load_key<KeyT, RAW>(keys, i, bound);
+    atomicAdd(&s_hist[(uint32_t)(k >> shift) & (RADIX - 1)], 1u);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < RADIX; d += RS_THREADS)
+    hist[(int64_t)blockIdx.x * RADIX + d] = s_hist[d];
+}
+
+// ---- pass kernel 2: hist[b][d] -> exclusive offsets (digit-major order), in place ----
+// One block, thread d owns digit d: column prefix over blocks, then digit bases.
+__global__ void __launch_bounds__(RADIX)
+radix_scan_kernel(uint32_t* __restrict__ hist, int n_blocks) {
+  __shared__ uint32_t s_tot[RADIX];
+  const int d = threadIdx.x;
+  uint32_t run = 0;
+  for (int b = 0; b < n_blocks; ++b) {
+    const uint32_t c = hist[(int64_t)b * RADIX + d];
+    hist[(int64_t)b * RADIX + d] = run;
+    run += c;
+  }
+  s_tot[d] = run;
+  __syncthreads();
+  // exclusive scan over 256 digit totals (Hillis-Steele in smem)
+  uint32_t v = run;
+  for (int o = 1; o < RADIX; o <<= 1) {
+    uint32_t t = (d >= o) ? s_tot[d - o] : 0u;
+    __syncthreads();
+    v += t;
+    s_tot[d] = v;
+    __syncthreads();
+  }
+  hist[(int64_t)n_blocks * RADIX + d] = v - run;  // digit base
+}
+
+// ---- pass kernel 3: stable scatter ----
+template <typename KeyT, bool RAW>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                     typename UKeyOf<KeyT>::type* __restrict__ keys_out, int32_t* __restrict__ vals_out,
+                     int64_t n, int shift, uint64_t bound, int tiles_per_block,
+                     const uint32_t* __restrict__ hist, int n_blocks) {
+  using U = typename UKeyOf<KeyT>::type;
+  __shared__ uint32_t s_cnt[RS_WARPS][RADIX];
+  __shared__ uint32_t s_base[RADIX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int d = tid; d < RADIX; d += RS_THREADS)
+    s_base[d] = hist[(int64_t)blockIdx.x * RADIX + d] + hist[(int64_t)n_blocks * RADIX + d];
+
+  const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
+  for (int t = 0; t < tiles_per_block; ++t) {
+    const int64_t tile0 = begin + (int64_t)t * RS_TILE;
+    if (tile0 >= n) break;
+    for (int d = tid; d < RS_WARPS * RADIX; d += RS_THREADS) (&s_cnt[0][0])[d] = 0;
+    __syncthreads();
+
+    U key[RS_ITEMS];
+    int32_t val[RS_ITEMS];
+    uint32_t dig[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+      const int64_t idx = tile0 + warp * (RS_ITEMS * 32) + i * 32 + lane;
+      if (idx < n) {
+        key[i] = load_key<KeyT, RAW>(keys_in, idx, bound);
+        val[i] = RAW ? (int32_t)idx : vals_in[idx];
+        dig[i] = (uint32_t)(key[i] >> shift) & (RADIX - 1);
+      } else {
+        key[i] = 0;
+        val[i] = 0;
+        dig[i] = RADIX;  // invalid marker
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, dig[i]);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader && dig[i] < RADIX) {
+        old = s_cnt[warp][dig[i]];
+        s_cnt[warp][dig[i]] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rank[i] = old + __popc(peers & lt_mask);
+      __syncwarp();
+    }
+    __syncthreads();
+    // per-digit exclusive prefix over warps, plus the running block base
+    for (int d = tid; d < RADIX; d += RS_THREADS) {
+      uint32_t run = s_base[d];
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t c = s_cnt[w][d];
+        s_cnt[w][d] = run;
+        run += c;
+      }
+      s_base[d] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+      if (dig[i] < RADIX) {
+        const uint32_t pos = s_cnt[warp][dig[i]] + rank[i];
+        keys_out[pos] = key[i];
+        vals_out[pos] = val[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- unique from sorted keys ----
+template <typename UKey>
+__global__ void __launch_bounds__(RS_THREADS)
+seg_count_kernel(const UKey* __restrict__ sorted, int64_t n, uint32_t* __restrict__ tile_heads) {
+  __shared__ uint32_t s_warp[RS_WARPS];
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)threadIdx.x * RS_ITEMS;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int64_t i = base + k;
+    if (i < n) c += (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < RS_WARPS; ++w) t += s_warp[w];
+    tile_heads[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of tile_heads (in place), total -> count[0] and seg_start[total] = n
+__global__ void __launch_bounds__(1024)
+seg_scan_kernel(uint32_t* __restrict__ tile_heads, int n_tiles, int32_t* __restrict__ count,
+                int32_t* __restrict__ seg_start, int64_t n) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int i = base + tid;
+    const uint32_t x = (i < n_tiles) ? tile_heads[i] : 0u;
+    uint32_t v = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t warp_off = warp ? s_warp[warp - 1] : 0u;
+    const uint32_t carry = s_carry;
+    if (i < n_tiles) tile_heads[i] = carry + warp_off + v - x;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + warp_off + v;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    count[0] = (int32_t)s_carry;
+    seg_start[s_carry] = (int32_t)n;
+  }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+seg_emit_kernel(const typename UKeyOf<KeyT>::type* __restrict__ sorted,
+                const int32_t* __restrict__ perm, int64_t n, uint64_t bound,
+                const uint32_t* __restrict__ tile_offset, KeyT* __restrict__ uniq,
+                int32_t* __restrict__ inverse, int32_t* __restrict__ seg_start,
+                int32_t* __restrict__ seg_of) {
+  __shared__ uint32_t s_warp[RS_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)tid * RS_ITEMS;
+  uint32_t head[RS_ITEMS];
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int64_t i = base + k;
+    head[k] = (i < n && (i == 0 || sorted[i] != sorted[i - 1])) ? 1u : 0u;
+    c += head[k];
+  }
+  uint32_t v = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_warp[warp] = v;
+  __syncthreads();
+  uint32_t off = tile_offset[blockIdx.x];
+  for (int w = 0; w < warp; ++w) off += s_warp[w];
+  uint32_t seg = off + v - c;  // number of heads strictly before this thread's first item
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int64_t i = base + k;
+    if (i < n) {
+      seg += head[k];
+      const int32_t s = (int32_t)seg - 1;
+      seg_of[i] = s;
+      inverse[perm[i]] = s;
+      if (head[k]) {
+        uniq[s] = decode_key<KeyT>(sorted[i], bound);
+        seg_start[s] = (int32_t)i;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct SortPlan {
+  int64_t n;
+  int n_tiles, n_blocks, tiles_per_block, passes;
+  size_t off_keys_a, off_keys_b, off_vals_tmp, off_hist, off_tiles, total;
+};
+
+static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
+  SortPlan p;
+  p.n = n;
+  p.n_tiles = (int)cdiv(n > 0 ? n : 1, RS_TILE);
+  const int max_blocks = kNumSMs * 8;
+  p.tiles_per_block = (int)cdiv(p.n_tiles, max_blocks);
+  p.n_blocks = (int)cdiv(p.n_tiles, p.tiles_per_block);
+  p.passes = (int)cdiv(key_bits, RADIX_BITS);
+  if (p.passes < 1) p.passes = 1;
+  size_t o = 0;
+  p.off_keys_a = o; o = align_up(o + (size_t)n * key_bytes, 256);
+  p.off_keys_b = o; o = align_up(o + (size_t)n * key_bytes, 256);
+  p.off_vals_tmp = o; o = align_up(o + (size_t)n * 4, 256);
+  p.off_hist = o; o = align_up(o + (size_t)(p.n_blocks + 1) * RADIX * 4, 256);
+  p.off_tiles = o; o = align_up(o + (size_t)(p.n_tiles + 1) * 4, 256);
+  p.total = o;
+  return p;
+}
+
+size_t unique_workspace_bytes(int64_t n, int key_bytes) {
+  return make_plan(n, key_bytes, 8 * key_bytes).total;
+}
+
+int key_bits_for_bound(uint64_t bound) {
+  // keys are clamped to [0, bound] -> need bits to represent `bound`
+  int b = 1;
+  while (b < 64 && (bound >> b) != 0) ++b;
+  return b;
+}
+
+template <typename KeyT>
+int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t* inverse,
+                  int32_t* count, int32_t* perm, int32_t* seg_start, int32_t* seg_of, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
+  using U = typename UKeyOf<KeyT>::type;
+  const int key_bits = bound ? key_bits_for_bound(bound) : 8 * (int)sizeof(KeyT);
+  const SortPlan p = make_plan(n, sizeof(KeyT), key_bits);
+  if (ws_bytes < p.total)
+    return fail(ERR_WORKSPACE, "mrec_unique: workspace %zu bytes < required %zu", ws_bytes, p.total);
+  if (reinterpret_cast<uintptr_t>(ws) % 16 != 0)
+    return fail(ERR_ALIGN, "mrec_unique: workspace must be 16-byte aligned");
+  if (n >= (int64_t)1 << 31) return fail(ERR_SHAPE, "mrec_unique: N must be < 2^31");
+  if (n == 0) {
+    cudaMemsetAsync(count, 0, sizeof(int32_t), stream);
+    cudaMemsetAsync(seg_start, 0, sizeof(int32_t), stream);
+    return OK;
+  }
+  char* w = reinterpret_cast<char*>(ws);
+  U* kbuf[2] = {reinterpret_cast<U*>(w + p.off_keys_a), reinterpret_cast<U*>(w + p.off_keys_b)};
+  int32_t* vtmp = reinterpret_cast<int32_t*>(w + p.off_vals_tmp);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(w + p.off_hist);
+  uint32_t* tiles = reinterpret_cast<uint32_t*>(w + p.off_tiles);
+
+  const void* kin = ids;
+  const int32_t* vin = nullptr;
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const int shift = pass * RADIX_BITS;
+    U* kout = kbuf[pass & 1];
+    // the last pass must land in `perm`
+    int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vtmp;
+    if (pass == 0) {
+      MREC_LAUNCH((radix_hist_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift,
+                  bound, p.tiles_per_block, hist);
+      MREC_LAUNCH(radix_scan_kernel, 1, RADIX, 0, stream, hist, p.n_blocks);
+      MREC_LAUNCH((radix_scatter_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, vin,
+                  kout, vout, n, shift, bound, p.tiles_per_block, hist, p.n_blocks);
+    } else {
+      MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift,
+                  bound, p.tiles_per_block, hist);
+      MREC_LAUNCH(radix_scan_kernel, 1, RADIX, 0, stream, hist, p.n_blocks);
+      MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin,
+                  kout, vout, n, shift, bound, p.tiles_per_block, hist, p.n_blocks);
+    }
+    kin = kout;
+    vin = vout;
+  }
+  const U* sorted = reinterpret_cast<const U*>(kin);
+  MREC_LAUNCH(seg_count_kernel<U>, p.n_tiles, RS_THREADS, 0, stream, sorted, n, tiles);
+  MREC_LAUNCH(seg_scan_kernel, 1, 1024, 0, stream, tiles, p.n_tiles, count, seg_start, n);
+  MREC_LAUNCH(seg_emit_kernel<KeyT>, p.n_tiles, RS_THREADS, 0, stream, sorted, perm, n, bound, tiles,
+              uniq, inverse, seg_start, seg_of);
+  return check_launch("unique_sorted");
+}
+
+template int unique_sorted<int32_t>(const int32_t*, int64_t, uint64_t, int32_t*, int32_t*, int32_t*,
+                                    int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+template int unique_sorted<int64_t>(const int64_t*, int64_t, uint64_t, int64_t*, int32_t*, int32_t*,
+                                    int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+
+// ---- first-occurrence order (upstream CPU Unique) ----
+// Segments are re-ranked by their first position perm[seg_start[u]] (stable sort => minimum).
+__global__ void first_pos_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_start,
+                                 const int32_t* __restrict__ count, int32_t* __restrict__ first_pos,
+                                 int64_t n) {
+  const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  first_pos[u] = (u < count[0]) ? perm[seg_start[u]] : (int32_t)n;  // padding sorts last
+}
+
+template <typename KeyT>
+__global__ void reorder_first_kernel(const int32_t* __restrict__ order /* rank -> ascending seg */,
+                                     const int32_t* __restrict__ count, const KeyT* __restrict__ uniq_asc,
+                                     KeyT* __restrict__ uniq_first, int32_t* __restrict__ remap, int64_t n) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n || r >= count[0]) return;
+  const int32_t u = order[r];
+  uniq_first[r] = uniq_asc[u];
+  remap[u] = (int32_t)r;
+}
+
+__global__ void remap_inverse_kernel(int32_t* __restrict__ inverse, const int32_t* __restrict__ remap,
+                                     int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) inverse[i] = remap[inverse[i]];
+}
+
+size_t unique_first_workspace_bytes(int64_t n, int key_bytes) {
+  // ascending pass workspace + second (int32) sort workspace + 6 int32 arrays + uniq_asc
+  return unique_workspace_bytes(n, key_bytes) + unique_workspace_bytes(n, 4) +
+         align_up((size_t)(n + 1) * 4, 256) * 7 + align_up((size_t)n * key_bytes, 256);
+}
+
+template <typename KeyT>
+int unique_first(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t* inverse,
+                 int32_t* count, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ws_bytes < unique_first_workspace_bytes(n, sizeof(KeyT)))
+    return fail(ERR_WORKSPACE, "mrec_unique_first: workspace %zu bytes < required %zu", ws_bytes,
+                unique_first_workspace_bytes(n, sizeof(KeyT)));
+  char* w = reinterpret_cast<char*>(ws);
+  size_t o = 0;
+  void* ws1 = w + o; const size_t ws1_b = unique_workspace_bytes(n, sizeof(KeyT)); o += ws1_b;
+  void* ws2 = w + o; const size_t ws2_b = unique_workspace_bytes(n, 4); o += ws2_b;
+  const size_t arr = align_up((size_t)(n + 1) * 4, 256);
+  int32_t* perm = reinterpret_cast<int32_t*>(w + o); o += arr;
+  int32_t* seg_start = reinterpret_cast<int32_t*>(w + o); o += arr;
+  int32_t* seg_of = reinterpret_cast<int32_t*>(w + o); o += arr;
+  int32_t* first_pos = reinterpret_cast<int32_t*>(w + o); o += arr;
+  int32_t* order = reinterpret_cast<int32_t*>(w + o); o += arr;
+  int32_t* remap = reinterpret_cast<int32_t*>(w + o); o += arr;
+  int32_t* scratch = reinterpret_cast<int32_t*>(w + o); o += arr;
+  KeyT* uniq_asc = reinterpret_cast<KeyT*>(w + o);
+  int rc = unique_sorted<KeyT>(ids, n, bound, uniq_asc, inverse, count, perm, seg_start, seg_of, ws1,
+                               ws1_b, stream);
+  if (rc != OK || n == 0) return rc;
+  const int grid = (int)cdiv(n, 256);
+  MREC_LAUNCH(first_pos_kernel, grid, 256, 0, stream, perm, seg_start, count, first_pos, n);
+  // sort (first_pos, segment) by first_pos; reuse the pair sort through unique_sorted's machinery:
+  // keys are distinct for real segments, so `perm` of this second sort is the rank -> segment map.
+  // Outputs of the second unique that we do not need land in scratch buffers.
+  // After first_pos is built the first sort's perm/seg_start/seg_of are dead and are reused as the
+  // second sort's throw-away outputs.
+  rc = unique_sorted<int32_t>(first_pos, n, (uint64_t)n, /*uniq*/ seg_of, /*inverse*/ remap,
+                              /*count*/ scratch, /*perm*/ order, /*seg_start*/ seg_start,
+                              /*seg_of*/ perm, ws2, ws2_b, stream);
+  if (rc != OK) return rc;
+  MREC_LAUNCH(reorder_first_kernel<KeyT>, grid, 256, 0, stream, order, count, uniq_asc, uniq, remap, n);
+  MREC_LAUNCH(remap_inverse_kernel, grid, 256, 0, stream, inverse, remap, n);
+  return check_launch("unique_first");
+}
+
+template int unique_first<int32_t>(const int32_t*, int64_t, uint64_t, int32_t*, int32_t*, int32_t*,
+                                   void*, size_t, cudaStream_t);
+template int unique_first<int64_t>(const int64_t*, int64_t, uint64_t, int64_t*, int32_t*, int32_t*,
+                                   void*, size_t, cudaStream_t);
+
+}  // namespace mrec
+
+using namespace mrec;
+
+// Workspace size helpers (plain C, host only).
+MREC_API size_t mrec_unique_workspace_bytes(int64_t n, int key_bytes) {
+  return unique_workspace_bytes(n, key_bytes);
+}
+MREC_API size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes) {
+  return unique_first_workspace_bytes(n, key_bytes);
+}
+
+// inputs : ids[N] i32|i64, (bounded variant: table_like[V, ...] — only its dim 0 is read)
+// outputs: uniq[N] (ids dtype), inverse[N] i32, count[1] i32, perm[N] i32, seg_start[N+1] i32,
+//          seg_of[N] i32, workspace[bytes] uint8|int8
+static int unique_entry(const Aot& a, bool bounded) {
+  const int n_in = bounded ? 2 : 1;
+  if (a.nparam != n_in + 7)
+    return fail(ERR_NPARAM, "mrec_unique%s: expected %d params, got %d", bounded ? "_bounded" : "",
+                n_in + 7, a.nparam);
+  const int o = n_in;
+  const int64_t n = a.numel(0);
+  for (int i = 0; i < a.nparam; ++i)
+    if (!a.params[i] && a.numel(i) > 0 && !(bounded && i == 1))
+      return fail(ERR_NULL, "mrec_unique: param %d is null", i);
+  MREC_REQUIRE(a.is_i32(0) || a.is_i64(0), ERR_DTYPE, "mrec_unique: ids must be int32|int64");
+  MREC_REQUIRE(strcmp(a.dtypes[0], a.dtypes[o]) == 0, ERR_DTYPE, "mrec_unique: uniq dtype must match ids");
+  for (int i = 1; i <= 5; ++i)
+    MREC_REQUIRE(a.is_i32(o + i), ERR_DTYPE, "mrec_unique: output %d must be int32", i);
+  MREC_REQUIRE(a.numel(o) >= n && a.numel(o + 1) >= n && a.numel(o + 2) >= 1 && a.numel(o + 3) >= n &&
+                   a.numel(o + 4) >= n + 1 && a.numel(o + 5) >= n,
+               ERR_SHAPE, "mrec_unique: outputs must be padded to N (seg_start to N+1)");
+  uint64_t bound = 0;
+  if (bounded) {
+    MREC_REQUIRE(a.ndims[1] >= 1 && a.dim(1, 0) > 0, ERR_SHAPE, "mrec_unique_bounded: bad table shape");
+    bound = (uint64_t)a.dim(1, 0);
+    if (a.is_i32(0)) MREC_REQUIRE(bound < 0x7fffffffull, ERR_SHAPE, "mrec_unique_bounded: V too large for int32 ids");
+  }
+  const size_t ws_bytes = (size_t)a.numel(o + 6);
+  if (a.is_i32(0))
+    return unique_sorted<int32_t>(a.ptr<int32_t>(0), n, bound, a.ptr<int32_t>(o), a.ptr<int32_t>(o + 1),
+                                  a.ptr<int32_t>(o + 2), a.ptr<int32_t>(o + 3), a.ptr<int32_t>(o + 4),
+                                  a.ptr<int32_t>(o + 5), a.params[o + 6], ws_bytes, a.stream);
+  return unique_sorted<int64_t>(a.ptr<int64_t>(0), n, bound, a.ptr<int64_t>(o), a.ptr<int32_t>(o + 1),
+                                a.ptr<int32_t>(o + 2), a.ptr<int32_t>(o + 3), a.ptr<int32_t>(o + 4),
+                                a.ptr<int32_t>(o + 5), a.params[o + 6], ws_bytes, a.stream);
+}
+
+MREC_API int mrec_unique(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                         void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  return unique_entry(a, false);
+}
+
+MREC_API int mrec_unique_bounded(int nparam, void** params, int* ndims, int64_t** shapes,
+                                 const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  return unique_entry(a, true);
+}
+
+// First-occurrence order (the order of upstream's CPU Unique kernel).
+// inputs : ids[N] ; outputs: uniq[N], inverse[N] i32, count[1] i32, workspace[bytes]
+MREC_API int mrec_unique_first(int nparam, void** params, int* ndims, int64_t** shapes,
+                               const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 5);
+  const int64_t n = a.numel(0);
+  MREC_REQUIRE(a.is_i32(0) || a.is_i64(0), ERR_DTYPE, "mrec_unique_first: ids must be int32|int64");
+  MREC_REQUIRE(strcmp(a.dtypes[0], a.dtypes[1]) == 0, ERR_DTYPE, "mrec_unique_first: uniq dtype must match ids");
+  MREC_REQUIRE(a.is_i32(2) && a.is_i32(3), ERR_DTYPE, "mrec_unique_first: inverse/count must be int32");
+  MREC_REQUIRE(a.numel(1) >= n && a.numel(2) >= n && a.numel(3) >= 1, ERR_SHAPE,
+               "mrec_unique_first: outputs must be padded to N");
+  const size_t ws_bytes = (size_t)a.numel(4);
+  if (a.is_i32(0))
+    return unique_first<int32_t>(a.ptr<int32_t>(0), n, 0, a.ptr<int32_t>(1), a.ptr<int32_t>(2),
+                                 a.ptr<int32_t>(3), a.params[4], ws_bytes, a.stream);
+  return unique_first<int64_t>(a.ptr<int64_t>(0), n, 0, a.ptr<int64_t>(1), a.ptr<int32_t>(2),
+                               a.ptr<int32_t>(3), a.params[4], ws_bytes, a.stream);
+}

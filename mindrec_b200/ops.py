@@ -1,0 +1,194 @@
+"""Functional wrappers over the aot entry points (one Python function per exported symbol).
+
+Each wrapper only allocates outputs / workspaces (torch is the allocator here, MindSpore would be under
+``ops.Custom``) and forwards to the C-ABI; no arithmetic happens in Python.  Workspaces are cached per
+(symbol, size, device) so steady-state steps allocate nothing and can be captured in a CUDA graph.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_ws_cache = {}
+HYPER_LEN = 8
+
+
+def _ws(tag, nbytes, device):
+    key = (tag, device)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _dummy(device):
+    key = ("dummy", device)
+    buf = _ws_cache.get(key)
+    if buf is None:
+        buf = torch.zeros(1, dtype=torch.int32, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _size_fn(name):
+    f = getattr(_lib.lib(), name)
+    f.restype = ctypes.c_size_t
+    f.argtypes = [ctypes.c_int64, ctypes.c_int]
+    return f
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 gather
+# ------------------------------------------------------------------------------------------------
+def gather(table, ids, out=None, oob_flag=None):
+    """out[..., :] = table[ids[...], :]  (mrec_gather; nn.EmbeddingLookup / P.Gather axis 0)."""
+    dim = table.shape[1] if table.dim() == 2 else 1
+    if out is None:
+        out = torch.empty(tuple(ids.shape) + (dim,), dtype=torch.float32, device=table.device)
+    args = [table, ids, out] + ([oob_flag] if oob_flag is not None else [])
+    _lib.aot_call("mrec_gather", args)
+    return out
+
+
+def gather_masked(table, ids, mask, out=None, oob_flag=None):
+    """out[b, f*D:(f+1)*D] = table[ids[b,f]] * mask[b,f]  (gather + Mul + Reshape fused)."""
+    dim = table.shape[1] if table.dim() == 2 else 1
+    if out is None:
+        out = torch.empty((ids.shape[0], ids.numel() // ids.shape[0] * dim), dtype=torch.float32,
+                          device=table.device)
+    args = [table, ids, mask, out] + ([oob_flag] if oob_flag is not None else [])
+    _lib.aot_call("mrec_gather_masked", args)
+    return out
+
+
+def gather_reduce(table, ids, mask, bias, out=None, oob_flag=None):
+    """out[b] = sum_f table[ids[b,f]] * mask[b,f] + bias  for a dim-1 table (wide / linear term)."""
+    if out is None:
+        out = torch.empty((ids.shape[0], 1), dtype=torch.float32, device=table.device)
+    args = [table, ids, mask, bias, out] + ([oob_flag] if oob_flag is not None else [])
+    _lib.aot_call("mrec_gather_reduce", args)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 unique
+# ------------------------------------------------------------------------------------------------
+class UniqueResult:
+    """Outputs of mrec_unique (all padded to N; `count` is a device scalar)."""
+    __slots__ = ("uniq", "inverse", "count", "perm", "seg_start", "seg_of", "n")
+
+    def __init__(self, n, dtype, device):
+        self.n = n
+        self.uniq = torch.empty(n, dtype=dtype, device=device)
+        self.inverse = torch.empty(n, dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.perm = torch.empty(n, dtype=torch.int32, device=device)
+        self.seg_start = torch.empty(n + 1, dtype=torch.int32, device=device)
+        self.seg_of = torch.empty(n, dtype=torch.int32, device=device)
+
+    def outputs(self):
+        return [self.uniq, self.inverse, self.count, self.perm, self.seg_start, self.seg_of]
+
+
+def unique(ids, table_like=None, result=None):
+    """Ascending unique + inverse + stable sort permutation + segment map.
+
+    With `table_like` (any tensor whose dim 0 is the table's row count V) only ceil(log2(V+1)) key bits
+    are sorted and ids outside [0, V) collapse onto the value V (mrec_unique_bounded).
+    """
+    flat = ids.reshape(-1)
+    n = flat.numel()
+    if result is None:
+        result = UniqueResult(n, flat.dtype, flat.device)
+    nbytes = _size_fn("mrec_unique_workspace_bytes")(n, flat.element_size())
+    ws = _ws("unique", nbytes, flat.device)
+    if table_like is None:
+        _lib.aot_call("mrec_unique", [flat] + result.outputs() + [ws])
+    else:
+        _lib.aot_call("mrec_unique_bounded", [flat, table_like] + result.outputs() + [ws])
+    return result
+
+
+def unique_first(ids):
+    """First-occurrence-order unique (the order of upstream's CPU Unique): (uniq[N], inverse[N], count[1])."""
+    flat = ids.reshape(-1)
+    n = flat.numel()
+    uniq = torch.empty(n, dtype=flat.dtype, device=flat.device)
+    inverse = torch.empty(n, dtype=torch.int32, device=flat.device)
+    count = torch.zeros(1, dtype=torch.int32, device=flat.device)
+    nbytes = _size_fn("mrec_unique_first_workspace_bytes")(n, flat.element_size())
+    ws = _ws("unique_first", nbytes, flat.device)
+    _lib.aot_call("mrec_unique_first", [flat, uniq, inverse, count, ws])
+    return uniq, inverse, count
+
+
+# ------------------------------------------------------------------------------------------------
+# K3-K5 segment-sum + sparse optimizers
+# ------------------------------------------------------------------------------------------------
+_EMPTY = {}
+
+
+def _empty_mask(device):
+    m = _EMPTY.get(device)
+    if m is None:
+        m = torch.empty(0, dtype=torch.float32, device=device)
+        _EMPTY[device] = m
+    return m
+
+
+def _opt_ws(n, dim, device):
+    nbytes = _size_fn("mrec_sparse_opt_workspace_bytes")(n, dim)
+    return _ws("sparse_opt", nbytes, device)
+
+
+def segment_sum(g, mask, uq, dim=None, out=None):
+    """gsum[u] = sum over positions n of segment u of mask[n] * g[n // div]  (sorted order, no atomics)."""
+    dim = dim if dim is not None else (g.shape[-1] if g.dim() >= 2 else 1)
+    if out is None:
+        out = torch.zeros((uq.n, dim), dtype=torch.float32, device=g.device)
+    mask = _empty_mask(g.device) if mask is None else mask.reshape(-1)
+    _lib.aot_call("mrec_segment_sum", [g, mask, uq.perm, uq.seg_start, uq.seg_of, out,
+                                       _opt_ws(uq.n, dim, g.device)])
+    return out
+
+
+def sparse_lazy_adam(w, m, v, hyper, g, mask, uq):
+    """Fused segment-sum + LazyAdam row update on the rows named by uq.uniq (in place)."""
+    dim = w.shape[1] if w.dim() == 2 else 1
+    mask = _empty_mask(w.device) if mask is None else mask.reshape(-1)
+    _lib.aot_call("mrec_sparse_lazy_adam", [w, m, v, hyper, g, mask, uq.uniq, uq.perm, uq.seg_start,
+                                            uq.seg_of, _dummy(w.device), _opt_ws(uq.n, dim, w.device)])
+
+
+def sparse_ftrl(w, accum, linear, hyper, g, mask, uq):
+    """Fused segment-sum + FTRL row update on the rows named by uq.uniq (in place)."""
+    dim = w.shape[1] if w.dim() == 2 else 1
+    mask = _empty_mask(w.device) if mask is None else mask.reshape(-1)
+    _lib.aot_call("mrec_sparse_ftrl", [w, accum, linear, hyper, g, mask, uq.uniq, uq.perm, uq.seg_start,
+                                       uq.seg_of, _dummy(w.device), _opt_ws(uq.n, dim, w.device)])
+
+
+def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, loss_scale=1.0, device="cuda"):
+    """Device hyper block for Adam / LazyAdam: [lr, b1, b2, eps, b1^t, b2^t, lr_t, 1/loss_scale]."""
+    return torch.tensor([lr, beta1, beta2, eps, 1.0, 1.0, 0.0, 1.0 / loss_scale],
+                        dtype=torch.float32, device=device)
+
+
+def ftrl_hyper(lr, l1=0.0, l2=0.0, lr_power=-0.5, loss_scale=1.0, device="cuda"):
+    """Device hyper block for FTRL: [lr, l1, l2, lr_power, 1/loss_scale, 0, 0, 0]."""
+    return torch.tensor([lr, l1, l2, lr_power, 1.0 / loss_scale, 0.0, 0.0, 0.0],
+                        dtype=torch.float32, device=device)
+
+
+def adam_begin_step(hyper):
+    _lib.aot_call("mrec_adam_begin_step", [hyper, _dummy(hyper.device)])
+
+
+def adam_dense(w, m, v, hyper, g):
+    _lib.aot_call("mrec_adam_dense", [w, m, v, hyper, g, _dummy(w.device)])
+
+
+def ftrl_dense(w, accum, linear, hyper, g):
+    _lib.aot_call("mrec_ftrl_dense", [w, accum, linear, hyper, g, _dummy(w.device)])

@@ -1,0 +1,321 @@
+"""CPU oracle for the MindRec embedding-and-interaction hot path (numpy).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mindrec_b200/`` imports this module; it may be imported by
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` and nowhere else.
+
+PARITY UNPINNED.  The reference repository (mindspore-lab/mindrec) contains no kernels and no numerical
+tests for this path: every arithmetic op is delegated to the unpinned third-party dependency
+``mindspore`` (requirements/cpu_requirements.txt:3; >= 2.0 is needed for
+mindspore_rec/ops/embedding.py:22,27), which is neither vendored under /root/reference nor installable
+here.  This file therefore restates (a) the reference's own model code line by line and (b) the published
+semantics of the MindSpore ops that code calls (listed in oracle/ASSUMPTIONS.md, one testable item
+each).  The pins we can offer are algebraic identities and finite-difference checks in
+tests/test_oracle.py plus frozen seeded vectors in tests/golden/.
+
+Every function cites the reference file:line it follows.  Accumulations that the tolerance contract
+(1e-5 relative, fp32) is judged against are carried in float64 and rounded once at the end; index /
+key / gathered-row outputs are exact.
+"""
+import numpy as np
+
+F32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# a1/a2  gather, mask multiply, wide reduce
+# ------------------------------------------------------------------------------------------------
+def gather(table, ids):
+    """P.Gather(table, ids, 0) — models/wide_deep/src/wide_and_deep.py:300-302 via nn.EmbeddingLookup,
+    models/deepfm/src/deepfm.py:217,221, models/deep_and_cross/src/deep_and_cross.py:199.
+    Out-of-range ids give a zero row (GPU Gather semantics, ASSUMPTIONS B2)."""
+    table = np.asarray(table)
+    t2 = table.reshape(table.shape[0], -1)
+    ids = np.asarray(ids)
+    flat = ids.reshape(-1).astype(np.int64)
+    ok = (flat >= 0) & (flat < t2.shape[0])
+    out = np.zeros((flat.size, t2.shape[1]), dtype=table.dtype)
+    out[ok] = t2[flat[ok]]
+    return out.reshape(ids.shape + (t2.shape[1],))
+
+
+def gather_masked(table, ids, mask):
+    """deep_in = reshape(table[ids] * mask[..., None], (B, F*D)) — wide_and_deep.py:303,308-309;
+    deepfm.py:215,222,230; deep_and_cross.py:295-298.  One fp32 multiply per element: exact."""
+    e = gather(table, ids)
+    out = e * np.asarray(mask, dtype=F32)[..., None]
+    return out.reshape(ids.shape[0], -1).astype(F32)
+
+
+def gather_reduce(table, ids, mask, bias=None):
+    """wide_out = sum_f table[ids] * mask + Wide_b — wide_and_deep.py:300,305-306; deepfm.py:217-219."""
+    e = gather(np.asarray(table).reshape(-1, 1), ids)[..., 0].astype(np.float64)
+    s = (e * np.asarray(mask, dtype=np.float64)).sum(axis=1)
+    if bias is not None:
+        s = s + np.float64(np.asarray(bias).reshape(-1)[0])
+    return s.astype(F32).reshape(-1, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# a4  unique (both orders) and deterministic segment-sum
+# ------------------------------------------------------------------------------------------------
+def unique_sorted(ids, bound=None):
+    """P.Unique, GPU order (ascending) — mindspore_rec/ops/embedding.py:191-192; ASSUMPTIONS B3.
+    Returns (uniq, inverse int32, perm int32 = stable argsort, seg_start int32[U+1]).
+    bound: ids outside [0, bound) collapse onto the value `bound` (mrec_unique_bounded)."""
+    flat = np.asarray(ids).reshape(-1)
+    if bound is not None:
+        flat = np.where((flat >= 0) & (flat < bound), flat, bound).astype(flat.dtype)
+    perm = np.argsort(flat, kind="stable").astype(np.int32)
+    s = flat[perm]
+    head = np.ones(s.size, dtype=bool)
+    head[1:] = s[1:] != s[:-1]
+    uniq = s[head]
+    seg_of = np.cumsum(head) - 1
+    inverse = np.empty(flat.size, dtype=np.int32)
+    inverse[perm] = seg_of.astype(np.int32)
+    seg_start = np.concatenate([np.nonzero(head)[0], [flat.size]]).astype(np.int32)
+    return uniq, inverse, perm, seg_start
+
+
+def unique_first(ids):
+    """P.Unique, CPU order (first occurrence) — ASSUMPTIONS B3; docs example [1,2,5,2] -> ([1,2,5],[0,1,2,1])."""
+    flat = np.asarray(ids).reshape(-1)
+    seen = {}
+    uniq = []
+    inverse = np.empty(flat.size, dtype=np.int32)
+    for i, k in enumerate(flat.tolist()):
+        j = seen.get(k)
+        if j is None:
+            j = len(uniq)
+            seen[k] = j
+            uniq.append(k)
+        inverse[i] = j
+    return np.asarray(uniq, dtype=flat.dtype), inverse
+
+
+def segment_sum(values, inverse, num_segments, mask=None, div=1):
+    """UnsortedSegmentSum(values, inverse, U) — the RowTensor dedup of ASSUMPTIONS B4 (float64 accumulate).
+    values[n // div] is the row of lookup position n; mask[n] scales it (the bprop of the mask Mul,
+    wide_and_deep.py:307-308)."""
+    values = np.asarray(values)
+    v2 = values.reshape(values.shape[0], -1) if values.ndim > 1 else values.reshape(-1, 1)
+    n = np.asarray(inverse).size
+    rows = v2[np.arange(n) // div].astype(np.float64)
+    if mask is not None:
+        rows = rows * np.asarray(mask, dtype=np.float64).reshape(-1, 1)
+    out = np.zeros((num_segments, v2.shape[1]), dtype=np.float64)
+    np.add.at(out, np.asarray(inverse, dtype=np.int64), rows)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a5/a6  optimizers (ASSUMPTIONS B4-B7)
+# ------------------------------------------------------------------------------------------------
+class AdamState:
+    """nn.Adam / nn.LazyAdam state — wide_and_deep.py:420-422,435-437 (lr 3.5e-4, eps 1e-8, loss_scale sens)."""
+
+    def __init__(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, loss_scale=1.0):
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.grad_scale = F32(1.0) / F32(loss_scale)
+        self.beta1_power = F32(1.0)
+        self.beta2_power = F32(1.0)
+        self.lr_t = F32(0.0)
+
+    def begin_step(self):
+        """beta powers are multiplied before use (step t uses beta^t); lr_t = lr*sqrt(1-b2^t)/(1-b1^t)."""
+        self.beta1_power = F32(self.beta1_power * F32(self.beta1))
+        self.beta2_power = F32(self.beta2_power * F32(self.beta2))
+        self.lr_t = F32(F32(self.lr) * np.sqrt(F32(1) - self.beta2_power) / (F32(1) - self.beta1_power))
+
+
+def adam_rows(w, m, v, g, st):
+    """m = b1*m + (1-b1)g; v = b2*v + (1-b2)g^2; w -= lr_t*m/(sqrt(v)+eps)  (float64 math, fp32 state)."""
+    g = np.asarray(g, dtype=np.float64) * np.float64(st.grad_scale)
+    m64 = st.beta1 * m.astype(np.float64) + (1.0 - st.beta1) * g
+    v64 = st.beta2 * v.astype(np.float64) + (1.0 - st.beta2) * g * g
+    w64 = w.astype(np.float64) - np.float64(st.lr_t) * m64 / (np.sqrt(v64) + st.eps)
+    return w64.astype(F32), m64.astype(F32), v64.astype(F32)
+
+
+def lazy_adam_sparse(w, m, v, uniq, gsum, st):
+    """nn.LazyAdam with a deduplicated RowTensor gradient: only rows in `uniq` move (ASSUMPTIONS B6)."""
+    uniq = np.asarray(uniq, dtype=np.int64)
+    ok = (uniq >= 0) & (uniq < w.shape[0])
+    r = uniq[ok]
+    w[r], m[r], v[r] = adam_rows(w[r], m[r], v[r], np.asarray(gsum)[ok], st)
+
+
+def adam_dense(w, m, v, g, st):
+    """nn.Adam dense kernel (ASSUMPTIONS B5) — in place."""
+    w[...], m[...], v[...] = adam_rows(w, m, v, g, st)
+
+
+class FtrlState:
+    """nn.FTRL hyper-parameters — wide_and_deep.py:423-430 (lr 5e-2, l1=l2=1e-8, initial_accum 1.0)."""
+
+    def __init__(self, lr, l1=0.0, l2=0.0, lr_power=-0.5, loss_scale=1.0):
+        self.lr, self.l1, self.l2, self.lr_power = lr, l1, l2, lr_power
+        self.grad_scale = F32(1.0) / F32(loss_scale)
+
+
+def ftrl_rows(w, acc, lin, g, st):
+    """ApplyFtrl (ASSUMPTIONS B7): a'=a+g^2; sigma=(a'^-p - a^-p)/lr; lin+=g-sigma*w;
+    w = |lin|>l1 ? (sign(lin)*l1-lin)/(a'^-p/lr+2*l2) : 0."""
+    g = np.asarray(g, dtype=np.float64) * np.float64(st.grad_scale)
+    a = acc.astype(np.float64)
+    a_new = a + g * g
+    p = -st.lr_power
+    pa_new, pa_old = np.power(a_new, p), np.power(a, p)
+    sigma = (pa_new - pa_old) / st.lr
+    lin64 = lin.astype(np.float64) + g - sigma * w.astype(np.float64)
+    q = pa_new / st.lr + 2.0 * st.l2
+    w64 = np.where(np.abs(lin64) > st.l1, (np.sign(lin64) * st.l1 - lin64) / q, 0.0)
+    return w64.astype(F32), a_new.astype(F32), lin64.astype(F32)
+
+
+def ftrl_sparse(w, acc, lin, uniq, gsum, st):
+    """SparseApplyFtrl / FusedSparseFtrl: identical math on the touched (deduplicated) rows only."""
+    uniq = np.asarray(uniq, dtype=np.int64)
+    ok = (uniq >= 0) & (uniq < w.shape[0])
+    r = uniq[ok]
+    w[r], acc[r], lin[r] = ftrl_rows(w[r], acc[r], lin[r], np.asarray(gsum)[ok].reshape(w[r].shape), st)
+
+
+def ftrl_dense(w, acc, lin, g, st):
+    w[...], acc[...], lin[...] = ftrl_rows(w, acc, lin, g, st)
+
+
+# ------------------------------------------------------------------------------------------------
+# a8  loss
+# ------------------------------------------------------------------------------------------------
+def sigmoid_xent(logit, label):
+    """SigmoidCrossEntropyWithLogits = max(x,0) - x*z + log1p(exp(-|x|)) — wide_and_deep.py:354 (B11)."""
+    x = np.asarray(logit, dtype=np.float64)
+    z = np.asarray(label, dtype=np.float64)
+    return np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
+
+
+def sigmoid(x):
+    x = np.asarray(x, dtype=np.float64)
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+# ------------------------------------------------------------------------------------------------
+# a11  DeepFM second-order FM  — models/deepfm/src/deepfm.py:222-228
+# ------------------------------------------------------------------------------------------------
+def fm_forward(vx):
+    """fm = 0.5 * sum_d[(sum_f vx)^2 - sum_f vx^2]; vx is [B,F,D] (already multiplied by the mask)."""
+    vx = np.asarray(vx, dtype=np.float64)
+    v1 = np.square(vx.sum(axis=1))
+    v2 = np.square(vx).sum(axis=1)
+    return (0.5 * (v1 - v2).sum(axis=1)).reshape(-1, 1)
+
+
+def fm_backward(vx, gout):
+    """d fm / d vx[b,f,d] = g[b] * (S[b,d] - vx[b,f,d]),  S = sum_f vx."""
+    vx = np.asarray(vx, dtype=np.float64)
+    s = vx.sum(axis=1, keepdims=True)
+    return np.asarray(gout, dtype=np.float64).reshape(-1, 1, 1) * (s - vx)
+
+
+def fm_pairwise(vx):
+    """Independent statement of the same quantity: sum_{i<j} <v_i, v_j> (used only to pin fm_forward)."""
+    vx = np.asarray(vx, dtype=np.float64)
+    b, f, _ = vx.shape
+    out = np.zeros((b, 1))
+    for i in range(f):
+        for j in range(i + 1, f):
+            out[:, 0] += (vx[:, i] * vx[:, j]).sum(axis=1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a13  DCN cross stack — models/deep_and_cross/src/deep_and_cross.py:139-149 (x6: 301-306)
+# ------------------------------------------------------------------------------------------------
+def cross_forward(x0, w, b):
+    """x_{l+1} = x_0 * (x_l . w_l) + b_l + x_l, layer by layer exactly as CrossLayer.construct.
+    w, b: [L, D'].  Returns (x_L, [x_0..x_{L-1}], s[B,L])."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    xl = x0
+    xs, ss = [], []
+    for l in range(w.shape[0]):
+        s = xl @ np.asarray(w[l], dtype=np.float64)
+        xs.append(xl)
+        ss.append(s)
+        xl = x0 * s[:, None] + np.asarray(b[l], dtype=np.float64)[None, :] + xl
+    return xl, xs, np.stack(ss, axis=1) if ss else np.zeros((x0.shape[0], 0))
+
+
+def cross_backward(x0, w, b, gy):
+    """Reverse-mode through the L layers: returns (dx0_total, dw[L,D'], db[L,D'])."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    _, xs, ss = cross_forward(x0, w, b)
+    g = np.asarray(gy, dtype=np.float64)
+    dx0 = np.zeros_like(x0)
+    dw = np.zeros(w.shape, dtype=np.float64)
+    db = np.zeros(b.shape, dtype=np.float64)
+    for l in range(w.shape[0] - 1, -1, -1):
+        db[l] = g.sum(axis=0)
+        ds = (g * x0).sum(axis=1)
+        dx0 += g * ss[:, l][:, None]
+        dw[l] = (ds[:, None] * xs[l]).sum(axis=0)
+        g = g + ds[:, None] * np.asarray(w[l], dtype=np.float64)[None, :]
+    return g + dx0, dw, db
+
+
+# ------------------------------------------------------------------------------------------------
+# a9  MapParameter (hash) model — README.md:155-205, mindspore_rec/ops/embedding.py:136-149 (B9)
+# ------------------------------------------------------------------------------------------------
+class MapParameterModel:
+    """dict-backed model of mindspore.experimental.MapParameter with permit / evict filters."""
+
+    def __init__(self, dim, default_value=0.0, permit_filter_value=1, evict_filter_value=None):
+        self.dim = dim
+        self.default = np.full((dim,), default_value, dtype=F32) if np.isscalar(default_value) \
+            else np.asarray(default_value, dtype=F32)
+        self.permit = permit_filter_value
+        self.evict_after = evict_filter_value
+        self.rows = {}       # key -> row (resident)
+        self.seen = {}       # key -> number of steps in which it was looked up
+        self.last = {}       # key -> last step it was looked up
+        self.step = 0
+
+    def get(self, keys, insert_default_value=True):
+        """MapTensorGet: one sighting per distinct key per call; a key becomes resident on its
+        `permit`-th sighting; before that the default row is returned and nothing is stored."""
+        keys = np.asarray(keys).reshape(-1)
+        self.step += 1
+        out = np.empty((keys.size, self.dim), dtype=F32)
+        touched = set()
+        for i, k in enumerate(keys.tolist()):
+            if k not in touched:
+                touched.add(k)
+                self.seen[k] = self.seen.get(k, 0) + 1
+                self.last[k] = self.step
+                if k not in self.rows and insert_default_value and self.seen[k] >= self.permit:
+                    self.rows[k] = self.default.copy()
+            out[i] = self.rows[k] if k in self.rows else self.default
+        return out
+
+    def put(self, keys, values):
+        for k, v in zip(np.asarray(keys).reshape(-1).tolist(), np.asarray(values, dtype=F32)):
+            self.rows[k] = v.copy()
+            self.last[k] = self.step
+            self.seen[k] = max(self.seen.get(k, 0), self.permit)
+
+    def erase(self, keys):
+        for k in np.asarray(keys).reshape(-1).tolist():
+            self.rows.pop(k, None)
+            self.seen.pop(k, None)
+            self.last.pop(k, None)
+
+    def evict(self):
+        """Drop every key not looked up for more than `evict_filter_value` steps."""
+        if self.evict_after is None:
+            return
+        for k in [k for k, s in self.last.items() if self.step - s > self.evict_after]:
+            self.erase([k])
+
+    def keys(self):
+        return np.asarray(sorted(self.rows.keys()), dtype=np.int64)

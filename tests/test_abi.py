@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol that
+include/mindrec_b200.h declares, and validates its arguments without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from mindrec_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mindrec_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrec_\w+)\s*\(", text)))
+
+
+def test_header_declares_symbols():
+    syms = _declared_symbols()
+    assert "mrec_gather" in syms and "mrec_unique" in syms and "mrec_sparse_lazy_adam" in syms
+    assert len(syms) >= 15
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
+    assert not missing, "declared in include/mindrec_b200.h but not exported: %s" % missing
+
+
+def test_version_and_counters(built_lib):
+    assert "sm_100a" in _lib.version()
+    assert _lib.launch_count() >= 0
+
+
+def test_bad_nparam_is_rejected_without_gpu(built_lib):
+    # validation happens before any CUDA call, so this is safe on a CPU-only box
+    rc = _lib.aot_call_raw("mrec_gather", [16, 32], [(4, 4), (2,)], ["float32", "int32"])
+    assert rc == 1  # MREC_ERR_NPARAM
+    assert "expected" in _lib.last_error()
+
+
+def test_bad_dtype_is_rejected_without_gpu(built_lib):
+    rc = _lib.aot_call_raw("mrec_gather", [16, 32, 64], [(4, 4), (2,), (2, 4)],
+                           ["float16", "int32", "float32"])
+    assert rc == 2  # MREC_ERR_DTYPE
+    rc = _lib.aot_call_raw("mrec_gather", [16, 32, 64], [(4, 4), (2,), (2, 4)],
+                           ["float32", "float32", "float32"])
+    assert rc == 2
+
+
+def test_bad_shape_and_alignment_are_rejected_without_gpu(built_lib):
+    rc = _lib.aot_call_raw("mrec_gather", [16, 32, 64], [(4, 4), (2,), (3, 4)],
+                           ["float32", "int32", "float32"])
+    assert rc == 3  # MREC_ERR_SHAPE
+    rc = _lib.aot_call_raw("mrec_gather", [20, 32, 64], [(4, 4), (2,), (2, 4)],
+                           ["float32", "int32", "float32"])
+    assert rc == 4  # MREC_ERR_ALIGN
+    rc = _lib.aot_call_raw("mrec_gather", [0, 32, 64], [(4, 4), (2,), (2, 4)],
+                           ["float32", "int32", "float32"])
+    assert rc == 8  # MREC_ERR_NULL
+
+
+def test_workspace_size_helpers(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    for name in ("mrec_unique_workspace_bytes", "mrec_unique_first_workspace_bytes",
+                 "mrec_sparse_opt_workspace_bytes"):
+        f = getattr(lib, name)
+        f.restype = ctypes.c_size_t
+        f.argtypes = [ctypes.c_int64, ctypes.c_int]
+    assert lib.mrec_unique_workspace_bytes(624000, 4) >= 624000 * 12
+    assert lib.mrec_unique_workspace_bytes(0, 4) > 0
+    assert lib.mrec_sparse_opt_workspace_bytes(624000, 80) >= 624000 // 32 * 2 * 80 * 4
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        _lib.lib()

@@ -1,0 +1,121 @@
+"""Per-kernel micro-benchmarks at BASELINE config sizes (CUDA events, L2 flushed between iterations).
+
+    python tools/kbench.py [gather|unique|adam|ftrl|all] [--vocab V]
+Prints one line per kernel: name, median ms, algorithmic MB, achieved GB/s, fraction of measured HBM peak.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mindrec_b200 import ops  # noqa: E402
+
+
+def hbm_peak():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(p))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def report(name, ms, nbytes):
+    peak, how = hbm_peak()
+    gbs = nbytes / ms / 1e6
+    print("%-28s %8.3f ms  %9.1f MB  %8.1f GB/s  %5.1f%% of %s HBM peak" %
+          (name, ms, nbytes / 1e6, gbs, 100 * gbs / peak, how), flush=True)
+
+
+def zipf_ids(b, f, vocab, seed=0):
+    rng = np.random.default_rng(seed)
+    ids = (rng.zipf(1.05, size=(b, f)) % vocab).astype(np.int32)
+    ids[:, :13] = np.arange(13)
+    return torch.from_numpy(ids).cuda()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--vocab", type=int, default=33762616)
+    ap.add_argument("--batch", type=int, default=16000)
+    ap.add_argument("--dim", type=int, default=80)
+    a = ap.parse_args()
+    b, f, d, v = a.batch, 39, a.dim, a.vocab
+    n = b * f
+    ids = zipf_ids(b, f, v)
+    mask = torch.rand((b, f), device="cuda")
+    table = torch.empty((v, d), device="cuda").normal_(0, 0.01)
+    if a.what in ("gather", "all"):
+        out = torch.empty((b, f * d), device="cuda")
+        report("gather D=%d" % d, timeit(lambda: ops.gather(table, ids, out=out)), n * (8 * d + 4))
+        report("gather_masked D=%d" % d, timeit(lambda: ops.gather_masked(table, ids, mask, out=out)),
+               n * (8 * d + 8))
+        uni = torch.randint(0, v, (b, f), device="cuda", dtype=torch.int32)
+        report("gather uniform ids", timeit(lambda: ops.gather(table, uni, out=out)), n * (8 * d + 4))
+        wt = torch.empty((v, 1), device="cuda").normal_(0, 0.01)
+        bias = torch.zeros(1, device="cuda")
+        wo = torch.empty((b, 1), device="cuda")
+        report("gather_reduce D=1", timeit(lambda: ops.gather_reduce(wt, ids, mask, bias, out=wo)),
+               n * 12 + b * 4)
+    if a.what in ("unique", "all"):
+        res = ops.UniqueResult(n, torch.int32, ids.device)
+        ms = timeit(lambda: ops.unique(ids, table_like=table, result=res))
+        u = int(res.count.item())
+        report("unique_bounded N=%d U=%d" % (n, u), ms, n * 8 + u * 4)
+        ms = timeit(lambda: ops.unique(ids, result=res))
+        report("unique 32-bit", ms, n * 8 + u * 4)
+    if a.what in ("adam", "all"):
+        res = ops.unique(ids, table_like=table)
+        u = int(res.count.item())
+        m_, v_ = torch.zeros_like(table), torch.zeros_like(table)
+        g = torch.randn((n, d), device="cuda")
+        hyper = ops.adam_hyper(3.5e-4, loss_scale=1024.0)
+        ops.adam_begin_step(hyper)
+        ms = timeit(lambda: ops.sparse_lazy_adam(table, m_, v_, hyper, g, mask, res))
+        report("segsum+lazy_adam U=%d" % u, ms, n * d * 4 + u * 7 * d * 4)
+        gs = torch.empty((n, d), device="cuda")
+        ms = timeit(lambda: ops.segment_sum(g, mask, res, out=gs))
+        report("segment_sum", ms, n * d * 4 + u * d * 4)
+        del m_, v_, g, gs
+    if a.what in ("ftrl", "all"):
+        res = ops.unique(ids, table_like=table)
+        u = int(res.count.item())
+        wt = torch.empty((v, 1), device="cuda").normal_(0, 0.01)
+        acc, lin = torch.ones_like(wt), torch.zeros_like(wt)
+        g = torch.randn((b, 1), device="cuda")
+        hyper = ops.ftrl_hyper(5e-2, 1e-8, 1e-8, loss_scale=1024.0)
+        ms = timeit(lambda: ops.sparse_ftrl(wt, acc, lin, hyper, g, mask, res))
+        report("segsum+ftrl D=1 U=%d" % u, ms, u * 28 + n * 8)
+
+
+if __name__ == "__main__":
+    main()
