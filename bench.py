@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: Wide&Deep training samples/s on synthetic Criteo-shaped data (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+N = 1 measures BASELINE config 2: Wide&Deep, one B200, Criteo-Kaggle vocabulary (33 762 616 rows, dim 80,
+fp32 tables), batch 16000, LazyAdam on the deep table + FTRL on the wide table, DenseLayers in fp16 like the
+reference's `use_mixed_precision`.  A step = lookup (gather + mask + wide reduce) -> DenseLayer fwd/bwd
+(cuBLAS) -> loss -> sparse-gradient dedup -> fused segment-sum + LazyAdam / FTRL row updates -> dense Adam.
+N > 1 row-shards the tables over the ranks with all-to-all exchange (mindrec_b200.sharded), weak scaling.
+
+`--impl reference` times the reference's CPU path as restated in oracle/ (MindSpore itself cannot be
+installed here) on the host cores.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "wide_deep_train_samples_per_s"
+UNIT = "samples/s"
+BATCH = 16000
+FIELDS = 39
+EMB = 80
+HIDDEN = (1024, 512, 256, 128)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--vocab-scale", type=float, default=1.0, help="shrink the Kaggle cardinalities (debug)")
+    ap.add_argument("--alpha", type=float, default=1.05)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2000)
+    ap.add_argument("--cpu-vocab", type=int, default=4000000)
+    return ap.parse_args()
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def scaled_cards(scale):
+    from mindrec_b200 import synth
+    return [max(3, int(c * scale)) for c in synth.CARD_KAGGLE]
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference path restated in oracle/ (kind = "port"), bounded sample of the same workload
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline_run(args, steps, warmup):
+    import numpy as np
+    from mindrec_b200 import synth
+    from oracle import ref_c
+    cards = scaled_cards(args.vocab_scale)
+    full_vocab = synth.vocab_size(cards)
+    vocab = min(full_vocab, args.cpu_vocab)
+    b = args.cpu_sample_batch
+    model = ref_c.WideDeepCpu(vocab, EMB, hidden=HIDDEN, fields=FIELDS, seed=0)
+    gen = synth.CriteoSynth(b, cards=cards, alpha=args.alpha, seed=20260101)
+    batches = []
+    for _ in range(4):
+        ids, wts, label = gen.next()
+        batches.append((np.ascontiguousarray(ids % vocab), wts, label))
+    for i in range(warmup):
+        model.step(*batches[i % 4])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        model.step(*batches[i % 4])
+    dt = time.perf_counter() - t0
+    sample = ("batch %d of the config-2 stream (Zipf %.2f, 39 fields, dim 80, MLP 3120-1024-512-256-128-1 fp32); "
+              "tables held at %d rows (ids mod rows) to bound host memory; %d steps after %d warm-up" %
+              (b, args.alpha, vocab, steps, warmup))
+    return {"value": b * steps / dt, "unit": UNIT, "cores": ref_c.threads(), "kind": "port",
+            "sample": sample, "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    cb = cpu_baseline_run(args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's CPU path as restated in oracle/ (C/OpenMP + numpy BLAS); MindSpore is not installable here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    from mindrec_b200 import synth
+    cards = scaled_cards(args.vocab_scale)
+    return {
+        "workload": "BASELINE config 2: Wide&Deep, Criteo-Kaggle vocab, dim 80, fp32 tables, batch 16000/GPU, "
+                    "LazyAdam deep + FTRL wide sparse updates" + ("" if n_gpus == 1 else
+                                                                  ", tables row-sharded over %d GPUs (all-to-all)" % n_gpus),
+        "global_batch": args.batch * n_gpus, "batch_per_gpu": args.batch, "fields": FIELDS, "emb_dim": EMB,
+        "vocab_rows": synth.vocab_size(cards), "zipf_alpha": args.alpha, "mlp": [FIELDS * EMB] + list(HIDDEN) + [1],
+        "mlp_dtype": "fp16 (use_mixed_precision)", "loss_scale": 1024,
+        "parallelism": "single" if n_gpus == 1 else "row-sharded embeddings (a2a) + data-parallel MLP x%d" % n_gpus,
+        "l2": "per-step working set (>= 0.8 GB of table rows, activations and gradients) exceeds the 126 MB L2; "
+              "batches rotate over a ring of 8",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mindrec_b200 import _lib, cells, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the CUDA extension is missing
+
+    cards = scaled_cards(args.vocab_scale)
+    vocab = synth.vocab_size(cards)
+    b = args.batch
+    if world == 1:
+        cfg = cells.WideDeepConfig(batch_size=b, field_size=FIELDS, vocab_size=vocab, emb_dim=EMB,
+                                   deep_layer_dim=HIDDEN, use_mixed_precision=True, sparse=True, seed=1)
+        model = cells.WideDeepModel(cfg, device=dev)
+        step = cells.TrainStepWrap(cells.NetWithLossClass(model, cfg), sens=1024.0, sparse=True, lazy_adam=True)
+    else:
+        from mindrec_b200 import sharded
+        step = sharded.build_sharded_wide_deep(b, vocab, EMB, HIDDEN, dev, seed=1)
+
+    ring = 8
+    gen = synth.CriteoSynth(b, cards=cards, alpha=args.alpha, seed=20260101, rank=rank)
+    host = []
+    for _ in range(ring):
+        ids, wts, label = gen.next()
+        host.append(tuple(torch.from_numpy(x).pin_memory() for x in (ids, wts, label)))
+    devb = [tuple(x.to(dev) for x in hb) for hb in host]
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
+
+    launches0 = _lib.launch_count()
+    step.capture(*devb[0], warmup=3)
+    per_step_launches = (_lib.launch_count() - launches0) // 4  # 3 warm-up steps + 1 captured
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: W warm-up + K timed graph replays -------------------------
+    for i in range(max(3, args.warmup)):
+        step.replay(*devb[i % ring])
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step.replay(*devb[i % ring])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = b * world / (ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss D2H ---------
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    for i in range(3):
+        out = step.replay(*host[i % ring])
+        loss_host.copy_(out[0].reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step.replay(*host[i % ring])                         # three pinned H2D copies + graph
+        loss_host.copy_(out[0].reshape(1), non_blocking=True)      # loss D2H
+        torch.cuda.current_stream().synchronize()                  # the user reads the loss every step
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    final_loss = float(loss_host.item())
+
+    # ---- per-phase breakdown + roofline of the dominant product kernel (eager, CUDA events) ------
+    breakdown, roofline = {}, None
+    if hasattr(step, "profile"):
+        step.profile = cells.StepProfile()
+        n_prof = min(args.steps, 20)
+        for i in range(n_prof):
+            step(*devb[i % ring])
+        tot = step.profile.totals()
+        step.profile = None
+        breakdown = {k: round(statistics.median(v), 4) for k, v in tot.items()}
+        u = int(step._uq.count.item())
+        n = b * FIELDS
+        peak, how = hbm_peak()
+        alg = n * EMB * 4 + u * 7 * EMB * 4      # segment-sum read N*D*4 + LazyAdam U*7*D*4
+        adam_ms = breakdown.get("adam_deep")
+        if adam_ms:
+            gbs = alg / adam_ms / 1e6
+            roofline = {"kernel": "segsum_tiles_kernel<float4, LazyAdamSink> (+ boundary/long + dense Adam, "
+                                  "phase 'adam_deep')", "bound": "hbm", "achieved": round(gbs, 1),
+                        "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json)" if how == "measured" else how,
+                        "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": None,
+                        "algorithmic_bytes": alg, "unique_rows": u, "lookups": n, "ms": adam_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb_full = cpu_baseline_run(args, steps=8, warmup=2)
+        cb = {k: cb_full[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": b * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(per_step_launches * args.steps),
+        "gpu_launches_per_step": int(per_step_launches),
+        "roofline": roofline, "cpu_baseline": cb, "breakdown_ms": breakdown, "final_loss": final_loss,
+        "lib": _lib.version(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

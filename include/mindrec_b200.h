@@ -85,24 +85,30 @@ size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes);
  *   models/wide_and_deep_multitable/src/wide_and_deep.py:525-535.
  * g[N/div, D] holds one gradient row per `div` consecutive lookup positions (div = F for the wide
  * logit gradient, 1 for the deep input gradient); mask[N] is the Mul(mask) bprop factor (numel 0 = none).
- * Hyper blocks are f32[8] device tensors:
- *   Adam : lr, beta1, beta2, eps, beta1_power, beta2_power, lr_t, 1/loss_scale
- *   FTRL : lr, l1, l2, lr_power, 1/loss_scale, -, -, -
- *   in : w[V,D] m[V,D] v[V,D] hyper[8] g mask uniq[N] perm[N] seg_start[N+1] seg_of[N]
+ * Hyper blocks are f32[16] device tensors:
+ *   Adam : lr, beta1, beta2, eps, beta1_power, beta2_power, lr_t, 1/loss_scale, l2 (dense-mode table
+ *          regulariser, wide_and_deep.py:359-360), 7 reserved
+ *   FTRL : lr, l1, l2, lr_power, 1/loss_scale, 11 reserved
+ *   in : w[V,D] m[V,D] v[V,D] hyper[16] g mask uniq[N] perm[N] seg_start[N+1] seg_of[N]
  *   out: dummy[1] i32, workspace[mrec_sparse_opt_workspace_bytes(N, D)] u8                       */
 int mrec_sparse_lazy_adam(MREC_AOT_ARGS);
-/*   in : w[V,D] accum[V,D] linear[V,D] hyper[8] g mask uniq perm seg_start seg_of   out: dummy, workspace */
+/*   in : w[V,D] accum[V,D] linear[V,D] hyper[16] g mask uniq perm seg_start seg_of   out: dummy, workspace */
 int mrec_sparse_ftrl(MREC_AOT_ARGS);
 /* Stand-alone UnsortedSegmentSum in sorted-segment order (no atomics, bit-reproducible):
  *   in : g mask perm seg_start seg_of     out: gsum[N,D] f32 (rows >= count untouched), workspace */
 int mrec_segment_sum(MREC_AOT_ARGS);
+/* nn.Adam (not Lazy) with a RowTensor gradient = dense-equivalent update of the WHOLE table (every
+ * row's moments decay; wide_and_deep.py:435-437 when sparse=True on one device):
+ *   in : w m v hyper[16] g mask uniq perm seg_start seg_of row_flags[V] u8 (zero on entry and exit)
+ *   out: dummy[1], workspace                                                                       */
+int mrec_adam_rowsparse(MREC_AOT_ARGS);
 size_t mrec_sparse_opt_workspace_bytes(int64_t n, int dim);
-/* nn.Adam preamble: beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  in: hyper[8]  out: dummy[1] */
+/* nn.Adam preamble: beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  in: hyper[16]  out: dummy[1] */
 int mrec_adam_begin_step(MREC_AOT_ARGS);
 /* nn.Adam dense kernel (MLP weights, Wide_b: wide_and_deep.py:405-413,435-437).
- *   in : w m v hyper[8] g (same numel)   out: dummy[1]                                            */
+ *   in : w m v hyper[16] g (same numel)   out: dummy[1]                                            */
 int mrec_adam_dense(MREC_AOT_ARGS);
-/* nn.FTRL dense kernel (ApplyFtrl).  in : w accum linear hyper[8] g   out: dummy[1]               */
+/* nn.FTRL dense kernel (ApplyFtrl).  in : w accum linear hyper[16] g   out: dummy[1]               */
 int mrec_ftrl_dense(MREC_AOT_ARGS);
 
 #ifdef __cplusplus

@@ -1,0 +1,253 @@
+"""Model cells of the reference, restated over the aot kernels.
+
+    WideDeepModel / NetWithLossClass / TrainStepWrap / PredictWithSigmoid
+        models/wide_deep/src/wide_and_deep.py:136-519
+The embedding lookup, mask multiply, wide reduce, sparse gradient dedup and the optimizer updates run in
+libmindrec_b200.so; the DenseLayer stack uses library GEMMs (torch.mm -> cuBLAS), as SURVEY 2b scopes it.
+Because there is no graph compiler here, TrainStepWrap states forward, backward and update explicitly; a
+step touches only pre-allocated buffers and can be captured in a CUDA graph (`TrainStepWrap.capture`).
+"""
+import contextlib
+
+import torch
+
+from . import ops
+from .nn import Adam, DenseStack, EmbeddingLookup, FTRL, LazyAdam, Parameter, RowTensor
+
+
+class StepProfile:
+    """Optional per-phase CUDA-event timing of an eager step (bench.py's breakdown / roofline source)."""
+
+    def __init__(self):
+        self.records = []
+
+    @contextlib.contextmanager
+    def range(self, name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.records.append((name, a, b))
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+@contextlib.contextmanager
+def _null_range(name):
+    yield
+
+
+class WideDeepConfig:
+    """Hyper-parameters of models/wide_deep/default_config.yaml:16-44 (same names)."""
+
+    def __init__(self, batch_size=16000, field_size=39, vocab_size=200000, emb_dim=80,
+                 deep_layer_dim=(1024, 512, 256, 128), deep_layer_act="relu", keep_prob=1.0,
+                 dropout_flag=False, l2_coef=8e-5, emb_init="normal", weight_bias_init=("normal", "normal"),
+                 use_mixed_precision=True, sparse=False, dynamic_embedding=False, parameter_server=False,
+                 vocab_cache_size=0, seed=1):
+        self.batch_size = batch_size
+        self.field_size = field_size
+        self.vocab_size = vocab_size
+        self.emb_dim = emb_dim
+        self.deep_layer_dim = list(deep_layer_dim)
+        self.deep_layer_act = deep_layer_act
+        self.keep_prob = keep_prob
+        self.dropout_flag = dropout_flag
+        self.l2_coef = l2_coef
+        self.emb_init = emb_init
+        self.weight_bias_init = tuple(weight_bias_init)
+        self.use_mixed_precision = use_mixed_precision
+        self.sparse = sparse
+        self.dynamic_embedding = dynamic_embedding
+        self.parameter_server = parameter_server
+        self.vocab_cache_size = vocab_cache_size
+        self.seed = seed
+
+
+class WideDeepModel:
+    """wide_and_deep.py:136-316.  construct(ids, wts) -> (logit[B,1], embedding_table)."""
+
+    def __init__(self, config, device="cuda"):
+        if config.deep_layer_act != "relu":
+            raise ValueError("only the reference default deep_layer_act='relu' is implemented")
+        if config.dropout_flag:
+            raise ValueError("dropout_flag=True is not on the benchmarked path (keep_prob 1.0)")
+        if config.dynamic_embedding:
+            raise ValueError("dynamic_embedding=True: build the model with mindrec_b200.hash.HashEmbeddingLookup")
+        self.config = config
+        self.batch_size = config.batch_size
+        self.field_size = config.field_size
+        self.emb_dim = config.emb_dim
+        self.device = torch.device(device)
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(config.seed)
+        self.wide_embeddinglookup = EmbeddingLookup(config.vocab_size, 1, param_init=config.emb_init,
+                                                    sparse=config.sparse, device=self.device,
+                                                    name="wide_embeddinglookup.embedding_table", generator=gen)
+        self.deep_embeddinglookup = EmbeddingLookup(config.vocab_size, config.emb_dim,
+                                                    param_init=config.emb_init, sparse=config.sparse,
+                                                    device=self.device,
+                                                    name="deep_embeddinglookup.embedding_table", generator=gen)
+        self.embedding_table = self.deep_embeddinglookup.embedding_table
+        dims = [self.field_size * self.emb_dim] + list(config.deep_layer_dim) + [1]
+        w_init, b_init = config.weight_bias_init
+        self.dense = DenseStack(dims, config.use_mixed_precision, self.device, generator=gen,
+                                weight_init=w_init, bias_init=b_init, extra=1)
+        # "Wide_b" (capital W): lives in the Adam group, wide_and_deep.py:161-163,405-413
+        self.wide_b = Parameter(self.dense.extra, name="Wide_b")
+        if config.emb_init == "normal":
+            self.wide_b.data.normal_(0.0, 0.01, generator=gen)
+        self._wide_out = None
+        self._deep_in = None
+
+    def trainable_params(self):
+        return [self.wide_embeddinglookup.embedding_table, self.deep_embeddinglookup.embedding_table,
+                Parameter(self.dense.flat, name="dense_layers+Wide_b")]
+
+    def __call__(self, id_hldr, wt_hldr):
+        return self.construct(id_hldr, wt_hldr)
+
+    def construct(self, id_hldr, wt_hldr):
+        b, f, d = id_hldr.shape[0], self.field_size, self.emb_dim
+        if self._wide_out is None or self._wide_out.shape[0] != b:
+            self._wide_out = torch.empty((b, 1), dtype=torch.float32, device=self.device)
+            self._deep_in = torch.empty((b, f * d), dtype=torch.float32, device=self.device)
+        # wide_and_deep.py:300,303,305-306: gather(dim 1) * mask, ReduceSum(axis 1) + Wide_b
+        ops.gather_reduce(self.wide_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
+                          self.wide_b.data, out=self._wide_out)
+        # wide_and_deep.py:302,308-309: gather(dim D) * mask -> [B, F*D]
+        ops.gather_masked(self.deep_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
+                          out=self._deep_in)
+        deep_out = self.dense.forward(self._deep_in)       # :310-314
+        out = self._wide_out + deep_out                     # :315
+        return out, self.embedding_table
+
+
+class NetWithLossClass:
+    """wide_and_deep.py:319-362: (wide_loss, deep_loss); the l2 term exists only in dense mode."""
+
+    def __init__(self, network, config):
+        self.network = network
+        self.no_l2loss = bool(config.parameter_server) or bool(config.sparse)
+        self.l2_coef = config.l2_coef
+        self.logit = None
+
+    def __call__(self, batch_ids, batch_wts, label):
+        return self.construct(batch_ids, batch_wts, label)
+
+    def construct(self, batch_ids, batch_wts, label):
+        predict, embedding_table = self.network(batch_ids, batch_wts)
+        self.logit = predict
+        # SigmoidCrossEntropyWithLogits: max(x,0) - x*z + log1p(exp(-|x|))
+        log_loss = torch.clamp(predict, min=0) - predict * label + torch.log1p(torch.exp(-predict.abs()))
+        wide_loss = log_loss.mean()
+        if self.no_l2loss:
+            deep_loss = wide_loss
+        else:
+            l2_loss_v = embedding_table.data.square().sum() / 2
+            deep_loss = wide_loss + self.l2_coef * l2_loss_v
+        return wide_loss, deep_loss
+
+
+class TrainStepWrap:
+    """wide_and_deep.py:376-492: FTRL on the "wide" group, Adam / LazyAdam on the rest, loss scale `sens`.
+
+    LazyAdam is chosen exactly when the reference chooses it (`:415-419`): sparse with auto-parallel or
+    parameter server, or dynamic embedding; pass lazy_adam=True to request the row-sparse semantics on a
+    single device (what BASELINE config 2 measures — nn.Adam there would stream the whole 34 M-row table)."""
+
+    def __init__(self, network, sens=1024.0, parameter_server=False, sparse=False, cache_enable=False,
+                 dynamic_embedding=False, is_auto_parallel=False, lazy_adam=None):
+        self.network = network
+        model = network.network
+        self.model = model
+        self.sens = float(sens)
+        self.sparse = sparse
+        if lazy_adam is None:
+            lazy_adam = (sparse and is_auto_parallel) or (sparse and parameter_server) or dynamic_embedding
+        self.lazy_adam = bool(lazy_adam)
+        # weights_w: names containing "wide" (lower case) -> only the wide table
+        self.weights_w = [model.wide_embeddinglookup.embedding_table]
+        self.weights_d = [model.deep_embeddinglookup.embedding_table,
+                          Parameter(model.dense.flat, name="dense_layers+Wide_b")]
+        opt_cls = LazyAdam if self.lazy_adam else Adam
+        self.optimizer_d = opt_cls(self.weights_d, learning_rate=3.5e-4, eps=1e-8, loss_scale=sens)
+        self.optimizer_w = FTRL(learning_rate=5e-2, params=self.weights_w, l1=1e-8, l2=1e-8,
+                                initial_accum=1.0, loss_scale=sens)
+        if not network.no_l2loss:
+            # dense mode: d(deep_loss)/dWd carries l2_coef * Wd on every row (wide_and_deep.py:359-360)
+            self.optimizer_d.hyper[8] = network.l2_coef
+        self._uq = None
+        self._graph = None
+        self._static = None
+        self.profile = None
+
+    def __call__(self, batch_ids, batch_wts, label):
+        return self.construct(batch_ids, batch_wts, label)
+
+    def construct(self, batch_ids, batch_wts, label):
+        model = self.model
+        rng = self.profile.range if self.profile is not None else _null_range
+        b = batch_ids.shape[0]
+        with rng("forward"):
+            loss_w, loss_d = self.network(batch_ids, batch_wts, label)
+        logit = self.network.logit
+        with rng("dense_backward"):
+            # d(mean xent)/d logit, times sens (wide_and_deep.py:479-486)
+            delta = (torch.sigmoid(logit) - label) * (self.sens / b)             # [B,1]
+            gx = model.dense.backward(delta)                                      # [B, F*D]
+            model.dense.extra_grad.copy_(delta.sum().reshape(1))                  # Wide_b gradient
+        n = batch_ids.numel()
+        if self._uq is None or self._uq.n != n:
+            self._uq = ops.UniqueResult(n, batch_ids.dtype, batch_ids.device)
+        with rng("unique"):
+            uq = ops.unique(batch_ids, table_like=model.embedding_table.data, result=self._uq)
+        mask = batch_wts.reshape(-1)
+        grads_w = [RowTensor(batch_ids, delta, mask, uq)]
+        grads_d = [RowTensor(batch_ids, gx.view(n, model.emb_dim), mask, uq), model.dense.flat_grad]
+        with rng("ftrl_wide"):
+            self.optimizer_w(grads_w)
+        with rng("adam_deep"):
+            self.optimizer_d(grads_d)
+        return loss_w, loss_d
+
+    # ---- CUDA-graph replay of the whole step -------------------------------------------------------
+    def capture(self, batch_ids, batch_wts, label, warmup=3):
+        """Capture construct() on static input buffers.  Afterwards `replay(ids, wts, label)` copies the
+        inputs in and launches the graph."""
+        self._static = (batch_ids.clone(), batch_wts.clone(), label.clone())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.construct(*self._static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self.construct(*self._static)
+        return self._static
+
+    def replay(self, batch_ids=None, batch_wts=None, label=None):
+        if batch_ids is not None:
+            self._static[0].copy_(batch_ids, non_blocking=True)
+            self._static[1].copy_(batch_wts, non_blocking=True)
+            self._static[2].copy_(label, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+
+class PredictWithSigmoid:
+    """wide_and_deep.py:495-519."""
+
+    def __init__(self, network):
+        self.network = network
+
+    def __call__(self, batch_ids, batch_wts, labels):
+        logits, _ = self.network(batch_ids, batch_wts)
+        return logits, torch.sigmoid(logits), labels

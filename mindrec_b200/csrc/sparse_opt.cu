@@ -47,8 +47,9 @@ template <> struct VOps<float> {
 
 // ---- hyper-parameter blocks (device f32 tensors, so schedules / bias-correction never sync the host)
 // Adam : [0] lr [1] beta1 [2] beta2 [3] eps [4] beta1_power [5] beta2_power [6] lr_t [7] grad_scale
+//        [8] l2 (dense-mode table regulariser: g += l2 * w after scaling, wide_and_deep.py:359-360)
 // FTRL : [0] lr [1] l1 [2] l2 [3] lr_power [4] grad_scale
-constexpr int kHyperLen = 8;
+constexpr int kHyperLen = 16;
 
 __device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, float b1, float b2,
                                           float eps, float lr_t) {
@@ -89,12 +90,13 @@ struct LazyAdamSink<float4, IdT> {
     const int64_t row = (int64_t)uniq[seg];
     if ((uint64_t)row >= (uint64_t)vocab) return;  // out-of-range ids carry no row
     const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6], sc = hyper[7];
+    const float l2 = hyper[8];
     const int64_t o = row * cpr + c;
     float4 W = w[o], M = m[o], V = v[o];
-    adam_elem(W.x, M.x, V.x, gs.x * sc, b1, b2, eps, lr_t);
-    adam_elem(W.y, M.y, V.y, gs.y * sc, b1, b2, eps, lr_t);
-    adam_elem(W.z, M.z, V.z, gs.z * sc, b1, b2, eps, lr_t);
-    adam_elem(W.w, M.w, V.w, gs.w * sc, b1, b2, eps, lr_t);
+    adam_elem(W.x, M.x, V.x, fmaf(l2, W.x, gs.x * sc), b1, b2, eps, lr_t);
+    adam_elem(W.y, M.y, V.y, fmaf(l2, W.y, gs.y * sc), b1, b2, eps, lr_t);
+    adam_elem(W.z, M.z, V.z, fmaf(l2, W.z, gs.z * sc), b1, b2, eps, lr_t);
+    adam_elem(W.w, M.w, V.w, fmaf(l2, W.w, gs.w * sc), b1, b2, eps, lr_t);
     w[o] = W; m[o] = M; v[o] = V;
   }
 };
@@ -110,7 +112,7 @@ struct LazyAdamSink<float, IdT> {
     if ((uint64_t)row >= (uint64_t)vocab) return;
     const int64_t o = row * cpr + c;
     float W = w[o], M = m[o], V = v[o];
-    adam_elem(W, M, V, gs * hyper[7], hyper[1], hyper[2], hyper[3], hyper[6]);
+    adam_elem(W, M, V, fmaf(hyper[8], W, gs * hyper[7]), hyper[1], hyper[2], hyper[3], hyper[6]);
     w[o] = W; m[o] = M; v[o] = V;
   }
 };
@@ -385,6 +387,36 @@ ftrl_dense_kernel(float* __restrict__ w, float* __restrict__ acc, float* __restr
   }
 }
 
+
+// ---- nn.Adam with a RowTensor gradient on GPU = dense-equivalent: every row's moments
+// decay and every row moves; looked-up rows additionally receive their summed gradient.  Rows are
+// flagged by the looked-up keys, the streaming kernel handles the unflagged rows (g = l2 * w), the fused
+// segment-sum kernel handles the flagged ones, and the flags are cleared again.
+template <typename IdT>
+__global__ void mark_rows_kernel(const IdT* __restrict__ uniq, const int32_t* __restrict__ seg_of,
+                                 int64_t n, int64_t vocab, uint8_t* __restrict__ flags, uint8_t value) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t row = (int64_t)uniq[seg_of[i]];
+  if ((uint64_t)row < (uint64_t)vocab) flags[row] = value;
+}
+
+__global__ void __launch_bounds__(256)
+adam_untouched_rows_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                           const float* __restrict__ hyper, const uint8_t* __restrict__ flags,
+                           int64_t vocab, int dim) {
+  const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6], l2 = hyper[8];
+  const int64_t total = vocab * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / dim;
+    if (flags[row]) continue;
+    float W = w[e], M = m[e], V = v[e];
+    adam_elem(W, M, V, l2 * W, b1, b2, eps, lr_t);
+    w[e] = W; m[e] = M; v[e] = V;
+  }
+}
+
 }  // namespace mrec
 
 using namespace mrec;
@@ -545,12 +577,51 @@ MREC_API int mrec_segment_sum(int nparam, void** params, int* ndims, int64_t** s
   return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
 }
 
-// inputs: hyper[8] ; outputs: dummy[1].  beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).
+
+// nn.Adam (not Lazy) with a RowTensor gradient: dense-equivalent update of the whole table.
+// inputs : w m v hyper[16] g mask uniq perm seg_start seg_of row_flags[V] u8 (all zero on entry and exit)
+// outputs: dummy[1] i32, workspace[mrec_sparse_opt_workspace_bytes]
+MREC_API int mrec_adam_rowsparse(int nparam, void** params, int* ndims, int64_t** shapes,
+                                 const char** dtypes, void* stream, void* extra) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 13);
+  MREC_REQUIRE(a.is(10, "uint8") || a.is(10, "int8") || a.is(10, "bool"), ERR_DTYPE,
+               "mrec_adam_rowsparse: row_flags must be a 1-byte type");
+  const int64_t vocab = a.dim(0, 0);
+  const int dim = a.ndims[0] >= 2 ? (int)a.dim(0, 1) : 1;
+  MREC_REQUIRE(a.numel(10) >= vocab, ERR_SHAPE, "mrec_adam_rowsparse: row_flags needs V entries");
+  MREC_REQUIRE(a.is_i32(6) || a.is_i64(6), ERR_DTYPE, "mrec_adam_rowsparse: uniq must be int32|int64");
+  MREC_REQUIRE(a.is_i32(9), ERR_DTYPE, "mrec_adam_rowsparse: seg_of must be int32");
+  const int64_t n = a.numel(7);
+  uint8_t* flags = a.ptr<uint8_t>(10);
+  const int grid_n = (int)cdiv(n > 0 ? n : 1, 256);
+  if (n > 0) {
+    if (a.is_i64(6)) MREC_LAUNCH(mark_rows_kernel<int64_t>, grid_n, 256, 0, a.stream, a.ptr<int64_t>(6), a.ptr<int32_t>(9), n, vocab, flags, (uint8_t)1);
+    else MREC_LAUNCH(mark_rows_kernel<int32_t>, grid_n, 256, 0, a.stream, a.ptr<int32_t>(6), a.ptr<int32_t>(9), n, vocab, flags, (uint8_t)1);
+  }
+  MREC_REQUIRE(a.is_f32(0) && a.is_f32(1) && a.is_f32(2) && a.is_f32(3) && a.numel(3) >= kHyperLen, ERR_DTYPE,
+               "mrec_adam_rowsparse: w/m/v/hyper must be float32 (hyper[16])");
+  MREC_LAUNCH(adam_untouched_rows_kernel, grid_for(cdiv(vocab * dim, 1024), 8), 256, 0, a.stream,
+              a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2), a.ptr<float>(3), flags, vocab, dim);
+  // touched rows: the LazyAdam path (same formula, g = gsum/scale + l2*w)
+  void* p2[12]; int nd2[12]; int64_t* sh2[12]; const char* dt2[12];
+  const int map[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12};
+  for (int i = 0; i < 12; ++i) { p2[i] = params[map[i]]; nd2[i] = ndims[map[i]]; sh2[i] = shapes[map[i]]; dt2[i] = dtypes[map[i]]; }
+  int rc = mrec_sparse_lazy_adam(12, p2, nd2, sh2, dt2, stream, extra);
+  if (rc) return rc;
+  if (n > 0) {
+    if (a.is_i64(6)) MREC_LAUNCH(mark_rows_kernel<int64_t>, grid_n, 256, 0, a.stream, a.ptr<int64_t>(6), a.ptr<int32_t>(9), n, vocab, flags, (uint8_t)0);
+    else MREC_LAUNCH(mark_rows_kernel<int32_t>, grid_n, 256, 0, a.stream, a.ptr<int32_t>(6), a.ptr<int32_t>(9), n, vocab, flags, (uint8_t)0);
+  }
+  return check_launch("adam_rowsparse");
+}
+
+// inputs: hyper[16] ; outputs: dummy[1].  beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).
 MREC_API int mrec_adam_begin_step(int nparam, void** params, int* ndims, int64_t** shapes,
                                   const char** dtypes, void* stream, void* /*extra*/) {
   Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
   MREC_CHECK_NPARAM(a, 2);
-  MREC_REQUIRE(a.is_f32(0) && a.numel(0) >= kHyperLen, ERR_SHAPE, "mrec_adam_begin_step: hyper must be f32[8]");
+  MREC_REQUIRE(a.is_f32(0) && a.numel(0) >= kHyperLen, ERR_SHAPE, "mrec_adam_begin_step: hyper must be f32[16]");
   MREC_LAUNCH(adam_begin_step_kernel, 1, 32, 0, a.stream, a.ptr<float>(0));
   return check_launch("adam_begin_step");
 }

@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's operator surface for the hot path.
+
+Names, constructor arguments and error behaviour follow the reference / the MindSpore cells it calls:
+
+    EmbeddingLookup      mindspore.nn.EmbeddingLookup as used at models/wide_deep/src/wide_and_deep.py:234-290
+    Adam / LazyAdam      mindspore.nn.optim (wide_and_deep.py:420-422,435-437; deepfm.py:272)
+    FTRL                 mindspore.nn.optim.FTRL (wide_and_deep.py:423-430)
+    RowTensor            the sparse gradient of SparseGatherV2
+
+All arithmetic runs in libmindrec_b200.so through the aot C-ABI (mindrec_b200.ops); torch only owns the
+device buffers.
+"""
+import math
+
+import torch
+
+from . import ops
+
+
+class Parameter:
+    """A named device buffer (mindspore.Parameter stand-in)."""
+
+    def __init__(self, data, name, requires_grad=True):
+        self.data = data
+        self.name = name
+        self.requires_grad = requires_grad
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def __repr__(self):
+        return "Parameter(name=%s, shape=%s)" % (self.name, self.shape)
+
+
+class RowTensor:
+    """Sparse gradient of a gather: lookup position n contributes mask[n] * values[n // div] to row
+    indices[n].  `uq` caches the dedup (mrec_unique) so that several tables looked up with the same ids
+    (wide + deep) sort them once."""
+
+    def __init__(self, indices, values, mask=None, uq=None):
+        self.indices = indices
+        self.values = values
+        self.mask = mask
+        self.uq = uq
+
+
+def _init_table(shape, param_init, device, generator=None):
+    if isinstance(param_init, torch.Tensor):
+        assert tuple(param_init.shape) == tuple(shape)
+        return param_init.to(device=device, dtype=torch.float32).contiguous()
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    if param_init == "normal":
+        t.normal_(0.0, 0.01, generator=generator)  # initializer("normal") = N(0, 0.01^2)
+    elif param_init in ("zeros", "zero"):
+        t.zero_()
+    elif param_init in ("ones", "one"):
+        t.fill_(1.0)
+    elif isinstance(param_init, (int, float)):
+        t.fill_(float(param_init))
+    else:
+        raise ValueError("unsupported param_init %r" % (param_init,))
+    return t
+
+
+class EmbeddingLookup:
+    """nn.EmbeddingLookup(vocab_size, embedding_size, param_init='normal', target='CPU',
+    slice_mode='batch_slice', manual_shapes=None, max_norm=None, sparse=True, vocab_cache_size=0).
+
+    Only target='DEVICE' exists here (there is no CPU path); slice modes other than batch_slice are
+    provided by mindrec_b200.sharded.ShardedEmbedding."""
+
+    BATCH_SLICE = "batch_slice"
+    FIELD_SLICE = "field_slice"
+    TABLE_ROW_SLICE = "table_row_slice"
+    TABLE_COLUMN_SLICE = "table_column_slice"
+
+    def __init__(self, vocab_size, embedding_size, param_init="normal", target="DEVICE",
+                 slice_mode="batch_slice", manual_shapes=None, max_norm=None, sparse=True,
+                 vocab_cache_size=0, device="cuda", name="embedding_table", generator=None):
+        if not isinstance(vocab_size, int) or vocab_size <= 0:
+            raise ValueError("For 'EmbeddingLookup', 'vocab_size' must be a positive int, got %r" % (vocab_size,))
+        if not isinstance(embedding_size, int) or embedding_size <= 0:
+            raise ValueError("For 'EmbeddingLookup', 'embedding_size' must be a positive int, got %r" % (embedding_size,))
+        if target not in ("CPU", "DEVICE"):
+            raise ValueError("For 'EmbeddingLookup', 'target' must be 'CPU' or 'DEVICE', got %r" % (target,))
+        if target == "CPU":
+            raise RuntimeError("mindrec_b200.EmbeddingLookup has no CPU path: use target='DEVICE'")
+        if not isinstance(sparse, bool):
+            raise TypeError("For 'EmbeddingLookup', 'sparse' must be bool")
+        if slice_mode != self.BATCH_SLICE:
+            raise ValueError("slice_mode %r: use mindrec_b200.sharded.ShardedEmbedding" % (slice_mode,))
+        self.vocab_size = vocab_size
+        self.embedding_size = embedding_size
+        self.sparse = sparse
+        self.max_norm = max_norm
+        self.embedding_table = Parameter(_init_table((vocab_size, embedding_size), param_init, device, generator),
+                                         name=name)
+
+    def __call__(self, indices):
+        return self.construct(indices)
+
+    def construct(self, indices):
+        out = ops.gather(self.embedding_table.data, indices)
+        if self.max_norm is not None:
+            norm = out.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+            out = out * torch.clamp(self.max_norm / norm, max=1.0)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizers
+# ------------------------------------------------------------------------------------------------
+class _Optimizer:
+    def __init__(self, params, loss_scale):
+        self.parameters = list(params)
+        if not self.parameters:
+            raise ValueError("Optimizer got an empty parameter list")
+        self.loss_scale = float(loss_scale)
+        self.device = self.parameters[0].data.device
+
+    def _dedup(self, p, g):
+        if g.uq is None:
+            g.uq = ops.unique(g.indices, table_like=p.data)
+        return g.uq
+
+    def __call__(self, grads):
+        if len(grads) != len(self.parameters):
+            raise ValueError("expected %d gradients, got %d" % (len(self.parameters), len(grads)))
+        self.step(grads)
+        return True
+
+
+class Adam(_Optimizer):
+    """nn.Adam(params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, use_locking=False,
+    use_nesterov=False, weight_decay=0.0, loss_scale=1.0).  RowTensor gradients are applied with the
+    dense-equivalent rule (every row's moments decay) unless `lazy` (LazyAdam)."""
+    lazy = False
+
+    def __init__(self, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, use_locking=False,
+                 use_nesterov=False, weight_decay=0.0, loss_scale=1.0):
+        super().__init__(params, loss_scale)
+        if not 0.0 < beta1 < 1.0 or not 0.0 < beta2 < 1.0:
+            raise ValueError("beta1/beta2 must be in (0, 1)")
+        if eps <= 0:
+            raise ValueError("eps must be > 0")
+        if use_nesterov or weight_decay != 0.0:
+            raise NotImplementedError("use_nesterov / weight_decay are not used on the reference's hot path")
+        self.hyper = ops.adam_hyper(learning_rate, beta1, beta2, eps, loss_scale, device=self.device)
+        self.moment1 = [torch.zeros_like(p.data) for p in self.parameters]
+        self.moment2 = [torch.zeros_like(p.data) for p in self.parameters]
+
+    def _row_flags(self, p):
+        flags = getattr(p, "_row_flags", None)
+        if flags is None:
+            flags = torch.zeros(p.data.shape[0], dtype=torch.uint8, device=p.data.device)
+            p._row_flags = flags
+        return flags
+
+    def step(self, grads):
+        ops.adam_begin_step(self.hyper)
+        for p, m, v, g in zip(self.parameters, self.moment1, self.moment2, grads):
+            if isinstance(g, RowTensor):
+                uq = self._dedup(p, g)
+                if self.lazy:
+                    ops.sparse_lazy_adam(p.data, m, v, self.hyper, g.values, g.mask, uq)
+                else:
+                    ops.adam_rowsparse_dense_equiv(p.data, m, v, self.hyper, g.values, g.mask, uq,
+                                                   self._row_flags(p))
+            else:
+                ops.adam_dense(p.data, m, v, self.hyper, g)
+
+
+class LazyAdam(Adam):
+    """nn.LazyAdam: with RowTensor gradients only the looked-up rows move."""
+    lazy = True
+
+
+class FTRL(_Optimizer):
+    """nn.FTRL(params, initial_accum=0.1, learning_rate=0.001, lr_power=-0.5, l1=0.0, l2=0.0,
+    use_locking=False, loss_scale=1.0, weight_decay=0.0)."""
+
+    def __init__(self, params, initial_accum=0.1, learning_rate=0.001, lr_power=-0.5, l1=0.0, l2=0.0,
+                 use_locking=False, loss_scale=1.0, weight_decay=0.0):
+        super().__init__(params, loss_scale)
+        if initial_accum < 0:
+            raise ValueError("initial_accum must be >= 0")
+        if learning_rate <= 0:
+            raise ValueError("learning_rate must be > 0")
+        if lr_power > 0:
+            raise ValueError("lr_power must be <= 0")
+        if l1 < 0 or l2 < 0:
+            raise ValueError("l1/l2 must be >= 0")
+        self.hyper = ops.ftrl_hyper(learning_rate, l1, l2, lr_power, loss_scale, device=self.device)
+        self.accum = [torch.full_like(p.data, float(initial_accum)) for p in self.parameters]
+        self.linear = [torch.zeros_like(p.data) for p in self.parameters]
+
+    def step(self, grads):
+        for p, a, l, g in zip(self.parameters, self.accum, self.linear, grads):
+            if isinstance(g, RowTensor):
+                ops.sparse_ftrl(p.data, a, l, self.hyper, g.values, g.mask, self._dedup(p, g))
+            else:
+                ops.ftrl_dense(p.data, a, l, self.hyper, g)
+
+
+# ------------------------------------------------------------------------------------------------
+# DenseLayer stack (library GEMMs: not a product kernel, SURVEY 2b last rows)
+# ------------------------------------------------------------------------------------------------
+class DenseStack:
+    """The reference's DenseLayer chain (wide_and_deep.py:72-133): MatMul + BiasAdd + ReLU, optionally in
+    fp16 (`convert_dtype`), with an explicit backward.  All weights / grads live in ONE flat fp32 buffer so
+    that the dense Adam update is a single mrec_adam_dense launch.  `extra` reserves trailing scalars in
+    the same buffer (W&D's Wide_b lands in the Adam group)."""
+
+    def __init__(self, dims, convert_dtype, device, generator=None, weight_init="normal", bias_init="zero",
+                 last_activation=False, extra=0):
+        self.dims = list(dims)
+        self.convert_dtype = convert_dtype
+        self.last_activation = last_activation
+        n = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)) + extra
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
+        self.weights, self.biases, self.gw, self.gb = [], [], [], []
+        o = 0
+        for i in range(len(dims) - 1):
+            k, m = dims[i], dims[i + 1]
+            self.weights.append(self.flat[o:o + k * m].view(k, m)); self.gw.append(self.flat_grad[o:o + k * m].view(k, m)); o += k * m
+            self.biases.append(self.flat[o:o + m]); self.gb.append(self.flat_grad[o:o + m]); o += m
+        self.extra = self.flat[o:o + extra]
+        self.extra_grad = self.flat_grad[o:o + extra]
+        for w in self.weights:
+            if weight_init == "normal":
+                w.normal_(0.0, 0.01, generator=generator)
+            elif weight_init == "uniform":
+                bound = 1.0 / math.sqrt(w.shape[0])
+                w.uniform_(-bound, bound, generator=generator)
+        for b in self.biases:
+            if bias_init == "normal":
+                b.normal_(0.0, 0.01, generator=generator)
+        self._acts = None
+
+    def forward(self, x):
+        acts = [x]
+        h = x
+        nl = len(self.weights)
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            if self.convert_dtype:
+                a = torch.addmm(b.half(), h.half(), w.half())
+            else:
+                a = torch.addmm(b, h, w)
+            if i + 1 < nl or self.last_activation:
+                a = torch.relu(a)
+            h = a.float() if self.convert_dtype else a
+            acts.append(h)
+        self._acts = acts
+        return h
+
+    def backward(self, g_out):
+        """g_out: gradient wrt the stack output.  Fills flat_grad, returns the gradient wrt the input."""
+        acts = self._acts
+        g = g_out
+        nl = len(self.weights)
+        for i in range(nl - 1, -1, -1):
+            h_in, h_out = acts[i], acts[i + 1]
+            if i + 1 < nl or self.last_activation:
+                g = g * (h_out > 0).to(g.dtype)
+            if self.convert_dtype:
+                g16 = g.half()
+                self.gw[i].copy_(torch.mm(h_in.half().t(), g16))
+                self.gb[i].copy_(g16.float().sum(0))
+                g = torch.mm(g16, self.weights[i].half().t()).float()
+            else:
+                torch.mm(h_in.t(), g, out=self.gw[i])
+                torch.sum(g, 0, out=self.gb[i])
+                g = torch.mm(g, self.weights[i].t())
+        return g

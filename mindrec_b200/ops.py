@@ -11,7 +11,7 @@ import torch
 from . import _lib
 
 _ws_cache = {}
-HYPER_LEN = 8
+HYPER_LEN = 16
 
 
 def _ws(tag, nbytes, device):
@@ -162,6 +162,15 @@ def sparse_lazy_adam(w, m, v, hyper, g, mask, uq):
                                             uq.seg_of, _dummy(w.device), _opt_ws(uq.n, dim, w.device)])
 
 
+def adam_rowsparse_dense_equiv(w, m, v, hyper, g, mask, uq, row_flags):
+    """nn.Adam with a RowTensor gradient: dense-equivalent update of every row (in place)."""
+    dim = w.shape[1] if w.dim() == 2 else 1
+    mask = _empty_mask(w.device) if mask is None else mask.reshape(-1)
+    _lib.aot_call("mrec_adam_rowsparse", [w, m, v, hyper, g, mask, uq.uniq, uq.perm, uq.seg_start,
+                                          uq.seg_of, row_flags, _dummy(w.device),
+                                          _opt_ws(uq.n, dim, w.device)])
+
+
 def sparse_ftrl(w, accum, linear, hyper, g, mask, uq):
     """Fused segment-sum + FTRL row update on the rows named by uq.uniq (in place)."""
     dim = w.shape[1] if w.dim() == 2 else 1
@@ -170,15 +179,15 @@ def sparse_ftrl(w, accum, linear, hyper, g, mask, uq):
                                        uq.seg_of, _dummy(w.device), _opt_ws(uq.n, dim, w.device)])
 
 
-def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, loss_scale=1.0, device="cuda"):
-    """Device hyper block for Adam / LazyAdam: [lr, b1, b2, eps, b1^t, b2^t, lr_t, 1/loss_scale]."""
-    return torch.tensor([lr, beta1, beta2, eps, 1.0, 1.0, 0.0, 1.0 / loss_scale],
+def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, loss_scale=1.0, l2=0.0, device="cuda"):
+    """Device hyper block for Adam / LazyAdam: [lr, b1, b2, eps, b1^t, b2^t, lr_t, 1/loss_scale, l2, 0...]."""
+    return torch.tensor([lr, beta1, beta2, eps, 1.0, 1.0, 0.0, 1.0 / loss_scale, l2] + [0.0] * 7,
                         dtype=torch.float32, device=device)
 
 
 def ftrl_hyper(lr, l1=0.0, l2=0.0, lr_power=-0.5, loss_scale=1.0, device="cuda"):
-    """Device hyper block for FTRL: [lr, l1, l2, lr_power, 1/loss_scale, 0, 0, 0]."""
-    return torch.tensor([lr, l1, l2, lr_power, 1.0 / loss_scale, 0.0, 0.0, 0.0],
+    """Device hyper block for FTRL: [lr, l1, l2, lr_power, 1/loss_scale, 0...]."""
+    return torch.tensor([lr, l1, l2, lr_power, 1.0 / loss_scale] + [0.0] * 11,
                         dtype=torch.float32, device=device)
 
 

@@ -132,8 +132,11 @@ class AdamState:
 def adam_rows(w, m, v, g, st):
     """m = b1*m + (1-b1)g; v = b2*v + (1-b2)g^2; w -= lr_t*m/(sqrt(v)+eps)  (float64 math, fp32 state)."""
     g = np.asarray(g, dtype=np.float64) * np.float64(st.grad_scale)
-    m64 = st.beta1 * m.astype(np.float64) + (1.0 - st.beta1) * g
-    v64 = st.beta2 * v.astype(np.float64) + (1.0 - st.beta2) * g * g
+    # beta and (1 - beta) are fp32 scalars in the upstream kernels (1 - 0.999f != 0.001 to 1.3e-5)
+    b1, b2 = np.float64(F32(st.beta1)), np.float64(F32(st.beta2))
+    omb1, omb2 = np.float64(F32(1) - F32(st.beta1)), np.float64(F32(1) - F32(st.beta2))
+    m64 = b1 * m.astype(np.float64) + omb1 * g
+    v64 = b2 * v.astype(np.float64) + omb2 * g * g
     w64 = w.astype(np.float64) - np.float64(st.lr_t) * m64 / (np.sqrt(v64) + st.eps)
     return w64.astype(F32), m64.astype(F32), v64.astype(F32)
 
@@ -319,3 +322,87 @@ class MapParameterModel:
 
     def keys(self):
         return np.asarray(sorted(self.rows.keys()), dtype=np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# Appendix D of SURVEY.md: one full Wide&Deep training step
+# ------------------------------------------------------------------------------------------------
+class WideDeepOracle:
+    """models/wide_deep/src/wide_and_deep.py:293-316 (forward), :349-362 (losses), :472-492 (step), fp32
+    DenseLayers (use_mixed_precision=False).  State arrays are float32, arithmetic is float64.
+
+    mode: "lazy"  LazyAdam on the deep table (sparse + auto-parallel / PS / dynamic embedding, :415-422)
+          "adam"  nn.Adam with a RowTensor gradient = dense-equivalent update (sparse=True, one device)
+          "dense" sparse=False: dense gradient + l2_coef * sum(Wd^2)/2 in deep_loss (:359-360)."""
+
+    def __init__(self, wide_w, deep_w, mlp_w, mlp_b, wide_b, sens=1024.0, mode="lazy", l2_coef=8e-5):
+        self.ww = wide_w.astype(F32).copy()
+        self.wd = deep_w.astype(F32).copy()
+        self.mlp_w = [w.astype(F32).copy() for w in mlp_w]
+        self.mlp_b = [b.astype(F32).copy() for b in mlp_b]
+        self.wide_b = np.asarray(wide_b, dtype=F32).reshape(1).copy()
+        self.sens = sens
+        self.mode = mode
+        self.l2_coef = l2_coef
+        self.adam = AdamState(3.5e-4, eps=1e-8, loss_scale=sens)
+        self.ftrl = FtrlState(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens)
+        self.acc = np.full_like(self.ww, 1.0)
+        self.lin = np.zeros_like(self.ww)
+        self.md, self.vd = np.zeros_like(self.wd), np.zeros_like(self.wd)
+        self.m_w = [np.zeros_like(w) for w in self.mlp_w]
+        self.v_w = [np.zeros_like(w) for w in self.mlp_w]
+        self.m_b = [np.zeros_like(b) for b in self.mlp_b]
+        self.v_b = [np.zeros_like(b) for b in self.mlp_b]
+        self.m_wb, self.v_wb = np.zeros(1, F32), np.zeros(1, F32)
+
+    def forward(self, ids, wts):
+        b, f = ids.shape
+        wide = gather_reduce(self.ww, ids, wts, self.wide_b).astype(np.float64)
+        x = gather_masked(self.wd, ids, wts).astype(np.float64)
+        acts = [x]
+        h = x
+        for i, (w, bb) in enumerate(zip(self.mlp_w, self.mlp_b)):
+            a = h @ w.astype(np.float64) + bb.astype(np.float64)
+            h = np.maximum(a, 0) if i + 1 < len(self.mlp_w) else a
+            acts.append(h)
+        return wide + h, acts
+
+    def step(self, ids, wts, label):
+        b, f = ids.shape
+        d = self.wd.shape[1]
+        logit, acts = self.forward(ids, wts)
+        loss = sigmoid_xent(logit, label).mean()
+        loss_d = loss
+        if self.mode == "dense":
+            loss_d = loss + self.l2_coef * np.square(self.wd.astype(np.float64)).sum() / 2
+        delta = self.sens * (sigmoid(logit) - label) / b                      # [B,1]
+        g = delta
+        gw, gb = [None] * len(self.mlp_w), [None] * len(self.mlp_w)
+        for i in range(len(self.mlp_w) - 1, -1, -1):
+            if i + 1 < len(self.mlp_w):
+                g = g * (acts[i + 1] > 0)
+            gw[i] = acts[i].T @ g
+            gb[i] = g.sum(axis=0)
+            g = g @ self.mlp_w[i].astype(np.float64).T
+        gx = g.reshape(b * f, d)
+        mask = np.asarray(wts, dtype=np.float64).reshape(-1)
+        uniq, inverse, _, _ = unique_sorted(ids, bound=self.wd.shape[0])
+        gsum_w = segment_sum(delta, inverse, uniq.size, mask, div=f)
+        gsum_d = segment_sum(gx, inverse, uniq.size, mask)
+        # optimizer_w = FTRL on the wide table only (Wide_b is in the Adam group, :405-413)
+        ftrl_sparse(self.ww, self.acc, self.lin, uniq, gsum_w, self.ftrl)
+        self.adam.begin_step()
+        if self.mode == "lazy":
+            lazy_adam_sparse(self.wd, self.md, self.vd, uniq, gsum_d, self.adam)
+        else:
+            gd = np.zeros(self.wd.shape, dtype=np.float64)
+            ok = uniq < self.wd.shape[0]
+            gd[uniq[ok]] = gsum_d[ok]
+            if self.mode == "dense":
+                gd += self.sens * self.l2_coef * self.wd.astype(np.float64)
+            adam_dense(self.wd, self.md, self.vd, gd, self.adam)
+        for i in range(len(self.mlp_w)):
+            adam_dense(self.mlp_w[i], self.m_w[i], self.v_w[i], gw[i], self.adam)
+            adam_dense(self.mlp_b[i], self.m_b[i], self.v_b[i], gb[i], self.adam)
+        adam_dense(self.wide_b, self.m_wb, self.v_wb, np.array([delta.sum()]), self.adam)
+        return F32(loss), F32(loss_d)

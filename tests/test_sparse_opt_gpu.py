@@ -62,11 +62,16 @@ def test_segment_sum_broadcast_rows_div(cuda):
 
 @pytest.mark.parametrize("dim", [80, 128, 1, 6])
 def test_sparse_lazy_adam_three_steps(cuda, dim):
+    """Two oracles run side by side: `tight` is fed the kernel's own fp32 segment sums (mrec_segment_sum
+    shares the fused kernel's summation order), so it isolates the LazyAdam row math at 1e-5; `e2e` sums
+    in float64 and is compared at a bound that allows for fp32 cancellation in the 600-term hot segments
+    (|err| <= 1e-5 * sum|terms| can exceed 1e-5 * |sum| there)."""
     rng = np.random.default_rng(dim)
     vocab, b, f = 4000, 600, 39
     w = (rng.standard_normal((vocab, dim)) * 0.01).astype(np.float32)
     m = np.zeros_like(w)
     v = np.zeros_like(w)
+    tw, tm, tv = w.copy(), m.copy(), v.copy()
     dw, dm, dv = (torch.from_numpy(x.copy()).to(cuda) for x in (w, m, v))
     st = R.AdamState(3.5e-4, eps=1e-8, loss_scale=1024.0)
     hyper = ops.adam_hyper(3.5e-4, eps=1e-8, loss_scale=1024.0, device=cuda)
@@ -74,17 +79,21 @@ def test_sparse_lazy_adam_three_steps(cuda, dim):
         ids = _zipf_ids(rng, b, f, vocab + 50)  # some ids out of range: must be skipped
         g = (rng.standard_normal((b * f, dim)) * 1024).astype(np.float32)
         mask = rng.random(b * f).astype(np.float32)
+        dg, dmask = torch.from_numpy(g).to(cuda), torch.from_numpy(mask).to(cuda)
         uq = ops.unique(torch.from_numpy(ids).to(cuda), table_like=dw)
+        gsum_gpu = ops.segment_sum(dg, dmask, uq, dim=dim).cpu().numpy()
         ops.adam_begin_step(hyper)
-        ops.sparse_lazy_adam(dw, dm, dv, hyper, torch.from_numpy(g).to(cuda),
-                             torch.from_numpy(mask).to(cuda), uq)
+        ops.sparse_lazy_adam(dw, dm, dv, hyper, dg, dmask, uq)
         uniq, inverse, _, _ = R.unique_sorted(ids, bound=vocab)
         st.begin_step()
         R.lazy_adam_sparse(w, m, v, uniq, R.segment_sum(g, inverse, uniq.size, mask), st)
+        R.lazy_adam_sparse(tw, tm, tv, uniq, gsum_gpu[:uniq.size], st)
     np.testing.assert_allclose(hyper[4:7].cpu().numpy(),
                                [st.beta1_power, st.beta2_power, st.lr_t], rtol=1e-6)
-    for got, ref in ((dw, w), (dm, m), (dv, v)):
+    for got, ref in ((dw, tw), (dm, tm), (dv, tv)):
         np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+    for got, ref in ((dw, w), (dm, m), (dv, v)):
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
 
 
 @pytest.mark.parametrize("dim", [1, 64])
