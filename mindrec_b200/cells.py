@@ -116,7 +116,9 @@ class WideDeepModel:
         b, f, d = id_hldr.shape[0], self.field_size, self.emb_dim
         if self._wide_out is None or self._wide_out.shape[0] != b:
             self._wide_out = torch.empty((b, 1), dtype=torch.float32, device=self.device)
-            self._deep_in = torch.empty((b, f * d), dtype=torch.float32, device=self.device)
+            # fp16 when the DenseLayers run in mixed precision: the Cast is fused into the gather store
+            self._deep_in = torch.empty((b, f * d), device=self.device,
+                                        dtype=torch.float16 if self.config.use_mixed_precision else torch.float32)
         # wide_and_deep.py:300,303,305-306: gather(dim 1) * mask, ReduceSum(axis 1) + Wide_b
         ops.gather_reduce(self.wide_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
                           self.wide_b.data, out=self._wide_out)

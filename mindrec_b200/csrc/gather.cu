@@ -18,20 +18,39 @@
 // Out-of-range ids follow the upstream GPU Gather: the output row is zeros; in addition a
 // device flag (optional trailing output) is raised so a debug caller can mirror the CPU kernel's error.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace mrec {
 
 constexpr int kGatherThreads = 256;
+
+// One 16-byte table chunk becomes 4 outputs: fp32 (16 B) or fp16 (8 B; the Cast(x, float16) at the head
+// of the reference's DenseLayer, wide_and_deep.py:119-120, fused into the gather store).
+template <typename OutT> struct OutChunk;
+template <> struct OutChunk<float> {
+  using type = float4;
+  static __device__ __forceinline__ void store(float4* p, const float4& v) { st_stream_f4(p, v); }
+};
+template <> struct OutChunk<__half> {
+  using type = uint2;
+  static __device__ __forceinline__ void store(uint2* p, const float4& v) {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+    asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(u.x), "r"(u.y) : "memory");
+  }
+};
 
 __host__ __device__ constexpr int tile_rows_for(int cpr) {
   // aim for >= 1024 chunks per tile, tile rows a multiple of 64 (bulk-copy alignment)
   return cpr >= 16 ? 64 : (cpr >= 8 ? 128 : 256);
 }
 
-template <int CPR, typename IdT, bool MASKED>
+template <int CPR, typename IdT, bool MASKED, typename OutT>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids,
-                   const float* __restrict__ mask, float4* __restrict__ out, int64_t n_rows,
+                   const float* __restrict__ mask, typename OutChunk<OutT>::type* __restrict__ out, int64_t n_rows,
                    int64_t vocab, int cpr_rt, int bulk_ok, int* __restrict__ oob) {
   constexpr int TR = tile_rows_for(CPR == 0 ? 16 : CPR);
   const int cpr = (CPR == 0) ? cpr_rt : CPR;
@@ -84,7 +103,7 @@ gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
     }
 
     const int n_chunks = rows_here * cpr;
-    float4* out_tile = out + row0 * cpr;
+    typename OutChunk<OutT>::type* out_tile = out + row0 * cpr;
     if constexpr (CPR != 0) {
       constexpr int CH = (TR * CPR + kGatherThreads - 1) / kGatherThreads;
       float4 v[CH];
@@ -112,7 +131,7 @@ gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
         if (c < n_chunks) {
           float4 o = v[k];
           if (MASKED) o = f4_scale(o, mk[k]);
-          st_stream_f4(out_tile + c, o);
+          OutChunk<OutT>::store(out_tile + c, o);
         }
       }
     } else {
@@ -142,7 +161,7 @@ gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
           if (c < n_chunks) {
             float4 o = v[k];
             if (MASKED) o = f4_scale(o, mk[k]);
-            st_stream_f4(out_tile + c, o);
+            OutChunk<OutT>::store(out_tile + c, o);
           }
         }
       }
@@ -152,9 +171,9 @@ gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
 }
 
 // D not a multiple of 4 (rows not 16-B aligned): one thread per element.
-template <typename IdT, bool MASKED>
+template <typename IdT, bool MASKED, typename OutT>
 __global__ void gather_scalar_kernel(const float* __restrict__ table, const IdT* __restrict__ ids,
-                                     const float* __restrict__ mask, float* __restrict__ out,
+                                     const float* __restrict__ mask, OutT* __restrict__ out,
                                      int64_t n_rows, int dim, int64_t vocab, int* __restrict__ oob) {
   const int64_t total = n_rows * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
@@ -169,7 +188,7 @@ __global__ void gather_scalar_kernel(const float* __restrict__ table, const IdT*
       atomicOr(oob, 1);
     }
     if (MASKED) v *= mask[r];
-    out[e] = v;
+    out[e] = (OutT)v;
   }
 }
 
@@ -201,14 +220,14 @@ gather_reduce_kernel(const float* __restrict__ table, const IdT* __restrict__ id
   }
 }
 
-template <typename IdT, bool MASKED>
-static int launch_gather(const float* table, const IdT* ids, const float* mask, float* out,
+template <typename IdT, bool MASKED, typename OutT>
+static int launch_gather(const float* table, const IdT* ids, const float* mask, OutT* out,
                          int64_t n_rows, int dim, int64_t vocab, int* oob, cudaStream_t stream) {
   if (n_rows == 0) return OK;
   if (dim % 4 != 0) {
     const int64_t total = n_rows * dim;
     int grid = grid_for(cdiv(total, 256), 16);
-    MREC_LAUNCH((gather_scalar_kernel<IdT, MASKED>), grid, 256, 0, stream, table, ids, mask, out,
+    MREC_LAUNCH((gather_scalar_kernel<IdT, MASKED, OutT>), grid, 256, 0, stream, table, ids, mask, out,
                 n_rows, dim, vocab, oob);
     return check_launch("gather_scalar");
   }
@@ -216,12 +235,12 @@ static int launch_gather(const float* table, const IdT* ids, const float* mask, 
   const int bulk_ok = ((reinterpret_cast<uintptr_t>(ids) % 16) == 0) &&
                       (!MASKED || (reinterpret_cast<uintptr_t>(mask) % 16) == 0);
   const float4* t4 = reinterpret_cast<const float4*>(table);
-  float4* o4 = reinterpret_cast<float4*>(out);
+  auto* o4 = reinterpret_cast<typename OutChunk<OutT>::type*>(out);
 #define MREC_GATHER_CASE(C)                                                                   \
   case C: {                                                                                   \
     constexpr int TR = tile_rows_for(C);                                                      \
     int grid = grid_for(cdiv(n_rows, TR), 8);                     \
-    MREC_LAUNCH((gather_rows_kernel<C, IdT, MASKED>), grid, kGatherThreads, 0, stream, t4, ids, \
+    MREC_LAUNCH((gather_rows_kernel<C, IdT, MASKED, OutT>), grid, kGatherThreads, 0, stream, t4, ids, \
                 mask, o4, n_rows, vocab, cpr, bulk_ok, oob);                                  \
   } break;
   switch (cpr) {
@@ -233,7 +252,7 @@ static int launch_gather(const float* table, const IdT* ids, const float* mask, 
     default: {
       constexpr int TR = tile_rows_for(16);
       int grid = grid_for(cdiv(n_rows, TR), 8);
-      MREC_LAUNCH((gather_rows_kernel<0, IdT, MASKED>), grid, kGatherThreads, 0, stream, t4, ids,
+      MREC_LAUNCH((gather_rows_kernel<0, IdT, MASKED, OutT>), grid, kGatherThreads, 0, stream, t4, ids,
                   mask, o4, n_rows, vocab, cpr, bulk_ok, oob);
     } break;
   }
@@ -250,7 +269,9 @@ static int gather_entry(const Aot& a, bool masked) {
   for (int i = 0; i < a.nparam; ++i)
     if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "mrec_gather: param %d is null", i);
   const int o = n_in;
-  MREC_REQUIRE(a.is_f32(0) && a.is_f32(o), ERR_DTYPE, "mrec_gather: table/out must be float32");
+  const bool out16 = a.is(o, "float16");
+  MREC_REQUIRE(a.is_f32(0) && (a.is_f32(o) || out16), ERR_DTYPE,
+               "mrec_gather: table must be float32, out float32 or float16");
   MREC_REQUIRE(a.is_i32(1) || a.is_i64(1), ERR_DTYPE, "mrec_gather: ids must be int32 or int64");
   MREC_REQUIRE(a.ndims[0] == 2 || a.ndims[0] == 1, ERR_SHAPE, "mrec_gather: table must be [V,D] or [V]");
   const int64_t vocab = a.dim(0, 0);
@@ -264,7 +285,7 @@ static int gather_entry(const Aot& a, bool masked) {
     MREC_REQUIRE(a.numel(2) == n, ERR_SHAPE, "mrec_gather_masked: mask numel must equal ids numel");
   }
   if (dim % 4 == 0)
-    MREC_REQUIRE(a.aligned(0, 16) && a.aligned(o, 16), ERR_ALIGN,
+    MREC_REQUIRE(a.aligned(0, 16) && a.aligned(o, out16 ? 8 : 16), ERR_ALIGN,
                  "mrec_gather: table/out must be 16-byte aligned");
   int* oob = nullptr;
   if (a.nparam == n_in + 2) {
@@ -272,16 +293,18 @@ static int gather_entry(const Aot& a, bool masked) {
     oob = a.ptr<int>(o + 1);
   }
   const float* mask = masked ? a.ptr<float>(2) : nullptr;
+#define MREC_GATHER_DISPATCH(IDT, MASKED_, OUTT)                                                   \
+  return launch_gather<IDT, MASKED_, OUTT>(a.ptr<float>(0), a.ptr<IDT>(1), mask, a.ptr<OUTT>(o), n, dim, \
+                                           vocab, oob, a.stream)
   if (a.is_i32(1)) {
-    return masked ? launch_gather<int32_t, true>(a.ptr<float>(0), a.ptr<int32_t>(1), mask,
-                                                 a.ptr<float>(o), n, dim, vocab, oob, a.stream)
-                  : launch_gather<int32_t, false>(a.ptr<float>(0), a.ptr<int32_t>(1), mask,
-                                                  a.ptr<float>(o), n, dim, vocab, oob, a.stream);
+    if (masked) { if (out16) MREC_GATHER_DISPATCH(int32_t, true, __half); MREC_GATHER_DISPATCH(int32_t, true, float); }
+    if (out16) MREC_GATHER_DISPATCH(int32_t, false, __half);
+    MREC_GATHER_DISPATCH(int32_t, false, float);
   }
-  return masked ? launch_gather<int64_t, true>(a.ptr<float>(0), a.ptr<int64_t>(1), mask,
-                                               a.ptr<float>(o), n, dim, vocab, oob, a.stream)
-                : launch_gather<int64_t, false>(a.ptr<float>(0), a.ptr<int64_t>(1), mask,
-                                                a.ptr<float>(o), n, dim, vocab, oob, a.stream);
+  if (masked) { if (out16) MREC_GATHER_DISPATCH(int64_t, true, __half); MREC_GATHER_DISPATCH(int64_t, true, float); }
+  if (out16) MREC_GATHER_DISPATCH(int64_t, false, __half);
+  MREC_GATHER_DISPATCH(int64_t, false, float);
+#undef MREC_GATHER_DISPATCH
 }
 
 }  // namespace mrec

@@ -20,6 +20,7 @@
 // result is bit-reproducible run to run.
 #include "common.cuh"
 #include "kernels.h"
+#include <cuda_fp16.h>
 
 namespace mrec {
 
@@ -36,13 +37,26 @@ template <> struct VOps<float4> {
   static __device__ __forceinline__ void add(float4& a, const float4& x) {
     a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
   }
-  static __device__ __forceinline__ float4 ldg(const float4* p) { return ld_stream_f4(p); }
+  // gradient rows: fp32, or fp16 (the DenseLayer backward emits fp16 when use_mixed_precision; the
+  // Cast-to-fp32 of wide_and_deep.py:119 bprop is fused into this load)
+  static __device__ __forceinline__ float4 ldg(const float* g, int64_t chunk) {
+    return ld_stream_f4(reinterpret_cast<const float4*>(g) + chunk);
+  }
+  static __device__ __forceinline__ float4 ldg(const __half* g, int64_t chunk) {
+    uint2 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];"
+                 : "=r"(u.x), "=r"(u.y) : "l"(reinterpret_cast<const uint2*>(g) + chunk));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
 };
 template <> struct VOps<float> {
   static __device__ __forceinline__ float zero() { return 0.f; }
   static __device__ __forceinline__ void fma(float& a, const float& x, float s) { a = fmaf(x, s, a); }
   static __device__ __forceinline__ void add(float& a, const float& x) { a += x; }
-  static __device__ __forceinline__ float ldg(const float* p) { return ld_stream_f1(p); }
+  static __device__ __forceinline__ float ldg(const float* g, int64_t i) { return ld_stream_f1(g + i); }
+  static __device__ __forceinline__ float ldg(const __half* g, int64_t i) { return __half2float(g[i]); }
 };
 
 // ---- hyper-parameter blocks (device f32 tensors, so schedules / bias-correction never sync the host)
@@ -166,9 +180,9 @@ struct StoreSink {
 };
 
 // ---- kernel A: walk tiles ----
-template <typename Vec, typename Sink, bool HAS_MASK>
+template <typename Vec, typename GT, typename Sink, bool HAS_MASK>
 __global__ void __launch_bounds__(kSegThreads)
-segsum_tiles_kernel(const Vec* __restrict__ g, int cpr, int div, const float* __restrict__ mask,
+segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __restrict__ mask,
                     const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of, int64_t n,
                     int64_t n_tiles, Vec* __restrict__ part, Sink sink) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -197,7 +211,7 @@ segsum_tiles_kernel(const Vec* __restrict__ g, int cpr, int div, const float* __
     for (int k = 0; k < kSegBatch; ++k) {
       if (seg[k] >= 0) {
         const int64_t grow = (div == 1) ? (int64_t)p[k] : (int64_t)(p[k] / div);
-        gv[k] = VOps<Vec>::ldg(g + grow * cpr + c);
+        gv[k] = VOps<Vec>::ldg(g, grow * cpr + c);
         mk[k] = HAS_MASK ? mask[p[k]] : 1.f;
       } else {
         gv[k] = VOps<Vec>::zero();
@@ -300,8 +314,8 @@ static SegWorkspace seg_ws(int64_t n, int dim) {
 }
 size_t sparse_opt_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim).total; }
 
-template <typename Vec, typename Sink>
-static int run_segsum(const float* g, int dim, int div, const float* mask, const int32_t* perm,
+template <typename Vec, typename GT, typename Sink>
+static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
                       const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws,
                       size_t ws_bytes, Sink sink, cudaStream_t stream) {
   if (n == 0) return OK;
@@ -320,12 +334,11 @@ static int run_segsum(const float* g, int dim, int div, const float* mask, const
   const int64_t threads = n_tiles * cpr;
   const int grid = (int)cdiv(threads, kSegThreads);
   cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
-  const Vec* gv = reinterpret_cast<const Vec*>(g);
   if (mask) {
-    MREC_LAUNCH((segsum_tiles_kernel<Vec, Sink, true>), grid, kSegThreads, 0, stream, gv, cpr, div, mask,
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, Sink, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask,
                 perm, seg_of, n, n_tiles, part, sink);
   } else {
-    MREC_LAUNCH((segsum_tiles_kernel<Vec, Sink, false>), grid, kSegThreads, 0, stream, gv, cpr, div, mask,
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, Sink, false>), grid, kSegThreads, 0, stream, g, cpr, div, mask,
                 perm, seg_of, n, n_tiles, part, sink);
   }
   if (n_tiles > 1) {
@@ -335,6 +348,18 @@ static int run_segsum(const float* g, int dim, int div, const float* mask, const
                 seg_start, part, long_list, long_count, sink);
   }
   return check_launch("segment_sum");
+}
+
+// g is float32 unless g16 (float16 gradient rows)
+template <typename Vec, typename Sink>
+static int run_segsum(const void* g, bool g16, int dim, int div, const float* mask, const int32_t* perm,
+                      const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws, size_t ws_bytes,
+                      Sink sink, cudaStream_t stream) {
+  if (g16)
+    return run_segsum_t<Vec, __half, Sink>(reinterpret_cast<const __half*>(g), dim, div, mask, perm, seg_start,
+                                           seg_of, n, ws, ws_bytes, sink, stream);
+  return run_segsum_t<Vec, float, Sink>(reinterpret_cast<const float*>(g), dim, div, mask, perm, seg_start,
+                                        seg_of, n, ws, ws_bytes, sink, stream);
 }
 
 // ---- dense optimizers (MLP parameters, Wide_b: SURVEY a5/a7) ----
@@ -427,16 +452,17 @@ MREC_API size_t mrec_sparse_opt_workspace_bytes(int64_t n, int dim) {
 
 // Shared validation of (g, mask, uniq, perm, seg_start, seg_of) starting at param index `b`.
 struct SegArgs {
-  const float* g; const float* mask; const void* uniq; bool uniq64;
+  const void* g; bool g16; const float* mask; const void* uniq; bool uniq64;
   const int32_t* perm; const int32_t* seg_start; const int32_t* seg_of;
   int64_t n; int div;
 };
 static int parse_seg_args(const Aot& a, int b, int dim, bool has_uniq, SegArgs* s, const char* who) {
   int i = b;
-  MREC_REQUIRE(a.is_f32(i), ERR_DTYPE, "%s: grad rows must be float32", who);
+  MREC_REQUIRE(a.is_f32(i) || a.is(i, "float16"), ERR_DTYPE, "%s: grad rows must be float32|float16", who);
+  s->g16 = a.is(i, "float16");
   MREC_REQUIRE(dim == 1 || a.last(i) == dim, ERR_SHAPE, "%s: grad rows must have last dim %d", who, dim);
   const int64_t g_rows = a.numel(i) / dim;
-  s->g = a.ptr<float>(i++);
+  s->g = a.params[i++];
   MREC_REQUIRE(a.is_f32(i), ERR_DTYPE, "%s: mask must be float32 (numel 0 = no mask)", who);
   const int64_t mask_n = a.numel(i);
   s->mask = mask_n ? a.ptr<float>(i) : nullptr;
@@ -460,7 +486,8 @@ static int parse_seg_args(const Aot& a, int b, int dim, bool has_uniq, SegArgs* 
                (long long)g_rows);
   s->div = g_rows > 0 ? (int)(s->n / g_rows) : 1;
   if (dim % 4 == 0)
-    MREC_REQUIRE(reinterpret_cast<uintptr_t>(s->g) % 16 == 0, ERR_ALIGN, "%s: grad rows must be 16-B aligned", who);
+    MREC_REQUIRE(reinterpret_cast<uintptr_t>(s->g) % (s->g16 ? 8 : 16) == 0, ERR_ALIGN,
+                 "%s: grad rows must be 16-B aligned", who);
   return OK;
 }
 
@@ -491,21 +518,21 @@ MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_
     if (s.uniq64) {
       LazyAdamSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                          (const int64_t*)s.uniq, hyper, vocab, cpr};
-      return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
     }
     LazyAdamSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                        (const int32_t*)s.uniq, hyper, vocab, cpr};
-    return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_lazy_adam: D too large");
   if (s.uniq64) {
     LazyAdamSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                       (const int64_t*)s.uniq, hyper, vocab, dim};
-    return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
   }
   LazyAdamSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                     (const int32_t*)s.uniq, hyper, vocab, dim};
-  return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
 }
 
 // inputs : w[V,D] accum[V,D] linear[V,D] hyper[8] g[N/div,D] mask[N|0] uniq[N] perm[N] seg_start[N+1] seg_of[N]
@@ -535,21 +562,21 @@ MREC_API int mrec_sparse_ftrl(int nparam, void** params, int* ndims, int64_t** s
     if (s.uniq64) {
       FtrlSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                      (const int64_t*)s.uniq, hyper, vocab, cpr};
-      return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
     }
     FtrlSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                    (const int32_t*)s.uniq, hyper, vocab, cpr};
-    return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_ftrl: D too large");
   if (s.uniq64) {
     FtrlSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                   (const int64_t*)s.uniq, hyper, vocab, dim};
-    return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
   }
   FtrlSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                 (const int32_t*)s.uniq, hyper, vocab, dim};
-  return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
 }
 
 // Standalone deterministic segment-sum (the UnsortedSegmentSum of SURVEY a4, in sorted-segment order).
@@ -570,11 +597,11 @@ MREC_API int mrec_segment_sum(int nparam, void** params, int* ndims, int64_t** s
     MREC_REQUIRE(a.aligned(5, 16), ERR_ALIGN, "mrec_segment_sum: gsum must be 16-byte aligned");
     MREC_REQUIRE(dim / 4 <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
     StoreSink<float4> sink{a.ptr<float4>(5), dim / 4};
-    return run_segsum<float4>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
   StoreSink<float> sink{a.ptr<float>(5), dim};
-  return run_segsum<float>(s.g, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
 }
 
 

@@ -238,37 +238,62 @@ class DenseStack:
             if bias_init == "normal":
                 b.normal_(0.0, 0.01, generator=generator)
         self._acts = None
+        self._flat16 = None
+
+    def refresh_half(self):
+        """fp16 shadow of the weights (the per-layer Cast(weight, float16) of the reference, done once
+        per step for the whole flat buffer)."""
+        if self._flat16 is None:
+            self._flat16 = torch.empty_like(self.flat, dtype=torch.float16)
+            self.w16, self.b16 = [], []
+            o = 0
+            for i in range(len(self.dims) - 1):
+                k, m = self.dims[i], self.dims[i + 1]
+                self.w16.append(self._flat16[o:o + k * m].view(k, m)); o += k * m
+                self.b16.append(self._flat16[o:o + m]); o += m
+        self._flat16.copy_(self.flat)
 
     def forward(self, x):
-        acts = [x]
-        h = x
+        """x: [B, dims[0]] fp32, or fp16 when convert_dtype (mrec_gather_masked can emit it directly).
+        Returns the stack output in fp32."""
         nl = len(self.weights)
+        acts = [x]
+        if self.convert_dtype:
+            self.refresh_half()
+            h = x if x.dtype == torch.float16 else x.half()
+            acts[0] = h
+            for i in range(nl):
+                if i + 1 < nl or self.last_activation:
+                    h = torch._addmm_activation(self.b16[i], h, self.w16[i], use_gelu=False)
+                else:
+                    h = torch.addmm(self.b16[i], h, self.w16[i])
+                acts.append(h)
+            self._acts = acts
+            return h.float()
+        h = x
         for i, (w, b) in enumerate(zip(self.weights, self.biases)):
-            if self.convert_dtype:
-                a = torch.addmm(b.half(), h.half(), w.half())
-            else:
-                a = torch.addmm(b, h, w)
+            a = torch.addmm(b, h, w)
             if i + 1 < nl or self.last_activation:
-                a = torch.relu(a)
-            h = a.float() if self.convert_dtype else a
+                a = torch.relu_(a)
+            h = a
             acts.append(h)
         self._acts = acts
         return h
 
-    def backward(self, g_out):
-        """g_out: gradient wrt the stack output.  Fills flat_grad, returns the gradient wrt the input."""
+    def backward(self, g_out, input_grad_dtype=None):
+        """g_out: gradient wrt the stack output.  Fills flat_grad (fp32) and returns the gradient wrt the
+        input — fp16 when convert_dtype (the sparse optimizers read fp16 rows directly)."""
         acts = self._acts
-        g = g_out
         nl = len(self.weights)
+        g = g_out.half() if self.convert_dtype else g_out
         for i in range(nl - 1, -1, -1):
             h_in, h_out = acts[i], acts[i + 1]
             if i + 1 < nl or self.last_activation:
-                g = g * (h_out > 0).to(g.dtype)
+                g = torch.ops.aten.threshold_backward(g, h_out, 0)
             if self.convert_dtype:
-                g16 = g.half()
-                self.gw[i].copy_(torch.mm(h_in.half().t(), g16))
-                self.gb[i].copy_(g16.float().sum(0))
-                g = torch.mm(g16, self.weights[i].half().t()).float()
+                self.gw[i].copy_(torch.mm(h_in.t(), g))
+                torch.sum(g, 0, dtype=torch.float32, out=self.gb[i])
+                g = torch.mm(g, self.w16[i].t())
             else:
                 torch.mm(h_in.t(), g, out=self.gw[i])
                 torch.sum(g, 0, out=self.gb[i])

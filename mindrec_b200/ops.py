@@ -52,11 +52,12 @@ def gather(table, ids, out=None, oob_flag=None):
     return out
 
 
-def gather_masked(table, ids, mask, out=None, oob_flag=None):
-    """out[b, f*D:(f+1)*D] = table[ids[b,f]] * mask[b,f]  (gather + Mul + Reshape fused)."""
+def gather_masked(table, ids, mask, out=None, oob_flag=None, out_dtype=torch.float32):
+    """out[b, f*D:(f+1)*D] = table[ids[b,f]] * mask[b,f]  (gather + Mul + Reshape fused).
+    A float16 `out` additionally fuses the Cast at the head of a mixed-precision DenseLayer."""
     dim = table.shape[1] if table.dim() == 2 else 1
     if out is None:
-        out = torch.empty((ids.shape[0], ids.numel() // ids.shape[0] * dim), dtype=torch.float32,
+        out = torch.empty((ids.shape[0], ids.numel() // ids.shape[0] * dim), dtype=out_dtype,
                           device=table.device)
     args = [table, ids, mask, out] + ([oob_flag] if oob_flag is not None else [])
     _lib.aot_call("mrec_gather_masked", args)

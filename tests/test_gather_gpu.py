@@ -102,3 +102,18 @@ def test_gather_full_size_roundtrip_property(cuda):
 def test_wrong_device_is_rejected(built_lib):
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.gather(torch.zeros((4, 4)), torch.zeros(2, dtype=torch.int32))
+
+
+@pytest.mark.parametrize("dim", [16, 80, 27])
+def test_gather_masked_fp16_output_equals_cast_after(cuda, dim):
+    """fp16 `out` fuses DenseLayer's Cast(x, float16): bit-identical to rounding the fp32 product."""
+    v, b, f = 9000, 333, 39
+    tab = _table(v, dim, 8)
+    rng = np.random.default_rng(9)
+    ids = rng.integers(0, v, size=(b, f)).astype(np.int32)
+    mask = rng.random((b, f)).astype(np.float32)
+    out = ops.gather_masked(torch.from_numpy(tab).to(cuda), torch.from_numpy(ids).to(cuda),
+                            torch.from_numpy(mask).to(cuda), out_dtype=torch.float16)
+    assert out.dtype == torch.float16
+    ref = R.gather_masked(tab, ids, mask).astype(np.float16)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)

@@ -168,3 +168,27 @@ def test_dense_adam_and_ftrl_match_oracle(cuda):
     R.ftrl_dense(w2, acc, lin, g, fst)
     np.testing.assert_allclose(dw2.cpu().numpy(), w2, rtol=2e-5, atol=1e-7)
     np.testing.assert_allclose(da.cpu().numpy(), acc, rtol=RTOL)
+
+
+@pytest.mark.parametrize("dim", [80, 6])
+def test_fp16_gradient_rows_equal_cast_then_fp32(cuda, dim):
+    """fp16 gradient rows fuse the Cast-to-fp32 of the DenseLayer bprop: same bits as casting first."""
+    rng = np.random.default_rng(21 + dim)
+    vocab, b, f = 3000, 300, 39
+    ids = torch.from_numpy(_zipf_ids(rng, b, f, vocab)).to(cuda)
+    g16 = torch.from_numpy(rng.standard_normal((b * f, dim)).astype(np.float16)).to(cuda)
+    mask = torch.from_numpy(rng.random(b * f).astype(np.float32)).to(cuda)
+    w0 = torch.from_numpy((rng.standard_normal((vocab, dim)) * 0.01).astype(np.float32)).to(cuda)
+    uq = ops.unique(ids, table_like=w0)
+    a = ops.segment_sum(g16, mask, uq, dim=dim).clone()
+    b32 = ops.segment_sum(g16.float(), mask, uq, dim=dim).clone()
+    u = int(uq.count.item())
+    assert torch.equal(a[:u], b32[:u])
+    res = []
+    for g in (g16, g16.float()):
+        w, m, v = w0.clone(), torch.zeros_like(w0), torch.zeros_like(w0)
+        hyper = ops.adam_hyper(1e-3, device=cuda)
+        ops.adam_begin_step(hyper)
+        ops.sparse_lazy_adam(w, m, v, hyper, g, mask, uq)
+        res.append(w)
+    assert torch.equal(res[0], res[1])
