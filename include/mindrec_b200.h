@@ -95,7 +95,8 @@ int mrec_sparse_lazy_adam(MREC_AOT_ARGS);
 /*   in : w[V,D] accum[V,D] linear[V,D] hyper[16] g mask uniq perm seg_start seg_of   out: dummy, workspace */
 int mrec_sparse_ftrl(MREC_AOT_ARGS);
 /* Stand-alone UnsortedSegmentSum in sorted-segment order (no atomics, bit-reproducible):
- *   in : g mask perm seg_start seg_of     out: gsum[N,D] f32 (rows >= count untouched), workspace */
+ *   in : g mask perm seg_start seg_of     out: gsum[N,D] f32 (rows >= count untouched),
+ *        workspace[mrec_segment_sum_workspace_bytes(N, D)]                                        */
 int mrec_segment_sum(MREC_AOT_ARGS);
 /* nn.Adam (not Lazy) with a RowTensor gradient = dense-equivalent update of the WHOLE table (every
  * row's moments decay; wide_and_deep.py:435-437 when sparse=True on one device):
@@ -103,6 +104,7 @@ int mrec_segment_sum(MREC_AOT_ARGS);
  *   out: dummy[1], workspace                                                                       */
 int mrec_adam_rowsparse(MREC_AOT_ARGS);
 size_t mrec_sparse_opt_workspace_bytes(int64_t n, int dim);
+size_t mrec_segment_sum_workspace_bytes(int64_t n, int dim);
 /* nn.Adam preamble: beta powers advance, lr_t = lr*sqrt(1-b2^t)/(1-b1^t).  in: hyper[16]  out: dummy[1] */
 int mrec_adam_begin_step(MREC_AOT_ARGS);
 /* nn.Adam dense kernel (MLP weights, Wide_b: wide_and_deep.py:405-413,435-437).

@@ -21,5 +21,6 @@ int unique_first(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t
 
 // sparse_opt.cu ----------------------------------------------------------------------------------
 size_t sparse_opt_workspace_bytes(int64_t n, int dim);
+size_t segment_sum_workspace_bytes(int64_t n, int dim);
 
 }  // namespace mrec

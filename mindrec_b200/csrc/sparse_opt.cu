@@ -7,20 +7,26 @@
 // the upstream chain  Gather-bprop -> RowTensor -> Unique -> UnsortedSegmentSum(atomicAdd) ->
 // FusedSparseLazyAdam / FusedSparseFtrl  (SURVEY B4-B7).
 //
-// Input is the stable sort of the lookup ids (mrec_unique: perm / seg_of / seg_start / uniq).  The
-// sorted positions are cut into fixed tiles of 32; a group of D/4 threads (one float4 column chunk
-// each) walks a tile in order, accumulating mask[p] * g[p] for each run of equal keys:
-//   * a run that starts and ends inside the tile is final: the optimizer update for its row is applied
-//     on the spot, so the summed gradient never touches HBM;
+// Input is the stable sort of the lookup ids (mrec_unique: perm / seg_of / seg_start / uniq).
+// Phase 1 (segment sum).  The sorted positions are cut into fixed tiles of 32; a group of D/4 threads
+// (one float4 column chunk each) walks a tile in order, accumulating mask[p] * g[p] for each run of equal
+// keys, 8 independent row loads in flight per thread:
+//   * a run that starts and ends inside the tile is complete: its sum is stored to gsum[segment];
 //   * a run that crosses a tile edge writes a partial (at most 2 per tile); a second kernel, launched
-//     over tiles, lets the tile in which such a segment starts add the partials in tile order and apply
-//     the update; chains longer than kLongChain tiles (Zipf head keys, the 13 dense Criteo fields that
-//     appear once per sample) go to a third kernel that sums them with a fixed-shape CTA reduction.
+//     over tiles, lets the tile in which such a segment starts add the partials in tile order; chains
+//     longer than kLongChain tiles (Zipf head keys, the 13 dense Criteo fields that appear once per
+//     sample) go to a third kernel that sums them with a fixed-shape CTA reduction.
+// Phase 2 (row update).  One thread group per unique row reads gsum[u] (still L2-resident: U*D*4 bytes,
+// 39 MB at BASELINE config 2 against a 126 MB L2) and w/m/v[uniq[u]] as four independent 16-byte loads
+// and writes the LazyAdam / FTRL result.  Splitting the update from the tile walk removes the dependent
+// load chain that an in-line update puts after every run (ncu r1a: 110 regs, 22 % warps active, 17 %
+// of DRAM peak when fused) and lets both phases run at full memory-level parallelism.
 // No atomics touch floating-point data: the summation order depends only on the sorted order, so the
 // result is bit-reproducible run to run.
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace mrec {
 
@@ -169,22 +175,12 @@ struct FtrlSink<float, IdT> {
   }
 };
 
-// plain segment-sum: gsum[seg] = sum
-template <typename Vec>
-struct StoreSink {
-  Vec* out;
-  int cpr;
-  __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const {
-    out[(int64_t)seg * cpr + c] = gs;
-  }
-};
-
 // ---- kernel A: walk tiles ----
-template <typename Vec, typename GT, typename Sink, bool HAS_MASK>
-__global__ void __launch_bounds__(kSegThreads)
+template <typename Vec, typename GT, bool HAS_MASK>
+__global__ void __launch_bounds__(kSegThreads, 3)
 segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __restrict__ mask,
                     const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of, int64_t n,
-                    int64_t n_tiles, Vec* __restrict__ part, Sink sink) {
+                    int64_t n_tiles, Vec* __restrict__ part, Vec* __restrict__ gsum) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t j = gid / cpr;
   if (j >= n_tiles) return;
@@ -224,7 +220,7 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
         if (seg[k] != cur) {
           // run [.., here) ended inside the tile
           if (enters) part[(j * 2 + 0) * cpr + c] = acc;
-          else sink.apply(cur, c, acc);
+          else gsum[(int64_t)cur * cpr + c] = acc;
           cur = seg[k];
           enters = false;
           acc = VOps<Vec>::zero();
@@ -236,15 +232,16 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
   const bool leaves = (pos1 < n) && (seg_of[pos1] == cur);
   if (enters) part[(j * 2 + 0) * cpr + c] = acc;        // entered (and maybe also leaves): slot 0
   else if (leaves) part[(j * 2 + 1) * cpr + c] = acc;   // starts here, continues right: slot 1
-  else sink.apply(cur, c, acc);
+  else gsum[(int64_t)cur * cpr + c] = acc;
 }
 
 // ---- kernel B: short partial chains, one thread group per tile in which a crossing segment starts
-template <typename Vec, typename Sink>
+template <typename Vec>
 __global__ void __launch_bounds__(kSegThreads)
 segsum_boundary_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                        int64_t n, int64_t n_tiles, const Vec* __restrict__ part,
-                       int32_t* __restrict__ long_list, int32_t* __restrict__ long_count, Sink sink) {
+                       int32_t* __restrict__ long_list, int32_t* __restrict__ long_count,
+                       Vec* __restrict__ gsum) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t j = gid / cpr;
   if (j >= n_tiles) return;
@@ -262,15 +259,15 @@ segsum_boundary_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_
   }
   Vec acc = part[(j * 2 + 1) * cpr + c];
   for (int64_t jj = j + 1; jj <= j_last; ++jj) VOps<Vec>::add(acc, part[(jj * 2 + 0) * cpr + c]);
-  sink.apply(s, c, acc);
+  gsum[(int64_t)s * cpr + c] = acc;
 }
 
 // ---- kernel C: long chains, one CTA per segment, fixed-shape reduction ----
-template <typename Vec, typename Sink>
+template <typename Vec>
 __global__ void __launch_bounds__(kSegThreads)
 segsum_long_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                    const Vec* __restrict__ part, const int32_t* __restrict__ long_list,
-                   const int32_t* __restrict__ long_count, Sink sink) {
+                   const int32_t* __restrict__ long_count, Vec* __restrict__ gsum) {
   __shared__ Vec s_part[kSegThreads];
   const int groups = min(kSegThreads / cpr, 32);
   const int gi = threadIdx.x / cpr;
@@ -293,40 +290,51 @@ segsum_long_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* _
     if (gi == 0) {
       Vec acc = s_part[c];
       for (int q = 1; q < groups; ++q) VOps<Vec>::add(acc, s_part[q * cpr + c]);
-      sink.apply(s, c, acc);
+      gsum[(int64_t)s * cpr + c] = acc;
     }
     __syncthreads();
   }
 }
 
+// ---- phase 2: one thread group per unique row ----
+template <typename Vec, typename Sink>
+__global__ void __launch_bounds__(kSegThreads)
+rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, int64_t n, const Vec* __restrict__ gsum,
+                   Sink sink) {
+  const int n_seg = seg_of[n - 1] + 1;  // U: segment id of the last sorted position + 1
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / cpr;
+  const int64_t grp = gid / cpr;
+  if (grp >= n_groups) return;
+  const int c = (int)(gid - grp * cpr);
+  for (int64_t u = grp; u < n_seg; u += n_groups) sink.apply((int)u, c, gsum[u * cpr + c]);
+}
+
 struct SegWorkspace {
-  size_t off_part, off_list, off_count, total;
+  size_t off_part, off_list, off_count, off_gsum, total;
 };
-static SegWorkspace seg_ws(int64_t n, int dim) {
+static SegWorkspace seg_ws(int64_t n, int dim, bool with_gsum) {
   const int64_t n_tiles = cdiv(n > 0 ? n : 1, kSegTile);
   SegWorkspace w;
   size_t o = 0;
   w.off_part = o; o = align_up(o + (size_t)n_tiles * 2 * dim * 4, 256);
   w.off_list = o; o = align_up(o + (size_t)n_tiles * 4, 256);
   w.off_count = o; o = align_up(o + 16, 256);
+  w.off_gsum = o;
+  if (with_gsum) o = align_up(o + (size_t)(n > 0 ? n : 1) * dim * 4, 256);
   w.total = o;
   return w;
 }
-size_t sparse_opt_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim).total; }
+size_t sparse_opt_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim, true).total; }
+size_t segment_sum_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim, false).total; }
 
-template <typename Vec, typename GT, typename Sink>
-static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
-                      const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws,
-                      size_t ws_bytes, Sink sink, cudaStream_t stream) {
-  if (n == 0) return OK;
+// Phase 1 into `gsum` ([U, dim], caller buffer or workspace).
+template <typename Vec, typename GT>
+static int run_segment_sum(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
+                           const int32_t* seg_start, const int32_t* seg_of, int64_t n, char* w,
+                           const SegWorkspace& W, Vec* gsum, cudaStream_t stream) {
   const int vec = sizeof(Vec) / 4;
   const int cpr = dim / vec;
-  const SegWorkspace W = seg_ws(n, dim);
-  if (ws_bytes < W.total)
-    return fail(ERR_WORKSPACE, "sparse update: workspace %zu bytes < required %zu", ws_bytes, W.total);
-  if (reinterpret_cast<uintptr_t>(ws) % 16 != 0)
-    return fail(ERR_ALIGN, "sparse update: workspace must be 16-byte aligned");
-  char* w = reinterpret_cast<char*>(ws);
   Vec* part = reinterpret_cast<Vec*>(w + W.off_part);
   int32_t* long_list = reinterpret_cast<int32_t*>(w + W.off_list);
   int32_t* long_count = reinterpret_cast<int32_t*>(w + W.off_count);
@@ -335,17 +343,42 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
   const int grid = (int)cdiv(threads, kSegThreads);
   cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
   if (mask) {
-    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, Sink, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask,
-                perm, seg_of, n, n_tiles, part, sink);
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
+                seg_of, n, n_tiles, part, gsum);
   } else {
-    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, Sink, false>), grid, kSegThreads, 0, stream, g, cpr, div, mask,
-                perm, seg_of, n, n_tiles, part, sink);
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, false>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
+                seg_of, n, n_tiles, part, gsum);
   }
   if (n_tiles > 1) {
-    MREC_LAUNCH((segsum_boundary_kernel<Vec, Sink>), grid, kSegThreads, 0, stream, cpr, seg_of, seg_start,
-                n, n_tiles, part, long_list, long_count, sink);
-    MREC_LAUNCH((segsum_long_kernel<Vec, Sink>), kNumSMs * 2, kSegThreads, 0, stream, cpr, seg_of,
-                seg_start, part, long_list, long_count, sink);
+    MREC_LAUNCH((segsum_boundary_kernel<Vec>), grid, kSegThreads, 0, stream, cpr, seg_of, seg_start, n,
+                n_tiles, part, long_list, long_count, gsum);
+    MREC_LAUNCH((segsum_long_kernel<Vec>), kNumSMs * 2, kSegThreads, 0, stream, cpr, seg_of, seg_start,
+                part, long_list, long_count, gsum);
+  }
+  return OK;
+}
+
+struct NoSink {};
+
+// Sink = NoSink: stand-alone segment sum into `out`; otherwise phase 1 into the workspace + phase 2.
+template <typename Vec, typename GT, typename Sink>
+static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
+                        const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws,
+                        size_t ws_bytes, Sink sink, Vec* out, cudaStream_t stream) {
+  if (n == 0) return OK;
+  constexpr bool kStandalone = std::is_same<Sink, NoSink>::value;
+  const SegWorkspace W = seg_ws(n, dim, !kStandalone);
+  if (ws_bytes < W.total)
+    return fail(ERR_WORKSPACE, "sparse update: workspace %zu bytes < required %zu", ws_bytes, W.total);
+  if (reinterpret_cast<uintptr_t>(ws) % 16 != 0)
+    return fail(ERR_ALIGN, "sparse update: workspace must be 16-byte aligned");
+  char* w = reinterpret_cast<char*>(ws);
+  Vec* gsum = kStandalone ? out : reinterpret_cast<Vec*>(w + W.off_gsum);
+  run_segment_sum<Vec, GT>(g, dim, div, mask, perm, seg_start, seg_of, n, w, W, gsum, stream);
+  if constexpr (!kStandalone) {
+    const int cpr = dim / (int)(sizeof(Vec) / 4);
+    MREC_LAUNCH((rows_update_kernel<Vec, Sink>), grid_for(cdiv(n * cpr, kSegThreads), 8), kSegThreads, 0,
+                stream, cpr, seg_of, n, gsum, sink);
   }
   return check_launch("segment_sum");
 }
@@ -354,12 +387,12 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
 template <typename Vec, typename Sink>
 static int run_segsum(const void* g, bool g16, int dim, int div, const float* mask, const int32_t* perm,
                       const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws, size_t ws_bytes,
-                      Sink sink, cudaStream_t stream) {
+                      Sink sink, cudaStream_t stream, Vec* out = nullptr) {
   if (g16)
     return run_segsum_t<Vec, __half, Sink>(reinterpret_cast<const __half*>(g), dim, div, mask, perm, seg_start,
-                                           seg_of, n, ws, ws_bytes, sink, stream);
+                                           seg_of, n, ws, ws_bytes, sink, out, stream);
   return run_segsum_t<Vec, float, Sink>(reinterpret_cast<const float*>(g), dim, div, mask, perm, seg_start,
-                                        seg_of, n, ws, ws_bytes, sink, stream);
+                                        seg_of, n, ws, ws_bytes, sink, out, stream);
 }
 
 // ---- dense optimizers (MLP parameters, Wide_b: SURVEY a5/a7) ----
@@ -448,6 +481,9 @@ using namespace mrec;
 
 MREC_API size_t mrec_sparse_opt_workspace_bytes(int64_t n, int dim) {
   return sparse_opt_workspace_bytes(n, dim);
+}
+MREC_API size_t mrec_segment_sum_workspace_bytes(int64_t n, int dim) {
+  return segment_sum_workspace_bytes(n, dim);
 }
 
 // Shared validation of (g, mask, uniq, perm, seg_start, seg_of) starting at param index `b`.
@@ -596,12 +632,12 @@ MREC_API int mrec_segment_sum(int nparam, void** params, int* ndims, int64_t** s
   if (dim % 4 == 0) {
     MREC_REQUIRE(a.aligned(5, 16), ERR_ALIGN, "mrec_segment_sum: gsum must be 16-byte aligned");
     MREC_REQUIRE(dim / 4 <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
-    StoreSink<float4> sink{a.ptr<float4>(5), dim / 4};
-    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6],
+                              ws_bytes, NoSink{}, a.stream, a.ptr<float4>(5));
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
-  StoreSink<float> sink{a.ptr<float>(5), dim};
-  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6], ws_bytes, sink, a.stream);
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6],
+                           ws_bytes, NoSink{}, a.stream, a.ptr<float>(5));
 }
 
 

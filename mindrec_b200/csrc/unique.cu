@@ -11,8 +11,8 @@
 //   seg_start[N+1]  first sorted position of each segment, seg_start[U] = N
 //   seg_of[N]    segment id of each sorted position
 //
-// The sort is an 8-bit-digit LSD radix sort over only the significant key bits (a table with V rows
-// needs ceil(log2(V+1)) bits: 26 bits -> 4 passes for the 33.8 M-row Criteo table).  Each pass is
+// The sort is an LSD radix sort over only the significant key bits with digits of up to 9 bits (a table
+// with V rows needs ceil(log2(V+1)) bits: 26 bits -> 3 passes of 9 bits for the 33.8 M-row Criteo table).  Each pass is
 // histogram -> column scan -> stable scatter; ranking inside a tile uses warp match-any so equal digits
 // keep their input order (stability is what makes perm's first entry of a segment the first occurrence).
 // All buffers (ping-pong keys/values, histograms) come from the caller-provided workspace: the library
@@ -26,8 +26,8 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_RADIX_BITS = 9;             // digit width is chosen per sort: ceil(bits / passes) <= 9
+constexpr int MAX_RADIX = 1 << MAX_RADIX_BITS;  // shared-memory tables are sized for 512 bins
 
 template <typename KeyT> struct UKeyOf;
 template <> struct UKeyOf<int32_t> { using type = uint32_t; static constexpr uint32_t sign = 0x80000000u; };
@@ -58,9 +58,10 @@ __device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys
 // ---- pass kernel 1: per-block digit histogram -> hist[block][digit] ----
 template <typename KeyT, bool RAW>
 __global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, uint64_t bound,
+radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, int radix, uint64_t bound,
                   int tiles_per_block, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t s_hist[RADIX];
+  __shared__ uint32_t s_hist[MAX_RADIX];
+  const int RADIX = radix;
   for (int d = threadIdx.x; d < RADIX; d += RS_THREADS) s_hist[d] = 0;
   __syncthreads();
   const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
@@ -74,30 +75,28 @@ radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, uint64_t 
     hist[(int64_t)blockIdx.x * RADIX + d] = s_hist[d];
 }
 
-// ---- pass kernel 2: hist[b][d] -> exclusive offsets (digit-major order), in place ----
-// One block, thread d owns digit d: column prefix over blocks, then digit bases.
-__global__ void __launch_bounds__(RADIX)
-radix_scan_kernel(uint32_t* __restrict__ hist, int n_blocks) {
-  __shared__ uint32_t s_tot[RADIX];
-  const int d = threadIdx.x;
-  uint32_t run = 0;
-  for (int b = 0; b < n_blocks; ++b) {
-    const uint32_t c = hist[(int64_t)b * RADIX + d];
-    hist[(int64_t)b * RADIX + d] = run;
-    run += c;
+// ---- pass kernel 2: hist[b][d] -> exclusive prefix over blocks (per digit), digit totals ----
+// One warp per digit: lanes stride over blocks, warp-scan 32 blocks at a time.  The cross-digit base is
+// a 512-entry scan that every scatter block redoes in shared memory from the totals row.
+__global__ void __launch_bounds__(1024)
+radix_scan_kernel(uint32_t* __restrict__ hist, int n_blocks, int radix) {
+  const int lane = threadIdx.x & 31;
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (d >= radix) return;
+  uint32_t carry = 0;
+  for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+    const int b = b0 + lane;
+    const uint32_t c = (b < n_blocks) ? hist[(int64_t)b * radix + d] : 0u;
+    uint32_t v = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (b < n_blocks) hist[(int64_t)b * radix + d] = carry + v - c;
+    carry += __shfl_sync(0xffffffffu, v, 31);
   }
-  s_tot[d] = run;
-  __syncthreads();
-  // exclusive scan over 256 digit totals (Hillis-Steele in smem)
-  uint32_t v = run;
-  for (int o = 1; o < RADIX; o <<= 1) {
-    uint32_t t = (d >= o) ? s_tot[d - o] : 0u;
-    __syncthreads();
-    v += t;
-    s_tot[d] = v;
-    __syncthreads();
-  }
-  hist[(int64_t)n_blocks * RADIX + d] = v - run;  // digit base
+  if (lane == 0) hist[(int64_t)n_blocks * radix + d] = carry;  // digit total
 }
 
 // ---- pass kernel 3: stable scatter ----
@@ -105,21 +104,41 @@ template <typename KeyT, bool RAW>
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      typename UKeyOf<KeyT>::type* __restrict__ keys_out, int32_t* __restrict__ vals_out,
-                     int64_t n, int shift, uint64_t bound, int tiles_per_block,
+                     int64_t n, int shift, int radix, uint64_t bound, int tiles_per_block,
                      const uint32_t* __restrict__ hist, int n_blocks) {
   using U = typename UKeyOf<KeyT>::type;
-  __shared__ uint32_t s_cnt[RS_WARPS][RADIX];
-  __shared__ uint32_t s_base[RADIX];
+  __shared__ uint32_t s_cnt[RS_WARPS][MAX_RADIX];
+  __shared__ uint32_t s_base[MAX_RADIX];
+  __shared__ uint32_t s_wsum[RS_WARPS];
+  const int RADIX = radix;
+  const int rbits = __ffs(radix) - 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int d = tid; d < RADIX; d += RS_THREADS)
-    s_base[d] = hist[(int64_t)blockIdx.x * RADIX + d] + hist[(int64_t)n_blocks * RADIX + d];
+  {
+    // exclusive scan of the digit totals (<= 512 entries, 2 per thread) -> digit base
+    const uint32_t* tot = hist + (int64_t)n_blocks * RADIX;
+    const int d0 = 2 * tid, d1 = 2 * tid + 1;
+    const uint32_t t0 = d0 < RADIX ? tot[d0] : 0u, t1 = d1 < RADIX ? tot[d1] : 0u;
+    uint32_t v = t0 + t1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_wsum[warp] = v;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    const uint32_t excl = off + v - (t0 + t1);
+    if (d0 < RADIX) s_base[d0] = excl + hist[(int64_t)blockIdx.x * RADIX + d0];
+    if (d1 < RADIX) s_base[d1] = excl + t0 + hist[(int64_t)blockIdx.x * RADIX + d1];
+  }
 
   const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
   for (int t = 0; t < tiles_per_block; ++t) {
     const int64_t tile0 = begin + (int64_t)t * RS_TILE;
     if (tile0 >= n) break;
-    for (int d = tid; d < RS_WARPS * RADIX; d += RS_THREADS) (&s_cnt[0][0])[d] = 0;
+    for (int d = tid; d < RS_WARPS * RADIX; d += RS_THREADS) s_cnt[d >> rbits][d & (RADIX - 1)] = 0;
     __syncthreads();
 
     U key[RS_ITEMS];
@@ -292,7 +311,7 @@ seg_emit_kernel(const typename UKeyOf<KeyT>::type* __restrict__ sorted,
 // ---------------------------------------------------------------------------------------------
 struct SortPlan {
   int64_t n;
-  int n_tiles, n_blocks, tiles_per_block, passes;
+  int n_tiles, n_blocks, tiles_per_block, passes, digit_bits;
   size_t off_keys_a, off_keys_b, off_vals_tmp, off_hist, off_tiles, total;
 };
 
@@ -303,13 +322,14 @@ static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
   const int max_blocks = kNumSMs * 8;
   p.tiles_per_block = (int)cdiv(p.n_tiles, max_blocks);
   p.n_blocks = (int)cdiv(p.n_tiles, p.tiles_per_block);
-  p.passes = (int)cdiv(key_bits, RADIX_BITS);
+  p.passes = (int)cdiv(key_bits, MAX_RADIX_BITS);
   if (p.passes < 1) p.passes = 1;
+  p.digit_bits = (int)cdiv(key_bits, p.passes);
   size_t o = 0;
   p.off_keys_a = o; o = align_up(o + (size_t)n * key_bytes, 256);
   p.off_keys_b = o; o = align_up(o + (size_t)n * key_bytes, 256);
   p.off_vals_tmp = o; o = align_up(o + (size_t)n * 4, 256);
-  p.off_hist = o; o = align_up(o + (size_t)(p.n_blocks + 1) * RADIX * 4, 256);
+  p.off_hist = o; o = align_up(o + (size_t)(p.n_blocks + 1) * MAX_RADIX * 4, 256);
   p.off_tiles = o; o = align_up(o + (size_t)(p.n_tiles + 1) * 4, 256);
   p.total = o;
   return p;
@@ -351,23 +371,25 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
 
   const void* kin = ids;
   const int32_t* vin = nullptr;
+  const int radix = 1 << p.digit_bits;
+  const int scan_grid = (int)cdiv((int64_t)radix * 32, 1024);
   for (int pass = 0; pass < p.passes; ++pass) {
-    const int shift = pass * RADIX_BITS;
+    const int shift = pass * p.digit_bits;
     U* kout = kbuf[pass & 1];
     // the last pass must land in `perm`
     int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vtmp;
     if (pass == 0) {
-      MREC_LAUNCH((radix_hist_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift,
+      MREC_LAUNCH((radix_hist_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
                   bound, p.tiles_per_block, hist);
-      MREC_LAUNCH(radix_scan_kernel, 1, RADIX, 0, stream, hist, p.n_blocks);
-      MREC_LAUNCH((radix_scatter_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, vin,
-                  kout, vout, n, shift, bound, p.tiles_per_block, hist, p.n_blocks);
+      MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, hist, p.n_blocks, radix);
+      MREC_LAUNCH((radix_scatter_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
+                  vout, n, shift, radix, bound, p.tiles_per_block, hist, p.n_blocks);
     } else {
-      MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift,
+      MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
                   bound, p.tiles_per_block, hist);
-      MREC_LAUNCH(radix_scan_kernel, 1, RADIX, 0, stream, hist, p.n_blocks);
-      MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin,
-                  kout, vout, n, shift, bound, p.tiles_per_block, hist, p.n_blocks);
+      MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, hist, p.n_blocks, radix);
+      MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
+                  vout, n, shift, radix, bound, p.tiles_per_block, hist, p.n_blocks);
     }
     kin = kout;
     vin = vout;

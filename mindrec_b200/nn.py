@@ -239,6 +239,12 @@ class DenseStack:
                 b.normal_(0.0, 0.01, generator=generator)
         self._acts = None
         self._flat16 = None
+        self._ones = None
+
+    def _ones16(self, b):
+        if self._ones is None or self._ones.shape[1] != b:
+            self._ones = torch.ones((1, b), dtype=torch.float16, device=self.flat.device)
+        return self._ones
 
     def refresh_half(self):
         """fp16 shadow of the weights (the per-layer Cast(weight, float16) of the reference, done once
@@ -292,7 +298,8 @@ class DenseStack:
                 g = torch.ops.aten.threshold_backward(g, h_out, 0)
             if self.convert_dtype:
                 self.gw[i].copy_(torch.mm(h_in.t(), g))
-                torch.sum(g, 0, dtype=torch.float32, out=self.gb[i])
+                # BiasAddGrad as a GEMV on the tensor cores (fp32 accumulate, fp16 result like the fp16 op)
+                self.gb[i].copy_(torch.mm(self._ones16(g.shape[0]), g).view(-1))
                 g = torch.mm(g, self.w16[i].t())
             else:
                 torch.mm(h_in.t(), g, out=self.gw[i])
