@@ -205,15 +205,20 @@ gather_reduce_kernel(const float* __restrict__ table, const IdT* __restrict__ id
   const float b0 = bias ? bias[0] : 0.f;
   for (int64_t b = warp; b < batch; b += n_warps) {
     float acc = 0.f;
-    for (int f = lane; f < fields; f += 32) {
-      const int64_t id = (int64_t)ids[b * fields + f];
-      float w = 0.f;
-      if ((uint64_t)id < (uint64_t)vocab) {
-        w = ld_stream_f1(table + id);
-      } else if (oob) {
-        atomicOr(oob, 1);
-      }
-      acc = fmaf(w, mask[b * fields + f], acc);
+    for (int f0 = 0; f0 < fields; f0 += 64) {
+      // two lookups per lane in flight (F = 39 -> one trip)
+      const int fa = f0 + lane, fb = f0 + 32 + lane;
+      int64_t ia = -1, ib = -1;
+      float ma = 0.f, mb = 0.f;
+      if (fa < fields) { ia = (int64_t)ids[b * fields + fa]; ma = mask[b * fields + fa]; }
+      if (fb < fields) { ib = (int64_t)ids[b * fields + fb]; mb = mask[b * fields + fb]; }
+      float wa = 0.f, wb = 0.f;
+      if ((uint64_t)ia < (uint64_t)vocab) wa = ld_stream_f1(table + ia);
+      else if (fa < fields && oob) atomicOr(oob, 1);
+      if ((uint64_t)ib < (uint64_t)vocab) wb = ld_stream_f1(table + ib);
+      else if (fb < fields && oob) atomicOr(oob, 1);
+      acc = fmaf(wa, ma, acc);
+      acc = fmaf(wb, mb, acc);
     }
     acc = warp_sum(acc);
     if (lane == 0) out[b] = acc + b0;
@@ -343,7 +348,7 @@ MREC_API int mrec_gather_reduce(int nparam, void** params, int* ndims, int64_t**
   MREC_REQUIRE(a.numel(4) == batch, ERR_SHAPE, "mrec_gather_reduce: out must have B elements");
   int* oob = a.nparam == 6 ? a.ptr<int>(5) : nullptr;
   if (batch == 0) return OK;
-  int grid = grid_for(cdiv(batch, 8), 8);
+  int grid = grid_for(cdiv(batch, 8), 32);
   if (a.is_i32(1)) {
     MREC_LAUNCH(gather_reduce_kernel<int32_t>, grid, 256, 0, a.stream, a.ptr<float>(0),
                 a.ptr<int32_t>(1), a.ptr<float>(2), a.ptr<float>(3), a.ptr<float>(4), batch, fields,

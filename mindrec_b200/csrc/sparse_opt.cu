@@ -262,14 +262,18 @@ segsum_boundary_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_
   gsum[(int64_t)s * cpr + c] = acc;
 }
 
-// ---- kernel C: long chains, one CTA per segment, fixed-shape reduction ----
+// ---- kernel C: long chains, one 1024-thread CTA per segment, fixed-shape reduction ----
+// Group q of the CTA adds pieces q, q+G, q+2G, ... (4 independent loads in flight), then the G group
+// partials are added in group order: the shape depends only on (pieces, G), never on timing.
+constexpr int kLongThreads = 1024;
+constexpr int kLongGroups = 64;
 template <typename Vec>
-__global__ void __launch_bounds__(kSegThreads)
+__global__ void __launch_bounds__(kLongThreads)
 segsum_long_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                    const Vec* __restrict__ part, const int32_t* __restrict__ long_list,
                    const int32_t* __restrict__ long_count, Vec* __restrict__ gsum) {
-  __shared__ Vec s_part[kSegThreads];
-  const int groups = min(kSegThreads / cpr, 32);
+  __shared__ Vec s_part[kLongThreads];
+  const int groups = min(kLongThreads / cpr, kLongGroups);
   const int gi = threadIdx.x / cpr;
   const int c = threadIdx.x - gi * cpr;
   const int n_long = *long_count;
@@ -280,9 +284,19 @@ segsum_long_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* _
     const int64_t pieces = j_last - j + 1;  // piece 0 = slot 1 of tile j, piece k = slot 0 of tile j+k
     if (gi < groups) {
       Vec acc = VOps<Vec>::zero();
-      for (int64_t k = gi; k < pieces; k += groups) {
-        const int64_t slot = (k == 0) ? (j * 2 + 1) : ((j + k) * 2 + 0);
-        VOps<Vec>::add(acc, part[slot * cpr + c]);
+      for (int64_t k0 = gi; k0 < pieces; k0 += 4 * (int64_t)groups) {
+        Vec v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t k = k0 + (int64_t)q * groups;
+          v[q] = VOps<Vec>::zero();
+          if (k < pieces) {
+            const int64_t slot = (k == 0) ? (j * 2 + 1) : ((j + k) * 2 + 0);
+            v[q] = part[slot * cpr + c];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) VOps<Vec>::add(acc, v[q]);
       }
       s_part[gi * cpr + c] = acc;
     }
@@ -352,7 +366,7 @@ static int run_segment_sum(const GT* g, int dim, int div, const float* mask, con
   if (n_tiles > 1) {
     MREC_LAUNCH((segsum_boundary_kernel<Vec>), grid, kSegThreads, 0, stream, cpr, seg_of, seg_start, n,
                 n_tiles, part, long_list, long_count, gsum);
-    MREC_LAUNCH((segsum_long_kernel<Vec>), kNumSMs * 2, kSegThreads, 0, stream, cpr, seg_of, seg_start,
+    MREC_LAUNCH((segsum_long_kernel<Vec>), kNumSMs, kLongThreads, 0, stream, cpr, seg_of, seg_start,
                 part, long_list, long_count, gsum);
   }
   return OK;

@@ -33,15 +33,27 @@ def flush_l2():
     _flush.zero_()
 
 
+GRAPH = True
+
+
 def timeit(fn, iters=20, warmup=3):
+    """Median device time of fn(); with GRAPH the call is captured once and replayed, so host launch
+    latency of multi-kernel ops does not leak into the number."""
     for _ in range(warmup):
         fn()
+    run = fn
+    if GRAPH:
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        run = g.replay
     ts = []
     for _ in range(iters):
         flush_l2()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        run()
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
@@ -68,7 +80,10 @@ def main():
     ap.add_argument("--vocab", type=int, default=33762616)
     ap.add_argument("--batch", type=int, default=16000)
     ap.add_argument("--dim", type=int, default=80)
+    ap.add_argument("--eager", action="store_true")
     a = ap.parse_args()
+    global GRAPH
+    GRAPH = not a.eager
     b, f, d, v = a.batch, 39, a.dim, a.vocab
     n = b * f
     ids = zipf_ids(b, f, v)
