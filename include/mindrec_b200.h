@@ -113,6 +113,24 @@ int mrec_adam_dense(MREC_AOT_ARGS);
 /* nn.FTRL dense kernel (ApplyFtrl).  in : w accum linear hyper[16] g   out: dummy[1]               */
 int mrec_ftrl_dense(MREC_AOT_ARGS);
 
+/* ---- K7 FM second-order interaction -------------------------------------------------------------
+ * Replaces Square/ReduceSum/Sub x6 of models/deepfm/src/deepfm.py:222-228 and their autodiff.
+ *   fwd  in : vx[B,F,D] f32 (already multiplied by the mask)      out: fm[B]|[B,1] f32
+ *   bwd  in : vx[B,F,D], gout[B]|[B,1]                            out: dvx[B,F,D] = g * (sum_f vx - vx)  */
+int mrec_fm_fwd(MREC_AOT_ARGS);
+int mrec_fm_bwd(MREC_AOT_ARGS);
+
+/* ---- K8 DCN cross stack --------------------------------------------------------------------------
+ * Replaces CrossLayer.construct (models/deep_and_cross/src/deep_and_cross.py:139-149) applied L times
+ * (:301-306) and its autodiff.  w[l], b[l] are the layer's cross_weight / cross_bias ([D',1] each in the
+ * reference, stacked here as [L, D']); 1 <= L <= 8.
+ *   fwd  in : x0[B,D'] w[L,D'] b[L,D']            out: y[B,D'] (= x_L), p[B,L] (saved dots x0.w_l),
+ *                                                      workspace[mrec_cross_workspace_bytes(L, D')]
+ *   bwd  in : x0 dy[B,D'] w b p[B,L]              out: dx[B,D'] dw[L,D'] db[L,D'], workspace          */
+int mrec_cross_fwd(MREC_AOT_ARGS);
+int mrec_cross_bwd(MREC_AOT_ARGS);
+size_t mrec_cross_workspace_bytes(int64_t layers, int dp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,421 @@
+// K8 — DCN cross-layer stack, forward and backward, fused over all layers.
+//
+// Replaces, per layer, tensor_dot + batched MatMul([B,D',1] x [B,1,1]) + two adds
+// (models/deep_and_cross/src/deep_and_cross.py:139-149) applied six times (:301-306) and its autodiff.
+//
+// The layer  x_{l+1} = x_0 * (x_l . w_l) + b_l + x_l  keeps every x_l in the plane spanned by x_0 and a
+// row-independent vector:  x_l = c_l * x_0 + Bcum_l  with  Bcum_l = sum_{k<l} b_k,  c_0 = 1,
+//     s_l = x_l . w_l = c_l * p_l + q_l,   p_l = x_0 . w_l,   q_l = Bcum_l . w_l,   c_{l+1} = c_l + s_l.
+// So one pass over a row computes the L dots p_l at once (one block reduction of L values instead of L
+// dependent ones), a scalar recurrence, and y = c_L * x_0 + Bcum_L: x_0 is read once, y written once
+// (2*B*D'*4 bytes, the fused-stack roofline of SURVEY 8d).  Backward, with r = dy . x_0:
+//     ds_l = r + sum_{k>l} ds_k p_k,    dx = c_L * dy + sum_k (ds_k c_k) w_k,
+//     dw_l = sum_rows (ds_l c_l) x_0 + (sum_rows ds_l) Bcum_l,   db_l = sum_rows dy + sum_{k>l} (sum_rows ds_k) w_k
+// i.e. one block reduction per row, x_0 and dy read once, dx written once (3*B*D'*4 bytes); the column
+// accumulators for dw/db live in registers per CTA and are combined over CTAs in a fixed order by a
+// second kernel (deterministic, no atomics).  w/Bcum (L*D'*4 = 75 KB at D' = 3120) are read through L1
+// (plain cached loads) while x_0 / dy / y / dx bypass it (no_allocate / streaming stores).
+#include "common.cuh"
+
+namespace mrec {
+
+constexpr int kCrossThreads = 512;
+constexpr int kCrossWarps = kCrossThreads / 32;
+constexpr int kCrossMaxL = 8;
+
+template <typename Vec> struct CrV;
+template <> struct CrV<float4> {
+  static constexpr int width = 4;
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ float4 ld_stream(const float* p, int64_t i) {
+    return ld_stream_f4(reinterpret_cast<const float4*>(p) + i);
+  }
+  static __device__ __forceinline__ float4 ld(const float* p, int64_t i) {
+    return reinterpret_cast<const float4*>(p)[i];
+  }
+  static __device__ __forceinline__ void st_stream(float* p, int64_t i, const float4& v) {
+    st_stream_f4(reinterpret_cast<float4*>(p) + i, v);
+  }
+  static __device__ __forceinline__ void st(float* p, int64_t i, const float4& v) {
+    reinterpret_cast<float4*>(p)[i] = v;
+  }
+  static __device__ __forceinline__ float dot(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+  }
+  static __device__ __forceinline__ void axpy(float4& y, float a, const float4& x) { f4_fma(y, x, a); }
+  static __device__ __forceinline__ float4 scale_add(const float4& x, float a, const float4& b) {
+    return make_float4(fmaf(x.x, a, b.x), fmaf(x.y, a, b.y), fmaf(x.z, a, b.z), fmaf(x.w, a, b.w));
+  }
+  static __device__ __forceinline__ void add(float4& y, const float4& x) {
+    y.x += x.x; y.y += x.y; y.z += x.z; y.w += x.w;
+  }
+};
+template <> struct CrV<float> {
+  static constexpr int width = 1;
+  static __device__ __forceinline__ float zero() { return 0.f; }
+  static __device__ __forceinline__ float ld_stream(const float* p, int64_t i) { return ld_stream_f1(p + i); }
+  static __device__ __forceinline__ float ld(const float* p, int64_t i) { return p[i]; }
+  static __device__ __forceinline__ void st_stream(float* p, int64_t i, const float& v) { p[i] = v; }
+  static __device__ __forceinline__ void st(float* p, int64_t i, const float& v) { p[i] = v; }
+  static __device__ __forceinline__ float dot(const float& a, const float& b) { return a * b; }
+  static __device__ __forceinline__ void axpy(float& y, float a, const float& x) { y = fmaf(x, a, y); }
+  static __device__ __forceinline__ float scale_add(const float& x, float a, const float& b) { return fmaf(x, a, b); }
+  static __device__ __forceinline__ void add(float& y, const float& x) { y += x; }
+};
+
+// bcum[l][d] = sum_{k<l} b[k][d] (l = 0..L), q[l] = <bcum[l], w[l]>.  One block; fixed reduction order.
+__global__ void __launch_bounds__(1024)
+cross_prep_kernel(const float* __restrict__ w, const float* __restrict__ b, int layers, int dp,
+                  float* __restrict__ bcum, float* __restrict__ q) {
+  __shared__ float s_red[32][kCrossMaxL];
+  float acc[kCrossMaxL];
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) acc[l] = 0.f;
+  for (int d = threadIdx.x; d < dp; d += blockDim.x) {
+    float run = 0.f;
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      if (l < layers) {
+        bcum[(int64_t)l * dp + d] = run;
+        acc[l] = fmaf(run, w[(int64_t)l * dp + d], acc[l]);
+        run += b[(int64_t)l * dp + d];
+      }
+    }
+    bcum[(int64_t)layers * dp + d] = run;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) {
+    const float v = warp_sum(acc[l]);
+    if (lane == 0) s_red[warp][l] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < layers) {
+    float t = 0.f;
+    for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) t += s_red[wp][threadIdx.x];
+    q[threadIdx.x] = t;
+  }
+}
+
+// block-wide sum of NV values; every thread returns all totals.  `buf` is a [kCrossWarps][NV] smem slab
+// (callers alternate two slabs by row parity so one __syncthreads per row suffices).
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float (*buf)[NV]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = warp_sum(v[i]);
+    if (lane == 0) buf[warp][i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < kCrossWarps; ++wp) t += buf[wp][i];
+    v[i] = t;
+  }
+}
+
+template <typename Vec, int SLOTS, int L>
+__global__ void __launch_bounds__(kCrossThreads, 1)
+cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ q,
+                 const float* __restrict__ bcum, int64_t batch, int dpv /* D' / vec width */,
+                 float* __restrict__ y, float* __restrict__ p_out) {
+  __shared__ float s_red[2][kCrossWarps][L];
+  const int tid = threadIdx.x;
+  float ql[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) ql[l] = q[l];
+  Vec bl[SLOTS];
+#pragma unroll
+  for (int k = 0; k < SLOTS; ++k) {
+    const int i = tid + k * kCrossThreads;
+    bl[k] = (i < dpv) ? CrV<Vec>::ld(bcum, (int64_t)L * dpv + i) : CrV<Vec>::zero();
+  }
+  int par = 0;
+  for (int64_t row = blockIdx.x; row < batch; row += gridDim.x, par ^= 1) {
+    Vec x[SLOTS];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int i = tid + k * kCrossThreads;
+      x[k] = (i < dpv) ? CrV<Vec>::ld_stream(x0, row * dpv + i) : CrV<Vec>::zero();
+    }
+    float p[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) p[l] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int i = tid + k * kCrossThreads;
+      if (i < dpv) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) p[l] += CrV<Vec>::dot(x[k], CrV<Vec>::ld(w, (int64_t)l * dpv + i));
+      }
+    }
+    block_sum<L>(p, s_red[par]);
+    float c = 1.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) c += fmaf(c, p[l], ql[l]);
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int i = tid + k * kCrossThreads;
+      if (i < dpv) CrV<Vec>::st_stream(y, row * dpv + i, CrV<Vec>::scale_add(x[k], c, bl[k]));
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+      if (tid == l) p_out[row * L + l] = p[l];
+  }
+}
+
+template <typename Vec, int SLOTS, int L>
+__global__ void __launch_bounds__(kCrossThreads, 1)
+cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, const float* __restrict__ w,
+                 const float* __restrict__ q, const float* __restrict__ p_in, int64_t batch, int dpv,
+                 float* __restrict__ dx, float* __restrict__ part /* [grid][L+1][D'] */,
+                 float* __restrict__ sd_part /* [grid][L] */) {
+  __shared__ float s_red[2][kCrossWarps][1];
+  const int tid = threadIdx.x;
+  float ql[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) ql[l] = q[l];
+  Vec A[L][SLOTS], Y[SLOTS];
+  float sd[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    sd[l] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) A[l][k] = CrV<Vec>::zero();
+  }
+#pragma unroll
+  for (int k = 0; k < SLOTS; ++k) Y[k] = CrV<Vec>::zero();
+
+  int par = 0;
+  for (int64_t row = blockIdx.x; row < batch; row += gridDim.x, par ^= 1) {
+    Vec x[SLOTS], g[SLOTS];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int i = tid + k * kCrossThreads;
+      x[k] = (i < dpv) ? CrV<Vec>::ld_stream(x0, row * dpv + i) : CrV<Vec>::zero();
+      g[k] = (i < dpv) ? CrV<Vec>::ld_stream(dy, row * dpv + i) : CrV<Vec>::zero();
+    }
+    float p[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) p[l] = p_in[row * L + l];
+    float r[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) r[0] += CrV<Vec>::dot(x[k], g[k]);
+    block_sum<1>(r, s_red[par]);
+    // forward scalars c_l, then backward scalars ds_l
+    float c[L + 1];
+    c[0] = 1.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) c[l + 1] = c[l] + fmaf(c[l], p[l], ql[l]);
+    float coef[L];
+    float t = 0.f;
+#pragma unroll
+    for (int l = L - 1; l >= 0; --l) {
+      const float ds = r[0] + t;
+      t = fmaf(ds, p[l], t);
+      sd[l] += ds;
+      coef[l] = ds * c[l];
+    }
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int i = tid + k * kCrossThreads;
+      if (i < dpv) {
+        Vec o = CrV<Vec>::scale_add(g[k], c[L], CrV<Vec>::zero());
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          CrV<Vec>::axpy(o, coef[l], CrV<Vec>::ld(w, (int64_t)l * dpv + i));
+          CrV<Vec>::axpy(A[l][k], coef[l], x[k]);
+        }
+        CrV<Vec>::add(Y[k], g[k]);
+        CrV<Vec>::st_stream(dx, row * dpv + i, o);
+      }
+    }
+  }
+  float* mine = part + (int64_t)blockIdx.x * (L + 1) * dpv * CrV<Vec>::width;
+#pragma unroll
+  for (int k = 0; k < SLOTS; ++k) {
+    const int i = tid + k * kCrossThreads;
+    if (i < dpv) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) CrV<Vec>::st(mine, (int64_t)l * dpv + i, A[l][k]);
+      CrV<Vec>::st(mine, (int64_t)L * dpv + i, Y[k]);
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) sd_part[blockIdx.x * L + l] = sd[l];
+  }
+}
+
+// dw_l = sum_cta A_l + (sum ds_l) Bcum_l ;  db_l = sum_cta Ysum + sum_{k>l} (sum ds_k) w_k   (CTA order fixed)
+__global__ void __launch_bounds__(256)
+cross_bwd_finish_kernel(const float* __restrict__ part, const float* __restrict__ sd_part, int nparts,
+                        const float* __restrict__ w, const float* __restrict__ bcum, int layers, int dp,
+                        float* __restrict__ dw, float* __restrict__ db) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dp) return;
+  float sdt[kCrossMaxL];
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) {
+    sdt[l] = 0.f;
+    if (l < layers)
+      for (int pth = 0; pth < nparts; ++pth) sdt[l] += sd_part[pth * layers + l];
+  }
+  float ysum = 0.f;
+  for (int pth = 0; pth < nparts; ++pth) ysum += part[((int64_t)pth * (layers + 1) + layers) * dp + d];
+  float tail = 0.f;  // sum_{k>l} sdt[k] * w[k][d], built from the last layer down
+  for (int l = layers - 1; l >= 0; --l) {
+    float al = 0.f;
+    for (int pth = 0; pth < nparts; ++pth) al += part[((int64_t)pth * (layers + 1) + l) * dp + d];
+    dw[(int64_t)l * dp + d] = fmaf(sdt[l], bcum[(int64_t)l * dp + d], al);
+    db[(int64_t)l * dp + d] = ysum + tail;
+    tail = fmaf(sdt[l], w[(int64_t)l * dp + d], tail);
+  }
+}
+
+struct CrossWs {
+  size_t off_bcum, off_q, off_part, off_sd, total;
+  int nparts;
+};
+static CrossWs cross_ws(int layers, int dp, bool backward) {
+  CrossWs W;
+  size_t o = 0;
+  W.off_bcum = o; o = align_up(o + (size_t)(layers + 1) * dp * 4, 256);
+  W.off_q = o; o = align_up(o + (size_t)kCrossMaxL * 4, 256);
+  W.nparts = kNumSMs;
+  W.off_part = o;
+  if (backward) o = align_up(o + (size_t)W.nparts * (layers + 1) * dp * 4, 256);
+  W.off_sd = o;
+  if (backward) o = align_up(o + (size_t)W.nparts * layers * 4, 256);
+  W.total = o;
+  return W;
+}
+
+template <typename Vec, int SLOTS>
+static int launch_fwd(int layers, int grid, cudaStream_t st, const float* x0, const float* w, const float* q,
+                      const float* bcum, int64_t batch, int dpv, float* y, float* p) {
+  switch (layers) {
+#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL>), grid, kCrossThreads, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
+    C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
+#undef C
+    default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
+  }
+  return OK;
+}
+template <typename Vec, int SLOTS>
+static int launch_bwd(int layers, int grid, cudaStream_t st, const float* x0, const float* dy, const float* w,
+                      const float* q, const float* p, int64_t batch, int dpv, float* dx, float* part, float* sd) {
+  switch (layers) {
+#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL>), grid, kCrossThreads, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
+    C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
+#undef C
+    default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
+  }
+  return OK;
+}
+
+static int cross_shapes(const Aot& a, int xi, int wi, int bi, int64_t* batch, int* dp, int* layers) {
+  MREC_REQUIRE(a.is_f32(xi) && a.is_f32(wi) && a.is_f32(bi), ERR_DTYPE, "mrec_cross: x0/w/b must be float32");
+  MREC_REQUIRE(a.ndims[xi] == 2, ERR_SHAPE, "mrec_cross: x0 must be [B, D']");
+  *batch = a.dim(xi, 0);
+  *dp = (int)a.dim(xi, 1);
+  MREC_REQUIRE(a.ndims[wi] >= 2 && a.numel(wi) % *dp == 0, ERR_SHAPE, "mrec_cross: w must be [L, D']");
+  *layers = (int)(a.numel(wi) / *dp);
+  MREC_REQUIRE(a.numel(bi) == a.numel(wi), ERR_SHAPE, "mrec_cross: b must have w's shape");
+  MREC_REQUIRE(*layers >= 1 && *layers <= kCrossMaxL, ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
+  const bool v4 = (*dp % 4 == 0);
+  const int dpv = v4 ? *dp / 4 : *dp;
+  MREC_REQUIRE(dpv <= kCrossThreads * (v4 ? 4 : 8), ERR_DIM, "mrec_cross: D' = %d too large", *dp);
+  return OK;
+}
+
+}  // namespace mrec
+
+using namespace mrec;
+
+MREC_API size_t mrec_cross_workspace_bytes(int64_t layers, int dp) {
+  return cross_ws((int)layers, dp, true).total;
+}
+
+// in : x0[B,D'] w[L,D'] b[L,D'] f32      out: y[B,D'] f32, p[B,L] f32 (saved dots x0.w_l), workspace
+MREC_API int mrec_cross_fwd(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                            void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 6);
+  int64_t batch; int dp, layers;
+  int rc = cross_shapes(a, 0, 1, 2, &batch, &dp, &layers);
+  if (rc) return rc;
+  MREC_REQUIRE(a.is_f32(3) && a.numel(3) == batch * dp, ERR_SHAPE, "mrec_cross_fwd: y must be [B, D'] f32");
+  MREC_REQUIRE(a.is_f32(4) && a.numel(4) == batch * layers, ERR_SHAPE, "mrec_cross_fwd: p must be [B, L] f32");
+  const CrossWs W = cross_ws(layers, dp, false);
+  MREC_REQUIRE((size_t)a.numel(5) >= W.total, ERR_WORKSPACE, "mrec_cross_fwd: workspace %lld < %zu",
+               (long long)a.numel(5), W.total);
+  MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(3, 16) && a.aligned(5, 16), ERR_ALIGN,
+               "mrec_cross_fwd: buffers must be 16-byte aligned");
+  char* ws = a.ptr<char>(5);
+  float* bcum = reinterpret_cast<float*>(ws + W.off_bcum);
+  float* q = reinterpret_cast<float*>(ws + W.off_q);
+  MREC_LAUNCH(cross_prep_kernel, 1, 1024, 0, a.stream, a.ptr<float>(1), a.ptr<float>(2), layers, dp, bcum, q);
+  if (batch == 0) return check_launch("cross_prep");
+  const int grid = grid_for(batch, 1);
+  const float *x0 = a.ptr<float>(0), *w = a.ptr<float>(1);
+  float *y = a.ptr<float>(3), *p = a.ptr<float>(4);
+  if (dp % 4 == 0) {
+    const int dpv = dp / 4;
+    if (dpv <= kCrossThreads) rc = launch_fwd<float4, 1>(layers, grid, a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    else if (dpv <= 2 * kCrossThreads) rc = launch_fwd<float4, 2>(layers, grid, a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    else rc = launch_fwd<float4, 4>(layers, grid, a.stream, x0, w, q, bcum, batch, dpv, y, p);
+  } else {
+    if (dp <= 2 * kCrossThreads) rc = launch_fwd<float, 2>(layers, grid, a.stream, x0, w, q, bcum, batch, dp, y, p);
+    else if (dp <= 4 * kCrossThreads) rc = launch_fwd<float, 4>(layers, grid, a.stream, x0, w, q, bcum, batch, dp, y, p);
+    else rc = launch_fwd<float, 8>(layers, grid, a.stream, x0, w, q, bcum, batch, dp, y, p);
+  }
+  if (rc) return rc;
+  return check_launch("cross_fwd");
+}
+
+// in : x0[B,D'] dy[B,D'] w[L,D'] b[L,D'] p[B,L]     out: dx[B,D'] dw[L,D'] db[L,D'] f32, workspace
+MREC_API int mrec_cross_bwd(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                            void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 9);
+  int64_t batch; int dp, layers;
+  int rc = cross_shapes(a, 0, 2, 3, &batch, &dp, &layers);
+  if (rc) return rc;
+  MREC_REQUIRE(a.is_f32(1) && a.numel(1) == batch * dp, ERR_SHAPE, "mrec_cross_bwd: dy must be [B, D'] f32");
+  MREC_REQUIRE(a.is_f32(4) && a.numel(4) == batch * layers, ERR_SHAPE, "mrec_cross_bwd: p must be [B, L] f32");
+  MREC_REQUIRE(a.is_f32(5) && a.numel(5) == batch * dp, ERR_SHAPE, "mrec_cross_bwd: dx must be [B, D'] f32");
+  MREC_REQUIRE(a.is_f32(6) && a.is_f32(7) && a.numel(6) == (int64_t)layers * dp && a.numel(7) == a.numel(6),
+               ERR_SHAPE, "mrec_cross_bwd: dw/db must be [L, D'] f32");
+  const CrossWs W = cross_ws(layers, dp, true);
+  MREC_REQUIRE((size_t)a.numel(8) >= W.total, ERR_WORKSPACE, "mrec_cross_bwd: workspace %lld < %zu",
+               (long long)a.numel(8), W.total);
+  MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(2, 16) && a.aligned(5, 16) && a.aligned(8, 16),
+               ERR_ALIGN, "mrec_cross_bwd: buffers must be 16-byte aligned");
+  char* ws = a.ptr<char>(8);
+  float* bcum = reinterpret_cast<float*>(ws + W.off_bcum);
+  float* q = reinterpret_cast<float*>(ws + W.off_q);
+  float* part = reinterpret_cast<float*>(ws + W.off_part);
+  float* sd = reinterpret_cast<float*>(ws + W.off_sd);
+  MREC_LAUNCH(cross_prep_kernel, 1, 1024, 0, a.stream, a.ptr<float>(2), a.ptr<float>(3), layers, dp, bcum, q);
+  const int grid = W.nparts;  // every CTA writes its (possibly zero) partial: the finish sums all of them
+  const float *x0 = a.ptr<float>(0), *dy = a.ptr<float>(1), *w = a.ptr<float>(2), *p = a.ptr<float>(4);
+  float* dx = a.ptr<float>(5);
+  if (dp % 4 == 0) {
+    const int dpv = dp / 4;
+    if (dpv <= kCrossThreads) rc = launch_bwd<float4, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    else if (dpv <= 2 * kCrossThreads) rc = launch_bwd<float4, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    else rc = launch_bwd<float4, 4>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+  } else {
+    if (dp <= 2 * kCrossThreads) rc = launch_bwd<float, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    else if (dp <= 4 * kCrossThreads) rc = launch_bwd<float, 4>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    else rc = launch_bwd<float, 8>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+  }
+  if (rc) return rc;
+  MREC_LAUNCH(cross_bwd_finish_kernel, (int)cdiv(dp, 256), 256, 0, a.stream, part, sd, W.nparts, w, bcum, layers,
+              dp, a.ptr<float>(6), a.ptr<float>(7));
+  return check_launch("cross_bwd");
+}

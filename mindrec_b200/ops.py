@@ -202,3 +202,50 @@ def adam_dense(w, m, v, hyper, g):
 
 def ftrl_dense(w, accum, linear, hyper, g):
     _lib.aot_call("mrec_ftrl_dense", [w, accum, linear, hyper, g, _dummy(w.device)])
+
+
+# ------------------------------------------------------------------------------------------------
+# K7 FM second-order interaction, K8 DCN cross stack
+# ------------------------------------------------------------------------------------------------
+def fm_fwd(vx, out=None):
+    """fm[b] = 0.5 * sum_d[(sum_f vx)^2 - sum_f vx^2]; vx is [B,F,D] (already masked)."""
+    if out is None:
+        out = torch.empty((vx.shape[0], 1), dtype=torch.float32, device=vx.device)
+    _lib.aot_call("mrec_fm_fwd", [vx, out])
+    return out
+
+
+def fm_bwd(vx, gout, out=None):
+    """dvx[b,f,d] = gout[b] * (S[b,d] - vx[b,f,d])."""
+    if out is None:
+        out = torch.empty_like(vx)
+    _lib.aot_call("mrec_fm_bwd", [vx, gout, out])
+    return out
+
+
+def _cross_ws(layers, dp, device):
+    f = getattr(_lib.lib(), "mrec_cross_workspace_bytes")
+    f.restype = ctypes.c_size_t
+    f.argtypes = [ctypes.c_int64, ctypes.c_int]
+    return _ws("cross", f(layers, dp), device)
+
+
+def cross_fwd(x0, w, b, y=None, p=None):
+    """The whole cross stack: y = x_L, p[B,L] = saved dots x0.w_l (needed by cross_bwd).  w, b: [L, D']."""
+    layers = w.numel() // x0.shape[1]
+    if y is None:
+        y = torch.empty_like(x0)
+    if p is None:
+        p = torch.empty((x0.shape[0], layers), dtype=torch.float32, device=x0.device)
+    _lib.aot_call("mrec_cross_fwd", [x0, w, b, y, p, _cross_ws(layers, x0.shape[1], x0.device)])
+    return y, p
+
+
+def cross_bwd(x0, dy, w, b, p, dx=None, dw=None, db=None):
+    """Backward of the cross stack: (dx0 total, dw[L,D'], db[L,D'])."""
+    layers = w.numel() // x0.shape[1]
+    dx = torch.empty_like(x0) if dx is None else dx
+    dw = torch.empty((layers, x0.shape[1]), dtype=torch.float32, device=x0.device) if dw is None else dw
+    db = torch.empty((layers, x0.shape[1]), dtype=torch.float32, device=x0.device) if db is None else db
+    _lib.aot_call("mrec_cross_bwd", [x0, dy, w, b, p, dx, dw, db, _cross_ws(layers, x0.shape[1], x0.device)])
+    return dx, dw, db

@@ -132,5 +132,28 @@ def main():
         report("segsum+ftrl D=1 U=%d" % u, ms, u * 28 + n * 8)
 
 
+def interaction():
+    b = 16384
+    vx = torch.randn((b, 39, 16), device="cuda")
+    g = torch.randn((b, 1), device="cuda")
+    out = torch.empty((b, 1), device="cuda")
+    dvx = torch.empty_like(vx)
+    report("fm_fwd 16384x39x16", timeit(lambda: ops.fm_fwd(vx, out=out)), vx.numel() * 4 + b * 4)
+    report("fm_bwd 16384x39x16", timeit(lambda: ops.fm_bwd(vx, g, out=dvx)), 2 * vx.numel() * 4 + b * 4)
+    dp, layers = 3120, 6
+    x0 = torch.randn((b, dp), device="cuda") * 0.1
+    w = torch.randn((layers, dp), device="cuda") * 0.02
+    bb = torch.randn((layers, dp), device="cuda") * 0.02
+    gy = torch.randn((b, dp), device="cuda")
+    y, p = ops.cross_fwd(x0, w, bb)
+    dx, dw, db = ops.cross_bwd(x0, gy, w, bb, p)
+    report("cross_fwd 16384x3120 L6", timeit(lambda: ops.cross_fwd(x0, w, bb, y=y, p=p)), 2 * x0.numel() * 4)
+    report("cross_bwd 16384x3120 L6", timeit(lambda: ops.cross_bwd(x0, gy, w, bb, p, dx=dx, dw=dw, db=db)),
+           3 * x0.numel() * 4)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "interaction":
+        interaction()
+    else:
+        main()
