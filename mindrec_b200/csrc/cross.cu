@@ -97,83 +97,97 @@ cross_prep_kernel(const float* __restrict__ w, const float* __restrict__ b, int 
   }
 }
 
-// block-wide sum of NV values; every thread returns all totals.  `buf` is a [kCrossWarps][NV] smem slab
-// (callers alternate two slabs by row parity so one __syncthreads per row suffices).
+// Block-wide sum of NV values; every thread returns all totals.  Stage 1: warp shuffles, one smem row
+// per warp.  Stage 2: in every warp lane i < NV adds column i over the warps (fixed order) and the totals
+// are broadcast by shuffle, so there is one __syncthreads per call; callers alternate two smem slabs by
+// iteration parity.
 template <int NV>
 __device__ __forceinline__ void block_sum(float (&v)[NV], float (*buf)[NV]) {
+  static_assert(NV <= 32, "block_sum handles at most 32 values");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    v[i] = warp_sum(v[i]);
-    if (lane == 0) buf[warp][i] = v[i];
+    const float t = warp_sum(v[i]);
+    if (lane == 0) buf[warp][i] = t;
   }
   __syncthreads();
+  float col = 0.f;
+  if (lane < NV) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float t = 0.f;
-#pragma unroll
-    for (int wp = 0; wp < kCrossWarps; ++wp) t += buf[wp][i];
-    v[i] = t;
+    for (int wp = 0; wp < kCrossWarps; ++wp) col += buf[wp][lane];
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __shfl_sync(0xffffffffu, col, i);
 }
 
-template <typename Vec, int SLOTS, int L>
+// R rows per CTA iteration: all R * SLOTS row loads are issued before the reduction, and each w chunk
+// read from L1 is used for R rows.
+template <typename Vec, int SLOTS, int L, int R>
 __global__ void __launch_bounds__(kCrossThreads, 1)
 cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ q,
                  const float* __restrict__ bcum, int64_t batch, int dpv /* D' / vec width */,
                  float* __restrict__ y, float* __restrict__ p_out) {
-  __shared__ float s_red[2][kCrossWarps][L];
+  __shared__ float s_red[2][kCrossWarps][R * L];
   const int tid = threadIdx.x;
   float ql[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) ql[l] = q[l];
-  Vec bl[SLOTS];
-#pragma unroll
-  for (int k = 0; k < SLOTS; ++k) {
-    const int i = tid + k * kCrossThreads;
-    bl[k] = (i < dpv) ? CrV<Vec>::ld(bcum, (int64_t)L * dpv + i) : CrV<Vec>::zero();
-  }
   int par = 0;
-  for (int64_t row = blockIdx.x; row < batch; row += gridDim.x, par ^= 1) {
-    Vec x[SLOTS];
+  for (int64_t row0 = (int64_t)blockIdx.x * R; row0 < batch; row0 += (int64_t)gridDim.x * R, par ^= 1) {
+    Vec x[R][SLOTS];
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      const int i = tid + k * kCrossThreads;
-      x[k] = (i < dpv) ? CrV<Vec>::ld_stream(x0, row * dpv + i) : CrV<Vec>::zero();
-    }
-    float p[L];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int l = 0; l < L; ++l) p[l] = 0.f;
+      for (int k = 0; k < SLOTS; ++k) {
+        const int i = tid + k * kCrossThreads;
+        x[r][k] = (i < dpv && row0 + r < batch) ? CrV<Vec>::ld_stream(x0, (row0 + r) * dpv + i) : CrV<Vec>::zero();
+      }
+    float p[R * L];
+#pragma unroll
+    for (int i = 0; i < R * L; ++i) p[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
       const int i = tid + k * kCrossThreads;
       if (i < dpv) {
 #pragma unroll
-        for (int l = 0; l < L; ++l) p[l] += CrV<Vec>::dot(x[k], CrV<Vec>::ld(w, (int64_t)l * dpv + i));
+        for (int l = 0; l < L; ++l) {
+          const Vec wv = CrV<Vec>::ld(w, (int64_t)l * dpv + i);
+#pragma unroll
+          for (int r = 0; r < R; ++r) p[r * L + l] += CrV<Vec>::dot(x[r][k], wv);
+        }
       }
     }
-    block_sum<L>(p, s_red[par]);
-    float c = 1.f;
+    block_sum<R * L>(p, s_red[par]);
+    float c[R];
 #pragma unroll
-    for (int l = 0; l < L; ++l) c += fmaf(c, p[l], ql[l]);
+    for (int r = 0; r < R; ++r) {
+      c[r] = 1.f;
+#pragma unroll
+      for (int l = 0; l < L; ++l) c[r] += fmaf(c[r], p[r * L + l], ql[l]);
+    }
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
       const int i = tid + k * kCrossThreads;
-      if (i < dpv) CrV<Vec>::st_stream(y, row * dpv + i, CrV<Vec>::scale_add(x[k], c, bl[k]));
+      if (i < dpv) {
+        const Vec bl = CrV<Vec>::ld(bcum, (int64_t)L * dpv + i);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (row0 + r < batch) CrV<Vec>::st_stream(y, (row0 + r) * dpv + i, CrV<Vec>::scale_add(x[r][k], c[r], bl));
+      }
     }
 #pragma unroll
-    for (int l = 0; l < L; ++l)
-      if (tid == l) p_out[row * L + l] = p[l];
+    for (int i = 0; i < R * L; ++i)
+      if (tid == i && row0 + i / L < batch) p_out[(row0 + i / L) * L + (i % L)] = p[i];
   }
 }
 
-template <typename Vec, int SLOTS, int L>
+template <typename Vec, int SLOTS, int L, int R>
 __global__ void __launch_bounds__(kCrossThreads, 1)
 cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, const float* __restrict__ w,
                  const float* __restrict__ q, const float* __restrict__ p_in, int64_t batch, int dpv,
                  float* __restrict__ dx, float* __restrict__ part /* [grid][L+1][D'] */,
                  float* __restrict__ sd_part /* [grid][L] */) {
-  __shared__ float s_red[2][kCrossWarps][1];
+  __shared__ float s_red[2][kCrossWarps][R];
   const int tid = threadIdx.x;
   float ql[L];
 #pragma unroll
@@ -190,47 +204,68 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
   for (int k = 0; k < SLOTS; ++k) Y[k] = CrV<Vec>::zero();
 
   int par = 0;
-  for (int64_t row = blockIdx.x; row < batch; row += gridDim.x, par ^= 1) {
-    Vec x[SLOTS], g[SLOTS];
+  for (int64_t row0 = (int64_t)blockIdx.x * R; row0 < batch; row0 += (int64_t)gridDim.x * R, par ^= 1) {
+    Vec x[R][SLOTS], g[R][SLOTS];
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      const int i = tid + k * kCrossThreads;
-      x[k] = (i < dpv) ? CrV<Vec>::ld_stream(x0, row * dpv + i) : CrV<Vec>::zero();
-      g[k] = (i < dpv) ? CrV<Vec>::ld_stream(dy, row * dpv + i) : CrV<Vec>::zero();
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) {
+        const int i = tid + k * kCrossThreads;
+        const bool ok = (i < dpv) && (row0 + r < batch);
+        x[r][k] = ok ? CrV<Vec>::ld_stream(x0, (row0 + r) * dpv + i) : CrV<Vec>::zero();
+        g[r][k] = ok ? CrV<Vec>::ld_stream(dy, (row0 + r) * dpv + i) : CrV<Vec>::zero();
+      }
+    float rr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rr[r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) rr[r] += CrV<Vec>::dot(x[r][k], g[r][k]);
     }
-    float p[L];
+    block_sum<R>(rr, s_red[par]);
+    // per row: forward scalars c_l, backward scalars ds_l -> coef_l = ds_l * c_l
+    float coef[R][L], cl[R];
 #pragma unroll
-    for (int l = 0; l < L; ++l) p[l] = p_in[row * L + l];
-    float r[1] = {0.f};
+    for (int r = 0; r < R; ++r) {
+      const bool live = row0 + r < batch;
+      float p[L], c[L + 1];
+      c[0] = 1.f;
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) r[0] += CrV<Vec>::dot(x[k], g[k]);
-    block_sum<1>(r, s_red[par]);
-    // forward scalars c_l, then backward scalars ds_l
-    float c[L + 1];
-    c[0] = 1.f;
+      for (int l = 0; l < L; ++l) {
+        p[l] = live ? p_in[(row0 + r) * L + l] : 0.f;
+        c[l + 1] = c[l] + fmaf(c[l], p[l], ql[l]);
+      }
+      cl[r] = c[L];
+      float t = 0.f;
 #pragma unroll
-    for (int l = 0; l < L; ++l) c[l + 1] = c[l] + fmaf(c[l], p[l], ql[l]);
-    float coef[L];
-    float t = 0.f;
-#pragma unroll
-    for (int l = L - 1; l >= 0; --l) {
-      const float ds = r[0] + t;
-      t = fmaf(ds, p[l], t);
-      sd[l] += ds;
-      coef[l] = ds * c[l];
+      for (int l = L - 1; l >= 0; --l) {
+        const float ds = live ? rr[r] + t : 0.f;
+        t = fmaf(ds, p[l], t);
+        sd[l] += ds;
+        coef[r][l] = ds * c[l];
+      }
     }
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
       const int i = tid + k * kCrossThreads;
       if (i < dpv) {
-        Vec o = CrV<Vec>::scale_add(g[k], c[L], CrV<Vec>::zero());
+        Vec o[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = CrV<Vec>::scale_add(g[r][k], cl[r], CrV<Vec>::zero());
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-          CrV<Vec>::axpy(o, coef[l], CrV<Vec>::ld(w, (int64_t)l * dpv + i));
-          CrV<Vec>::axpy(A[l][k], coef[l], x[k]);
+          const Vec wv = CrV<Vec>::ld(w, (int64_t)l * dpv + i);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            CrV<Vec>::axpy(o[r], coef[r][l], wv);
+            CrV<Vec>::axpy(A[l][k], coef[r][l], x[r][k]);
+          }
         }
-        CrV<Vec>::add(Y[k], g[k]);
-        CrV<Vec>::st_stream(dx, row * dpv + i, o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          CrV<Vec>::add(Y[k], g[r][k]);  // zero for rows past the end
+          if (row0 + r < batch) CrV<Vec>::st_stream(dx, (row0 + r) * dpv + i, o[r]);
+        }
       }
     }
   }
@@ -298,7 +333,7 @@ template <typename Vec, int SLOTS>
 static int launch_fwd(int layers, int grid, cudaStream_t st, const float* x0, const float* w, const float* q,
                       const float* bcum, int64_t batch, int dpv, float* y, float* p) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL>), grid, kCrossThreads, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, (SLOTS * LL <= 12 ? 4 : (SLOTS * LL <= 24 ? 2 : 1))>), grid, kCrossThreads, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
@@ -309,7 +344,7 @@ template <typename Vec, int SLOTS>
 static int launch_bwd(int layers, int grid, cudaStream_t st, const float* x0, const float* dy, const float* w,
                       const float* q, const float* p, int64_t batch, int dpv, float* dx, float* part, float* sd) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL>), grid, kCrossThreads, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL, (SLOTS <= 2 ? 2 : 1)>), grid, kCrossThreads, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
@@ -360,7 +395,7 @@ MREC_API int mrec_cross_fwd(int nparam, void** params, int* ndims, int64_t** sha
   float* q = reinterpret_cast<float*>(ws + W.off_q);
   MREC_LAUNCH(cross_prep_kernel, 1, 1024, 0, a.stream, a.ptr<float>(1), a.ptr<float>(2), layers, dp, bcum, q);
   if (batch == 0) return check_launch("cross_prep");
-  const int grid = grid_for(batch, 1);
+  const int grid = grid_for(cdiv(batch, 4), 1);
   const float *x0 = a.ptr<float>(0), *w = a.ptr<float>(1);
   float *y = a.ptr<float>(3), *p = a.ptr<float>(4);
   if (dp % 4 == 0) {

@@ -17,7 +17,9 @@ def test_fm_forward_backward(cuda, b, f, d):
     dvx_in = torch.from_numpy(vx).to(cuda)
     out = ops.fm_fwd(dvx_in)
     ref = R.fm_forward(vx)
-    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    # fm is a difference of two O(sum vx^2) terms: fp32 tolerance is relative to that magnitude
+    scale = 0.5 * np.square(vx.astype(np.float64)).sum(axis=(1, 2)).max()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * scale)
     dv = ops.fm_bwd(dvx_in, torch.from_numpy(g).to(cuda))
     rdv = R.fm_backward(vx, g)
     np.testing.assert_allclose(dv.cpu().numpy(), rdv, rtol=1e-5, atol=1e-5 * np.abs(rdv).max())
