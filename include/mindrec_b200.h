@@ -116,7 +116,7 @@ int mrec_ftrl_dense(MREC_AOT_ARGS);
 /* ---- K7 FM second-order interaction -------------------------------------------------------------
  * Replaces Square/ReduceSum/Sub x6 of models/deepfm/src/deepfm.py:222-228 and their autodiff.
  *   fwd  in : vx[B,F,D] f32 (already multiplied by the mask)      out: fm[B]|[B,1] f32
- *   bwd  in : vx[B,F,D], gout[B]|[B,1]                            out: dvx[B,F,D] = g * (sum_f vx - vx)  */
+ *   bwd  in : vx[B,F,D], gout[B]|[B,1], (addend[B,F,D] f32|f16)   out: dvx[B,F,D] = g * (sum_f vx - vx) + addend */
 int mrec_fm_fwd(MREC_AOT_ARGS);
 int mrec_fm_bwd(MREC_AOT_ARGS);
 
@@ -130,6 +130,37 @@ int mrec_fm_bwd(MREC_AOT_ARGS);
 int mrec_cross_fwd(MREC_AOT_ARGS);
 int mrec_cross_bwd(MREC_AOT_ARGS);
 size_t mrec_cross_workspace_bytes(int64_t layers, int dp);
+
+/* ---- K6 hash table behind MapParameter / HashEmbeddingLookup -------------------------------------
+ * Replaces mindspore.experimental.MapParameter's GPUHashTable and the MapTensorGet/Put/Erase primitives
+ * (mindspore_rec/ops/embedding.py:136-149,193; README.md:176-195).  The table maps key -> slot; values and
+ * optimizer state are [C+1, D] arenas indexed by slot (row C = default row), so rows are fetched with
+ * mrec_gather and updated with mrec_sparse_lazy_adam / mrec_sparse_ftrl on slot indices.
+ * Framework-owned state, passed on every call and mutated in place:
+ *   tkeys[C] i64 (-1 empty, -2 erased; C a power of two >= 8, 64-byte aligned), meta[C] i64
+ *   ((sightings << 32) | last_step), state[8] i32 {resident, step, tombstones, overflow, occupied, ...},
+ *   cfg[2] i32 {permit_filter_value, evict_filter_value}.
+ * Probe entry points:   in : keys[N] i32|i64, tkeys, meta, state, cfg
+ *   mrec_hash_find            MapTensorGet(insert_default_value=False)   out: slots[N] i32 (C = default row)
+ *   mrec_hash_find_or_insert  MapTensorGet(True): a key becomes resident on its permit-th sighting
+ *                             (one sighting per key per call)             out: slots[N], new_slots[N], new_count[1]
+ *   mrec_hash_insert          MapTensorPut / import_data                  out: slots[N], new_slots[N], new_count[1]
+ *   mrec_hash_erase           MapTensorErase                              out: slots[N]                       */
+int mrec_hash_find(MREC_AOT_ARGS);
+int mrec_hash_find_or_insert(MREC_AOT_ARGS);
+int mrec_hash_insert(MREC_AOT_ARGS);
+int mrec_hash_erase(MREC_AOT_ARGS);
+/* Initialise the rows of newly resident keys in one arena:
+ *   in : arena[C+1,D] f32, new_slots[N], new_count[1], tkeys[C], rng[2] i64 {seed, mode}, sigma[1] f32
+ *   out: dummy[1].  mode 0 = copy the arena's default row; mode 1 = N(0, sigma^2), Philox keyed by the KEY. */
+int mrec_hash_init_rows(MREC_AOT_ARGS);
+/*   in : arena[C+1,D], slots[N], values[N,D]     out: dummy[1]     (put / import: arena[slots[i]] = values[i]) */
+int mrec_hash_scatter_rows(MREC_AOT_ARGS);
+/* Eviction sweep: erase every key not looked up for more than evict_filter_value calls.
+ *   in : tkeys, meta, state, cfg                  out: dummy[1]                                               */
+int mrec_hash_evict(MREC_AOT_ARGS);
+/* get_keys / export_data:  in : tkeys, meta, state, cfg   out: keys_out[C] i64, slots_out[C] i32, count[1] i32 */
+int mrec_hash_export(MREC_AOT_ARGS);
 
 #ifdef __cplusplus
 }

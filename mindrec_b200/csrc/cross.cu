@@ -123,7 +123,7 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float (*buf)[NV]) {
 // R rows per CTA iteration: all R * SLOTS row loads are issued before the reduction, and each w chunk
 // read from L1 is used for R rows.
 template <typename Vec, int SLOTS, int L, int R>
-__global__ void __launch_bounds__(kCrossThreads, 1)
+__global__ void __launch_bounds__(kCrossThreads, (SLOTS <= 2 ? 2 : 1))
 cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ q,
                  const float* __restrict__ bcum, int64_t batch, int dpv /* D' / vec width */,
                  float* __restrict__ y, float* __restrict__ p_out) {
@@ -285,34 +285,56 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
   }
 }
 
-// dw_l = sum_cta A_l + (sum ds_l) Bcum_l ;  db_l = sum_cta Ysum + sum_{k>l} (sum ds_k) w_k   (CTA order fixed)
+// Stage 1 of the finish: column sums of the per-CTA partials in a fixed order.  grid = (ceil(D'/32), L+2):
+// blockIdx.y <= L sums array y (A_0..A_{L-1}, Ysum) over the CTAs, blockIdx.y == L+1 sums the ds scalars.
+// Block (32 columns x 8 part-groups): group q adds parts q, q+8, ...; the 8 group partials are added in order.
 __global__ void __launch_bounds__(256)
-cross_bwd_finish_kernel(const float* __restrict__ part, const float* __restrict__ sd_part, int nparts,
+cross_bwd_colsum_kernel(const float* __restrict__ part, const float* __restrict__ sd_part, int nparts,
+                        int layers, int dp, float* __restrict__ sums /* [L+1][D'] */, float* __restrict__ sdt) {
+  __shared__ float s_acc[8][32];
+  const int tx = threadIdx.x & 31, q = threadIdx.x >> 5;
+  if ((int)blockIdx.y == layers + 1) {
+    if (blockIdx.x == 0 && threadIdx.x < layers) {
+      float t = 0.f;
+      for (int pth = 0; pth < nparts; ++pth) t += sd_part[pth * layers + threadIdx.x];
+      sdt[threadIdx.x] = t;
+    }
+    return;
+  }
+  const int d = blockIdx.x * 32 + tx;
+  const int arr = blockIdx.y;
+  float acc = 0.f;
+  if (d < dp)
+    for (int pth = q; pth < nparts; pth += 8) acc += part[((int64_t)pth * (layers + 1) + arr) * dp + d];
+  s_acc[q][tx] = acc;
+  __syncthreads();
+  if (q == 0 && d < dp) {
+    float t = s_acc[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += s_acc[k][tx];
+    sums[(int64_t)arr * dp + d] = t;
+  }
+}
+
+// Stage 2: dw_l = A_l + (sum ds_l) Bcum_l ;  db_l = Ysum + sum_{k>l} (sum ds_k) w_k
+__global__ void __launch_bounds__(256)
+cross_bwd_finish_kernel(const float* __restrict__ sums, const float* __restrict__ sdt,
                         const float* __restrict__ w, const float* __restrict__ bcum, int layers, int dp,
                         float* __restrict__ dw, float* __restrict__ db) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= dp) return;
-  float sdt[kCrossMaxL];
-#pragma unroll
-  for (int l = 0; l < kCrossMaxL; ++l) {
-    sdt[l] = 0.f;
-    if (l < layers)
-      for (int pth = 0; pth < nparts; ++pth) sdt[l] += sd_part[pth * layers + l];
-  }
-  float ysum = 0.f;
-  for (int pth = 0; pth < nparts; ++pth) ysum += part[((int64_t)pth * (layers + 1) + layers) * dp + d];
+  const float ysum = sums[(int64_t)layers * dp + d];
   float tail = 0.f;  // sum_{k>l} sdt[k] * w[k][d], built from the last layer down
   for (int l = layers - 1; l >= 0; --l) {
-    float al = 0.f;
-    for (int pth = 0; pth < nparts; ++pth) al += part[((int64_t)pth * (layers + 1) + l) * dp + d];
-    dw[(int64_t)l * dp + d] = fmaf(sdt[l], bcum[(int64_t)l * dp + d], al);
+    const float sl = sdt[l];
+    dw[(int64_t)l * dp + d] = fmaf(sl, bcum[(int64_t)l * dp + d], sums[(int64_t)l * dp + d]);
     db[(int64_t)l * dp + d] = ysum + tail;
-    tail = fmaf(sdt[l], w[(int64_t)l * dp + d], tail);
+    tail = fmaf(sl, w[(int64_t)l * dp + d], tail);
   }
 }
 
 struct CrossWs {
-  size_t off_bcum, off_q, off_part, off_sd, total;
+  size_t off_bcum, off_q, off_part, off_sd, off_sums, off_sdt, total;
   int nparts;
 };
 static CrossWs cross_ws(int layers, int dp, bool backward) {
@@ -325,6 +347,10 @@ static CrossWs cross_ws(int layers, int dp, bool backward) {
   if (backward) o = align_up(o + (size_t)W.nparts * (layers + 1) * dp * 4, 256);
   W.off_sd = o;
   if (backward) o = align_up(o + (size_t)W.nparts * layers * 4, 256);
+  W.off_sums = o;
+  if (backward) o = align_up(o + (size_t)(layers + 1) * dp * 4, 256);
+  W.off_sdt = o;
+  if (backward) o = align_up(o + (size_t)kCrossMaxL * 4, 256);
   W.total = o;
   return W;
 }
@@ -333,7 +359,7 @@ template <typename Vec, int SLOTS>
 static int launch_fwd(int layers, int grid, cudaStream_t st, const float* x0, const float* w, const float* q,
                       const float* bcum, int64_t batch, int dpv, float* y, float* p) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, (SLOTS * LL <= 12 ? 4 : (SLOTS * LL <= 24 ? 2 : 1))>), grid, kCrossThreads, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, (SLOTS * LL <= 12 ? 2 : 1)>), grid, kCrossThreads, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
@@ -395,7 +421,7 @@ MREC_API int mrec_cross_fwd(int nparam, void** params, int* ndims, int64_t** sha
   float* q = reinterpret_cast<float*>(ws + W.off_q);
   MREC_LAUNCH(cross_prep_kernel, 1, 1024, 0, a.stream, a.ptr<float>(1), a.ptr<float>(2), layers, dp, bcum, q);
   if (batch == 0) return check_launch("cross_prep");
-  const int grid = grid_for(cdiv(batch, 4), 1);
+  const int grid = grid_for(cdiv(batch, 2), 2);
   const float *x0 = a.ptr<float>(0), *w = a.ptr<float>(1);
   float *y = a.ptr<float>(3), *p = a.ptr<float>(4);
   if (dp % 4 == 0) {
@@ -450,7 +476,11 @@ MREC_API int mrec_cross_bwd(int nparam, void** params, int* ndims, int64_t** sha
     else rc = launch_bwd<float, 8>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
   }
   if (rc) return rc;
-  MREC_LAUNCH(cross_bwd_finish_kernel, (int)cdiv(dp, 256), 256, 0, a.stream, part, sd, W.nparts, w, bcum, layers,
-              dp, a.ptr<float>(6), a.ptr<float>(7));
+  float* sums = reinterpret_cast<float*>(ws + W.off_sums);
+  float* sdt = reinterpret_cast<float*>(ws + W.off_sdt);
+  MREC_LAUNCH(cross_bwd_colsum_kernel, dim3((unsigned)cdiv(dp, 32), (unsigned)(layers + 2)), 256, 0, a.stream, part,
+              sd, W.nparts, layers, dp, sums, sdt);
+  MREC_LAUNCH(cross_bwd_finish_kernel, (int)cdiv(dp, 256), 256, 0, a.stream, sums, sdt, w, bcum, layers, dp,
+              a.ptr<float>(6), a.ptr<float>(7));
   return check_launch("cross_bwd");
 }

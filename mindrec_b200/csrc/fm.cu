@@ -11,6 +11,7 @@
 // re-walks the fields for the store pass out of L1/L2 (the sample's 2.5 KB..12 KB were just read by the
 // same threads) and writes dvx once.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace mrec {
 
@@ -34,10 +35,23 @@ template <> struct FmV<float4> {
   static __device__ __forceinline__ float finish(const float4& s, const float4& s2) {
     return (s.x * s.x - s2.x) + (s.y * s.y - s2.y) + (s.z * s.z - s2.z) + (s.w * s.w - s2.w);
   }
+  // dvx = g * (S - vx) (+ addend: the DenseLayer-path gradient of the same vx, fp32 or fp16)
   static __device__ __forceinline__ void st_grad(float* p, int64_t i, float g, const float4& s,
-                                                 const float4& x) {
+                                                 const float4& x, const void* add, bool add16) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add) {
+      if (add16) {
+        const uint2 u = reinterpret_cast<const uint2*>(add)[i];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        a = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        a = ld_stream_f4(reinterpret_cast<const float4*>(add) + i);
+      }
+    }
     st_stream_f4(reinterpret_cast<float4*>(p) + i,
-                 make_float4(g * (s.x - x.x), g * (s.y - x.y), g * (s.z - x.z), g * (s.w - x.w)));
+                 make_float4(fmaf(g, s.x - x.x, a.x), fmaf(g, s.y - x.y, a.y), fmaf(g, s.z - x.z, a.z),
+                             fmaf(g, s.w - x.w, a.w)));
   }
 };
 template <> struct FmV<float> {
@@ -50,8 +64,10 @@ template <> struct FmV<float> {
   }
   static __device__ __forceinline__ float finish(const float& s, const float& s2) { return s * s - s2; }
   static __device__ __forceinline__ void st_grad(float* p, int64_t i, float g, const float& s,
-                                                 const float& x) {
-    p[i] = g * (s - x);
+                                                 const float& x, const void* add, bool add16) {
+    float a = 0.f;
+    if (add) a = add16 ? __half2float(reinterpret_cast<const __half*>(add)[i]) : reinterpret_cast<const float*>(add)[i];
+    p[i] = fmaf(g, s - x, a);
   }
 };
 
@@ -59,7 +75,8 @@ template <> struct FmV<float> {
 template <typename Vec, bool BACKWARD>
 __global__ void __launch_bounds__(kFmThreads)
 fm_kernel(const float* __restrict__ vx, const float* __restrict__ gout, float* __restrict__ out,
-          float* __restrict__ dvx, int64_t batch, int fields, int cpr) {
+          float* __restrict__ dvx, int64_t batch, int fields, int cpr, const void* __restrict__ addend,
+          bool add16) {
   __shared__ float s_part[kFmThreads];
   const int spb = kFmThreads / cpr;
   const int gi = threadIdx.x / cpr;
@@ -99,7 +116,7 @@ fm_kernel(const float* __restrict__ vx, const float* __restrict__ gout, float* _
           x[k] = (f0 + k < fields) ? FmV<Vec>::ld_cached(vx, base + (int64_t)(f0 + k) * cpr) : FmV<Vec>::zero();
 #pragma unroll
         for (int k = 0; k < kFmBatch; ++k)
-          if (f0 + k < fields) FmV<Vec>::st_grad(dvx, base + (int64_t)(f0 + k) * cpr, g, s, x[k]);
+          if (f0 + k < fields) FmV<Vec>::st_grad(dvx, base + (int64_t)(f0 + k) * cpr, g, s, x[k], addend, add16);
       }
     }
   }
@@ -135,35 +152,49 @@ MREC_API int mrec_fm_fwd(int nparam, void** params, int* ndims, int64_t** shapes
   if (dim % 4 == 0) {
     const int cpr = dim / 4, spb = kFmThreads / cpr;
     MREC_LAUNCH((fm_kernel<float4, false>), grid_for(cdiv(batch, spb), 8), kFmThreads, 0, a.stream,
-                a.ptr<float>(0), nullptr, a.ptr<float>(1), nullptr, batch, fields, cpr);
+                a.ptr<float>(0), nullptr, a.ptr<float>(1), nullptr, batch, fields, cpr, nullptr, false);
   } else {
     const int spb = kFmThreads / dim;
     MREC_LAUNCH((fm_kernel<float, false>), grid_for(cdiv(batch, spb), 8), kFmThreads, 0, a.stream,
-                a.ptr<float>(0), nullptr, a.ptr<float>(1), nullptr, batch, fields, dim);
+                a.ptr<float>(0), nullptr, a.ptr<float>(1), nullptr, batch, fields, dim, nullptr, false);
   }
   return check_launch("fm_fwd");
 }
 
-// in : vx[B,F,D] f32, gout[B] | [B,1] f32                       out: dvx[B,F,D] f32
+// in : vx[B,F,D] f32, gout[B] | [B,1] f32, (addend[B,F,D] f32|f16)     out: dvx[B,F,D] f32
+// dvx = gout * (sum_f vx - vx) + addend   (addend = gradient reaching the same vx through the DenseLayers)
 MREC_API int mrec_fm_bwd(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
                          void* stream, void* /*extra*/) {
   Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
-  MREC_CHECK_NPARAM(a, 3);
+  if (a.nparam != 3 && a.nparam != 4)
+    return fail(ERR_NPARAM, "mrec_fm_bwd: expected 3 or 4 params, got %d", a.nparam);
+  for (int i = 0; i < a.nparam; ++i)
+    if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "mrec_fm_bwd: param %d is null", i);
+  const int o = a.nparam - 1;
   int64_t batch; int fields, dim;
   int rc = fm_common(a, 0, &batch, &fields, &dim);
   if (rc) return rc;
   MREC_REQUIRE(a.is_f32(1) && a.numel(1) == batch, ERR_SHAPE, "mrec_fm_bwd: gout must be f32 with B elements");
-  MREC_REQUIRE(a.is_f32(2) && a.numel(2) == a.numel(0), ERR_SHAPE, "mrec_fm_bwd: dvx must match vx");
+  MREC_REQUIRE(a.is_f32(o) && a.numel(o) == a.numel(0), ERR_SHAPE, "mrec_fm_bwd: dvx must match vx");
+  const void* addend = nullptr;
+  bool add16 = false;
+  if (a.nparam == 4) {
+    MREC_REQUIRE((a.is_f32(2) || a.is(2, "float16")) && a.numel(2) == a.numel(0), ERR_SHAPE,
+                 "mrec_fm_bwd: addend must be f32|f16 with vx's shape");
+    addend = a.params[2];
+    add16 = a.is(2, "float16");
+  }
   if (batch == 0) return OK;
   if (dim % 4 == 0) {
-    MREC_REQUIRE(a.aligned(2, 16), ERR_ALIGN, "mrec_fm_bwd: dvx must be 16-byte aligned");
+    MREC_REQUIRE(a.aligned(o, 16) && (!addend || a.aligned(2, add16 ? 8 : 16)), ERR_ALIGN,
+                 "mrec_fm_bwd: dvx/addend must be 16-byte aligned");
     const int cpr = dim / 4, spb = kFmThreads / cpr;
     MREC_LAUNCH((fm_kernel<float4, true>), grid_for(cdiv(batch, spb), 8), kFmThreads, 0, a.stream,
-                a.ptr<float>(0), a.ptr<float>(1), nullptr, a.ptr<float>(2), batch, fields, cpr);
+                a.ptr<float>(0), a.ptr<float>(1), nullptr, a.ptr<float>(o), batch, fields, cpr, addend, add16);
   } else {
     const int spb = kFmThreads / dim;
     MREC_LAUNCH((fm_kernel<float, true>), grid_for(cdiv(batch, spb), 8), kFmThreads, 0, a.stream,
-                a.ptr<float>(0), a.ptr<float>(1), nullptr, a.ptr<float>(2), batch, fields, dim);
+                a.ptr<float>(0), a.ptr<float>(1), nullptr, a.ptr<float>(o), batch, fields, dim, addend, add16);
   }
   return check_launch("fm_bwd");
 }

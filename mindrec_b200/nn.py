@@ -212,14 +212,22 @@ class DenseStack:
     that the dense Adam update is a single mrec_adam_dense launch.  `extra` reserves trailing scalars in
     the same buffer (W&D's Wide_b lands in the Adam group)."""
 
+    @staticmethod
+    def numel(dims, extra=0):
+        return sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)) + extra
+
     def __init__(self, dims, convert_dtype, device, generator=None, weight_init="normal", bias_init="zero",
-                 last_activation=False, extra=0):
+                 last_activation=False, extra=0, storage=None):
         self.dims = list(dims)
         self.convert_dtype = convert_dtype
         self.last_activation = last_activation
-        n = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)) + extra
-        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
+        n = self.numel(dims, extra)
+        if storage is None:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+            self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
+        else:  # slices of a larger flat parameter / gradient buffer owned by the model
+            self.flat, self.flat_grad = storage
+            assert self.flat.numel() == n and self.flat_grad.numel() == n
         self.weights, self.biases, self.gw, self.gb = [], [], [], []
         o = 0
         for i in range(len(dims) - 1):

@@ -215,11 +215,11 @@ def fm_fwd(vx, out=None):
     return out
 
 
-def fm_bwd(vx, gout, out=None):
-    """dvx[b,f,d] = gout[b] * (S[b,d] - vx[b,f,d])."""
+def fm_bwd(vx, gout, out=None, addend=None):
+    """dvx[b,f,d] = gout[b] * (S[b,d] - vx[b,f,d]) (+ addend[b,f,d], fp32 or fp16, fused into the store)."""
     if out is None:
         out = torch.empty_like(vx)
-    _lib.aot_call("mrec_fm_bwd", [vx, gout, out])
+    _lib.aot_call("mrec_fm_bwd", [vx, gout] + ([addend] if addend is not None else []) + [out])
     return out
 
 

@@ -406,3 +406,119 @@ class WideDeepOracle:
             adam_dense(self.mlp_b[i], self.m_b[i], self.v_b[i], gb[i], self.adam)
         adam_dense(self.wide_b, self.m_wb, self.v_wb, np.array([delta.sum()]), self.adam)
         return F32(loss), F32(loss_d)
+
+
+def _mlp_forward(x, ws, bs, last_activation=False):
+    acts = [x]
+    h = x
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        a = h @ w.astype(np.float64) + b.astype(np.float64)
+        h = np.maximum(a, 0) if (i + 1 < len(ws) or last_activation) else a
+        acts.append(h)
+    return h, acts
+
+
+def _mlp_backward(g, acts, ws, last_activation=False):
+    gw, gb = [None] * len(ws), [None] * len(ws)
+    for i in range(len(ws) - 1, -1, -1):
+        if i + 1 < len(ws) or last_activation:
+            g = g * (acts[i + 1] > 0)
+        gw[i] = acts[i].T @ g
+        gb[i] = g.sum(axis=0)
+        g = g @ ws[i].astype(np.float64).T
+    return g, gw, gb
+
+
+def _scatter_rows(shape, ids, rows, mask, div=1):
+    """Dense gradient of P.Gather: UnsortedSegmentSum(mask * rows, ids, V) (sparse=False)."""
+    out = np.zeros(shape, dtype=np.float64)
+    flat = np.asarray(ids).reshape(-1).astype(np.int64)
+    r = np.asarray(rows, dtype=np.float64).reshape(-1, shape[1])[np.arange(flat.size) // div]
+    np.add.at(out, flat, r * np.asarray(mask, dtype=np.float64).reshape(-1, 1))
+    return out
+
+
+class DeepFMOracle:
+    """models/deepfm/src/deepfm.py:208-237 (forward), :252-260 (loss with full-table l2), :263-297 (one
+    nn.Adam over everything, dense gradients).  fp32 DenseLayers (convert_dtype=False)."""
+
+    def __init__(self, fm_w, fm_v, mlp_w, mlp_b, lr=5e-4, eps=5e-8, l2_coef=8e-5, sens=1024.0):
+        self.w = fm_w.astype(F32).copy()
+        self.v = fm_v.astype(F32).copy()
+        self.mlp_w = [x.astype(F32).copy() for x in mlp_w]
+        self.mlp_b = [x.astype(F32).copy() for x in mlp_b]
+        self.l2, self.sens = l2_coef, sens
+        self.adam = AdamState(lr, eps=eps, loss_scale=sens)
+        z = np.zeros_like
+        self.m = {k: z(a) for k, a in (("w", self.w), ("v", self.v))}
+        self.s = {k: z(a) for k, a in (("w", self.w), ("v", self.v))}
+        self.mm = [(z(a), z(a)) for a in self.mlp_w]
+        self.mb = [(z(a), z(a)) for a in self.mlp_b]
+
+    def step(self, ids, wts, label):
+        b, f = ids.shape
+        d = self.v.shape[1]
+        linear = gather_reduce(self.w, ids, wts).astype(np.float64)
+        vx = gather_masked(self.v, ids, wts).astype(np.float64)
+        fm = fm_forward(vx.reshape(b, f, d))
+        deep, acts = _mlp_forward(vx, self.mlp_w, self.mlp_b)
+        logit = linear + fm + deep
+        loss = sigmoid_xent(logit, label).mean() + self.l2 * 0.5 * (
+            np.square(self.v.astype(np.float64)).sum() + np.square(self.w.astype(np.float64)).sum())
+        delta = self.sens * (sigmoid(logit) - label) / b
+        gx, gw, gb = _mlp_backward(delta, acts, self.mlp_w)
+        dvx = fm_backward(vx.reshape(b, f, d), delta).reshape(b * f, d) + gx.reshape(b * f, d)
+        g_w = _scatter_rows(self.w.shape, ids, delta, wts, div=f) + self.sens * self.l2 * self.w.astype(np.float64)
+        g_v = _scatter_rows(self.v.shape, ids, dvx, wts) + self.sens * self.l2 * self.v.astype(np.float64)
+        self.adam.begin_step()
+        adam_dense(self.w, self.m["w"], self.s["w"], g_w, self.adam)
+        adam_dense(self.v, self.m["v"], self.s["v"], g_v, self.adam)
+        for i in range(len(self.mlp_w)):
+            adam_dense(self.mlp_w[i], self.mm[i][0], self.mm[i][1], gw[i], self.adam)
+            adam_dense(self.mlp_b[i], self.mb[i][0], self.mb[i][1], gb[i], self.adam)
+        return F32(loss)
+
+
+class DeepCrossOracle:
+    """models/deep_and_cross/src/deep_and_cross.py:293-309 (forward), :312-328 (loss), :331-357 (nn.Adam,
+    dense gradients), all fp32."""
+
+    def __init__(self, table, tower_w, tower_b, head_w, head_b, cross_w, cross_b, lr=1e-4, eps=1e-8, sens=1000.0):
+        c = lambda a: np.asarray(a, dtype=F32).copy()
+        self.table = c(table)
+        self.tw, self.tb = [c(x) for x in tower_w], [c(x) for x in tower_b]
+        self.hw, self.hb = [c(x) for x in head_w], [c(x) for x in head_b]
+        self.cw, self.cb = c(cross_w), c(cross_b)
+        self.sens = sens
+        self.adam = AdamState(lr, eps=eps, loss_scale=sens)
+        self.state = {}
+
+    def _adam(self, name, param, grad):
+        if name not in self.state:
+            self.state[name] = (np.zeros_like(param), np.zeros_like(param))
+        m, v = self.state[name]
+        adam_dense(param, m, v, grad, self.adam)
+
+    def step(self, ids, wts, label):
+        b, f = ids.shape
+        d = self.table.shape[1]
+        x = gather_masked(self.table, ids, wts).astype(np.float64)
+        d2, t_acts = _mlp_forward(x, self.tw, self.tb, last_activation=True)
+        c6, _, _ = cross_forward(x, self.cw, self.cb)
+        cat = np.concatenate([d2, c6], axis=1)
+        logit, h_acts = _mlp_forward(cat, self.hw, self.hb)
+        loss = sigmoid_xent(logit, label).mean()
+        delta = self.sens * (sigmoid(logit) - label) / b
+        g_cat, ghw, ghb = _mlp_backward(delta, h_acts, self.hw)
+        k = d2.shape[1]
+        gx_t, gtw, gtb = _mlp_backward(g_cat[:, :k], t_acts, self.tw, last_activation=True)
+        gx_c, gcw, gcb = cross_backward(x, self.cw, self.cb, g_cat[:, k:])
+        g_table = _scatter_rows(self.table.shape, ids, (gx_t + gx_c).reshape(b * f, d), wts)
+        self.adam.begin_step()
+        self._adam("table", self.table, g_table)
+        for i in range(len(self.tw)):
+            self._adam("tw%d" % i, self.tw[i], gtw[i]); self._adam("tb%d" % i, self.tb[i], gtb[i])
+        for i in range(len(self.hw)):
+            self._adam("hw%d" % i, self.hw[i], ghw[i]); self._adam("hb%d" % i, self.hb[i], ghb[i])
+        self._adam("cw", self.cw, gcw); self._adam("cb", self.cb, gcb)
+        return F32(loss)

@@ -1,0 +1,147 @@
+"""K6 parity: the GPU hash table behind MapParameter / HashEmbeddingLookup vs the dict model of the oracle.
+Key membership, counts and returned rows are exact; slot indices are implementation-private."""
+import numpy as np
+import pytest
+import torch
+
+from mindrec_b200 import hash as H
+from mindrec_b200 import ops
+from oracle import ref_numpy as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _keys(rng, n, space, dtype):
+    return (rng.zipf(1.2, size=n) % space).astype(dtype)
+
+
+@pytest.mark.parametrize("kdt", [torch.int32, torch.int64])
+def test_get_put_erase_against_dict_model(cuda, kdt):
+    rng = np.random.default_rng(0)
+    dim = 8
+    mp = H.MapParameter(key_dtype=kdt, value_shape=dim, default_value=0.5, capacity=4096, device=cuda)
+    model = R.MapParameterModel(dim, default_value=0.5)
+    npdt = np.int32 if kdt == torch.int32 else np.int64
+    space = 3000 if kdt == torch.int32 else 2 ** 40
+    for it in range(6):
+        keys = _keys(rng, 700, space, npdt)
+        got = mp.get(torch.from_numpy(keys).to(cuda)).cpu().numpy()
+        np.testing.assert_array_equal(got, model.get(keys))
+        pk = rng.choice(keys, size=50, replace=False) if it % 2 == 0 else _keys(rng, 50, space, npdt)
+        pk = np.unique(pk)
+        pv = rng.standard_normal((pk.size, dim)).astype(np.float32)
+        mp.put(torch.from_numpy(pk).to(cuda), torch.from_numpy(pv).to(cuda))
+        model.put(pk, pv)
+        ek = np.unique(rng.choice(keys, size=30))
+        mp.erase(torch.from_numpy(ek).to(cuda))
+        model.erase(ek)
+        np.testing.assert_array_equal(mp.get_keys().cpu().numpy().astype(np.int64), model.keys())
+        assert len(mp) == model.keys().size
+    k, v = mp.get_data()
+    ref_rows = np.stack([model.rows[int(x)] for x in k.cpu().numpy()])
+    np.testing.assert_array_equal(v.cpu().numpy(), ref_rows)
+    assert not mp.overflowed
+
+
+def test_reserved_keys_and_missing_keys_read_default_row(cuda):
+    mp = H.MapParameter(key_dtype=torch.int64, value_shape=4, default_value="ones", capacity=64, device=cuda)
+    keys = torch.tensor([5, -1, -2, 5, 9], dtype=torch.int64, device=cuda)
+    out = mp.get(keys, insert_default_value=False)
+    assert torch.equal(out, torch.ones((5, 4), device=cuda)) and len(mp) == 0
+    mp.get(keys)
+    assert mp.get_keys().tolist() == [5, 9]          # -1 / -2 are never stored (embedding.py:55-57)
+
+
+def test_duplicates_in_one_call_resolve_to_one_slot(cuda):
+    mp = H.MapParameter(key_dtype=torch.int32, value_shape=4, default_value="normal", capacity=1 << 16, device=cuda)
+    keys = torch.randint(0, 50, (20000,), dtype=torch.int32, device=cuda)
+    slots = mp.lookup_slots(keys).clone()
+    assert len(mp) == torch.unique(keys).numel()
+    # same key -> same slot, different keys -> different slots
+    pairs = torch.unique(torch.stack([keys.long(), slots.long()], 1), dim=0)
+    assert pairs.shape[0] == torch.unique(keys).numel() == torch.unique(slots).numel()
+    rows = mp.get(keys)
+    assert torch.equal(rows, mp.values[slots.long()])
+
+
+def test_permit_and_evict_filters_follow_the_model(cuda):
+    dim = 4
+    mp = H.MapParameter(key_dtype=torch.int32, value_shape=dim, default_value=2.0, permit_filter_value=3,
+                        evict_filter_value=2, capacity=1024, device=cuda)
+    model = R.MapParameterModel(dim, default_value=2.0, permit_filter_value=3, evict_filter_value=2)
+    rng = np.random.default_rng(1)
+    for it in range(12):
+        keys = rng.integers(0, 40, size=60).astype(np.int32)
+        got = mp.get(torch.from_numpy(keys).to(cuda)).cpu().numpy()
+        np.testing.assert_array_equal(got, model.get(keys))
+        if it % 3 == 2:
+            mp.evict()
+            model.evict()
+        np.testing.assert_array_equal(mp.get_keys().cpu().numpy().astype(np.int64), model.keys())
+
+
+def test_normal_init_is_keyed_by_key_and_has_the_right_moments(cuda):
+    a = H.MapParameter(key_dtype=torch.int64, value_shape=80, default_value="normal", capacity=1 << 18, device=cuda, seed=7)
+    b = H.MapParameter(key_dtype=torch.int64, value_shape=80, default_value="normal", capacity=1 << 17, device=cuda, seed=7)
+    keys = torch.randperm(50000, device=cuda)[:20000].to(torch.int64) * 7919
+    ra = a.get(keys)
+    rb = b.get(keys.flip(0)).flip(0)
+    assert torch.equal(ra, rb)                       # row depends on (seed, key), not on slot or arrival order
+    assert abs(float(ra.mean())) < 2e-4 and abs(float(ra.std()) - 0.01) < 2e-4
+    assert torch.equal(a.get(keys), ra)              # second lookup returns the stored rows
+
+
+def test_full_table_raises_overflow_flag_not_corruption(cuda):
+    mp = H.MapParameter(key_dtype=torch.int32, value_shape=2, default_value=0.0, capacity=64, device=cuda)
+    keys = torch.arange(200, dtype=torch.int32, device=cuda)
+    out = mp.get(keys)
+    assert mp.overflowed and len(mp) == 64
+    assert out.shape == (200, 2)
+
+
+def test_hash_embedding_lookup_matches_reference_flow(cuda):
+    """embedding.py:189-195: Unique -> MapTensorGet -> Gather(inverse) equals a direct lookup."""
+    emb = H.HashEmbeddingLookup(16, key_dtype=torch.int64, param_init="normal", capacity=1 << 14, device=cuda)
+    ids = torch.randint(0, 2 ** 40, (64, 26), dtype=torch.int64, device=cuda)
+    ids[:, 0] = 12345
+    out = emb(ids)
+    assert out.shape == (64, 26, 16)
+    uq = ops.unique(ids)
+    u = int(uq.count.item())
+    weight_unique = emb.embedding_table.get(uq.uniq[:u])
+    ref = weight_unique[uq.inverse.long()].view(64, 26, 16)
+    assert torch.equal(out, ref)
+    assert torch.equal(out[0, 0], out[63, 0])
+
+
+def test_hash_embedding_lookup_argument_validation():
+    with pytest.raises(TypeError, match="sparse"):
+        H.HashEmbeddingLookup(8, sparse="yes", device="cpu")
+    with pytest.raises(ValueError, match="vocab_cache_size"):
+        H.HashEmbeddingLookup(8, vocab_cache_size=-1, device="cpu")
+    with pytest.raises(RuntimeError, match="parameter server"):
+        H.HashEmbeddingLookup(8, vocab_cache_size=10, device="cpu")
+    with pytest.raises(ValueError, match="embedding_size"):
+        H.HashEmbeddingLookup(0, device="cpu")
+
+
+def test_lazy_adam_on_map_parameter_by_slot(cuda):
+    """Optimizer on a MapParameter: rows addressed by slot, state in sibling arenas."""
+    dim = 16
+    mp = H.MapParameter(key_dtype=torch.int64, value_shape=dim, default_value="normal", capacity=1 << 12, device=cuda)
+    m, v = mp.add_arena(0.0), mp.add_arena(0.0)
+    keys = torch.randint(0, 300, (1000,), dtype=torch.int64, device=cuda) * 1000003
+    slots = mp.lookup_slots(keys).clone()
+    w0 = mp.values.clone()
+    g = torch.randn((1000, dim), device=cuda)
+    hyper = ops.adam_hyper(1e-2, device=cuda)
+    ops.adam_begin_step(hyper)
+    uq = ops.unique(slots, table_like=mp.values)
+    ops.sparse_lazy_adam(mp.values, m, v, hyper, g, None, uq)
+    # reference on the host, keyed by key
+    st = R.AdamState(1e-2); st.begin_step()
+    w_ref, m_ref, v_ref = w0.cpu().numpy(), np.zeros_like(w0.cpu().numpy()), np.zeros_like(w0.cpu().numpy())
+    uniq, inverse, _, _ = R.unique_sorted(slots.cpu().numpy())
+    R.lazy_adam_sparse(w_ref, m_ref, v_ref, uniq, R.segment_sum(g.cpu().numpy(), inverse, uniq.size), st)
+    np.testing.assert_allclose(mp.values.cpu().numpy(), w_ref, rtol=1e-5, atol=1e-7)
+    assert torch.equal(mp.values[mp.capacity], w0[mp.capacity])   # default row untouched
