@@ -76,6 +76,11 @@ int mrec_unique_bounded(MREC_AOT_ARGS);
 /* First-occurrence order = upstream CPU Unique kernel (BASELINE config 1 runs device_target=CPU).
  *   in : ids[N]   out: uniq[N], inverse[N] i32, count[1] i32, workspace[mrec_unique_first_workspace_bytes] */
 int mrec_unique_first(MREC_AOT_ARGS);
+/* Shard bucketing (row-sharded tables, replaces the AllGather/ReduceScatter pair auto-parallel inserts for
+ * nn.EmbeddingLookup(slice_mode=TABLE_ROW_SLICE), wide_and_deep.py:234-249): with keys remapped owner-major the
+ * per-owner runs of the unique keys are found by binary search on the device.
+ *   in : uniq[N] (ascending; first count entries valid), count[1] i32, edges[E] (uniq dtype)   out: bounds[E] i32 */
+int mrec_shard_bounds(MREC_AOT_ARGS);
 size_t mrec_unique_workspace_bytes(int64_t n, int key_bytes);
 size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes);
 

@@ -562,3 +562,43 @@ MREC_API int mrec_unique_first(int nparam, void** params, int* ndims, int64_t** 
   return unique_first<int64_t>(a.ptr<int64_t>(0), n, 0, a.ptr<int64_t>(1), a.ptr<int32_t>(2),
                                a.ptr<int32_t>(3), a.params[4], ws_bytes, a.stream);
 }
+
+// ---- shard bucketing helper -----------------------------------------------------------------------
+// bounds[r] = number of entries of the ascending array uniq[0 : count) that are < edges[r].
+// With keys remapped owner-major (key' = owner * rows_per_rank + local_row) the unique keys of one rank form
+// G contiguous runs; their boundaries are the all-to-all split sizes (mindrec_b200/sharded.py).
+template <typename KeyT>
+__global__ void shard_bounds_kernel(const KeyT* __restrict__ uniq, const int32_t* __restrict__ count,
+                                    const KeyT* __restrict__ edges, int n_edges, int32_t* __restrict__ bounds) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_edges) return;
+  const KeyT e = edges[r];
+  int lo = 0, hi = count[0];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (uniq[mid] < e) lo = mid + 1; else hi = mid;
+  }
+  bounds[r] = lo;
+}
+
+// in : uniq[N] i32|i64 (ascending, first count entries valid), count[1] i32, edges[E] (uniq dtype)
+// out: bounds[E] i32
+MREC_API int mrec_shard_bounds(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                               void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 4);
+  MREC_REQUIRE((a.is_i32(0) || a.is_i64(0)) && strcmp(a.dtypes[0], a.dtypes[2]) == 0, ERR_DTYPE,
+               "mrec_shard_bounds: uniq and edges must share an integer dtype");
+  MREC_REQUIRE(a.is_i32(1) && a.is_i32(3), ERR_DTYPE, "mrec_shard_bounds: count/bounds must be int32");
+  const int e = (int)a.numel(2);
+  MREC_REQUIRE(a.numel(3) >= e, ERR_SHAPE, "mrec_shard_bounds: bounds must have one entry per edge");
+  if (e == 0) return OK;
+  if (a.is_i32(0)) {
+    MREC_LAUNCH(shard_bounds_kernel<int32_t>, (int)cdiv(e, 128), 128, 0, a.stream, a.ptr<int32_t>(0),
+                a.ptr<int32_t>(1), a.ptr<int32_t>(2), e, a.ptr<int32_t>(3));
+  } else {
+    MREC_LAUNCH(shard_bounds_kernel<int64_t>, (int)cdiv(e, 128), 128, 0, a.stream, a.ptr<int64_t>(0),
+                a.ptr<int32_t>(1), a.ptr<int64_t>(2), e, a.ptr<int32_t>(3));
+  }
+  return check_launch("shard_bounds");
+}

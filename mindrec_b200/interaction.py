@@ -189,23 +189,24 @@ class DeepCrossModel:
         self.embedding_table = Parameter(table, name="deep_embeddinglookup.embedding_table")
         tower_dims = [self.input_size] + list(config.deep_layer_dim)
         head_dims = [self.input_size + config.deep_layer_dim[-1], 1]
+        al = lambda n: (n + 3) // 4 * 4          # keep every block 16-byte aligned inside the flat buffer
         n_tower = DenseStack.numel(tower_dims)
         n_head = DenseStack.numel(head_dims)
-        n_cross = 2 * self.layers * self.input_size
-        self.flat = torch.zeros(n_tower + n_head + n_cross, dtype=torch.float32, device=self.device)
+        lw = al(self.layers * self.input_size)
+        self.flat = torch.zeros(al(n_tower) + al(n_head) + 2 * lw, dtype=torch.float32, device=self.device)
         self.flat_grad = torch.zeros_like(self.flat)
         o = 0
         self.tower = DenseStack(tower_dims, False, self.device, generator=gen, weight_init="normal",
                                 bias_init="normal", last_activation=True,
                                 storage=(self.flat[o:o + n_tower], self.flat_grad[o:o + n_tower]))
-        o += n_tower
+        o += al(n_tower)
         self.head = DenseStack(head_dims, False, self.device, generator=gen, weight_init="normal",
                                bias_init="normal", storage=(self.flat[o:o + n_head], self.flat_grad[o:o + n_head]))
-        o += n_head
+        o += al(n_head)
         lw = self.layers * self.input_size
         self.cross_weight = self.flat[o:o + lw].view(self.layers, self.input_size)
         self.cross_weight_grad = self.flat_grad[o:o + lw].view(self.layers, self.input_size)
-        o += lw
+        o += al(lw)
         self.cross_bias = self.flat[o:o + lw].view(self.layers, self.input_size)
         self.cross_bias_grad = self.flat_grad[o:o + lw].view(self.layers, self.input_size)
         self.cross_weight.normal_(0.0, 0.01, generator=gen)

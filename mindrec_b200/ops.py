@@ -92,6 +92,14 @@ class UniqueResult:
     def outputs(self):
         return [self.uniq, self.inverse, self.count, self.perm, self.seg_start, self.seg_of]
 
+    def sliced(self, n):
+        """A view of these buffers for a dedup of n <= self.n keys (data-dependent sizes without reallocation)."""
+        v = UniqueResult.__new__(UniqueResult)
+        v.n = n
+        v.uniq, v.inverse, v.count = self.uniq[:n], self.inverse[:n], self.count
+        v.perm, v.seg_start, v.seg_of = self.perm[:n], self.seg_start[:n + 1], self.seg_of[:n]
+        return v
+
 
 def unique(ids, table_like=None, result=None):
     """Ascending unique + inverse + stable sort permutation + segment map.
@@ -249,3 +257,11 @@ def cross_bwd(x0, dy, w, b, p, dx=None, dw=None, db=None):
     db = torch.empty((layers, x0.shape[1]), dtype=torch.float32, device=x0.device) if db is None else db
     _lib.aot_call("mrec_cross_bwd", [x0, dy, w, b, p, dx, dw, db, _cross_ws(layers, x0.shape[1], x0.device)])
     return dx, dw, db
+
+
+def shard_bounds(uniq, count, edges, out=None):
+    """bounds[r] = #{i < count : uniq[i] < edges[r]} (device-side lower_bound, no host sync)."""
+    if out is None:
+        out = torch.empty(edges.numel(), dtype=torch.int32, device=uniq.device)
+    _lib.aot_call("mrec_shard_bounds", [uniq, count, edges, out])
+    return out
