@@ -36,7 +36,7 @@ HIDDEN = (1024, 512, 256, 128)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -94,6 +94,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.gpus > 1 and args.vocab_scale == 1.0:
+        args.vocab_scale = float(args.gpus)      # same workload description as our arm at N > 1
     steps = max(1, min(args.steps, 20))
     warmup = max(1, min(args.warmup, 3))
     cb = cpu_baseline_run(args, steps, warmup)
@@ -142,7 +144,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.index)], stdout=self.f,
+                                       "-lms", "20", "-i", str(self.index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -195,6 +197,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the CUDA extension is missing
 
+    if world > 1 and args.vocab_scale == 1.0:
+        args.vocab_scale = float(world)          # weak scaling: rows per GPU fixed at the config-2 table size
     cards = scaled_cards(args.vocab_scale)
     vocab = synth.vocab_size(cards)
     b = args.batch
@@ -227,14 +231,15 @@ def run_ours(args):
 
     # ---- device-resident throughput: W warm-up + K timed graph replays -------------------------
     for i in range(max(3, args.warmup)):
-        step.replay(*devb[i % ring])
+        step.replay(*devb[i % ring], next_batch=devb[(i + 1) % ring])
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    w0 = max(3, args.warmup)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step.replay(*devb[i % ring])
+    for i in range(w0, w0 + args.steps):
+        step.replay(*devb[i % ring], next_batch=devb[(i + 1) % ring])
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -247,15 +252,17 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss D2H ---------
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    if hasattr(step, "_pending"):
+        step._pending = None                                        # drop the look-ahead of the resident loop
     for i in range(3):
-        out = step.replay(*host[i % ring])
+        out = step.replay(*host[i % ring], next_batch=host[(i + 1) % ring])
         loss_host.copy_(out[0].reshape(1), non_blocking=True)
         torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        out = step.replay(*host[i % ring])                         # three pinned H2D copies + graph
+    for i in range(3, 3 + args.steps):
+        out = step.replay(*host[i % ring], next_batch=host[(i + 1) % ring])   # pinned H2D copies + step
         loss_host.copy_(out[0].reshape(1), non_blocking=True)      # loss D2H
         torch.cuda.current_stream().synchronize()                  # the user reads the loss every step
     e1.record()

@@ -235,7 +235,8 @@ class TrainStepWrap:
             self._static_out = self.construct(*self._static)
         return self._static
 
-    def replay(self, batch_ids=None, batch_wts=None, label=None):
+    def replay(self, batch_ids=None, batch_wts=None, label=None, next_batch=None):
+        # next_batch: accepted for call compatibility with sharded.ShardedWideDeepStep (look-ahead dedup)
         if batch_ids is not None:
             self._static[0].copy_(batch_ids, non_blocking=True)
             self._static[1].copy_(batch_wts, non_blocking=True)

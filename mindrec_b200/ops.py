@@ -101,18 +101,19 @@ class UniqueResult:
         return v
 
 
-def unique(ids, table_like=None, result=None):
+def unique(ids, table_like=None, result=None, ws_tag="unique"):
     """Ascending unique + inverse + stable sort permutation + segment map.
 
     With `table_like` (any tensor whose dim 0 is the table's row count V) only ceil(log2(V+1)) key bits
-    are sorted and ids outside [0, V) collapse onto the value V (mrec_unique_bounded).
+    are sorted and ids outside [0, V) collapse onto the value V (mrec_unique_bounded).  `ws_tag` names the
+    cached workspace: calls that may overlap on different streams must use different tags.
     """
     flat = ids.reshape(-1)
     n = flat.numel()
     if result is None:
         result = UniqueResult(n, flat.dtype, flat.device)
     nbytes = _size_fn("mrec_unique_workspace_bytes")(n, flat.element_size())
-    ws = _ws("unique", nbytes, flat.device)
+    ws = _ws(ws_tag, nbytes, flat.device)
     if table_like is None:
         _lib.aot_call("mrec_unique", [flat] + result.outputs() + [ws])
     else:

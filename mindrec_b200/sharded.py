@@ -52,6 +52,26 @@ def _a2a(out, inp, out_splits, in_splits, group):
     return out
 
 
+class BatchPlan:
+    """The data-dependent part of one batch's exchange: dedup result, per-owner split sizes.
+
+    Built by ShardedWideDeepTables.plan_batch — possibly one step ahead, on a side stream with its own
+    communicator — and finalised (one host read of G*(G+1) ints) when the batch is consumed."""
+
+    __slots__ = ("ids", "uq", "bounds_host", "event", "send", "recv", "n_u", "n_r")
+
+    def finalize(self, rank, world):
+        if self.send is not None:
+            return self
+        if self.event is not None:
+            self.event.synchronize()
+        b = self.bounds_host.view(world, world + 1).tolist()
+        self.send = [b[rank][r + 1] - b[rank][r] for r in range(world)]
+        self.recv = [b[r][rank + 1] - b[r][rank] for r in range(world)]
+        self.n_u, self.n_r = b[rank][world], sum(self.recv)
+        return self
+
+
 class ShardedWideDeepTables:
     """The wide (dim 1) and deep (dim D) tables of Wide&Deep, row-sharded, with their FTRL / LazyAdam state.
 
@@ -63,10 +83,14 @@ class ShardedWideDeepTables:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # planning runs on a side stream: it needs its own communicator (NCCL serialises per communicator)
+        self.plan_group = dist.new_group() if (dist.is_initialized() and self.world > 1) else None
         self.plan = ShardPlan(vocab_size, self.world)
         self.k = kernels
         self.dim = emb_dim
         self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.plan_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         r = self.plan.rows_per_rank
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + self.rank)
@@ -79,54 +103,91 @@ class ShardedWideDeepTables:
         # gradients_mean=True: the owner sums contributions of all ranks, each already divided by G
         self.adam_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=self.device)
         self.ftrl_hyper = kernels.ftrl_hyper(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens * self.world, device=self.device)
-        self._edges = None
+        self._bound_like = torch.empty((self.world * r, 0), device=self.device)
+        self._edges = {}
         self._ctx = None
         self._uq = {}
         self._gs = None
+        self._slot = 0
+        self._bufs = {}
+        n_b = self.world * (self.world + 1)
+        self._pinned = [torch.empty(n_b, dtype=torch.int32).pin_memory() for _ in range(2)] if self.cuda else None
 
     def _unique(self, key, table_like, tag):
-        """mrec_unique into cached output buffers (no per-step allocation)."""
+        """mrec_unique into cached, geometrically grown output buffers (no per-step allocation)."""
         n = key.numel()
         if not hasattr(self.k, "UniqueResult"):
             return self.k.unique(key, table_like=table_like)
         base = self._uq.get(tag)
-        if base is None or base.n < n:          # grow geometrically: the owner-side size varies per step
+        if base is None or base.n < n:
             base = self.k.UniqueResult(max(n, int(1.5 * base.n) if base else n), key.dtype, key.device)
             self._uq[tag] = base
-        return self.k.unique(key, table_like=table_like, result=base if base.n == n else base.sliced(n))
+        return self.k.unique(key, table_like=table_like, result=base if base.n == n else base.sliced(n),
+                             ws_tag="unique_" + tag)
+
+    def _buf(self, tag, rows, cols, dtype=torch.float32):
+        """Grow-only [rows, cols] scratch buffer (variable per-step sizes without reallocation)."""
+        b = self._bufs.get(tag)
+        if b is None or b.shape[0] < rows or b.shape[1] != cols:
+            b = torch.empty((max(rows, int(1.5 * b.shape[0]) if b is not None else rows, 1), cols), dtype=dtype,
+                            device=self.device)
+            self._bufs[tag] = b
+        return b
+
+    # ---- planning (may run one batch ahead) ---------------------------------------------------------
+    def plan_batch(self, ids, ahead=False):
+        """Dedup + bucket the batch's keys and exchange the bucket bounds.  With ahead=True the work is queued
+        on the side stream (double-buffered outputs) and the caller keeps enqueuing the current step."""
+        k, g = self.k, self.world
+        plan = BatchPlan()
+        plan.ids, plan.send = ids, None
+        slot = self._slot
+        self._slot ^= 1
+        side = self.plan_stream if (ahead and self.cuda) else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+        ctx = torch.cuda.stream(side) if side is not None else _Null()
+        with ctx:
+            key = self.plan.remap(ids)
+            plan.uq = self._unique(key, self._bound_like, "plan%d" % slot)
+            edges = self._edges.get(key.dtype)
+            if edges is None:
+                edges = self._edges[key.dtype] = self.plan.edges(key)
+            bounds = k.shard_bounds(plan.uq.uniq, plan.uq.count, edges)
+            if g > 1:
+                allb = torch.empty(g * (g + 1), dtype=torch.int32, device=ids.device)
+                dist.all_gather_into_tensor(allb, bounds, group=self.plan_group)
+            else:
+                allb = bounds
+            if self.cuda:
+                plan.bounds_host = self._pinned[slot]
+                plan.bounds_host.copy_(allb, non_blocking=True)
+                plan.event = torch.cuda.Event()
+                plan.event.record()
+            else:
+                plan.bounds_host, plan.event = allb.clone(), None
+        return plan
 
     # ---- forward ----------------------------------------------------------------------------------
-    def lookup(self, ids, wts, wide_bias, deep_dtype=torch.float32):
-        """ids/wts: [B, F] of this rank's batch shard.  Returns (wide_out [B,1], deep_in [B, F*D])."""
+    def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
+        """Fill deep_out [B, F*D] (fp32 | fp16) and wide_out [B,1] for the planned batch."""
         k, g = self.k, self.world
-        b, f = ids.shape
-        key = self.plan.remap(ids)
-        bound_like = torch.empty((g * self.plan.rows_per_rank, 0), device=ids.device)
-        uq = self._unique(key, bound_like, "fwd")
-        if self._edges is None:
-            self._edges = self.plan.edges(key)
-        bounds = k.shard_bounds(uq.uniq, uq.count, self._edges).tolist()      # the step's host read-back
-        n_u = bounds[g]
-        send = [bounds[r + 1] - bounds[r] for r in range(g)]
-        if g > 1:
-            t_send = torch.tensor(send, dtype=torch.int64, device=ids.device)
-            t_recv = torch.empty_like(t_send)
-            dist.all_to_all_single(t_recv, t_send, group=self.group)
-            recv = t_recv.tolist()
-        else:
-            recv = list(send)
-        n_r = sum(recv)
+        plan.finalize(self.rank, g)                                   # the step's one host read-back
+        if plan.event is not None:
+            torch.cuda.current_stream().wait_event(plan.event)
+        uq, n_u, n_r, send, recv = plan.uq, plan.n_u, plan.n_r, plan.send, plan.recv
+        b, f = plan.ids.shape
         local_rows_send = (uq.uniq[:n_u] % self.plan.rows_per_rank).contiguous()
-        rows_recv = torch.empty(n_r, dtype=ids.dtype, device=ids.device)
+        rows_recv = self._buf("rows_recv", n_r, 1, plan.ids.dtype).view(-1)[:n_r]
         if g > 1:
             _a2a(rows_recv, local_rows_send, recv, send, self.group)
         else:
             rows_recv.copy_(local_rows_send)
         # owner side: gather the requested rows of both tables
-        deep_rows = k.gather(self.deep, rows_recv)                            # [n_r, D]
-        wide_rows = k.gather(self.wide, rows_recv)                            # [n_r, 1]
-        got_deep = torch.empty((max(n_u, 1), self.dim), dtype=torch.float32, device=ids.device)
-        got_wide = torch.empty((max(n_u, 1), 1), dtype=torch.float32, device=ids.device)
+        deep_rows = k.gather(self.deep, rows_recv, out=self._buf("deep_rows", n_r, self.dim)[:n_r])
+        wide_rows = k.gather(self.wide, rows_recv, out=self._buf("wide_rows", n_r, 1)[:n_r])
+        got_deep = self._buf("got_deep", n_u, self.dim)
+        got_wide = self._buf("got_wide", n_u, 1)
         if g > 1:
             _a2a(got_deep[:n_u], deep_rows, send, recv, self.group)
             _a2a(got_wide[:n_u], wide_rows, send, recv, self.group)
@@ -135,39 +196,35 @@ class ShardedWideDeepTables:
             got_wide[:n_u].copy_(wide_rows)
         # requester side: expand unique rows to lookups with the inverse index, fused with mask / reduce
         inverse = uq.inverse.view(b, f)
-        deep_in = k.gather_masked(got_deep, inverse, wts, out_dtype=deep_dtype)
-        wide_out = k.gather_reduce(got_wide, inverse, wts, wide_bias)
-        self._ctx = (uq, n_u, send, recv, rows_recv, wts)
-        return wide_out, deep_in
+        k.gather_masked(got_deep[:max(n_u, 1)], inverse, wts, out=deep_out)
+        k.gather_reduce(got_wide[:max(n_u, 1)], inverse, wts, wide_bias, out=wide_out)
+        self._ctx = (plan, rows_recv, wts)
+        return wide_out, deep_out
 
     # ---- backward + update ------------------------------------------------------------------------
     def update(self, delta, gx):
         """delta: [B,1] logit gradient (x sens), gx: [B, F*D] deep-input gradient (x sens, fp32 or fp16)."""
         k, g = self.k, self.world
-        uq, n_u, send, recv, rows_recv, wts = self._ctx
+        plan, rows_recv, wts = self._ctx
+        uq, n_u, n_r, send, recv = plan.uq, plan.n_u, plan.n_r, plan.send, plan.recv
         n = uq.n
         mask = wts.reshape(-1)
-        if self._gs is None or self._gs[0].shape[0] != n:
-            self._gs = (torch.empty((n, self.dim), dtype=torch.float32, device=delta.device),
-                        torch.empty((n, 1), dtype=torch.float32, device=delta.device))
-        gs_deep = k.segment_sum(gx.view(n, self.dim), mask, uq, dim=self.dim, out=self._gs[0])  # first n_u rows valid
-        gs_wide = k.segment_sum(delta, mask, uq, dim=1, out=self._gs[1])
-        n_r = sum(recv)
-        rg_deep = torch.empty((max(n_r, 1), self.dim), dtype=torch.float32, device=delta.device)
-        rg_wide = torch.empty((max(n_r, 1), 1), dtype=torch.float32, device=delta.device)
+        gs_deep = k.segment_sum(gx.view(n, self.dim), mask, uq, dim=self.dim, out=self._buf("gs_deep", n, self.dim))
+        gs_wide = k.segment_sum(delta, mask, uq, dim=1, out=self._buf("gs_wide", n, 1))
+        rg_deep = self._buf("rg_deep", n_r, self.dim)
+        rg_wide = self._buf("rg_wide", n_r, 1)
         if g > 1:
             _a2a(rg_deep[:n_r], gs_deep[:n_u], recv, send, self.group)
             _a2a(rg_wide[:n_r], gs_wide[:n_u], recv, send, self.group)
         else:
             rg_deep[:n_r].copy_(gs_deep[:n_u])
             rg_wide[:n_r].copy_(gs_wide[:n_u])
+        k.adam_begin_step(self.adam_hyper)
         if n_r == 0:
-            k.adam_begin_step(self.adam_hyper)
             return
         # owner side: the same row can arrive from several ranks -> dedup again, then fused row updates
-        uq2 = self._unique(rows_recv, self.deep, "bwd")
+        uq2 = self._unique(rows_recv, self.deep, "owner")
         k.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, rg_wide[:n_r], None, uq2)
-        k.adam_begin_step(self.adam_hyper)
         k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
 
     # ---- test / checkpoint helper -----------------------------------------------------------------
@@ -185,17 +242,30 @@ class ShardedWideDeepTables:
         return wide, deep
 
 
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class ShardedWideDeepStep:
     """Wide&Deep training step with row-sharded tables and a data-parallel DenseLayer stack.  Same call
-    surface as cells.TrainStepWrap (`__call__`, `capture`, `replay`); the step runs eagerly because the
-    all-to-all split sizes are read back every step."""
+    surface as cells.TrainStepWrap (`__call__`, `capture`, `replay`).
+
+    The exchange is eager (its sizes are data dependent); the fixed-shape segment — DenseLayers forward, loss,
+    backward, mean all-reduce of the flat gradient, dense Adam — is captured in a CUDA graph.  `replay` takes
+    the NEXT batch too and plans its dedup one step ahead on a side stream, so the one host read-back per step
+    is already resident when it is needed and the launch pipeline never drains."""
 
     def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
-                 use_mixed_precision=True, group=None, kernels=_cuda_ops):
+                 use_mixed_precision=True, group=None, kernels=_cuda_ops, graph_dense=True):
         from .nn import DenseStack
         self.k = kernels
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device)
         self.sens = float(sens)
         self.fields, self.emb_dim = fields, emb_dim
         self.mixed = use_mixed_precision
@@ -211,39 +281,108 @@ class ShardedWideDeepStep:
         self.dense_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens, device=device)
         self.dense_m = torch.zeros_like(self.dense.flat)
         self.dense_v = torch.zeros_like(self.dense.flat)
-        self._static = None
+        self._use_graph = graph_dense and self.device.type == "cuda"
+        self._graph = None
+        self._calls = 0
+        self._io = None
+        self._slots = None
+        self._pending = None
 
-    def __call__(self, ids, wts, label):
+    # ---- fixed-shape segment -----------------------------------------------------------------------
+    def _dense_segment(self):
         k = self.k
-        b = ids.shape[0]
-        wide_out, deep_in = self.tables.lookup(ids, wts, self.wide_b,
-                                               torch.float16 if self.mixed else torch.float32)
+        deep_in, wide_out, label = self._io["deep_in"], self._io["wide_out"], self._io["label"]
+        b = label.shape[0]
         logit = wide_out + self.dense.forward(deep_in)
         log_loss = torch.clamp(logit, min=0) - logit * label + torch.log1p(torch.exp(-logit.abs()))
         loss = log_loss.mean()
         delta = (torch.sigmoid(logit) - label) * (self.sens / b)
         gx = self.dense.backward(delta)
         self.dense.extra_grad.copy_(delta.sum().reshape(1))
-        self.tables.update(delta, gx)
         if self.world > 1:                          # DistributedGradReducer(mean): wide_and_deep.py:455-470
             dist.all_reduce(self.dense.flat_grad, group=self.group)
             self.dense.flat_grad.div_(self.world)
         k.adam_begin_step(self.dense_hyper)
         k.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self.dense.flat_grad)
+        return loss, delta, gx
+
+    def _run_dense(self):
+        if not self._use_graph:
+            return self._dense_segment()
+        if self._graph is None:
+            if self._calls < 3:                      # eager warm-up (cuBLAS handles, NCCL channels)
+                return self._dense_segment()
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._graph_out = self._dense_segment()
+                self._graph = g
+            except Exception:                        # capture of the collective refused: stay eager
+                self._use_graph = False
+                torch.cuda.synchronize()
+                return self._dense_segment()
+        self._graph.replay()
+        return self._graph_out
+
+    def _ensure_io(self, ids):
+        b = ids.shape[0]
+        if self._io is None or self._io["label"].shape[0] != b:
+            dev = ids.device
+            self._io = dict(
+                deep_in=torch.empty((b, self.fields * self.emb_dim), device=dev,
+                                    dtype=torch.float16 if self.mixed else torch.float32),
+                wide_out=torch.empty((b, 1), dtype=torch.float32, device=dev),
+                label=torch.empty((b, 1), dtype=torch.float32, device=dev))
+            self._graph = None
+
+    def _step(self, plan, wts, label):
+        self._ensure_io(plan.ids)
+        self.tables.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
+        self._io["label"].copy_(label)
+        loss, delta, gx = self._run_dense()
+        self.tables.update(delta, gx)
+        self._calls += 1
         return loss, loss
 
-    def capture(self, ids, wts, label, warmup=3):
-        self._static = (ids.clone(), wts.clone(), label.clone())
-        for _ in range(warmup + 1):
-            self(*self._static)
-        return self._static
+    def __call__(self, ids, wts, label):
+        return self._step(self.tables.plan_batch(ids), wts, label)
 
-    def replay(self, ids=None, wts=None, label=None):
-        if ids is not None:
-            self._static[0].copy_(ids, non_blocking=True)
-            self._static[1].copy_(wts, non_blocking=True)
-            self._static[2].copy_(label, non_blocking=True)
-        return self(*self._static)
+    # ---- bench-facing surface (double-buffered inputs, dedup planned one batch ahead) ----------------
+    def capture(self, ids, wts, label, warmup=3):
+        self._slots = [tuple(t.clone() for t in (ids, wts, label)) for _ in range(2)]
+        self._cur = 0
+        for _ in range(warmup + 1):
+            self(*self._slots[0])
+        self._pending = None
+        return self._slots[0]
+
+    def replay(self, ids=None, wts=None, label=None, next_batch=None):
+        cur = self._slots[self._cur]
+        if self._pending is None:                    # first call, or no look-ahead was given
+            if ids is not None:
+                for d, s in zip(cur, (ids, wts, label)):
+                    d.copy_(s, non_blocking=True)
+            plan = self.tables.plan_batch(cur[0])
+        else:
+            plan = self._pending
+        self._pending = None
+        if next_batch is not None:
+            nxt = self._slots[self._cur ^ 1]
+            side = self.tables.plan_stream
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for d, s in zip(nxt, next_batch):
+                        d.copy_(s, non_blocking=True)
+            else:
+                for d, s in zip(nxt, next_batch):
+                    d.copy_(s)
+            self._pending = self.tables.plan_batch(nxt[0], ahead=True)
+        out = self._step(plan, cur[1], cur[2])
+        if self._pending is not None:
+            self._cur ^= 1
+        return out
 
 
 def build_sharded_wide_deep(batch_size, vocab_size, emb_dim, hidden, device, seed=1):

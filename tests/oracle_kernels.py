@@ -25,7 +25,7 @@ def ftrl_hyper(lr, l1=0.0, l2=0.0, lr_power=-0.5, loss_scale=1.0, device="cpu"):
     return torch.tensor([lr, l1, l2, lr_power, 1.0 / loss_scale] + [0.0] * 11, dtype=torch.float32)
 
 
-def unique(ids, table_like=None, result=None):
+def unique(ids, table_like=None, result=None, ws_tag=None):
     flat = _np(ids).reshape(-1)
     bound = table_like.shape[0] if table_like is not None else None
     uniq, inverse, perm, seg_start = R.unique_sorted(flat, bound)
@@ -51,11 +51,19 @@ def gather(table, ids, out=None, oob_flag=None):
 
 
 def gather_masked(table, ids, mask, out=None, oob_flag=None, out_dtype=torch.float32):
-    return torch.from_numpy(R.gather_masked(_np(table), _np(ids), _np(mask))).to(out_dtype)
+    res = torch.from_numpy(R.gather_masked(_np(table), _np(ids), _np(mask)))
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res.to(out_dtype)
 
 
 def gather_reduce(table, ids, mask, bias, out=None, oob_flag=None):
-    return torch.from_numpy(R.gather_reduce(_np(table), _np(ids), _np(mask), _np(bias)))
+    res = torch.from_numpy(R.gather_reduce(_np(table), _np(ids), _np(mask), _np(bias)))
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def segment_sum(g, mask, uq, dim=None, out=None):
