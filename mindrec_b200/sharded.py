@@ -14,10 +14,16 @@ runs whose boundaries (mrec_shard_bounds) are the all-to-all split sizes, and ke
 local row.  One process per GPU; collectives are torch.distributed (NCCL on the box, gloo in the CPU tests of
 the host logic).  The split sizes are data dependent, so each step reads G+1 ints back to the host.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops as _cuda_ops
+
+# MREC_SHARDED_GRAPH=0 keeps the DenseLayer segment eager; MREC_SHARDED_AHEAD=0 plans every batch in line.
+_ENV_GRAPH = os.environ.get("MREC_SHARDED_GRAPH", "1") != "0"
+_ENV_AHEAD = os.environ.get("MREC_SHARDED_AHEAD", "1") != "0"
 
 
 class ShardPlan:
@@ -281,7 +287,7 @@ class ShardedWideDeepStep:
         self.dense_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens, device=device)
         self.dense_m = torch.zeros_like(self.dense.flat)
         self.dense_v = torch.zeros_like(self.dense.flat)
-        self._use_graph = graph_dense and self.device.type == "cuda"
+        self._use_graph = graph_dense and _ENV_GRAPH and self.device.type == "cuda"
         self._graph = None
         self._calls = 0
         self._io = None
@@ -367,7 +373,7 @@ class ShardedWideDeepStep:
         else:
             plan = self._pending
         self._pending = None
-        if next_batch is not None:
+        if next_batch is not None and _ENV_AHEAD:
             nxt = self._slots[self._cur ^ 1]
             side = self.tables.plan_stream
             if side is not None:
