@@ -81,6 +81,9 @@ int mrec_unique_first(MREC_AOT_ARGS);
  * per-owner runs of the unique keys are found by binary search on the device.
  *   in : uniq[N] (ascending; first count entries valid), count[1] i32, edges[E] (uniq dtype)   out: bounds[E] i32 */
 int mrec_shard_bounds(MREC_AOT_ARGS);
+/* Owner-major key remap, key' = (key mod G) * R + key div G (out-of-range -> G*R):
+ *   in : ids[...] i32|i64, table_like[V,...], owners_like[G,R] (only the shapes are read)   out: keys[...] */
+int mrec_shard_remap(MREC_AOT_ARGS);
 size_t mrec_unique_workspace_bytes(int64_t n, int key_bytes);
 size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes);
 

@@ -602,3 +602,40 @@ MREC_API int mrec_shard_bounds(int nparam, void** params, int* ndims, int64_t** 
   }
   return check_launch("shard_bounds");
 }
+
+// key -> owner-major key' = (key mod G) * R + key div G ; keys outside [0, V) -> G * R (dropped by the bounded dedup)
+template <typename KeyT>
+__global__ void shard_remap_kernel(const KeyT* __restrict__ ids, KeyT* __restrict__ out, int64_t n,
+                                   int64_t vocab, int world, int64_t rows_per_rank) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = (int64_t)ids[i];
+    out[i] = ((uint64_t)k < (uint64_t)vocab) ? (KeyT)((k % world) * rows_per_rank + k / world)
+                                             : (KeyT)((int64_t)world * rows_per_rank);
+  }
+}
+
+// in : ids[...] i32|i64, table_like[V, ...] (dim 0 = global vocab), owners_like[G, R] (dims = world size, rows per rank)
+// out: keys[...] (ids dtype)
+MREC_API int mrec_shard_remap(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                              void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 4) return fail(ERR_NPARAM, "mrec_shard_remap: expected 4 params, got %d", a.nparam);
+  MREC_REQUIRE((a.is_i32(0) || a.is_i64(0)) && strcmp(a.dtypes[0], a.dtypes[3]) == 0, ERR_DTYPE,
+               "mrec_shard_remap: ids/keys must share an integer dtype");
+  MREC_REQUIRE(a.ndims[1] >= 1 && a.ndims[2] >= 2, ERR_SHAPE, "mrec_shard_remap: table_like[V,..], owners_like[G,R,..]");
+  const int64_t n = a.numel(0), vocab = a.dim(1, 0), rows = a.dim(2, 1);
+  const int world = (int)a.dim(2, 0);
+  MREC_REQUIRE(a.numel(3) == n, ERR_SHAPE, "mrec_shard_remap: keys must match ids");
+  MREC_REQUIRE(world >= 1 && rows * world >= vocab, ERR_SHAPE, "mrec_shard_remap: G * R must cover V");
+  if (a.is_i32(0)) MREC_REQUIRE((int64_t)world * rows < 0x7fffffffll, ERR_SHAPE, "mrec_shard_remap: G*R exceeds int32");
+  if (n == 0) return OK;
+  if (!a.params[0] || !a.params[3]) return fail(ERR_NULL, "mrec_shard_remap: null ids/keys");
+  if (a.is_i32(0)) {
+    MREC_LAUNCH(shard_remap_kernel<int32_t>, grid_for(cdiv(n, 256), 8), 256, 0, a.stream, a.ptr<int32_t>(0),
+                a.ptr<int32_t>(3), n, vocab, world, rows);
+  } else {
+    MREC_LAUNCH(shard_remap_kernel<int64_t>, grid_for(cdiv(n, 256), 8), 256, 0, a.stream, a.ptr<int64_t>(0),
+                a.ptr<int64_t>(3), n, vocab, world, rows);
+  }
+  return check_launch("shard_remap");
+}

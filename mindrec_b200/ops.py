@@ -266,3 +266,11 @@ def shard_bounds(uniq, count, edges, out=None):
         out = torch.empty(edges.numel(), dtype=torch.int32, device=uniq.device)
     _lib.aot_call("mrec_shard_bounds", [uniq, count, edges, out])
     return out
+
+
+def shard_remap(ids, table_like, owners_like, out=None):
+    """key -> (key mod G) * R + key div G with G, R = owners_like.shape (out-of-range keys -> G * R)."""
+    if out is None:
+        out = torch.empty_like(ids)
+    _lib.aot_call("mrec_shard_remap", [ids, table_like, owners_like, out])
+    return out

@@ -110,6 +110,8 @@ class ShardedWideDeepTables:
         self.adam_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=self.device)
         self.ftrl_hyper = kernels.ftrl_hyper(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens * self.world, device=self.device)
         self._bound_like = torch.empty((self.world * r, 0), device=self.device)
+        self._vocab_like = torch.empty((vocab_size, 0), device=self.device)
+        self._owners_like = torch.empty((self.world, r, 0), device=self.device)   # shape carrier: G, R
         self._edges = {}
         self._ctx = None
         self._uq = {}
@@ -154,7 +156,7 @@ class ShardedWideDeepTables:
             side.wait_stream(torch.cuda.current_stream())
         ctx = torch.cuda.stream(side) if side is not None else _Null()
         with ctx:
-            key = self.plan.remap(ids)
+            key = k.shard_remap(ids, self._vocab_like, self._owners_like)
             plan.uq = self._unique(key, self._bound_like, "plan%d" % slot)
             edges = self._edges.get(key.dtype)
             if edges is None:
@@ -284,7 +286,8 @@ class ShardedWideDeepStep:
                                 bias_init="normal", extra=1)
         self.wide_b = self.dense.extra
         self.wide_b.normal_(0.0, 0.01, generator=gen)
-        self.dense_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens, device=device)
+        # the mean of DistributedGradReducer is folded into the gradient scale: 1 / (sens * G)
+        self.dense_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=device)
         self.dense_m = torch.zeros_like(self.dense.flat)
         self.dense_v = torch.zeros_like(self.dense.flat)
         self._use_graph = graph_dense and _ENV_GRAPH and self.device.type == "cuda"
@@ -305,12 +308,14 @@ class ShardedWideDeepStep:
         delta = (torch.sigmoid(logit) - label) * (self.sens / b)
         gx = self.dense.backward(delta)
         self.dense.extra_grad.copy_(delta.sum().reshape(1))
+        return loss, delta, gx
+
+    def _dense_update(self):
+        k = self.k
         if self.world > 1:                          # DistributedGradReducer(mean): wide_and_deep.py:455-470
-            dist.all_reduce(self.dense.flat_grad, group=self.group)
-            self.dense.flat_grad.div_(self.world)
+            dist.all_reduce(self.dense.flat_grad, group=self.group)   # eager: capturing it in the graph hangs
         k.adam_begin_step(self.dense_hyper)
         k.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self.dense.flat_grad)
-        return loss, delta, gx
 
     def _run_dense(self):
         if not self._use_graph:
@@ -324,7 +329,7 @@ class ShardedWideDeepStep:
                 with torch.cuda.graph(g):
                     self._graph_out = self._dense_segment()
                 self._graph = g
-            except Exception:                        # capture of the collective refused: stay eager
+            except Exception:                        # capture refused: stay eager
                 self._use_graph = False
                 torch.cuda.synchronize()
                 return self._dense_segment()
@@ -347,6 +352,7 @@ class ShardedWideDeepStep:
         self.tables.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
         self._io["label"].copy_(label)
         loss, delta, gx = self._run_dense()
+        self._dense_update()
         self.tables.update(delta, gx)
         self._calls += 1
         return loss, loss

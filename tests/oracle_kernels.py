@@ -110,3 +110,11 @@ def adam_dense(w, m, v, hyper, g):
     wn, mn, vn = _np(w), _np(m), _np(v)
     R.adam_dense(wn, mn, vn, _np(g), _state(hyper))
     w.copy_(torch.from_numpy(wn)); m.copy_(torch.from_numpy(mn)); v.copy_(torch.from_numpy(vn))
+
+
+def shard_remap(ids, table_like, owners_like, out=None):
+    g, r = owners_like.shape[0], owners_like.shape[1]
+    v = table_like.shape[0]
+    ok = (ids >= 0) & (ids < v)
+    km = (ids % g) * r + torch.div(ids, g, rounding_mode="floor")
+    return torch.where(ok, km, torch.full_like(ids, g * r))

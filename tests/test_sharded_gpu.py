@@ -36,3 +36,11 @@ def test_shard_bounds_kernel(cuda):
     count = torch.tensor([5], dtype=torch.int32, device=cuda)
     edges = torch.tensor([0, 100, 200, 300, 400], dtype=torch.int32, device=cuda)
     assert ops.shard_bounds(uniq, count, edges).tolist() == [0, 2, 3, 4, 5]
+
+
+def test_shard_remap_kernel_matches_plan(cuda):
+    from mindrec_b200 import ops
+    plan = sharded.ShardPlan(1000, 8)
+    ids = torch.arange(-3, 1005, dtype=torch.int32, device=cuda)
+    got = ops.shard_remap(ids, torch.empty((1000, 0), device=cuda), torch.empty((8, plan.rows_per_rank, 0), device=cuda))
+    assert torch.equal(got, plan.remap(ids))
