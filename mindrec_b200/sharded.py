@@ -296,6 +296,7 @@ class ShardedWideDeepStep:
         self._io = None
         self._slots = None
         self._pending = None
+        self.profile = None          # cells.StepProfile: per-phase CUDA-event timing of eager calls
 
     # ---- fixed-shape segment -----------------------------------------------------------------------
     def _dense_segment(self):
@@ -347,18 +348,27 @@ class ShardedWideDeepStep:
                 label=torch.empty((b, 1), dtype=torch.float32, device=dev))
             self._graph = None
 
+    def _range(self, name):
+        return self.profile.range(name) if self.profile is not None else _Null()
+
     def _step(self, plan, wts, label):
         self._ensure_io(plan.ids)
-        self.tables.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
-        self._io["label"].copy_(label)
-        loss, delta, gx = self._run_dense()
-        self._dense_update()
-        self.tables.update(delta, gx)
+        with self._range("exchange_forward"):
+            self.tables.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
+        with self._range("dense_fwd_bwd"):
+            self._io["label"].copy_(label)
+            loss, delta, gx = self._run_dense()
+        with self._range("dense_allreduce_adam"):
+            self._dense_update()
+        with self._range("exchange_backward_update"):
+            self.tables.update(delta, gx)
         self._calls += 1
         return loss, loss
 
     def __call__(self, ids, wts, label):
-        return self._step(self.tables.plan_batch(ids), wts, label)
+        with self._range("plan_dedup"):
+            plan = self.tables.plan_batch(ids)
+        return self._step(plan, wts, label)
 
     # ---- bench-facing surface (double-buffered inputs, dedup planned one batch ahead) ----------------
     def capture(self, ids, wts, label, warmup=3):
