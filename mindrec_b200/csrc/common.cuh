@@ -129,6 +129,17 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
   return r;
 }
 
+// Scheduling fence: an empty volatile asm that "rewrites" the registers of a loaded value.  Volatile asms keep
+// their program order, so placing these after a batch of (volatile) loads forces every load of the batch to
+// be issued before the first use of any of them — without it nvcc interleaves load/use pairs to save
+// registers and a thread has only one or two loads in flight (seen in SASS and in ncu's source view).
+__device__ __forceinline__ void reg_fence(float4& v) {
+  asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w));
+}
+__device__ __forceinline__ void reg_fence(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void reg_fence(uint2& v) { asm volatile("" : "+r"(v.x), "+r"(v.y)); }
+__device__ __forceinline__ void reg_fence(int& v) { asm volatile("" : "+r"(v)); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -142,6 +142,10 @@ cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, cons
         const int i = tid + k * kCrossThreads;
         x[r][k] = (i < dpv && row0 + r < batch) ? CrV<Vec>::ld_stream(x0, (row0 + r) * dpv + i) : CrV<Vec>::zero();
       }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) reg_fence(x[r][k]);
     float p[R * L];
 #pragma unroll
     for (int i = 0; i < R * L; ++i) p[i] = 0.f;
@@ -214,6 +218,13 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
         const bool ok = (i < dpv) && (row0 + r < batch);
         x[r][k] = ok ? CrV<Vec>::ld_stream(x0, (row0 + r) * dpv + i) : CrV<Vec>::zero();
         g[r][k] = ok ? CrV<Vec>::ld_stream(dy, (row0 + r) * dpv + i) : CrV<Vec>::zero();
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) {
+        reg_fence(x[r][k]);
+        reg_fence(g[r][k]);
       }
     float rr[R];
 #pragma unroll

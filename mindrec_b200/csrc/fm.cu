@@ -24,7 +24,10 @@ template <> struct FmV<float4> {
     return ld_stream_f4(reinterpret_cast<const float4*>(p) + i);
   }
   static __device__ __forceinline__ float4 ld_cached(const float* p, int64_t i) {
-    return reinterpret_cast<const float4*>(p)[i];
+    float4 r;
+    asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4*>(p) + i));
+    return r;
   }
   static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
   static __device__ __forceinline__ void acc(float4& s, float4& s2, const float4& x) {
@@ -88,14 +91,19 @@ fm_kernel(const float* __restrict__ vx, const float* __restrict__ gout, float* _
     const int64_t base = b * fields * cpr + c;
     if (live) {
       for (int f0 = 0; f0 < fields; f0 += kFmBatch) {
+        // fields past the end are clamped to the last one (and skipped below): all loads unconditional
         Vec x[kFmBatch];
 #pragma unroll
-        for (int k = 0; k < kFmBatch; ++k)
-          x[k] = (f0 + k >= fields) ? FmV<Vec>::zero()
-                 : BACKWARD ? FmV<Vec>::ld_cached(vx, base + (int64_t)(f0 + k) * cpr)  // keep for pass 2
-                            : FmV<Vec>::ld(vx, base + (int64_t)(f0 + k) * cpr);
+        for (int k = 0; k < kFmBatch; ++k) {
+          const int f = min(f0 + k, fields - 1);
+          x[k] = BACKWARD ? FmV<Vec>::ld_cached(vx, base + (int64_t)f * cpr)  // keep in L1 for pass 2
+                          : FmV<Vec>::ld(vx, base + (int64_t)f * cpr);
+        }
 #pragma unroll
-        for (int k = 0; k < kFmBatch; ++k) FmV<Vec>::acc(s, s2, x[k]);
+        for (int k = 0; k < kFmBatch; ++k) reg_fence(x[k]);
+#pragma unroll
+        for (int k = 0; k < kFmBatch; ++k)
+          if (f0 + k < fields) FmV<Vec>::acc(s, s2, x[k]);
       }
     }
     if (!BACKWARD) {
@@ -113,7 +121,9 @@ fm_kernel(const float* __restrict__ vx, const float* __restrict__ gout, float* _
         Vec x[kFmBatch];
 #pragma unroll
         for (int k = 0; k < kFmBatch; ++k)
-          x[k] = (f0 + k < fields) ? FmV<Vec>::ld_cached(vx, base + (int64_t)(f0 + k) * cpr) : FmV<Vec>::zero();
+          x[k] = FmV<Vec>::ld_cached(vx, base + (int64_t)min(f0 + k, fields - 1) * cpr);
+#pragma unroll
+        for (int k = 0; k < kFmBatch; ++k) reg_fence(x[k]);
 #pragma unroll
         for (int k = 0; k < kFmBatch; ++k)
           if (f0 + k < fields) FmV<Vec>::st_grad(dvx, base + (int64_t)(f0 + k) * cpr, g, s, x[k], addend, add16);

@@ -45,13 +45,21 @@ template <> struct VOps<float4> {
   }
   // gradient rows: fp32, or fp16 (the DenseLayer backward emits fp16 when use_mixed_precision; the
   // Cast-to-fp32 of wide_and_deep.py:119 bprop is fused into this load)
-  static __device__ __forceinline__ float4 ldg(const float* g, int64_t chunk) {
+  // Raw loads are kept apart from the conversion so that a batch of loads can be issued back to back
+  // (ncu r1c: with load + convert inside one conditional the compiler serialised all 8 row loads).
+  using RawF = float4;
+  using RawH = uint2;
+  static __device__ __forceinline__ float4 ld_raw(const float* g, int64_t chunk) {
     return ld_stream_f4(reinterpret_cast<const float4*>(g) + chunk);
   }
-  static __device__ __forceinline__ float4 ldg(const __half* g, int64_t chunk) {
+  static __device__ __forceinline__ uint2 ld_raw(const __half* g, int64_t chunk) {
     uint2 u;
     asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];"
                  : "=r"(u.x), "=r"(u.y) : "l"(reinterpret_cast<const uint2*>(g) + chunk));
+    return u;
+  }
+  static __device__ __forceinline__ float4 cvt(const float4& r) { return r; }
+  static __device__ __forceinline__ float4 cvt(const uint2& u) {
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
     return make_float4(a.x, a.y, b.x, b.y);
@@ -61,8 +69,9 @@ template <> struct VOps<float> {
   static __device__ __forceinline__ float zero() { return 0.f; }
   static __device__ __forceinline__ void fma(float& a, const float& x, float s) { a = fmaf(x, s, a); }
   static __device__ __forceinline__ void add(float& a, const float& x) { a += x; }
-  static __device__ __forceinline__ float ldg(const float* g, int64_t i) { return ld_stream_f1(g + i); }
-  static __device__ __forceinline__ float ldg(const __half* g, int64_t i) { return __half2float(g[i]); }
+  static __device__ __forceinline__ float ld_raw(const float* g, int64_t i) { return ld_stream_f1(g + i); }
+  static __device__ __forceinline__ float ld_raw(const __half* g, int64_t i) { return __half2float(g[i]); }
+  static __device__ __forceinline__ float cvt(const float& r) { return r; }
 };
 
 // ---- hyper-parameter blocks (device f32 tensors, so schedules / bias-correction never sync the host)
@@ -193,40 +202,38 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
   Vec acc = VOps<Vec>::zero();
 
   for (int64_t b0 = pos0; b0 < pos1; b0 += kSegBatch) {
+    // Positions past the end of the tile are clamped to its last position with a zero weight: every load
+    // of the batch is unconditional, so all kSegBatch row loads are in flight together.
     int seg[kSegBatch];
     int32_t p[kSegBatch];
-    Vec gv[kSegBatch];
     float mk[kSegBatch];
+    decltype(VOps<Vec>::ld_raw(g, 0)) raw[kSegBatch];
 #pragma unroll
     for (int k = 0; k < kSegBatch; ++k) {
-      const int64_t i = b0 + k;
-      seg[k] = (i < pos1) ? seg_of[i] : -1;
-      p[k] = (i < pos1) ? perm[i] : 0;
+      const int64_t i = min(b0 + k, pos1 - 1);
+      seg[k] = seg_of[i];
+      p[k] = perm[i];
     }
 #pragma unroll
     for (int k = 0; k < kSegBatch; ++k) {
-      if (seg[k] >= 0) {
-        const int64_t grow = (div == 1) ? (int64_t)p[k] : (int64_t)(p[k] / div);
-        gv[k] = VOps<Vec>::ldg(g, grow * cpr + c);
-        mk[k] = HAS_MASK ? mask[p[k]] : 1.f;
-      } else {
-        gv[k] = VOps<Vec>::zero();
-        mk[k] = 0.f;
-      }
+      const int64_t grow = (div == 1) ? (int64_t)p[k] : (int64_t)(p[k] / div);
+      raw[k] = VOps<Vec>::ld_raw(g, grow * cpr + c);
+      mk[k] = HAS_MASK ? mask[p[k]] : 1.f;
     }
 #pragma unroll
+    for (int k = 0; k < kSegBatch; ++k) reg_fence(raw[k]);
+#pragma unroll
     for (int k = 0; k < kSegBatch; ++k) {
-      if (seg[k] >= 0) {
-        if (seg[k] != cur) {
-          // run [.., here) ended inside the tile
-          if (enters) part[(j * 2 + 0) * cpr + c] = acc;
-          else gsum[(int64_t)cur * cpr + c] = acc;
-          cur = seg[k];
-          enters = false;
-          acc = VOps<Vec>::zero();
-        }
-        VOps<Vec>::fma(acc, gv[k], mk[k]);
+      if (b0 + k >= pos1) mk[k] = 0.f;
+      if (seg[k] != cur) {
+        // run [.., here) ended inside the tile
+        if (enters) part[(j * 2 + 0) * cpr + c] = acc;
+        else gsum[(int64_t)cur * cpr + c] = acc;
+        cur = seg[k];
+        enters = false;
+        acc = VOps<Vec>::zero();
       }
+      VOps<Vec>::fma(acc, VOps<Vec>::cvt(raw[k]), mk[k]);
     }
   }
   const bool leaves = (pos1 < n) && (seg_of[pos1] == cur);
