@@ -12,13 +12,13 @@
 // (one float4 column chunk each) walks a tile in order, accumulating mask[p] * g[p] for each run of equal
 // keys, 8 independent row loads in flight per thread:
 //   * a run that starts and ends inside the tile is complete: its sum is stored to gsum[segment];
-//   * a run that crosses a tile edge writes a partial (at most 2 per tile); a second kernel, launched
-//     over tiles, lets the tile in which such a segment starts add the partials in tile order; chains
-//     longer than kLongChain tiles (Zipf head keys, the 13 dense Criteo fields that appear once per
-//     sample) go to a third kernel that sums them with a fixed-shape CTA reduction.
-// Phase 2 (row update).  One thread group per unique row reads gsum[u] (still L2-resident: U*D*4 bytes,
-// 39 MB at BASELINE config 2 against a 126 MB L2) and w/m/v[uniq[u]] as four independent 16-byte loads
-// and writes the LazyAdam / FTRL result.  Splitting the update from the tile walk removes the dependent
+//   * a run that crosses a tile edge writes a partial (at most 2 per tile).
+// Phase 2 (finish + row update, one launch).  One thread group per unique row reads gsum[u] (still
+// L2-resident: U*D*4 bytes, 39 MB at BASELINE config 2 against a 126 MB L2) — or adds the partials of a
+// short chain in tile order — and w/m/v[uniq[u]] as independent 16-byte loads, and writes the LazyAdam /
+// FTRL result.  Chains longer than kLongChain tiles (Zipf head keys, the 13 dense Criteo fields that
+// appear once per sample) are listed by phase 1 and reduced by a few dedicated CTAs of the same launch
+// with a fixed-shape tree.  Splitting the update from the tile walk removes the dependent
 // load chain that an in-line update puts after every run (ncu r1a: 110 regs, 22 % warps active, 17 %
 // of DRAM peak when fused) and lets both phases run at full memory-level parallelism.
 // No atomics touch floating-point data: the summation order depends only on the sorted order, so the
@@ -110,6 +110,7 @@ __device__ __forceinline__ void ftrl_elem(float& w, float& a, float& lin, float 
 template <typename Vec, typename IdT> struct LazyAdamSink;
 template <typename IdT>
 struct LazyAdamSink<float4, IdT> {
+  static constexpr bool kApplyComplete = true;
   float4* w; float4* m; float4* v;
   const IdT* uniq;
   const float* hyper;
@@ -131,6 +132,7 @@ struct LazyAdamSink<float4, IdT> {
 };
 template <typename IdT>
 struct LazyAdamSink<float, IdT> {
+  static constexpr bool kApplyComplete = true;
   float* w; float* m; float* v;
   const IdT* uniq;
   const float* hyper;
@@ -149,6 +151,7 @@ struct LazyAdamSink<float, IdT> {
 template <typename Vec, typename IdT> struct FtrlSink;
 template <typename IdT>
 struct FtrlSink<float4, IdT> {
+  static constexpr bool kApplyComplete = true;
   float4* w; float4* acc; float4* lin;
   const IdT* uniq;
   const float* hyper;
@@ -169,6 +172,7 @@ struct FtrlSink<float4, IdT> {
 };
 template <typename IdT>
 struct FtrlSink<float, IdT> {
+  static constexpr bool kApplyComplete = true;
   float* w; float* acc; float* lin;
   const IdT* uniq;
   const float* hyper;
@@ -188,8 +192,9 @@ struct FtrlSink<float, IdT> {
 template <typename Vec, typename GT, bool HAS_MASK>
 __global__ void __launch_bounds__(kSegThreads, 3)
 segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __restrict__ mask,
-                    const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of, int64_t n,
-                    int64_t n_tiles, Vec* __restrict__ part, Vec* __restrict__ gsum) {
+                    const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
+                    const int32_t* __restrict__ seg_start, int64_t n, int64_t n_tiles, Vec* __restrict__ part,
+                    Vec* __restrict__ gsum, int32_t* __restrict__ long_list, int32_t* __restrict__ long_count) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t j = gid / cpr;
   if (j >= n_tiles) return;
@@ -237,99 +242,96 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
     }
   }
   const bool leaves = (pos1 < n) && (seg_of[pos1] == cur);
-  if (enters) part[(j * 2 + 0) * cpr + c] = acc;        // entered (and maybe also leaves): slot 0
-  else if (leaves) part[(j * 2 + 1) * cpr + c] = acc;   // starts here, continues right: slot 1
-  else gsum[(int64_t)cur * cpr + c] = acc;
-}
-
-// ---- kernel B: short partial chains, one thread group per tile in which a crossing segment starts
-template <typename Vec>
-__global__ void __launch_bounds__(kSegThreads)
-segsum_boundary_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
-                       int64_t n, int64_t n_tiles, const Vec* __restrict__ part,
-                       int32_t* __restrict__ long_list, int32_t* __restrict__ long_count,
-                       Vec* __restrict__ gsum) {
-  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t j = gid / cpr;
-  if (j >= n_tiles) return;
-  const int c = (int)(gid - j * cpr);
-  const int64_t pos0 = j * kSegTile;
-  const int64_t pos1 = pos0 + kSegTile;
-  if (pos1 >= n) return;
-  const int s = seg_of[pos1 - 1];
-  if (seg_of[pos1] != s) return;         // nothing leaves this tile
-  if (seg_start[s] < pos0) return;       // it entered from the left: an earlier tile owns it
-  const int64_t j_last = ((int64_t)seg_start[s + 1] - 1) / kSegTile;
-  if (j_last - j > kLongChain) {
-    if (c == 0) long_list[atomicAdd(long_count, 1)] = (int32_t)j;
-    return;
-  }
-  Vec acc = part[(j * 2 + 1) * cpr + c];
-  for (int64_t jj = j + 1; jj <= j_last; ++jj) VOps<Vec>::add(acc, part[(jj * 2 + 0) * cpr + c]);
-  gsum[(int64_t)s * cpr + c] = acc;
-}
-
-// ---- kernel C: long chains, one 1024-thread CTA per segment, fixed-shape reduction ----
-// Group q of the CTA adds pieces q, q+G, q+2G, ... (4 independent loads in flight), then the G group
-// partials are added in group order: the shape depends only on (pieces, G), never on timing.
-constexpr int kLongThreads = 1024;
-constexpr int kLongGroups = 64;
-template <typename Vec>
-__global__ void __launch_bounds__(kLongThreads)
-segsum_long_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
-                   const Vec* __restrict__ part, const int32_t* __restrict__ long_list,
-                   const int32_t* __restrict__ long_count, Vec* __restrict__ gsum) {
-  __shared__ Vec s_part[kLongThreads];
-  const int groups = min(kLongThreads / cpr, kLongGroups);
-  const int gi = threadIdx.x / cpr;
-  const int c = threadIdx.x - gi * cpr;
-  const int n_long = *long_count;
-  for (int idx = blockIdx.x; idx < n_long; idx += gridDim.x) {
-    const int64_t j = long_list[idx];
-    const int s = seg_of[(j + 1) * kSegTile - 1];
-    const int64_t j_last = ((int64_t)seg_start[s + 1] - 1) / kSegTile;
-    const int64_t pieces = j_last - j + 1;  // piece 0 = slot 1 of tile j, piece k = slot 0 of tile j+k
-    if (gi < groups) {
-      Vec acc = VOps<Vec>::zero();
-      for (int64_t k0 = gi; k0 < pieces; k0 += 4 * (int64_t)groups) {
-        Vec v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int64_t k = k0 + (int64_t)q * groups;
-          v[q] = VOps<Vec>::zero();
-          if (k < pieces) {
-            const int64_t slot = (k == 0) ? (j * 2 + 1) : ((j + k) * 2 + 0);
-            v[q] = part[slot * cpr + c];
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) VOps<Vec>::add(acc, v[q]);
-      }
-      s_part[gi * cpr + c] = acc;
+  if (enters) {
+    part[(j * 2 + 0) * cpr + c] = acc;                   // entered (and maybe also leaves): slot 0
+  } else if (leaves) {
+    part[(j * 2 + 1) * cpr + c] = acc;                   // starts here, continues right: slot 1
+    if (c == 0) {                                        // chains of more than kLongChain tiles get a CTA each
+      const int64_t j_last = ((int64_t)seg_start[cur + 1] - 1) / kSegTile;
+      if (j_last - j > kLongChain) long_list[atomicAdd(long_count, 1)] = cur;
     }
-    __syncthreads();
-    if (gi == 0) {
-      Vec acc = s_part[c];
-      for (int q = 1; q < groups; ++q) VOps<Vec>::add(acc, s_part[q * cpr + c]);
-      gsum[(int64_t)s * cpr + c] = acc;
-    }
-    __syncthreads();
+  } else {
+    gsum[(int64_t)cur * cpr + c] = acc;
   }
 }
 
-// ---- phase 2: one thread group per unique row ----
+// ---- kernel B: finish every segment and hand its sum to the sink -------------------------------------
+// A segment [s, e) of the sorted order is "complete" when it lies inside one tile (its sum is already in
+// gsum), else it is a chain of partials: slot 1 of tile s/32, then slot 0 of every following tile up to
+// (e-1)/32, added in tile order.
+//   * blocks >= kChainBlocks: one D/4-thread group per unique row; complete rows and chains of up to
+//     kLongChain tiles are summed in line (independent loads, fixed order) and passed to sink.apply();
+//   * blocks <  kChainBlocks: one CTA per entry of the long-chain list (Zipf head keys, the dense Criteo
+//     fields): group q adds pieces q, q+G, ... with 4 loads in flight, the G group partials are added in
+//     group order, then sink.apply().  These CTAs run concurrently with the row groups of the same launch.
+// Sink::kApplyComplete = false (plain segment-sum into gsum) skips rows whose sum is already stored.
+constexpr int kChainBlocks = 64;
+
 template <typename Vec, typename Sink>
 __global__ void __launch_bounds__(kSegThreads)
-rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, int64_t n, const Vec* __restrict__ gsum,
-                   Sink sink) {
+rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
+                   int64_t n, const Vec* __restrict__ gsum, const Vec* __restrict__ part,
+                   const int32_t* __restrict__ long_list, const int32_t* __restrict__ long_count, Sink sink) {
+  __shared__ Vec s_part[kSegThreads];
+  const int gi = threadIdx.x / cpr;
+  const int c = threadIdx.x - gi * cpr;
+  const int groups = kSegThreads / cpr;
+  if (blockIdx.x < kChainBlocks) {
+    const int n_long = *long_count;
+    const int lg = min(groups, 32);
+    for (int idx = blockIdx.x; idx < n_long; idx += kChainBlocks) {
+      const int u = long_list[idx];
+      const int64_t j = seg_start[u] / kSegTile;
+      const int64_t pieces = ((int64_t)seg_start[u + 1] - 1) / kSegTile - j + 1;
+      if (gi < lg) {
+        Vec acc = VOps<Vec>::zero();
+        for (int64_t k0 = gi; k0 < pieces; k0 += 4 * (int64_t)lg) {
+          Vec v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int64_t k = k0 + (int64_t)q * lg;
+            v[q] = VOps<Vec>::zero();
+            if (k < pieces) v[q] = part[((k == 0) ? (j * 2 + 1) : ((j + k) * 2)) * cpr + c];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) VOps<Vec>::add(acc, v[q]);
+        }
+        s_part[gi * cpr + c] = acc;
+      }
+      __syncthreads();
+      if (gi == 0) {
+        Vec acc = s_part[c];
+        for (int q = 1; q < lg; ++q) VOps<Vec>::add(acc, s_part[q * cpr + c]);
+        sink.apply(u, c, acc);
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  if (gi >= groups) return;
   const int n_seg = seg_of[n - 1] + 1;  // U: segment id of the last sorted position + 1
-  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / cpr;
-  const int64_t grp = gid / cpr;
-  if (grp >= n_groups) return;
-  const int c = (int)(gid - grp * cpr);
-  for (int64_t u = grp; u < n_seg; u += n_groups) sink.apply((int)u, c, gsum[u * cpr + c]);
+  const int64_t n_groups = (int64_t)(gridDim.x - kChainBlocks) * groups;
+  for (int64_t u = (int64_t)(blockIdx.x - kChainBlocks) * groups + gi; u < n_seg; u += n_groups) {
+    const int64_t j0 = seg_start[u] / kSegTile;
+    const int64_t j1 = ((int64_t)seg_start[u + 1] - 1) / kSegTile;
+    if (j0 == j1) {
+      if (Sink::kApplyComplete) sink.apply((int)u, c, gsum[u * cpr + c]);
+    } else if (j1 - j0 <= kLongChain) {
+      Vec acc = part[(j0 * 2 + 1) * cpr + c];
+      for (int64_t jj = j0 + 1; jj <= j1; ++jj) VOps<Vec>::add(acc, part[(jj * 2) * cpr + c]);
+      sink.apply((int)u, c, acc);
+    }
+  }
 }
+
+// plain segment-sum: gsum[u] = total (complete rows are already in place)
+template <typename Vec>
+struct StoreSink {
+  static constexpr bool kApplyComplete = false;
+  Vec* out;
+  int cpr;
+  __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const { out[(int64_t)seg * cpr + c] = gs; }
+};
 
 struct SegWorkspace {
   size_t off_part, off_list, off_count, off_gsum, total;
@@ -349,39 +351,10 @@ static SegWorkspace seg_ws(int64_t n, int dim, bool with_gsum) {
 size_t sparse_opt_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim, true).total; }
 size_t segment_sum_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim, false).total; }
 
-// Phase 1 into `gsum` ([U, dim], caller buffer or workspace).
-template <typename Vec, typename GT>
-static int run_segment_sum(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
-                           const int32_t* seg_start, const int32_t* seg_of, int64_t n, char* w,
-                           const SegWorkspace& W, Vec* gsum, cudaStream_t stream) {
-  const int vec = sizeof(Vec) / 4;
-  const int cpr = dim / vec;
-  Vec* part = reinterpret_cast<Vec*>(w + W.off_part);
-  int32_t* long_list = reinterpret_cast<int32_t*>(w + W.off_list);
-  int32_t* long_count = reinterpret_cast<int32_t*>(w + W.off_count);
-  const int64_t n_tiles = cdiv(n, kSegTile);
-  const int64_t threads = n_tiles * cpr;
-  const int grid = (int)cdiv(threads, kSegThreads);
-  cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
-  if (mask) {
-    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
-                seg_of, n, n_tiles, part, gsum);
-  } else {
-    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, false>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
-                seg_of, n, n_tiles, part, gsum);
-  }
-  if (n_tiles > 1) {
-    MREC_LAUNCH((segsum_boundary_kernel<Vec>), grid, kSegThreads, 0, stream, cpr, seg_of, seg_start, n,
-                n_tiles, part, long_list, long_count, gsum);
-    MREC_LAUNCH((segsum_long_kernel<Vec>), kNumSMs, kLongThreads, 0, stream, cpr, seg_of, seg_start,
-                part, long_list, long_count, gsum);
-  }
-  return OK;
-}
-
 struct NoSink {};
 
-// Sink = NoSink: stand-alone segment sum into `out`; otherwise phase 1 into the workspace + phase 2.
+// Sink = NoSink: stand-alone segment sum into `out`; otherwise the sums go to the workspace and the sink
+// (optimizer update) is applied per unique row.  Two launches: tile walk, then finish + sink.
 template <typename Vec, typename GT, typename Sink>
 static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
                         const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws,
@@ -395,11 +368,31 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
     return fail(ERR_ALIGN, "sparse update: workspace must be 16-byte aligned");
   char* w = reinterpret_cast<char*>(ws);
   Vec* gsum = kStandalone ? out : reinterpret_cast<Vec*>(w + W.off_gsum);
-  run_segment_sum<Vec, GT>(g, dim, div, mask, perm, seg_start, seg_of, n, w, W, gsum, stream);
-  if constexpr (!kStandalone) {
-    const int cpr = dim / (int)(sizeof(Vec) / 4);
-    MREC_LAUNCH((rows_update_kernel<Vec, Sink>), grid_for(cdiv(n * cpr, kSegThreads), 8), kSegThreads, 0,
-                stream, cpr, seg_of, n, gsum, sink);
+  const int cpr = dim / (int)(sizeof(Vec) / 4);
+  Vec* part = reinterpret_cast<Vec*>(w + W.off_part);
+  int32_t* long_list = reinterpret_cast<int32_t*>(w + W.off_list);
+  int32_t* long_count = reinterpret_cast<int32_t*>(w + W.off_count);
+  const int64_t n_tiles = cdiv(n, kSegTile);
+  const int grid = (int)cdiv(n_tiles * cpr, kSegThreads);
+  cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
+  if (mask) {
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
+                seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count);
+  } else {
+    MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, false>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
+                seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count);
+  }
+  const int groups = kSegThreads / cpr;
+  const int row_blocks = grid_for(cdiv(n, groups), 8);
+  if constexpr (kStandalone) {
+    if (n_tiles > 1) {
+      StoreSink<Vec> store{gsum, cpr};
+      MREC_LAUNCH((rows_update_kernel<Vec, StoreSink<Vec>>), kChainBlocks + row_blocks, kSegThreads, 0, stream,
+                  cpr, seg_of, seg_start, n, gsum, part, long_list, long_count, store);
+    }
+  } else {
+    MREC_LAUNCH((rows_update_kernel<Vec, Sink>), kChainBlocks + row_blocks, kSegThreads, 0, stream, cpr, seg_of,
+                seg_start, n, gsum, part, long_list, long_count, sink);
   }
   return check_launch("segment_sum");
 }
