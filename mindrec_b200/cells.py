@@ -188,14 +188,28 @@ class TrainStepWrap:
         self._graph = None
         self._static = None
         self.profile = None
+        self.overlap = True          # fork dedup / FTRL onto a side stream (see construct)
+        self._side = None
 
     def __call__(self, batch_ids, batch_wts, label):
         return self.construct(batch_ids, batch_wts, label)
 
     def construct(self, batch_ids, batch_wts, label):
+        """One training step.  Two pieces of work are forked onto a side stream (parallel branches of the
+        captured graph): the dedup of the ids, which depends on nothing but the ids and hides under the
+        DenseLayer GEMMs, and the latency-bound FTRL update of the wide table, which runs beside the
+        bandwidth-bound LazyAdam update of the deep table."""
         model = self.model
         rng = self.profile.range if self.profile is not None else _null_range
         b = batch_ids.shape[0]
+        n = batch_ids.numel()
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.overlap else main
+        if self._uq is None or self._uq.n != n:
+            self._uq = ops.UniqueResult(n, batch_ids.dtype, batch_ids.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side), rng("unique"):
+            uq = ops.unique(batch_ids, table_like=model.embedding_table.data, result=self._uq)
         with rng("forward"):
             loss_w, loss_d = self.network(batch_ids, batch_wts, label)
         logit = self.network.logit
@@ -204,19 +218,22 @@ class TrainStepWrap:
             delta = (torch.sigmoid(logit) - label) * (self.sens / b)             # [B,1]
             gx = model.dense.backward(delta)                                      # [B, F*D]
             model.dense.extra_grad.copy_(delta.sum().reshape(1))                  # Wide_b gradient
-        n = batch_ids.numel()
-        if self._uq is None or self._uq.n != n:
-            self._uq = ops.UniqueResult(n, batch_ids.dtype, batch_ids.device)
-        with rng("unique"):
-            uq = ops.unique(batch_ids, table_like=model.embedding_table.data, result=self._uq)
         mask = batch_wts.reshape(-1)
         grads_w = [RowTensor(batch_ids, delta, mask, uq)]
         grads_d = [RowTensor(batch_ids, gx.view(n, model.emb_dim), mask, uq), model.dense.flat_grad]
-        with rng("ftrl_wide"):
+        main.wait_stream(side)                 # dedup done
+        side.wait_stream(main)                 # gradients ready
+        with torch.cuda.stream(side), rng("ftrl_wide"):
             self.optimizer_w(grads_w)
         with rng("adam_deep"):
             self.optimizer_d(grads_d)
+        main.wait_stream(side)
         return loss_w, loss_d
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.model.device)
+        return self._side
 
     # ---- CUDA-graph replay of the whole step -------------------------------------------------------
     def capture(self, batch_ids, batch_wts, label, warmup=3):

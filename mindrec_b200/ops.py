@@ -149,8 +149,9 @@ def _empty_mask(device):
 
 
 def _opt_ws(n, dim, device):
+    # one workspace per row width: updates of different tables may run concurrently on forked streams
     nbytes = _size_fn("mrec_sparse_opt_workspace_bytes")(n, dim)
-    return _ws("sparse_opt", nbytes, device)
+    return _ws("sparse_opt_%d" % dim, nbytes, device)
 
 
 def segment_sum(g, mask, uq, dim=None, out=None):
