@@ -121,6 +121,13 @@ int mrec_adam_dense(MREC_AOT_ARGS);
 /* nn.FTRL dense kernel (ApplyFtrl).  in : w accum linear hyper[16] g   out: dummy[1]               */
 int mrec_ftrl_dense(MREC_AOT_ARGS);
 
+/* ---- a8 loss ------------------------------------------------------------------------------------------
+ * SigmoidCrossEntropyWithLogits + ReduceMean and the bprop seed (wide_and_deep.py:315,354-355,479-486;
+ * deepfm.py:254-255; deep_and_cross.py:323-325), one launch, deterministic reduction:
+ *   in : a[B] f32, b[B] f32 | numel 0 (logit = a + b), label[B] f32, sens[1] f32
+ *   out: logit[B], loss[1] (mean), delta[B] = sens*(sigmoid(logit)-label)/B, delta16[B] f16 | numel 0, delta_sum[1] */
+int mrec_sigmoid_xent(MREC_AOT_ARGS);
+
 /* ---- K7 FM second-order interaction -------------------------------------------------------------
  * Replaces Square/ReduceSum/Sub x6 of models/deepfm/src/deepfm.py:222-228 and their autodiff.
  *   fwd  in : vx[B,F,D] f32 (already multiplied by the mask)      out: fm[B]|[B,1] f32

@@ -104,6 +104,7 @@ class WideDeepModel:
             self.wide_b.data.normal_(0.0, 0.01, generator=gen)
         self._wide_out = None
         self._deep_in = None
+        self.defer_add = False       # set by NetWithLossClass: `out = wide_out + deep_out` happens in mrec_sigmoid_xent
 
     def trainable_params(self):
         return [self.wide_embeddinglookup.embedding_table, self.deep_embeddinglookup.embedding_table,
@@ -126,8 +127,10 @@ class WideDeepModel:
         ops.gather_masked(self.deep_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
                           out=self._deep_in)
         deep_out = self.dense.forward(self._deep_in)       # :310-314
-        out = self._wide_out + deep_out                     # :315
-        return out, self.embedding_table
+        self.wide_out, self.deep_out = self._wide_out, deep_out
+        if self.defer_add:                                  # :315 is fused into the loss kernel
+            return None, self.embedding_table
+        return self._wide_out + deep_out, self.embedding_table
 
 
 class NetWithLossClass:
@@ -138,16 +141,30 @@ class NetWithLossClass:
         self.no_l2loss = bool(config.parameter_server) or bool(config.sparse)
         self.l2_coef = config.l2_coef
         self.logit = None
+        self._out = None
+        self.sens_t = torch.ones(1, dtype=torch.float32, device=network.device)   # TrainStepWrap sets sens
 
     def __call__(self, batch_ids, batch_wts, label):
         return self.construct(batch_ids, batch_wts, label)
 
     def construct(self, batch_ids, batch_wts, label):
-        predict, embedding_table = self.network(batch_ids, batch_wts)
-        self.logit = predict
-        # SigmoidCrossEntropyWithLogits: max(x,0) - x*z + log1p(exp(-|x|))
-        log_loss = torch.clamp(predict, min=0) - predict * label + torch.log1p(torch.exp(-predict.abs()))
-        wide_loss = log_loss.mean()
+        net = self.network
+        net.defer_add = True
+        _, embedding_table = net(batch_ids, batch_wts)
+        net.defer_add = False
+        b = batch_ids.shape[0]
+        if self._out is None or self._out[0].shape[0] != b:
+            dev = batch_ids.device
+            half = net.config.use_mixed_precision
+            self._out = (torch.empty((b, 1), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.float32, device=dev),
+                         torch.empty((b, 1), dtype=torch.float32, device=dev),
+                         torch.empty((b, 1) if half else (0,), dtype=torch.float16, device=dev),
+                         torch.empty(1, dtype=torch.float32, device=dev))
+        # logit = wide + deep (:315), mean SigmoidCrossEntropyWithLogits (:354-355) and the sens-scaled seed
+        # of the two backward passes (:479-486), in one kernel
+        self.logit, loss, self.delta, self.delta16, self.delta_sum = ops.sigmoid_xent(
+            net.wide_out, net.deep_out, label, self.sens_t, out=self._out)
+        wide_loss = loss[0]
         if self.no_l2loss:
             deep_loss = wide_loss
         else:
@@ -169,6 +186,7 @@ class TrainStepWrap:
         model = network.network
         self.model = model
         self.sens = float(sens)
+        network.sens_t.fill_(self.sens)
         self.sparse = sparse
         if lazy_adam is None:
             lazy_adam = (sparse and is_auto_parallel) or (sparse and parameter_server) or dynamic_embedding
@@ -212,12 +230,11 @@ class TrainStepWrap:
             uq = ops.unique(batch_ids, table_like=model.embedding_table.data, result=self._uq)
         with rng("forward"):
             loss_w, loss_d = self.network(batch_ids, batch_wts, label)
-        logit = self.network.logit
         with rng("dense_backward"):
-            # d(mean xent)/d logit, times sens (wide_and_deep.py:479-486)
-            delta = (torch.sigmoid(logit) - label) * (self.sens / b)             # [B,1]
-            gx = model.dense.backward(delta)                                      # [B, F*D]
-            model.dense.extra_grad.copy_(delta.sum().reshape(1))                  # Wide_b gradient
+            delta = self.network.delta                                            # sens*(sigmoid-y)/B, [B,1]
+            seed = self.network.delta16 if self.network.delta16.numel() else delta
+            gx = model.dense.backward(seed)                                       # [B, F*D]
+            model.dense.extra_grad.copy_(self.network.delta_sum)                  # Wide_b gradient
         mask = batch_wts.reshape(-1)
         grads_w = [RowTensor(batch_ids, delta, mask, uq)]
         grads_d = [RowTensor(batch_ids, gx.view(n, model.emb_dim), mask, uq), model.dense.flat_grad]

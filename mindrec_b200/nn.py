@@ -299,7 +299,7 @@ class DenseStack:
         input — fp16 when convert_dtype (the sparse optimizers read fp16 rows directly)."""
         acts = self._acts
         nl = len(self.weights)
-        g = g_out.half() if self.convert_dtype else g_out
+        g = g_out.half() if (self.convert_dtype and g_out.dtype != torch.float16) else g_out
         for i in range(nl - 1, -1, -1):
             h_in, h_out = acts[i], acts[i + 1]
             if i + 1 < nl or self.last_activation:

@@ -275,3 +275,18 @@ def shard_remap(ids, table_like, owners_like, out=None):
         out = torch.empty_like(ids)
     _lib.aot_call("mrec_shard_remap", [ids, table_like, owners_like, out])
     return out
+
+
+def sigmoid_xent(a, b, label, sens, out=None, half=False):
+    """Fused logit = a + b, mean sigmoid cross-entropy, delta = sens * (sigmoid(logit) - label) / B, sum(delta).
+    `out` = (logit, loss, delta, delta16, delta_sum) preallocated, or None."""
+    n = a.numel()
+    dev = a.device
+    if out is None:
+        out = (torch.empty((n, 1), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.float32, device=dev),
+               torch.empty((n, 1), dtype=torch.float32, device=dev),
+               torch.empty((n, 1) if half else (0,), dtype=torch.float16, device=dev),
+               torch.empty(1, dtype=torch.float32, device=dev))
+    b = _empty_mask(dev) if b is None else b
+    _lib.aot_call("mrec_sigmoid_xent", [a, b, label, sens, out[0], out[1], out[2], out[3], out[4]])
+    return out

@@ -87,3 +87,24 @@ def test_mixed_precision_step_runs_and_decreases_loss(cuda):
     ids, wts, label = (torch.from_numpy(x).to(cuda) for x in gen.next())
     losses = [float(step(ids, wts, label)[0]) for _ in range(30)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+def test_fused_sigmoid_xent_matches_oracle(cuda):
+    from mindrec_b200 import ops
+    rng = np.random.default_rng(3)
+    b = 16000
+    a = (rng.standard_normal((b, 1)) * 4).astype(np.float32)
+    d = (rng.standard_normal((b, 1)) * 4).astype(np.float32)
+    a[0], d[0] = 60.0, 60.0          # saturating logits must not overflow
+    a[1], d[1] = -70.0, -50.0
+    y = (rng.random((b, 1)) < 0.25).astype(np.float32)
+    sens = torch.tensor([1024.0], device=cuda)
+    logit, loss, delta, delta16, dsum = ops.sigmoid_xent(torch.from_numpy(a).to(cuda), torch.from_numpy(d).to(cuda),
+                                                          torch.from_numpy(y).to(cuda), sens, half=True)
+    x = a.astype(np.float64) + d.astype(np.float64)
+    np.testing.assert_allclose(logit.cpu().numpy(), (a + d), rtol=0, atol=0)
+    np.testing.assert_allclose(float(loss), R.sigmoid_xent(x, y).mean(), rtol=1e-5)
+    ref_delta = 1024.0 * (R.sigmoid(x) - y) / b
+    np.testing.assert_allclose(delta.cpu().numpy(), ref_delta, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(float(dsum), ref_delta.sum(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_array_equal(delta16.cpu().numpy(), delta.cpu().numpy().astype(np.float16))
