@@ -97,6 +97,7 @@ class ShardedWideDeepTables:
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
         self.plan_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.owner_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         r = self.plan.rows_per_rank
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + self.rank)
@@ -206,14 +207,26 @@ class ShardedWideDeepTables:
         inverse = uq.inverse.view(b, f)
         k.gather_masked(got_deep[:max(n_u, 1)], inverse, wts, out=deep_out)
         k.gather_reduce(got_wide[:max(n_u, 1)], inverse, wts, wide_bias, out=wide_out)
-        self._ctx = (plan, rows_recv, wts)
+        # owner-side dedup of the received rows: needs only rows_recv, so it runs on the side stream
+        # underneath the DenseLayer segment (the same row can arrive from several ranks)
+        uq2, ev = None, None
+        if n_r > 0:
+            if self.cuda:
+                self.owner_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.owner_stream):
+                    uq2 = self._unique(rows_recv, self.deep, "owner")
+                    ev = torch.cuda.Event()
+                    ev.record()
+            else:
+                uq2 = self._unique(rows_recv, self.deep, "owner")
+        self._ctx = (plan, rows_recv, wts, uq2, ev)
         return wide_out, deep_out
 
     # ---- backward + update ------------------------------------------------------------------------
     def update(self, delta, gx):
         """delta: [B,1] logit gradient (x sens), gx: [B, F*D] deep-input gradient (x sens, fp32 or fp16)."""
         k, g = self.k, self.world
-        plan, rows_recv, wts = self._ctx
+        plan, rows_recv, wts, uq2, ev = self._ctx
         uq, n_u, n_r, send, recv = plan.uq, plan.n_u, plan.n_r, plan.send, plan.recv
         n = uq.n
         mask = wts.reshape(-1)
@@ -230,10 +243,19 @@ class ShardedWideDeepTables:
         k.adam_begin_step(self.adam_hyper)
         if n_r == 0:
             return
-        # owner side: the same row can arrive from several ranks -> dedup again, then fused row updates
-        uq2 = self._unique(rows_recv, self.deep, "owner")
-        k.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, rg_wide[:n_r], None, uq2)
-        k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
+        # owner side: fused row updates over the (already deduplicated) received rows; the latency-bound FTRL
+        # update of the wide shard runs on the side stream beside the LazyAdam update of the deep shard
+        if ev is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(ev)
+            self.owner_stream.wait_stream(main)
+            with torch.cuda.stream(self.owner_stream):
+                k.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, rg_wide[:n_r], None, uq2)
+            k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
+            main.wait_stream(self.owner_stream)
+        else:
+            k.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, rg_wide[:n_r], None, uq2)
+            k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
 
     # ---- test / checkpoint helper -----------------------------------------------------------------
     def gather_full(self):
@@ -290,6 +312,7 @@ class ShardedWideDeepStep:
         self.dense_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=device)
         self.dense_m = torch.zeros_like(self.dense.flat)
         self.dense_v = torch.zeros_like(self.dense.flat)
+        self._sens_t = torch.tensor([self.sens], dtype=torch.float32, device=device)
         self._use_graph = graph_dense and _ENV_GRAPH and self.device.type == "cuda"
         self._graph = None
         self._calls = 0
@@ -302,14 +325,11 @@ class ShardedWideDeepStep:
     def _dense_segment(self):
         k = self.k
         deep_in, wide_out, label = self._io["deep_in"], self._io["wide_out"], self._io["label"]
-        b = label.shape[0]
-        logit = wide_out + self.dense.forward(deep_in)
-        log_loss = torch.clamp(logit, min=0) - logit * label + torch.log1p(torch.exp(-logit.abs()))
-        loss = log_loss.mean()
-        delta = (torch.sigmoid(logit) - label) * (self.sens / b)
-        gx = self.dense.backward(delta)
-        self.dense.extra_grad.copy_(delta.sum().reshape(1))
-        return loss, delta, gx
+        deep_out = self.dense.forward(deep_in)
+        _, loss, delta, delta16, dsum = k.sigmoid_xent(wide_out, deep_out, label, self._sens_t, out=self._io["loss_out"])
+        gx = self.dense.backward(delta16 if delta16.numel() else delta)
+        self.dense.extra_grad.copy_(dsum)
+        return loss[0], delta, gx
 
     def _dense_update(self):
         k = self.k
@@ -345,7 +365,12 @@ class ShardedWideDeepStep:
                 deep_in=torch.empty((b, self.fields * self.emb_dim), device=dev,
                                     dtype=torch.float16 if self.mixed else torch.float32),
                 wide_out=torch.empty((b, 1), dtype=torch.float32, device=dev),
-                label=torch.empty((b, 1), dtype=torch.float32, device=dev))
+                label=torch.empty((b, 1), dtype=torch.float32, device=dev),
+                loss_out=(torch.empty((b, 1), dtype=torch.float32, device=dev),
+                          torch.empty(1, dtype=torch.float32, device=dev),
+                          torch.empty((b, 1), dtype=torch.float32, device=dev),
+                          torch.empty((b, 1) if self.mixed else (0,), dtype=torch.float16, device=dev),
+                          torch.empty(1, dtype=torch.float32, device=dev)))
             self._graph = None
 
     def _range(self, name):

@@ -118,3 +118,17 @@ def shard_remap(ids, table_like, owners_like, out=None):
     ok = (ids >= 0) & (ids < v)
     km = (ids % g) * r + torch.div(ids, g, rounding_mode="floor")
     return torch.where(ok, km, torch.full_like(ids, g * r))
+
+
+def sigmoid_xent(a, b, label, sens, out=None, half=False):
+    x = a.double() + (b.double() if b is not None and b.numel() else 0)
+    n = x.numel()
+    loss = torch.from_numpy(np.array([R.sigmoid_xent(_np(x), _np(label)).mean()], dtype=np.float32))
+    delta = (float(sens[0]) * (torch.sigmoid(x) - label.double()) / n).float()
+    res = (x.float(), loss, delta, delta.half() if half else torch.empty(0, dtype=torch.float16), delta.sum().reshape(1))
+    if out is not None:
+        for o, r in zip(out, res):
+            if o.numel():
+                o.copy_(r.reshape(o.shape))
+        return out
+    return res

@@ -105,6 +105,7 @@ def test_fused_sigmoid_xent_matches_oracle(cuda):
     np.testing.assert_allclose(logit.cpu().numpy(), (a + d), rtol=0, atol=0)
     np.testing.assert_allclose(float(loss), R.sigmoid_xent(x, y).mean(), rtol=1e-5)
     ref_delta = 1024.0 * (R.sigmoid(x) - y) / b
-    np.testing.assert_allclose(delta.cpu().numpy(), ref_delta, rtol=1e-5, atol=1e-9)
+    # sigmoid(x) - 1 cancels in fp32 for large x: compare at 1e-6 of the gradient scale (sens / B)
+    np.testing.assert_allclose(delta.cpu().numpy(), ref_delta, rtol=1e-5, atol=1e-6 * 1024.0 / b)
     np.testing.assert_allclose(float(dsum), ref_delta.sum(), rtol=1e-4, atol=1e-6)
     np.testing.assert_array_equal(delta16.cpu().numpy(), delta.cpu().numpy().astype(np.float16))
