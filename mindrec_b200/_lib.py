@@ -88,26 +88,67 @@ def _fn(symbol):
     return f
 
 
-def aot_call(symbol, tensors, stream=None, check_device=True):
-    """Call aot entry point `symbol` with `tensors` (inputs then outputs, torch CUDA tensors)."""
-    import torch
+_pack_cache = {}
+_PACK_CACHE_MAX = 4096
+
+
+_I64 = ctypes.sizeof(ctypes.c_int64)
+_P_I64 = ctypes.POINTER(ctypes.c_int64)
+
+
+def _build_pack(symbol, tensors, check_device):
     n = len(tensors)
     params = (ctypes.c_void_p * n)()
     ndims = (ctypes.c_int * n)()
-    shapes = (ctypes.POINTER(ctypes.c_int64) * n)()
+    shapes = (_P_I64 * n)()
     dtypes = (ctypes.c_char_p * n)()
-    keep = []
+    flat = []
+    for t in tensors:
+        flat.extend(t.shape if t.dim() else (1,))
+    shape_store = (ctypes.c_int64 * max(1, len(flat)))(*flat)   # one array for every shape
+    base = ctypes.addressof(shape_store)
+    off = 0
     for i, t in enumerate(tensors):
         if check_device and not t.is_cuda:
             raise RuntimeError("%s: param %d is not a CUDA tensor (no CPU path exists)" % (symbol, i))
         if not t.is_contiguous():
             raise RuntimeError("%s: param %d is not contiguous" % (symbol, i))
         params[i] = t.data_ptr() if t.numel() > 0 else None
-        ndims[i] = t.dim()
-        shp = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
-        keep.append(shp)
-        shapes[i] = ctypes.cast(shp, ctypes.POINTER(ctypes.c_int64))
+        d = t.dim()
+        ndims[i] = d
+        shapes[i] = ctypes.cast(base + off * _I64, _P_I64)
+        off += d if d else 1
         dtypes[i] = _dtype_name(t)
+    return (n, params, ndims, shapes, dtypes, shape_store)
+
+
+def aot_call(symbol, tensors, stream=None, check_device=True):
+    """Call aot entry point `symbol` with `tensors` (inputs then outputs, torch CUDA tensors).
+
+    The marshalled argument pack is cached per (symbol, buffer addresses, shapes, dtypes): a training step
+    calls the same entry points on the same preallocated buffers, so the steady-state host cost of a call
+    is one dictionary lookup (this matters for the eager, launch-bound multi-GPU step)."""
+    import torch
+    # key: buffers, dtypes and ranks; extents are refreshed in place (they vary per step on the sharded path)
+    key = (symbol, tuple((t.data_ptr(), t.dtype, t.dim()) for t in tensors))
+    pack = _pack_cache.get(key)
+    if pack is None:
+        pack = _build_pack(symbol, tensors, check_device)
+        if len(_pack_cache) >= _PACK_CACHE_MAX:
+            _pack_cache.clear()
+        _pack_cache[key] = pack
+    else:
+        store = pack[5]
+        off = 0
+        for t in tensors:
+            if not t.is_contiguous():
+                raise RuntimeError("%s: a param is not contiguous" % symbol)
+            for d in t.shape:
+                store[off] = d
+                off += 1
+            if t.dim() == 0:
+                off += 1
+    n, params, ndims, shapes, dtypes, _ = pack
     if stream is None:
         stream = torch.cuda.current_stream().cuda_stream
     rc = _fn(symbol)(n, params, ndims, shapes, dtypes, ctypes.c_void_p(stream), None)
