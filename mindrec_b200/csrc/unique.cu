@@ -13,7 +13,7 @@
 //
 // The sort is an LSD radix sort over only the significant key bits with digits of up to 9 bits (a table
 // with V rows needs ceil(log2(V+1)) bits: 26 bits -> 3 passes of 9 bits for the 33.8 M-row Criteo table).  Each pass is
-// histogram -> column scan -> stable scatter; ranking inside a tile uses warp match-any so equal digits
+// histogram (pass 0 only: later passes get theirs from the previous scatter) -> column scan -> stable scatter; ranking inside a tile uses warp match-any so equal digits
 // keep their input order (stability is what makes perm's first entry of a segment the first occurrence).
 // All buffers (ping-pong keys/values, histograms) come from the caller-provided workspace: the library
 // never allocates (aot contract).
@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      typename UKeyOf<KeyT>::type* __restrict__ keys_out, int32_t* __restrict__ vals_out,
                      int64_t n, int shift, int radix, uint64_t bound, int tiles_per_block,
-                     const uint32_t* __restrict__ hist, int n_blocks) {
+                     const uint32_t* __restrict__ hist, int n_blocks, uint32_t* __restrict__ hist_next,
+                     int next_shift) {
   using U = typename UKeyOf<KeyT>::type;
   __shared__ uint32_t s_cnt[RS_WARPS][MAX_RADIX];
   __shared__ uint32_t s_base[MAX_RADIX];
@@ -189,6 +190,11 @@ radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
         const uint32_t pos = s_cnt[warp][dig[i]] + rank[i];
         keys_out[pos] = key[i];
         vals_out[pos] = val[i];
+        // histogram of the NEXT pass, binned by the block that will own this element's new position:
+        // saves that pass's histogram kernel (hist_next was zeroed by a memset node)
+        if (hist_next)
+          atomicAdd(&hist_next[(int64_t)(pos / (uint32_t)(tiles_per_block * RS_TILE)) * RADIX +
+                               ((uint32_t)(key[i] >> next_shift) & (RADIX - 1))], 1u);
       }
     }
     __syncthreads();
@@ -312,7 +318,7 @@ seg_emit_kernel(const typename UKeyOf<KeyT>::type* __restrict__ sorted,
 struct SortPlan {
   int64_t n;
   int n_tiles, n_blocks, tiles_per_block, passes, digit_bits;
-  size_t off_keys_a, off_keys_b, off_vals_tmp, off_hist, off_tiles, total;
+  size_t off_keys_a, off_keys_b, off_vals_tmp, off_hist, off_hist2, off_tiles, total;
 };
 
 static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
@@ -330,6 +336,7 @@ static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
   p.off_keys_b = o; o = align_up(o + (size_t)n * key_bytes, 256);
   p.off_vals_tmp = o; o = align_up(o + (size_t)n * 4, 256);
   p.off_hist = o; o = align_up(o + (size_t)(p.n_blocks + 1) * MAX_RADIX * 4, 256);
+  p.off_hist2 = o; o = align_up(o + (size_t)(p.n_blocks + 1) * MAX_RADIX * 4, 256);
   p.off_tiles = o; o = align_up(o + (size_t)(p.n_tiles + 1) * 4, 256);
   p.total = o;
   return p;
@@ -373,23 +380,27 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
   const int32_t* vin = nullptr;
   const int radix = 1 << p.digit_bits;
   const int scan_grid = (int)cdiv((int64_t)radix * 32, 1024);
+  uint32_t* hbuf[2] = {hist, reinterpret_cast<uint32_t*>(w + p.off_hist2)};
+  const size_t hist_bytes = (size_t)(p.n_blocks + 1) * radix * sizeof(uint32_t);
   for (int pass = 0; pass < p.passes; ++pass) {
     const int shift = pass * p.digit_bits;
     U* kout = kbuf[pass & 1];
     // the last pass must land in `perm`
     int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vtmp;
+    uint32_t* h = hbuf[pass & 1];
+    const bool more = pass + 1 < p.passes;
+    uint32_t* hn = more ? hbuf[(pass + 1) & 1] : nullptr;   // filled by this pass's scatter
+    if (more) cudaMemsetAsync(hn, 0, hist_bytes, stream);
     if (pass == 0) {
       MREC_LAUNCH((radix_hist_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
-                  bound, p.tiles_per_block, hist);
-      MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, hist, p.n_blocks, radix);
+                  bound, p.tiles_per_block, h);
+      MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, h, p.n_blocks, radix);
       MREC_LAUNCH((radix_scatter_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
-                  vout, n, shift, radix, bound, p.tiles_per_block, hist, p.n_blocks);
+                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits);
     } else {
-      MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
-                  bound, p.tiles_per_block, hist);
-      MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, hist, p.n_blocks, radix);
+      MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, h, p.n_blocks, radix);
       MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
-                  vout, n, shift, radix, bound, p.tiles_per_block, hist, p.n_blocks);
+                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits);
     }
     kin = kout;
     vin = vout;
