@@ -76,27 +76,47 @@ radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, int radix
 }
 
 // ---- pass kernel 2: hist[b][d] -> exclusive prefix over blocks (per digit), digit totals ----
-// One warp per digit: lanes stride over blocks, warp-scan 32 blocks at a time.  The cross-digit base is
-// a 512-entry scan that every scatter block redoes in shared memory from the totals row.
+// One CTA (32 warps) per group of 32 digits.  The [blocks x 32 digits] slab is walked in tiles of 32 blocks:
+// warp w reads row b0+w (32 consecutive digits = one 128-byte line, coalesced), the tile is transposed through
+// padded shared memory, warp w scans digit column w across the 32 blocks with shuffles, adds the running
+// carry, and the tile is written back row-wise (coalesced).  (The first version let each warp walk a digit
+// column directly: 32 cache lines per warp load, 21 us per pass on 16 SMs — ncu r1e.)  The cross-digit base
+// is a <= 512-entry scan that every scatter block redoes in shared memory from the totals row.
 __global__ void __launch_bounds__(1024)
 radix_scan_kernel(uint32_t* __restrict__ hist, int n_blocks, int radix) {
-  const int lane = threadIdx.x & 31;
-  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (d >= radix) return;
-  uint32_t carry = 0;
+  __shared__ uint32_t s_tile[32][33];
+  __shared__ uint32_t s_carry[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d0 = blockIdx.x * 32;             // first digit of this CTA's group
+  const bool d_ok = (d0 + lane) < radix;
+  if (warp == 0) s_carry[lane] = 0;
+  uint32_t next = 0;
+  if (warp < n_blocks && d_ok) next = hist[(int64_t)warp * radix + d0 + lane];
   for (int b0 = 0; b0 < n_blocks; b0 += 32) {
-    const int b = b0 + lane;
-    const uint32_t c = (b < n_blocks) ? hist[(int64_t)b * radix + d] : 0u;
+    const int b = b0 + warp;
+    const uint32_t cur = next;
+    // prefetch the next tile's row while this one is processed
+    next = 0;
+    if (b + 32 < n_blocks && d_ok) next = hist[(int64_t)(b + 32) * radix + d0 + lane];
+    s_tile[warp][lane] = (b < n_blocks) ? cur : 0u;
+    __syncthreads();
+    // warp w owns digit d0+w: lane = block index inside the tile
+    const uint32_t c = s_tile[lane][warp];
     uint32_t v = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
       if (lane >= o) v += t;
     }
-    if (b < n_blocks) hist[(int64_t)b * radix + d] = carry + v - c;
-    carry += __shfl_sync(0xffffffffu, v, 31);
+    const uint32_t carry = s_carry[warp];
+    __syncthreads();                            // everyone has read s_tile / s_carry
+    s_tile[lane][warp] = carry + v - c;         // exclusive prefix over blocks
+    if (lane == 31) s_carry[warp] = carry + v;
+    __syncthreads();
+    if (b < n_blocks && d_ok) hist[(int64_t)b * radix + d0 + lane] = s_tile[warp][lane];
+    __syncthreads();
   }
-  if (lane == 0) hist[(int64_t)n_blocks * radix + d] = carry;  // digit total
+  if (warp == 0 && d_ok) hist[(int64_t)n_blocks * radix + d0 + lane] = s_carry[lane];  // digit totals
 }
 
 // ---- pass kernel 3: stable scatter ----
@@ -379,7 +399,7 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
   const void* kin = ids;
   const int32_t* vin = nullptr;
   const int radix = 1 << p.digit_bits;
-  const int scan_grid = (int)cdiv((int64_t)radix * 32, 1024);
+  const int scan_grid = (int)cdiv(radix, 32);
   uint32_t* hbuf[2] = {hist, reinterpret_cast<uint32_t*>(w + p.off_hist2)};
   const size_t hist_bytes = (size_t)(p.n_blocks + 1) * radix * sizeof(uint32_t);
   for (int pass = 0; pass < p.passes; ++pass) {
