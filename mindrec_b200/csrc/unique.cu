@@ -28,6 +28,9 @@ constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048
 constexpr int MAX_RADIX_BITS = 9;             // digit width is chosen per sort: ceil(bits / passes) <= 9
 constexpr int MAX_RADIX = 1 << MAX_RADIX_BITS;  // shared-memory tables are sized for 512 bins
+// Accumulating the next pass's histogram with global atomics inside the scatter was measured (r1e) to cost as
+// much as the separate histogram kernel it saves; kept as a switch.
+constexpr bool kFuseNextHist = false;
 
 template <typename KeyT> struct UKeyOf;
 template <> struct UKeyOf<int32_t> { using type = uint32_t; static constexpr uint32_t sign = 0x80000000u; };
@@ -408,7 +411,7 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
     // the last pass must land in `perm`
     int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vtmp;
     uint32_t* h = hbuf[pass & 1];
-    const bool more = pass + 1 < p.passes;
+    const bool more = kFuseNextHist && (pass + 1 < p.passes);
     uint32_t* hn = more ? hbuf[(pass + 1) & 1] : nullptr;   // filled by this pass's scatter
     if (more) cudaMemsetAsync(hn, 0, hist_bytes, stream);
     if (pass == 0) {
@@ -418,6 +421,9 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
       MREC_LAUNCH((radix_scatter_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
                   vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits);
     } else {
+      if (!kFuseNextHist)
+        MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
+                    bound, p.tiles_per_block, h);
       MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, h, p.n_blocks, radix);
       MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
                   vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits);
