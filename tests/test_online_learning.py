@@ -1,0 +1,66 @@
+"""The reference's own CI tests for RecModel.online_train (ci/st/online_learning/test_online_learning.py:54-114),
+restated against mindrec_b200.train.RecModel: three argument-validation cases with the same messages, plus the
+loop's callback order.  CPU only (the toy net is a plain callable)."""
+import numpy as np
+import pytest
+
+from mindrec_b200.train import Callback, RecModel
+
+
+class StreamingDataset:
+    """Same fixture as the reference: an endless stream of ones, batches of 100 x 39."""
+
+    def __iter__(self):
+        while True:
+            yield (np.ones((100, 39), dtype=np.int32),)
+
+
+class Net:
+    def __init__(self):
+        self.calls = 0
+
+    def __call__(self, indices):
+        self.calls += 1
+        return indices.sum()
+
+
+def test_online_learning_api_sink_size_is_negative():
+    model = RecModel(Net(), device="cpu")
+    with pytest.raises(ValueError) as exc_info:
+        model.online_train(StreamingDataset(), dataset_sink_mode=True, sink_size=-1)
+    assert "The input value must be int and must > 0" in str(exc_info.value)
+
+
+def test_online_learning_api_sink_size_not_equal_one():
+    model = RecModel(Net(), device="cpu")
+    with pytest.raises(ValueError) as exc_info:
+        model.online_train(StreamingDataset(), dataset_sink_mode=True, sink_size=100)
+    assert "The sink_size parameter only support value of 1" in str(exc_info.value)
+
+
+def test_online_learning_api_data_sink_mode_not_bool():
+    model = RecModel(Net(), device="cpu")
+    with pytest.raises(TypeError) as exc_info:
+        model.online_train(StreamingDataset(), dataset_sink_mode="valid")
+    assert "The input value must be a bool, but got str" in str(exc_info.value)
+
+
+def test_online_train_runs_until_stopped_and_fires_hooks_in_order():
+    events = []
+
+    class Rec(Callback):
+        def on_train_begin(self, c): events.append("begin")
+        def on_train_epoch_begin(self, c): events.append("epoch_begin")
+        def on_train_step_begin(self, c): events.append("step_begin")
+        def on_train_step_end(self, c):
+            events.append("step_end")
+            if c.original_args().cur_step_num == 3:
+                c.request_stop()
+        def on_train_epoch_end(self, c): events.append("epoch_end")
+        def on_train_end(self, c): events.append("end")
+
+    net = Net()
+    params = RecModel(net, device="cpu").online_train(StreamingDataset(), callbacks=Rec())
+    assert net.calls == 3 and params.cur_step_num == 3 and params.cur_epoch_num == 1
+    assert events == ["begin", "epoch_begin"] + ["step_begin", "step_end"] * 3 + ["epoch_end", "end"]
+    assert float(params.net_outputs) == 3900.0

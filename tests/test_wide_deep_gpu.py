@@ -109,3 +109,24 @@ def test_fused_sigmoid_xent_matches_oracle(cuda):
     np.testing.assert_allclose(delta.cpu().numpy(), ref_delta, rtol=1e-5, atol=1e-6 * 1024.0 / b)
     np.testing.assert_allclose(float(dsum), ref_delta.sum(), rtol=1e-4, atol=1e-6)
     np.testing.assert_array_equal(delta16.cpu().numpy(), delta.cpu().numpy().astype(np.float16))
+
+
+def test_online_train_and_checkpoint_round_trip(cuda):
+    """RecModel.online_train drives the W&D step from host batches; export -> import reproduces the state."""
+    from mindrec_b200 import train
+    cfg, model, step, _ = _build(cuda, "lazy")
+    gen = synth.CriteoSynth(cfg.batch_size, cards=[50] * 26, vocab_pad=cfg.vocab_size, seed=21)
+
+    def stream():
+        while True:
+            yield gen.next()
+    params = train.RecModel(step, device=cuda).online_train(stream(), max_steps=4)
+    assert params.cur_step_num == 4 and np.isfinite(float(params.net_outputs[0]))
+    state = train.export_tables(step)
+    cfg2, model2, step2, _ = _build(cuda, "lazy")
+    train.import_tables(step2, state)
+    batch = tuple(torch.from_numpy(x).to(cuda) for x in gen.next())
+    step(*batch)
+    step2(*batch)
+    assert torch.equal(model.embedding_table.data, model2.embedding_table.data)
+    assert torch.equal(model.dense.flat, model2.dense.flat)

@@ -152,8 +152,43 @@ def interaction():
            3 * x0.numel() * 4)
 
 
+def hash_bench():
+    """BASELINE config 5 lookup shape: 16384 x 26 int64 Zipf keys over 2^40, dim 128."""
+    from mindrec_b200 import hash as H
+    n, d = 16384 * 26, 128
+    rng = np.random.default_rng(0)
+    keys = torch.from_numpy((rng.zipf(1.05, size=n) % (1 << 40)).astype(np.int64)).cuda()
+    mp = H.MapParameter(key_dtype=torch.int64, value_shape=d, default_value="normal", capacity=1 << 21, device="cuda")
+    mp.lookup_slots(keys)                                # insert pass
+    resident = len(mp)
+    slots = mp.lookup_slots(keys)
+    out = torch.empty((n, d), device="cuda")
+    report("hash find_or_insert (resident) n=%d U=%d" % (n, resident), timeit(lambda: mp.lookup_slots(keys)),
+           n * (8 + 4))
+    report("hash get = probe + gather D=128", timeit(lambda: ops.gather(mp.values, mp.lookup_slots(keys), out=out)),
+           n * (8 + 2 * d * 4))
+    fresh = torch.from_numpy(rng.integers(1 << 41, 1 << 42, size=n).astype(np.int64)).cuda()
+
+    def insert_new():
+        mp2 = insert_new.mp
+        mp2.lookup_slots(fresh)
+    insert_new.mp = H.MapParameter(key_dtype=torch.int64, value_shape=d, default_value="normal", capacity=1 << 21,
+                                   device="cuda")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    insert_new()
+    b.record()
+    torch.cuda.synchronize()
+    report("hash insert %d new keys + init rows" % n, a.elapsed_time(b), n * (8 + d * 4))
+    print("load factor %.3f, overflow %s" % (len(insert_new.mp) / insert_new.mp.capacity, insert_new.mp.overflowed))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "interaction":
         interaction()
+    elif len(sys.argv) > 1 and sys.argv[1] == "hash":
+        GRAPH = False
+        hash_bench()
     else:
         main()
