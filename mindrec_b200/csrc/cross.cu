@@ -19,8 +19,6 @@
 
 namespace mrec {
 
-constexpr int kCrossThreads = 512;
-constexpr int kCrossWarps = kCrossThreads / 32;
 constexpr int kCrossMaxL = 8;
 
 template <typename Vec> struct CrV;
@@ -101,7 +99,7 @@ cross_prep_kernel(const float* __restrict__ w, const float* __restrict__ b, int 
 // per warp.  Stage 2: in every warp lane i < NV adds column i over the warps (fixed order) and the totals
 // are broadcast by shuffle, so there is one __syncthreads per call; callers alternate two smem slabs by
 // iteration parity.
-template <int NV>
+template <int NV, int WARPS>
 __device__ __forceinline__ void block_sum(float (&v)[NV], float (*buf)[NV]) {
   static_assert(NV <= 32, "block_sum handles at most 32 values");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,54 +112,76 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float (*buf)[NV]) {
   float col = 0.f;
   if (lane < NV) {
 #pragma unroll
-    for (int wp = 0; wp < kCrossWarps; ++wp) col += buf[wp][lane];
+    for (int wp = 0; wp < WARPS; ++wp) col += buf[wp][lane];
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = __shfl_sync(0xffffffffu, col, i);
 }
 
-// R rows per CTA iteration: all R * SLOTS row loads are issued before the reduction, and each w chunk
-// read from L1 is used for R rows.
-template <typename Vec, int SLOTS, int L, int R>
-__global__ void __launch_bounds__(kCrossThreads, (SLOTS <= 2 ? 2 : 1))
-cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ q,
-                 const float* __restrict__ bcum, int64_t batch, int dpv /* D' / vec width */,
-                 float* __restrict__ y, float* __restrict__ p_out) {
-  __shared__ float s_red[2][kCrossWarps][R * L];
-  const int tid = threadIdx.x;
-  float ql[L];
-#pragma unroll
-  for (int l = 0; l < L; ++l) ql[l] = q[l];
-  int par = 0;
-  for (int64_t row0 = (int64_t)blockIdx.x * R; row0 < batch; row0 += (int64_t)gridDim.x * R, par ^= 1) {
-    Vec x[R][SLOTS];
+// Software pipeline shared by both kernels: a CTA owns rows row0, row0 + stride, ...; the loads of iteration
+// i+1 are issued (into a second register set) before iteration i's reduction, so HBM latency overlaps the
+// reduction, the FMA phase and the stores of the current rows.  R rows per iteration, SLOTS chunks per
+// thread, THREADS threads per CTA (1024 x 1 chunk for D' <= 4096 keeps the dw/db accumulators of the backward
+// at 7 float4 per thread, which leaves room for the second register set).
+template <typename Vec, int SLOTS, int R, int THREADS>
+struct RowTile {
+  Vec v[R][SLOTS];
+  __device__ __forceinline__ void load(const float* __restrict__ src, int64_t row0, int64_t batch, int dpv) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < SLOTS; ++k) {
-        const int i = tid + k * kCrossThreads;
-        x[r][k] = (i < dpv && row0 + r < batch) ? CrV<Vec>::ld_stream(x0, (row0 + r) * dpv + i) : CrV<Vec>::zero();
+        const int i = threadIdx.x + k * THREADS;
+        // clamp instead of branching: out-of-range chunks / rows re-read a valid element and are masked later
+        const int ic = min(i, dpv - 1);
+        const int64_t rc = min(row0 + r, batch - 1);
+        v[r][k] = CrV<Vec>::ld_stream(src, rc * dpv + ic);
       }
+  }
+  __device__ __forceinline__ void fence() {
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int k = 0; k < SLOTS; ++k) reg_fence(x[r][k]);
+      for (int k = 0; k < SLOTS; ++k) reg_fence(v[r][k]);
+  }
+};
+
+template <typename Vec, int SLOTS, int L, int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ q,
+                 const float* __restrict__ bcum, int64_t batch, int dpv /* D' / vec width */,
+                 float* __restrict__ y, float* __restrict__ p_out) {
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_red[2][WARPS][R * L];
+  const int tid = threadIdx.x;
+  float ql[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) ql[l] = q[l];
+  const int64_t stride = (int64_t)gridDim.x * R;
+  RowTile<Vec, SLOTS, R, THREADS> cur, nxt;
+  int64_t row0 = (int64_t)blockIdx.x * R;
+  if (row0 < batch) cur.load(x0, row0, batch, dpv);
+  int par = 0;
+  for (; row0 < batch; row0 += stride, par ^= 1) {
+    const bool more = row0 + stride < batch;
+    if (more) nxt.load(x0, row0 + stride, batch, dpv);   // in flight during everything below
+    cur.fence();
     float p[R * L];
 #pragma unroll
     for (int i = 0; i < R * L; ++i) p[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
-      const int i = tid + k * kCrossThreads;
+      const int i = tid + k * THREADS;
       if (i < dpv) {
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           const Vec wv = CrV<Vec>::ld(w, (int64_t)l * dpv + i);
 #pragma unroll
-          for (int r = 0; r < R; ++r) p[r * L + l] += CrV<Vec>::dot(x[r][k], wv);
+          for (int r = 0; r < R; ++r) p[r * L + l] += CrV<Vec>::dot(cur.v[r][k], wv);
         }
       }
     }
-    block_sum<R * L>(p, s_red[par]);
+    block_sum<R * L, WARPS>(p, s_red[par]);
     float c[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -171,27 +191,29 @@ cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, cons
     }
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
-      const int i = tid + k * kCrossThreads;
+      const int i = tid + k * THREADS;
       if (i < dpv) {
         const Vec bl = CrV<Vec>::ld(bcum, (int64_t)L * dpv + i);
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          if (row0 + r < batch) CrV<Vec>::st_stream(y, (row0 + r) * dpv + i, CrV<Vec>::scale_add(x[r][k], c[r], bl));
+          if (row0 + r < batch) CrV<Vec>::st_stream(y, (row0 + r) * dpv + i, CrV<Vec>::scale_add(cur.v[r][k], c[r], bl));
       }
     }
 #pragma unroll
     for (int i = 0; i < R * L; ++i)
       if (tid == i && row0 + i / L < batch) p_out[(row0 + i / L) * L + (i % L)] = p[i];
+    if (more) cur = nxt;
   }
 }
 
-template <typename Vec, int SLOTS, int L, int R>
-__global__ void __launch_bounds__(kCrossThreads, 1)
+template <typename Vec, int SLOTS, int L, int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, const float* __restrict__ w,
                  const float* __restrict__ q, const float* __restrict__ p_in, int64_t batch, int dpv,
                  float* __restrict__ dx, float* __restrict__ part /* [grid][L+1][D'] */,
                  float* __restrict__ sd_part /* [grid][L] */) {
-  __shared__ float s_red[2][kCrossWarps][R];
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_red[2][WARPS][R];
   const int tid = threadIdx.x;
   float ql[L];
 #pragma unroll
@@ -207,33 +229,31 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
 #pragma unroll
   for (int k = 0; k < SLOTS; ++k) Y[k] = CrV<Vec>::zero();
 
+  const int64_t stride = (int64_t)gridDim.x * R;
+  RowTile<Vec, SLOTS, R, THREADS> x, g, xn, gn;
+  int64_t row0 = (int64_t)blockIdx.x * R;
+  if (row0 < batch) {
+    x.load(x0, row0, batch, dpv);
+    g.load(dy, row0, batch, dpv);
+  }
   int par = 0;
-  for (int64_t row0 = (int64_t)blockIdx.x * R; row0 < batch; row0 += (int64_t)gridDim.x * R, par ^= 1) {
-    Vec x[R][SLOTS], g[R][SLOTS];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int k = 0; k < SLOTS; ++k) {
-        const int i = tid + k * kCrossThreads;
-        const bool ok = (i < dpv) && (row0 + r < batch);
-        x[r][k] = ok ? CrV<Vec>::ld_stream(x0, (row0 + r) * dpv + i) : CrV<Vec>::zero();
-        g[r][k] = ok ? CrV<Vec>::ld_stream(dy, (row0 + r) * dpv + i) : CrV<Vec>::zero();
-      }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int k = 0; k < SLOTS; ++k) {
-        reg_fence(x[r][k]);
-        reg_fence(g[r][k]);
-      }
+  for (; row0 < batch; row0 += stride, par ^= 1) {
+    const bool more = row0 + stride < batch;
+    if (more) {
+      xn.load(x0, row0 + stride, batch, dpv);
+      gn.load(dy, row0 + stride, batch, dpv);
+    }
+    x.fence();
+    g.fence();
     float rr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       rr[r] = 0.f;
 #pragma unroll
-      for (int k = 0; k < SLOTS; ++k) rr[r] += CrV<Vec>::dot(x[r][k], g[r][k]);
+      for (int k = 0; k < SLOTS; ++k)
+        if (tid + k * THREADS < dpv) rr[r] += CrV<Vec>::dot(x.v[r][k], g.v[r][k]);
     }
-    block_sum<R>(rr, s_red[par]);
+    block_sum<R, WARPS>(rr, s_red[par]);
     // per row: forward scalars c_l, backward scalars ds_l -> coef_l = ds_l * c_l
     float coef[R][L], cl[R];
 #pragma unroll
@@ -246,7 +266,7 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
         p[l] = live ? p_in[(row0 + r) * L + l] : 0.f;
         c[l + 1] = c[l] + fmaf(c[l], p[l], ql[l]);
       }
-      cl[r] = c[L];
+      cl[r] = live ? c[L] : 0.f;
       float t = 0.f;
 #pragma unroll
       for (int l = L - 1; l >= 0; --l) {
@@ -258,32 +278,38 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
     }
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
-      const int i = tid + k * kCrossThreads;
+      const int i = tid + k * THREADS;
       if (i < dpv) {
         Vec o[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) o[r] = CrV<Vec>::scale_add(g[r][k], cl[r], CrV<Vec>::zero());
+        for (int r = 0; r < R; ++r) o[r] = CrV<Vec>::scale_add(g.v[r][k], cl[r], CrV<Vec>::zero());
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           const Vec wv = CrV<Vec>::ld(w, (int64_t)l * dpv + i);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             CrV<Vec>::axpy(o[r], coef[r][l], wv);
-            CrV<Vec>::axpy(A[l][k], coef[r][l], x[r][k]);
+            CrV<Vec>::axpy(A[l][k], coef[r][l], x.v[r][k]);   // coef is 0 for rows past the end
           }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          CrV<Vec>::add(Y[k], g[r][k]);  // zero for rows past the end
-          if (row0 + r < batch) CrV<Vec>::st_stream(dx, (row0 + r) * dpv + i, o[r]);
+          if (row0 + r < batch) {
+            CrV<Vec>::add(Y[k], g.v[r][k]);
+            CrV<Vec>::st_stream(dx, (row0 + r) * dpv + i, o[r]);
+          }
         }
       }
+    }
+    if (more) {
+      x = xn;
+      g = gn;
     }
   }
   float* mine = part + (int64_t)blockIdx.x * (L + 1) * dpv * CrV<Vec>::width;
 #pragma unroll
   for (int k = 0; k < SLOTS; ++k) {
-    const int i = tid + k * kCrossThreads;
+    const int i = tid + k * THREADS;
     if (i < dpv) {
 #pragma unroll
       for (int l = 0; l < L; ++l) CrV<Vec>::st(mine, (int64_t)l * dpv + i, A[l][k]);
@@ -366,22 +392,22 @@ static CrossWs cross_ws(int layers, int dp, bool backward) {
   return W;
 }
 
-template <typename Vec, int SLOTS>
+template <typename Vec, int SLOTS, int THREADS, int R>
 static int launch_fwd(int layers, int grid, cudaStream_t st, const float* x0, const float* w, const float* q,
                       const float* bcum, int64_t batch, int dpv, float* y, float* p) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, (SLOTS * LL <= 12 ? 2 : 1)>), grid, kCrossThreads, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, R, THREADS>), grid, THREADS, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
   }
   return OK;
 }
-template <typename Vec, int SLOTS>
+template <typename Vec, int SLOTS, int THREADS, int R>
 static int launch_bwd(int layers, int grid, cudaStream_t st, const float* x0, const float* dy, const float* w,
                       const float* q, const float* p, int64_t batch, int dpv, float* dx, float* part, float* sd) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL, (SLOTS <= 2 ? 2 : 1)>), grid, kCrossThreads, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL, R, THREADS>), grid, THREADS, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
@@ -400,7 +426,7 @@ static int cross_shapes(const Aot& a, int xi, int wi, int bi, int64_t* batch, in
   MREC_REQUIRE(*layers >= 1 && *layers <= kCrossMaxL, ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
   const bool v4 = (*dp % 4 == 0);
   const int dpv = v4 ? *dp / 4 : *dp;
-  MREC_REQUIRE(dpv <= kCrossThreads * (v4 ? 4 : 8), ERR_DIM, "mrec_cross: D' = %d too large", *dp);
+  MREC_REQUIRE(dpv <= (v4 ? 2048 : 8192), ERR_DIM, "mrec_cross: D' = %d too large (max 8192)", *dp);
   return OK;
 }
 
@@ -432,18 +458,17 @@ MREC_API int mrec_cross_fwd(int nparam, void** params, int* ndims, int64_t** sha
   float* q = reinterpret_cast<float*>(ws + W.off_q);
   MREC_LAUNCH(cross_prep_kernel, 1, 1024, 0, a.stream, a.ptr<float>(1), a.ptr<float>(2), layers, dp, bcum, q);
   if (batch == 0) return check_launch("cross_prep");
-  const int grid = grid_for(cdiv(batch, 2), 2);
   const float *x0 = a.ptr<float>(0), *w = a.ptr<float>(1);
   float *y = a.ptr<float>(3), *p = a.ptr<float>(4);
+  // 1024 threads x 1 chunk with two rows per iteration when the row fits, wider rows one row at a time
   if (dp % 4 == 0) {
     const int dpv = dp / 4;
-    if (dpv <= kCrossThreads) rc = launch_fwd<float4, 1>(layers, grid, a.stream, x0, w, q, bcum, batch, dpv, y, p);
-    else if (dpv <= 2 * kCrossThreads) rc = launch_fwd<float4, 2>(layers, grid, a.stream, x0, w, q, bcum, batch, dpv, y, p);
-    else rc = launch_fwd<float4, 4>(layers, grid, a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    if (dpv <= 1024) rc = launch_fwd<float4, 1, 1024, 2>(layers, grid_for(cdiv(batch, 2), 1), a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    else rc = launch_fwd<float4, 2, 1024, 1>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dpv, y, p);
   } else {
-    if (dp <= 2 * kCrossThreads) rc = launch_fwd<float, 2>(layers, grid, a.stream, x0, w, q, bcum, batch, dp, y, p);
-    else if (dp <= 4 * kCrossThreads) rc = launch_fwd<float, 4>(layers, grid, a.stream, x0, w, q, bcum, batch, dp, y, p);
-    else rc = launch_fwd<float, 8>(layers, grid, a.stream, x0, w, q, bcum, batch, dp, y, p);
+    if (dp <= 1024) rc = launch_fwd<float, 1, 1024, 2>(layers, grid_for(cdiv(batch, 2), 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
+    else if (dp <= 4096) rc = launch_fwd<float, 4, 1024, 1>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
+    else rc = launch_fwd<float, 8, 1024, 1>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
   }
   if (rc) return rc;
   return check_launch("cross_fwd");
@@ -478,13 +503,12 @@ MREC_API int mrec_cross_bwd(int nparam, void** params, int* ndims, int64_t** sha
   float* dx = a.ptr<float>(5);
   if (dp % 4 == 0) {
     const int dpv = dp / 4;
-    if (dpv <= kCrossThreads) rc = launch_bwd<float4, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
-    else if (dpv <= 2 * kCrossThreads) rc = launch_bwd<float4, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
-    else rc = launch_bwd<float4, 4>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    if (dpv <= 1024) rc = launch_bwd<float4, 1, 1024, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    else rc = launch_bwd<float4, 2, 1024, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
   } else {
-    if (dp <= 2 * kCrossThreads) rc = launch_bwd<float, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
-    else if (dp <= 4 * kCrossThreads) rc = launch_bwd<float, 4>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
-    else rc = launch_bwd<float, 8>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    if (dp <= 1024) rc = launch_bwd<float, 1, 1024, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    else if (dp <= 4096) rc = launch_bwd<float, 4, 1024, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    else rc = launch_bwd<float, 8, 1024, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
   }
   if (rc) return rc;
   float* sums = reinterpret_cast<float*>(ws + W.off_sums);
