@@ -16,6 +16,7 @@
 // second kernel (deterministic, no atomics).  w/Bcum (L*D'*4 = 75 KB at D' = 3120) are read through L1
 // (plain cached loads) while x_0 / dy / y / dx bypass it (no_allocate / streaming stores).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mrec {
 
@@ -146,8 +147,8 @@ struct RowTile {
   }
 };
 
-template <typename Vec, int SLOTS, int L, int R, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+template <typename Vec, int SLOTS, int L, int R, int THREADS, int MINB, bool PF>
+__global__ void __launch_bounds__(THREADS, MINB)
 cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ q,
                  const float* __restrict__ bcum, int64_t batch, int dpv /* D' / vec width */,
                  float* __restrict__ y, float* __restrict__ p_out) {
@@ -163,7 +164,8 @@ cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, cons
   if (row0 < batch) cur.load(x0, row0, batch, dpv);
   int par = 0;
   for (; row0 < batch; row0 += stride, par ^= 1) {
-    const bool more = row0 + stride < batch;
+    const bool more = PF && (row0 + stride < batch);
+    if (!PF && par >= 0 && row0 != (int64_t)blockIdx.x * R) cur.load(x0, row0, batch, dpv);
     if (more) nxt.load(x0, row0 + stride, batch, dpv);   // in flight during everything below
     cur.fence();
     float p[R * L];
@@ -206,7 +208,7 @@ cross_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ w, cons
   }
 }
 
-template <typename Vec, int SLOTS, int L, int R, int THREADS>
+template <typename Vec, int SLOTS, int L, int R, int THREADS, bool PF>
 __global__ void __launch_bounds__(THREADS, 1)
 cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, const float* __restrict__ w,
                  const float* __restrict__ q, const float* __restrict__ p_in, int64_t batch, int dpv,
@@ -238,7 +240,11 @@ cross_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ dy, con
   }
   int par = 0;
   for (; row0 < batch; row0 += stride, par ^= 1) {
-    const bool more = row0 + stride < batch;
+    const bool more = PF && (row0 + stride < batch);
+    if (!PF && row0 != (int64_t)blockIdx.x * R) {
+      x.load(x0, row0, batch, dpv);
+      g.load(dy, row0, batch, dpv);
+    }
     if (more) {
       xn.load(x0, row0 + stride, batch, dpv);
       gn.load(dy, row0 + stride, batch, dpv);
@@ -392,22 +398,22 @@ static CrossWs cross_ws(int layers, int dp, bool backward) {
   return W;
 }
 
-template <typename Vec, int SLOTS, int THREADS, int R>
+template <typename Vec, int SLOTS, int THREADS, int R, int MINB, bool PF>
 static int launch_fwd(int layers, int grid, cudaStream_t st, const float* x0, const float* w, const float* q,
                       const float* bcum, int64_t batch, int dpv, float* y, float* p) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, R, THREADS>), grid, THREADS, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_fwd_kernel<Vec, SLOTS, LL, R, THREADS, MINB, PF>), grid, THREADS, 0, st, x0, w, q, bcum, batch, dpv, y, p); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
   }
   return OK;
 }
-template <typename Vec, int SLOTS, int THREADS, int R>
+template <typename Vec, int SLOTS, int THREADS, int R, bool PF>
 static int launch_bwd(int layers, int grid, cudaStream_t st, const float* x0, const float* dy, const float* w,
                       const float* q, const float* p, int64_t batch, int dpv, float* dx, float* part, float* sd) {
   switch (layers) {
-#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL, R, THREADS>), grid, THREADS, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
+#define C(LL) case LL: MREC_LAUNCH((cross_bwd_kernel<Vec, SLOTS, LL, R, THREADS, PF>), grid, THREADS, 0, st, x0, dy, w, q, p, batch, dpv, dx, part, sd); break;
     C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
 #undef C
     default: return fail(ERR_DIM, "mrec_cross: 1 <= layers <= %d", kCrossMaxL);
@@ -460,15 +466,20 @@ MREC_API int mrec_cross_fwd(int nparam, void** params, int* ndims, int64_t** sha
   if (batch == 0) return check_launch("cross_prep");
   const float *x0 = a.ptr<float>(0), *w = a.ptr<float>(1);
   float *y = a.ptr<float>(3), *p = a.ptr<float>(4);
-  // 1024 threads x 1 chunk with two rows per iteration when the row fits, wider rows one row at a time
+  const char* env = getenv("MREC_CROSS_CFG");
+  const int cfg = env ? atoi(env) : 0;
   if (dp % 4 == 0) {
     const int dpv = dp / 4;
-    if (dpv <= 1024) rc = launch_fwd<float4, 1, 1024, 2>(layers, grid_for(cdiv(batch, 2), 1), a.stream, x0, w, q, bcum, batch, dpv, y, p);
-    else rc = launch_fwd<float4, 2, 1024, 1>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    // measured r1f (16384 x 3120, L = 6): 512 thr x 2 chunks, 2 rows, 2 CTAs/SM, no prefetch: 0.129 ms;
+    // 256 thr x 4 chunks, 4 CTAs/SM: 0.131 ms; 1024 thr x 1 chunk with prefetch, 1 CTA/SM: 0.203 ms.
+    // ncu: 56 % issue-slot utilisation, 38 % DRAM — the 12-value block reduction per row pair is the cost.
+    if (dpv <= 1024 && cfg == 1) rc = launch_fwd<float4, 4, 256, 1, 4, false>(layers, grid_for(batch, 4), a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    else if (dpv <= 1024) rc = launch_fwd<float4, 2, 512, 2, 2, false>(layers, grid_for(cdiv(batch, 2), 2), a.stream, x0, w, q, bcum, batch, dpv, y, p);
+    else rc = launch_fwd<float4, 4, 512, 1, 1, false>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dpv, y, p);
   } else {
-    if (dp <= 1024) rc = launch_fwd<float, 1, 1024, 2>(layers, grid_for(cdiv(batch, 2), 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
-    else if (dp <= 4096) rc = launch_fwd<float, 4, 1024, 1>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
-    else rc = launch_fwd<float, 8, 1024, 1>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
+    if (dp <= 1024) rc = launch_fwd<float, 2, 512, 2, 2, false>(layers, grid_for(cdiv(batch, 2), 2), a.stream, x0, w, q, bcum, batch, dp, y, p);
+    else if (dp <= 4096) rc = launch_fwd<float, 8, 512, 1, 1, false>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
+    else rc = launch_fwd<float, 16, 512, 1, 1, false>(layers, grid_for(batch, 1), a.stream, x0, w, q, bcum, batch, dp, y, p);
   }
   if (rc) return rc;
   return check_launch("cross_fwd");
@@ -501,14 +512,19 @@ MREC_API int mrec_cross_bwd(int nparam, void** params, int* ndims, int64_t** sha
   const int grid = W.nparts;  // every CTA writes its (possibly zero) partial: the finish sums all of them
   const float *x0 = a.ptr<float>(0), *dy = a.ptr<float>(1), *w = a.ptr<float>(2), *p = a.ptr<float>(4);
   float* dx = a.ptr<float>(5);
+  const char* env = getenv("MREC_CROSS_CFG");
+  const int cfg = env ? atoi(env) : 0;
   if (dp % 4 == 0) {
     const int dpv = dp / 4;
-    if (dpv <= 1024) rc = launch_bwd<float4, 1, 1024, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
-    else rc = launch_bwd<float4, 2, 1024, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    // measured r1f: 512 thr x 2 chunks, 1 row + prefetch of the next: 0.206 ms; 2 rows, no prefetch: 0.219 ms;
+    // 1024 thr x 1 chunk: 0.29-0.31 ms (one CTA per SM: every barrier stalls the whole SM)
+    if (dpv <= 1024 && cfg != 1) rc = launch_bwd<float4, 2, 512, 1, true>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    else if (dpv <= 1024) rc = launch_bwd<float4, 2, 512, 2, false>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
+    else rc = launch_bwd<float4, 4, 512, 1, false>(layers, grid, a.stream, x0, dy, w, q, p, batch, dpv, dx, part, sd);
   } else {
-    if (dp <= 1024) rc = launch_bwd<float, 1, 1024, 2>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
-    else if (dp <= 4096) rc = launch_bwd<float, 4, 1024, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
-    else rc = launch_bwd<float, 8, 1024, 1>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    if (dp <= 1024) rc = launch_bwd<float, 2, 512, 2, false>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    else if (dp <= 4096) rc = launch_bwd<float, 8, 512, 1, false>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
+    else rc = launch_bwd<float, 16, 512, 1, false>(layers, grid, a.stream, x0, dy, w, q, p, batch, dp, dx, part, sd);
   }
   if (rc) return rc;
   float* sums = reinterpret_cast<float*>(ws + W.off_sums);
