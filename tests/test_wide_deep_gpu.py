@@ -130,3 +130,19 @@ def test_online_train_and_checkpoint_round_trip(cuda):
     step2(*batch)
     assert torch.equal(model.embedding_table.data, model2.embedding_table.data)
     assert torch.equal(model.dense.flat, model2.dense.flat)
+
+
+def test_replay_with_staged_next_batch_equals_plain_replay(cuda):
+    cfg, model, step, _ = _build(cuda, "lazy")
+    cfg2, model2, step2, _ = _build(cuda, "lazy")
+    gen = synth.CriteoSynth(cfg.batch_size, cards=[50] * 26, vocab_pad=cfg.vocab_size, seed=31)
+    host = [tuple(torch.from_numpy(x).pin_memory() for x in gen.next()) for _ in range(5)]
+    dev0 = tuple(t.to(cuda) for t in host[0])
+    step.capture(*dev0, warmup=1)
+    step2.capture(*dev0, warmup=1)
+    for i in range(5):
+        step.replay(*host[i], next_batch=host[(i + 1) % 5])
+        step2.replay(*host[i])
+    torch.cuda.synchronize()
+    assert torch.equal(model.embedding_table.data, model2.embedding_table.data)
+    assert torch.equal(model.dense.flat, model2.dense.flat)
