@@ -62,6 +62,11 @@ int mrec_gather_masked(MREC_AOT_ARGS);
  * deepfm.py:217-219):
  *   in : table[V]|[V,1], ids[B,F], mask[B,F], bias[1] out: out[B]|[B,1] f32, (oob[1])           */
 int mrec_gather_reduce(MREC_AOT_ARGS);
+/* multi-hot pooled lookup: gather + Mul(mask) + ReduceMean over the S slots (masked slots count in the mean),
+ * models/wide_and_deep_multitable/src/wide_and_deep.py:301-346.  The backward is mrec_sparse_* with the pooled
+ * gradient broadcast over the slots (g[B,D] for N = B*S positions) and mask / S as the weight.
+ *   in : table[V,D] (D % 4 == 0), ids[B,S], mask[B,S] f32                     out: out[B,D] f32, (oob[1])   */
+int mrec_gather_pool(MREC_AOT_ARGS);
 
 /* ---- K2 unique -------------------------------------------------------------------------------
  * Replaces P.Unique (mindspore_rec/ops/embedding.py:192) and the optimizer-side RowTensor dedup

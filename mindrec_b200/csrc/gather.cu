@@ -225,6 +225,40 @@ gather_reduce_kernel(const float* __restrict__ table, const IdT* __restrict__ id
   }
 }
 
+// Multi-hot pooled lookup: out[b, :] = (1/S) * sum_s table[ids[b,s], :] * mask[b,s]  (mean over ALL S slots,
+// masked ones included, like ReduceMean(axis 1) in models/wide_and_deep_multitable/src/wide_and_deep.py:301-346).
+// A group of D/4 threads owns one sample and keeps up to 8 slot rows in flight; the [B,S,D] intermediate of the
+// reference never exists.  Slots are added in slot order (deterministic).
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+gather_pool_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids, const float* __restrict__ mask,
+                   float4* __restrict__ out, int64_t batch, int slots, int cpr, int64_t vocab, float inv_slots,
+                   int* __restrict__ oob) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t b = gid / cpr;
+  if (b >= batch) return;
+  const int c = (int)(gid - b * cpr);
+  float4 acc = f4_zero();
+  for (int s0 = 0; s0 < slots; s0 += 8) {
+    float4 v[8];
+    float mk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int sidx = min(s0 + k, slots - 1);
+      const int64_t id = (int64_t)ids[b * slots + sidx];
+      const bool ok = (uint64_t)id < (uint64_t)vocab;
+      if (!ok && oob && s0 + k < slots) atomicOr(oob, 1);
+      v[k] = ld_stream_f4(table + (ok ? id : 0) * cpr + c);
+      mk[k] = (ok && s0 + k < slots) ? mask[b * slots + sidx] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) reg_fence(v[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f4_fma(acc, v[k], mk[k]);
+  }
+  st_stream_f4(out + b * cpr + c, f4_scale(acc, inv_slots));
+}
+
 template <typename IdT, bool MASKED, typename OutT>
 static int launch_gather(const float* table, const IdT* ids, const float* mask, OutT* out,
                          int64_t n_rows, int dim, int64_t vocab, int* oob, cudaStream_t stream) {
@@ -359,4 +393,36 @@ MREC_API int mrec_gather_reduce(int nparam, void** params, int* ndims, int64_t**
                 vocab, oob);
   }
   return check_launch("gather_reduce");
+}
+
+// in : table[V,D] f32 (D % 4 == 0), ids[B,S] i32|i64, mask[B,S] f32      out: out[B,D] f32, (oob[1] i32)
+MREC_API int mrec_gather_pool(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                              void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 4 && a.nparam != 5)
+    return fail(ERR_NPARAM, "mrec_gather_pool: expected 4 or 5 params, got %d", a.nparam);
+  for (int i = 0; i < a.nparam; ++i)
+    if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "mrec_gather_pool: param %d is null", i);
+  MREC_REQUIRE(a.is_f32(0) && a.is_f32(2) && a.is_f32(3), ERR_DTYPE, "mrec_gather_pool: table/mask/out must be float32");
+  MREC_REQUIRE(a.is_i32(1) || a.is_i64(1), ERR_DTYPE, "mrec_gather_pool: ids must be int32|int64");
+  MREC_REQUIRE(a.ndims[0] == 2 && a.ndims[1] == 2, ERR_SHAPE, "mrec_gather_pool: table[V,D], ids[B,S] expected");
+  const int64_t vocab = a.dim(0, 0), batch = a.dim(1, 0);
+  const int dim = (int)a.dim(0, 1), slots = (int)a.dim(1, 1);
+  MREC_REQUIRE(dim % 4 == 0 && dim >= 4, ERR_DIM, "mrec_gather_pool: D must be a multiple of 4");
+  MREC_REQUIRE(slots >= 1 && vocab >= 1, ERR_SHAPE, "mrec_gather_pool: S and V must be >= 1");
+  MREC_REQUIRE(a.numel(2) == batch * slots && a.numel(3) == batch * dim, ERR_SHAPE,
+               "mrec_gather_pool: mask must be [B,S] and out [B,D]");
+  MREC_REQUIRE(a.aligned(0, 16) && a.aligned(3, 16), ERR_ALIGN, "mrec_gather_pool: table/out must be 16-byte aligned");
+  int* oob = a.nparam == 5 ? a.ptr<int>(4) : nullptr;
+  if (batch == 0) return OK;
+  const int cpr = dim / 4;
+  const int grid = (int)cdiv(batch * cpr, 256);
+  if (a.is_i32(1)) {
+    MREC_LAUNCH(gather_pool_kernel<int32_t>, grid, 256, 0, a.stream, a.ptr<float4>(0), a.ptr<int32_t>(1),
+                a.ptr<float>(2), a.ptr<float4>(3), batch, slots, cpr, vocab, 1.f / (float)slots, oob);
+  } else {
+    MREC_LAUNCH(gather_pool_kernel<int64_t>, grid, 256, 0, a.stream, a.ptr<float4>(0), a.ptr<int64_t>(1),
+                a.ptr<float>(2), a.ptr<float4>(3), batch, slots, cpr, vocab, 1.f / (float)slots, oob);
+  }
+  return check_launch("gather_pool");
 }

@@ -73,6 +73,15 @@ def gather_reduce(table, ids, mask, bias, out=None, oob_flag=None):
     return out
 
 
+def gather_pool(table, ids, mask, out=None, oob_flag=None):
+    """out[b] = mean over the S slots of table[ids[b,s]] * mask[b,s]  (multi-hot fields of the multitable model)."""
+    if out is None:
+        out = torch.empty((ids.shape[0], table.shape[1]), dtype=torch.float32, device=table.device)
+    args = [table, ids, mask, out] + ([oob_flag] if oob_flag is not None else [])
+    _lib.aot_call("mrec_gather_pool", args)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # K2 unique
 # ------------------------------------------------------------------------------------------------

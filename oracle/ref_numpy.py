@@ -522,3 +522,10 @@ class DeepCrossOracle:
             self._adam("hw%d" % i, self.hw[i], ghw[i]); self._adam("hb%d" % i, self.hb[i], ghb[i])
         self._adam("cw", self.cw, gcw); self._adam("cb", self.cb, gcb)
         return F32(loss)
+
+
+def gather_pool(table, ids, mask):
+    """Multi-hot field of the multitable model: ReduceMean(table[ids] * mask[..., None], axis 1) over ALL slots
+    — models/wide_and_deep_multitable/src/wide_and_deep.py:301-307."""
+    e = gather(table, ids).astype(np.float64) * np.asarray(mask, dtype=np.float64)[..., None]
+    return e.mean(axis=1)

@@ -117,3 +117,24 @@ def test_gather_masked_fp16_output_equals_cast_after(cuda, dim):
     assert out.dtype == torch.float16
     ref = R.gather_masked(tab, ids, mask).astype(np.float16)
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("b,s,dim", [(1, 1, 64), (333, 12, 64), (100, 7, 128), (64, 30, 16)])
+def test_gather_pool_matches_oracle_and_backward_maps_to_sparse_update(cuda, b, s, dim):
+    """Forward: fused mean-pooled lookup (multitable a15).  Backward: the pooled gradient broadcast over the S
+    slots with weight mask/S is exactly mrec_segment_sum with div = S."""
+    v = 4000
+    rng = np.random.default_rng(b * 7 + s)
+    tab = _table(v, dim, 11)
+    ids = rng.integers(0, v, size=(b, s)).astype(np.int32)
+    mask = (rng.random((b, s)) < 0.7).astype(np.float32)
+    d_ids, d_mask = torch.from_numpy(ids).to(cuda), torch.from_numpy(mask).to(cuda)
+    out = ops.gather_pool(torch.from_numpy(tab).to(cuda), d_ids, d_mask)
+    ref = R.gather_pool(tab, ids, mask)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6 * np.abs(tab).max())
+    gout = rng.standard_normal((b, dim)).astype(np.float32)
+    uq = ops.unique(d_ids)
+    gs = ops.segment_sum(torch.from_numpy(gout).to(cuda), (d_mask / s).reshape(-1), uq, dim=dim)
+    uniq, inverse, _, _ = R.unique_sorted(ids)
+    gref = R.segment_sum(gout, inverse, uniq.size, (mask / s).reshape(-1), div=s)
+    np.testing.assert_allclose(gs[:uniq.size].cpu().numpy(), gref, rtol=1e-5, atol=1e-5 * np.abs(gref).max())
