@@ -89,6 +89,18 @@ int mrec_shard_bounds(MREC_AOT_ARGS);
 /* Owner-major key remap, key' = (key mod G) * R + key div G (out-of-range -> G*R):
  *   in : ids[...] i32|i64, table_like[V,...], owners_like[G,R] (only the shapes are read)   out: keys[...] */
 int mrec_shard_remap(MREC_AOT_ARGS);
+/* Fused owner-side gather + NVLink peer store (forward row exchange of row-sharded tables): every requested row
+ * is read once and stored directly into the requesting rank's landing buffer through a peer-mapped pointer.
+ *   in : table[R,D] f32 (local shard), rows[n_r] i32 (local row ids, concatenated by source rank),
+ *        peer_ptrs[G] i64 (landing-buffer base of every rank as mapped in this process), dst_off[G] i32,
+ *        src_off[G+1] i32                                                                      out: dummy[1] */
+int mrec_gather_to_peers(MREC_AOT_ARGS);
+/* CUDA-IPC plumbing for the peer buffers (host only, set-up time, not aot) */
+void *mrec_peer_alloc(size_t bytes);
+int mrec_peer_free(void *p);
+int mrec_ipc_get_handle(void *base_ptr, char *handle64);
+void *mrec_ipc_open_handle(const char *handle64);
+int mrec_ipc_close_handle(void *p);
 size_t mrec_unique_workspace_bytes(int64_t n, int key_bytes);
 size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes);
 

@@ -299,3 +299,8 @@ def sigmoid_xent(a, b, label, sens, out=None, half=False):
     b = _empty_mask(dev) if b is None else b
     _lib.aot_call("mrec_sigmoid_xent", [a, b, label, sens, out[0], out[1], out[2], out[3], out[4]])
     return out
+
+
+def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
+    """Owner-side gather fused with the NVLink peer store of every row into its requester's landing buffer."""
+    _lib.aot_call("mrec_gather_to_peers", [table, rows, peer_ptrs, dst_off, src_off, _dummy(table.device)])

@@ -24,6 +24,57 @@ from . import ops as _cuda_ops
 # MREC_SHARDED_GRAPH=0 keeps the DenseLayer segment eager; MREC_SHARDED_AHEAD=0 plans every batch in line.
 _ENV_GRAPH = os.environ.get("MREC_SHARDED_GRAPH", "1") != "0"
 _ENV_AHEAD = os.environ.get("MREC_SHARDED_AHEAD", "1") != "0"
+# MREC_SHARDED_PEER=0 returns rows with NCCL all-to-all instead of the fused gather + NVLink peer store.
+_ENV_PEER = os.environ.get("MREC_SHARDED_PEER", "1") != "0"
+
+
+class _RawCuda:
+    """__cuda_array_interface__ view of a raw device allocation (lets torch wrap memory from mrec_peer_alloc)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerLanding:
+    """Per-rank landing buffers [cap, D] that every other rank of the node can store into (CUDA IPC).
+
+    Allocated with cudaMalloc through the library (exportable with cudaIpcGetMemHandle), handles exchanged once
+    over the process group, peers mapped with cudaIpcOpenMemHandle (which also enables peer access)."""
+
+    def __init__(self, cap_rows, dims, device, group):
+        import ctypes
+        from . import _lib
+        lib = _lib.lib()
+        lib.mrec_peer_alloc.restype = ctypes.c_void_p
+        lib.mrec_peer_alloc.argtypes = [ctypes.c_size_t]
+        lib.mrec_ipc_open_handle.restype = ctypes.c_void_p
+        lib.mrec_ipc_open_handle.argtypes = [ctypes.c_char_p]
+        lib.mrec_ipc_get_handle.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buffers, self.ptr_tensors, handles = [], [], []
+        for d in dims:
+            ptr = lib.mrec_peer_alloc(cap_rows * d * 4)
+            if not ptr:
+                raise RuntimeError("mrec_peer_alloc failed: " + _lib.last_error())
+            h = ctypes.create_string_buffer(64)
+            if lib.mrec_ipc_get_handle(ctypes.c_void_p(ptr), h) != 0:
+                raise RuntimeError("mrec_ipc_get_handle failed: " + _lib.last_error())
+            handles.append((ptr, h.raw))
+            self.buffers.append(torch.as_tensor(_RawCuda(ptr, (cap_rows, d)), device=device))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [h for _, h in handles], group=group)
+        for j, (ptr, _) in enumerate(handles):
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(ptr)
+                else:
+                    p = lib.mrec_ipc_open_handle(gathered[r][j])
+                    if not p:
+                        raise RuntimeError("mrec_ipc_open_handle failed: " + _lib.last_error())
+                    ptrs.append(p)
+            self.ptr_tensors.append(torch.tensor(ptrs, dtype=torch.int64, device=device))
 
 
 class ShardPlan:
@@ -64,7 +115,7 @@ class BatchPlan:
     Built by ShardedWideDeepTables.plan_batch — possibly one step ahead, on a side stream with its own
     communicator — and finalised (one host read of G*(G+1) ints) when the batch is consumed."""
 
-    __slots__ = ("ids", "uq", "bounds_host", "event", "send", "recv", "n_u", "n_r")
+    __slots__ = ("ids", "uq", "bounds_host", "event", "send", "recv", "n_u", "n_r", "allb")
 
     def finalize(self, rank, world):
         if self.send is not None:
@@ -119,6 +170,9 @@ class ShardedWideDeepTables:
         self._gs = None
         self._slot = 0
         self._bufs = {}
+        self.peer = None
+        self._peer_tried = False
+        self._bar = torch.zeros(1, dtype=torch.float32, device=self.device) if self.cuda else None
         n_b = self.world * (self.world + 1)
         self._pinned = [torch.empty(n_b, dtype=torch.int32).pin_memory() for _ in range(2)] if self.cuda else None
 
@@ -168,6 +222,7 @@ class ShardedWideDeepTables:
                 dist.all_gather_into_tensor(allb, bounds, group=self.plan_group)
             else:
                 allb = bounds
+            plan.allb = allb
             if self.cuda:
                 plan.bounds_host = self._pinned[slot]
                 plan.bounds_host.copy_(allb, non_blocking=True)
@@ -192,17 +247,37 @@ class ShardedWideDeepTables:
             _a2a(rows_recv, local_rows_send, recv, send, self.group)
         else:
             rows_recv.copy_(local_rows_send)
-        # owner side: gather the requested rows of both tables
-        deep_rows = k.gather(self.deep, rows_recv, out=self._buf("deep_rows", n_r, self.dim)[:n_r])
-        wide_rows = k.gather(self.wide, rows_recv, out=self._buf("wide_rows", n_r, 1)[:n_r])
-        got_deep = self._buf("got_deep", n_u, self.dim)
-        got_wide = self._buf("got_wide", n_u, 1)
-        if g > 1:
-            _a2a(got_deep[:n_u], deep_rows, send, recv, self.group)
-            _a2a(got_wide[:n_u], wide_rows, send, recv, self.group)
+        # owner side: return the requested rows of both tables
+        if g > 1 and self.cuda and _ENV_PEER and not self._peer_tried:
+            self._peer_tried = True
+            try:                                   # landing buffers sized for the worst case U = N
+                self.peer = PeerLanding(uq.n, (self.dim, 1), self.device, self.group)
+            except Exception as exc:               # no IPC on this box: fall back to NCCL all-to-all
+                import warnings
+                warnings.warn("peer landing buffers unavailable (%s): using NCCL all-to-all" % (exc,))
+                self.peer = None
+        if g > 1 and self.peer is not None:
+            # fused gather + NVLink peer store straight into each requester's landing buffer, then a
+            # stream-ordered barrier publishes everybody's stores (the next key all-to-all orders re-use)
+            ab = plan.allb.view(g, g + 1)
+            dst_off = ab[:, self.rank].contiguous()
+            src_off = torch.zeros(g + 1, dtype=torch.int32, device=ab.device)
+            src_off[1:] = torch.cumsum(ab[:, self.rank + 1] - ab[:, self.rank], 0)
+            k.gather_to_peers(self.deep, rows_recv, self.peer.ptr_tensors[0], dst_off, src_off)
+            k.gather_to_peers(self.wide, rows_recv, self.peer.ptr_tensors[1], dst_off, src_off)
+            dist.all_reduce(self._bar, group=self.group)
+            got_deep, got_wide = self.peer.buffers
         else:
-            got_deep[:n_u].copy_(deep_rows)
-            got_wide[:n_u].copy_(wide_rows)
+            deep_rows = k.gather(self.deep, rows_recv, out=self._buf("deep_rows", n_r, self.dim)[:n_r])
+            wide_rows = k.gather(self.wide, rows_recv, out=self._buf("wide_rows", n_r, 1)[:n_r])
+            got_deep = self._buf("got_deep", n_u, self.dim)
+            got_wide = self._buf("got_wide", n_u, 1)
+            if g > 1:
+                _a2a(got_deep[:n_u], deep_rows, send, recv, self.group)
+                _a2a(got_wide[:n_u], wide_rows, send, recv, self.group)
+            else:
+                got_deep[:n_u].copy_(deep_rows)
+                got_wide[:n_u].copy_(wide_rows)
         # requester side: expand unique rows to lookups with the inverse index, fused with mask / reduce
         inverse = uq.inverse.view(b, f)
         k.gather_masked(got_deep[:max(n_u, 1)], inverse, wts, out=deep_out)
