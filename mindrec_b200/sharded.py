@@ -115,7 +115,7 @@ class BatchPlan:
     Built by ShardedWideDeepTables.plan_batch — possibly one step ahead, on a side stream with its own
     communicator — and finalised (one host read of G*(G+1) ints) when the batch is consumed."""
 
-    __slots__ = ("ids", "uq", "bounds_host", "event", "send", "recv", "n_u", "n_r", "allb")
+    __slots__ = ("ids", "uq", "bounds_host", "event", "send", "recv", "n_u", "n_r", "allb", "dst_off", "src_off")
 
     def finalize(self, rank, world):
         if self.send is not None:
@@ -223,6 +223,16 @@ class ShardedWideDeepTables:
             else:
                 allb = bounds
             plan.allb = allb
+            if g > 1:
+                # offsets of the fused gather + peer store, computed here so they are off the critical path:
+                # dst_off[s] = where rank s's bucket for this owner starts in s's landing buffer,
+                # src_off    = prefix sums of what every rank asks of this owner
+                ab = allb.view(g, g + 1)
+                plan.dst_off = ab[:, self.rank].contiguous()
+                plan.src_off = torch.zeros(g + 1, dtype=torch.int32, device=ids.device)
+                plan.src_off[1:] = torch.cumsum(ab[:, self.rank + 1] - ab[:, self.rank], 0)
+            else:
+                plan.dst_off = plan.src_off = None
             if self.cuda:
                 plan.bounds_host = self._pinned[slot]
                 plan.bounds_host.copy_(allb, non_blocking=True)
@@ -259,12 +269,8 @@ class ShardedWideDeepTables:
         if g > 1 and self.peer is not None:
             # fused gather + NVLink peer store straight into each requester's landing buffer, then a
             # stream-ordered barrier publishes everybody's stores (the next key all-to-all orders re-use)
-            ab = plan.allb.view(g, g + 1)
-            dst_off = ab[:, self.rank].contiguous()
-            src_off = torch.zeros(g + 1, dtype=torch.int32, device=ab.device)
-            src_off[1:] = torch.cumsum(ab[:, self.rank + 1] - ab[:, self.rank], 0)
-            k.gather_to_peers(self.deep, rows_recv, self.peer.ptr_tensors[0], dst_off, src_off)
-            k.gather_to_peers(self.wide, rows_recv, self.peer.ptr_tensors[1], dst_off, src_off)
+            k.gather_to_peers(self.deep, rows_recv, self.peer.ptr_tensors[0], plan.dst_off, plan.src_off)
+            k.gather_to_peers(self.wide, rows_recv, self.peer.ptr_tensors[1], plan.dst_off, plan.src_off)
             dist.all_reduce(self._bar, group=self.group)
             got_deep, got_wide = self.peer.buffers
         else:
