@@ -220,11 +220,16 @@ def measure_dominant_op(step, batch, b, iters=20):
     peak, how = hbm_peak()
     alg = n * d * 2 + u * 7 * d * 4
     gbs = alg / ms / 1e6
-    return {"kernel": "mrec_sparse_lazy_adam = segsum_tiles_kernel<float4,__half> + segsum_boundary + segsum_long + "
-                      "rows_update_kernel<float4,LazyAdamSink> (4 launches, timed as one op)",
+    traffic = None
+    try:      # dram__bytes_read + dram__bytes_write of the op's kernels from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return {"kernel": "mrec_sparse_lazy_adam = segsum_tiles_kernel<float4,__half> + "
+                      "rows_update_kernel<float4,LazyAdamSink> (2 launches, timed as one op)",
             "bound": "hbm", "achieved": round(gbs, 1), "peak": peak,
             "peak_source": "MEASURED_PEAKS.json (measured)" if how == "measured" else "fallback 6650",
-            "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": None, "algorithmic_bytes": alg,
+            "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": traffic, "algorithmic_bytes": alg,
             "unique_rows": u, "lookups": n, "ms": round(ms, 4),
             "how": "CUDA graph replay of the op alone, 256 MB L2 flush before each of %d iterations, CUDA events, median" % iters}
 
