@@ -76,7 +76,8 @@ int mrec_gather_pool(MREC_AOT_ARGS);
  *        permutation), seg_start[N+1] i32, seg_of[N] i32, workspace[mrec_unique_workspace_bytes] u8 */
 int mrec_unique(MREC_AOT_ARGS);
 /* Same, second input table_like[V,...]: only ceil(log2(V+1)) key bits are sorted; ids outside [0,V)
- * collapse onto the value V (they form the last segment, which the optimizers skip).            */
+ * collapse onto the value V (they form the last segment, which the optimizers skip).  Optional third input
+ * n_valid[1] i32: entries at i >= n_valid are padding and are read as out of range.            */
 int mrec_unique_bounded(MREC_AOT_ARGS);
 /* First-occurrence order = upstream CPU Unique kernel (BASELINE config 1 runs device_target=CPU).
  *   in : ids[N]   out: uniq[N], inverse[N] i32, count[1] i32, workspace[mrec_unique_first_workspace_bytes] */
@@ -95,6 +96,20 @@ int mrec_shard_remap(MREC_AOT_ARGS);
  *        peer_ptrs[G] i64 (landing-buffer base of every rank as mapped in this process), dst_off[G] i32,
  *        src_off[G+1] i32                                                                      out: dummy[1] */
 int mrec_gather_to_peers(MREC_AOT_ARGS);
+/* Device-driven exchange (no host-side sizes; the whole sharded step can be one CUDA graph).  With
+ * B[s][o] = start of rank s's bucket for owner o among its sorted unique keys (B[s][G] = U_s):
+ *   mrec_shard_offsets       in : bounds_all[G*(G+1)] i32, ctrl[2] i32 {rank, G}
+ *                            out: dst_off[G], src_off[G+1], inbox_off[G], n_r[1]  (all i32)
+ *   mrec_push_rows_to_peers  in : rows[cap,W] f32|i32, my_bounds[G+1], inbox_off[G], peer_ptrs[G] i64,
+ *                                 cap_like[cap_rows,..], mod_like[M,..] (M > 0: int32 keys are sent as key % M)
+ *                            out: err[1] i32 (bit 1: an inbox overflowed)
+ *   mrec_peer_signal         in : payload[K] i32, payload_ptrs[G] i64, flag_ptrs[G] i64, epoch[1] i32 (+1)  out: dummy[1]
+ *   mrec_peer_wait           in : flags[G] i32, epoch[1] i32 [, limit_log2[1] i32: spin limit 2^limit cycles, default ~4 s]
+ *                            out: err[1] i32 (bit 0: time-out) */
+int mrec_shard_offsets(MREC_AOT_ARGS);
+int mrec_push_rows_to_peers(MREC_AOT_ARGS);
+int mrec_peer_signal(MREC_AOT_ARGS);
+int mrec_peer_wait(MREC_AOT_ARGS);
 /* CUDA-IPC plumbing for the peer buffers (host only, set-up time, not aot) */
 void *mrec_peer_alloc(size_t bytes);
 int mrec_peer_free(void *p);
@@ -114,7 +129,8 @@ size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes);
  *   Adam : lr, beta1, beta2, eps, beta1_power, beta2_power, lr_t, 1/loss_scale, l2 (dense-mode table
  *          regulariser, wide_and_deep.py:359-360), 7 reserved
  *   FTRL : lr, l1, l2, lr_power, 1/loss_scale, 11 reserved
- *   in : w[V,D] m[V,D] v[V,D] hyper[16] g mask uniq[N] perm[N] seg_start[N+1] seg_of[N]
+ *   in : w[V,D] m[V,D] v[V,D] hyper[16] g mask uniq[N] perm[N] seg_start[N+1] seg_of[N], (n_valid[1] i32:
+ *        only the first n_valid sorted positions are real — statically sized inboxes of the sharded path)
  *   out: dummy[1] i32, workspace[mrec_sparse_opt_workspace_bytes(N, D)] u8                       */
 int mrec_sparse_lazy_adam(MREC_AOT_ARGS);
 /*   in : w[V,D] accum[V,D] linear[V,D] hyper[16] g mask uniq perm seg_start seg_of   out: dummy, workspace */

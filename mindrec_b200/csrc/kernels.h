@@ -14,7 +14,7 @@ int key_bits_for_bound(uint64_t bound);
 template <typename KeyT>
 int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t* inverse,
                   int32_t* count, int32_t* perm, int32_t* seg_start, int32_t* seg_of, void* ws,
-                  size_t ws_bytes, cudaStream_t stream);
+                  size_t ws_bytes, cudaStream_t stream, const int32_t* n_valid = nullptr);
 template <typename KeyT>
 int unique_first(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t* inverse,
                  int32_t* count, void* ws, size_t ws_bytes, cudaStream_t stream);

@@ -33,7 +33,8 @@ gather_to_peers_kernel(const float* __restrict__ table, const int32_t* __restric
   }
   if (threadIdx.x <= world) s_t.src_off[threadIdx.x] = src_off[threadIdx.x];
   __syncthreads();
-  const int64_t total = n_rows * cpr;
+  // rows beyond src_off[world] are padding of a statically sized inbox (device-driven exchange)
+  const int64_t total = min(n_rows, (int64_t)s_t.src_off[world]) * cpr;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e0 < total; e0 += 4 * stride) {
     Vec v[4];
@@ -131,4 +132,176 @@ MREC_API int mrec_gather_to_peers(int nparam, void** params, int* ndims, int64_t
                 a.ptr<int32_t>(1), n, dim, vocab, world, a.ptr<int64_t>(2), a.ptr<int32_t>(3), a.ptr<int32_t>(4));
   }
   return check_launch("gather_to_peers");
+}
+
+// =================================================================================================
+// Device-driven exchange protocol (no host-side sizes): every rank publishes its bucket bounds to all peers, and
+// keys / rows / gradients are stored straight into peer inboxes at offsets each rank derives on the device from
+// the bounds matrix  B[s][o] = first unique-key index of rank s's bucket for owner o  (B[s][G] = U_s):
+//   cnt[s][o]   = B[s][o+1] - B[s][o]                     keys rank s asks of owner o
+//   inbox_off   = sum_{s' < s} cnt[s'][o]                  where s's segment starts in o's inbox (keys and grads)
+//   n_r[o]      = sum_s cnt[s][o]                          valid entries of o's inbox
+// Phase completion is a pair of tiny kernels: `signal` stores an epoch into a flag slot on every peer (after a
+// system-scope fence), `wait` spins (bounded) until all G local slots reached the epoch.  Kernel boundaries
+// give the ordering of the data stores against the flags.  Everything is static-shaped, so the whole training
+// step can be captured in one CUDA graph.
+// =================================================================================================
+namespace mrec {
+
+// ctrl[0] = my rank, ctrl[1] = world size
+__global__ void shard_offsets_kernel(const int32_t* __restrict__ ball, const int32_t* __restrict__ ctrl,
+                                     int32_t* __restrict__ dst_off, int32_t* __restrict__ src_off,
+                                     int32_t* __restrict__ inbox_off, int32_t* __restrict__ n_r) {
+  const int me = ctrl[0], g = ctrl[1];
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int run = 0;
+  for (int s = 0; s < g; ++s) {                      // what every rank asks of me
+    src_off[s] = run;
+    dst_off[s] = ball[s * (g + 1) + me];             // where rank s wants my rows in its landing buffer
+    run += ball[s * (g + 1) + me + 1] - ball[s * (g + 1) + me];
+  }
+  src_off[g] = run;
+  n_r[0] = run;
+  for (int o = 0; o < g; ++o) {                      // where my segment starts in owner o's inbox
+    int off = 0;
+    for (int s = 0; s < me; ++s) off += ball[s * (g + 1) + o + 1] - ball[s * (g + 1) + o];
+    inbox_off[o] = off;
+  }
+}
+
+// rows[u, :] (4-byte elements, `width` per row) of my buckets -> owner o's inbox row inbox_off[o] + (u - B[me][o]).
+// transform_mod > 0: the element is an int32 owner-major key and is sent as key % transform_mod (local row id).
+__global__ void __launch_bounds__(256)
+push_rows_to_peers_kernel(const uint32_t* __restrict__ rows, int width, const int32_t* __restrict__ my_bounds,
+                          const int32_t* __restrict__ inbox_off, const int64_t* __restrict__ peer_ptrs, int world,
+                          int transform_mod, int64_t cap_rows, int32_t* __restrict__ err) {
+  __shared__ int32_t s_b[kPeerMaxRanks + 1];
+  __shared__ int32_t s_off[kPeerMaxRanks];
+  __shared__ uint32_t* s_ptr[kPeerMaxRanks];
+  if (threadIdx.x <= world) s_b[threadIdx.x] = my_bounds[threadIdx.x];
+  if (threadIdx.x < world) {
+    s_off[threadIdx.x] = inbox_off[threadIdx.x];
+    s_ptr[threadIdx.x] = reinterpret_cast<uint32_t*>(peer_ptrs[threadIdx.x]);
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)s_b[world] * width;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = e / width;
+    const int c = (int)(e - u * width);
+    int o = 0;
+    while (o + 1 < world && u >= s_b[o + 1]) ++o;
+    const int64_t drow = (int64_t)s_off[o] + (u - s_b[o]);
+    if (drow >= cap_rows) {                      // inbox capacity exceeded: flag it, drop the row
+      if (err) atomicOr(err, 2);
+      continue;
+    }
+    uint32_t v = rows[e];
+    if (transform_mod > 0) v = (uint32_t)((int32_t)v % transform_mod);
+    s_ptr[o][drow * width + c] = v;
+  }
+}
+
+// payload[K] -> every peer's payload slot, then (after a system fence) epoch -> every peer's flag slot.
+__global__ void peer_signal_kernel(const int32_t* __restrict__ payload, int k, const int64_t* __restrict__ payload_ptrs,
+                                   const int64_t* __restrict__ flag_ptrs, int world, int32_t* __restrict__ epoch) {
+  const int e = epoch[0] + 1;
+  for (int i = threadIdx.x; i < k * world; i += blockDim.x) {
+    const int s = i / k, j = i - s * k;
+    reinterpret_cast<int32_t*>(payload_ptrs[s])[j] = payload[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    volatile int32_t* f = reinterpret_cast<volatile int32_t*>(flag_ptrs[threadIdx.x]);
+    *f = e;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) epoch[0] = e;
+}
+
+// spin until all `world` local flag slots reached epoch[0]; bounded: on time-out raise err and return
+__global__ void peer_wait_kernel(const int32_t* __restrict__ flags, int world, const int32_t* __restrict__ epoch,
+                                 int32_t* __restrict__ err, const int32_t* __restrict__ limit_log2,
+                                 long long max_cycles) {
+  if (threadIdx.x >= world) return;
+  if (limit_log2) max_cycles = 1ll << limit_log2[0];
+  const int e = epoch[0];
+  const volatile int32_t* f = flags + threadIdx.x;
+  const long long t0 = clock64();
+  while (*f < e) {
+    if (clock64() - t0 > max_cycles) {
+      atomicOr(err, 1);
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+}  // namespace mrec
+
+// in : bounds_all[G*(G+1)] i32, ctrl[2] i32 {rank, world}     out: dst_off[G], src_off[G+1], inbox_off[G], n_r[1] (i32)
+MREC_API int mrec_shard_offsets(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 6);
+  for (int i = 0; i < 6; ++i) MREC_REQUIRE(a.is_i32(i), ERR_DTYPE, "mrec_shard_offsets: all params are int32");
+  MREC_REQUIRE(a.numel(1) >= 2, ERR_SHAPE, "mrec_shard_offsets: ctrl[2] expected");
+  MREC_LAUNCH(shard_offsets_kernel, 1, 32, 0, a.stream, a.ptr<int32_t>(0), a.ptr<int32_t>(1), a.ptr<int32_t>(2),
+              a.ptr<int32_t>(3), a.ptr<int32_t>(4), a.ptr<int32_t>(5));
+  return check_launch("shard_offsets");
+}
+
+// in : rows[U_cap, W] f32|i32 (first B[me][G] rows valid), my_bounds[G+1] i32, inbox_off[G] i32, peer_ptrs[G] i64,
+//      cap_like[cap_rows, 0..] (shape carrier: capacity of every inbox in rows), mod_like[M, 0..] (M > 0 and rows
+//      int32: send rows % M; numel-0 tensor with M = 0 rows: no transform)         out: err[1] i32 (bit 1 = overflow)
+MREC_API int mrec_push_rows_to_peers(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                     void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 7) return fail(ERR_NPARAM, "mrec_push_rows_to_peers: expected 7 params, got %d", a.nparam);
+  MREC_REQUIRE(a.is_f32(0) || a.is_i32(0), ERR_DTYPE, "mrec_push_rows_to_peers: rows must be 4-byte (f32|i32)");
+  MREC_REQUIRE(a.is_i32(1) && a.is_i32(2) && a.is_i64(3) && a.is_i32(6), ERR_DTYPE,
+               "mrec_push_rows_to_peers: bounds/inbox_off/err int32, peer_ptrs int64");
+  const int world = (int)a.numel(3);
+  MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks && a.numel(1) >= world + 1 && a.numel(2) >= world, ERR_SHAPE,
+               "mrec_push_rows_to_peers: G out of range or bounds/inbox_off too short");
+  const int64_t n = a.ndims[0] >= 2 ? a.dim(0, 0) : a.numel(0);
+  const int width = a.ndims[0] >= 2 ? (int)(a.numel(0) / (n > 0 ? n : 1)) : 1;
+  const int64_t cap_rows = a.dim(4, 0);
+  const int mod = (int)a.dim(5, 0);
+  MREC_REQUIRE(mod == 0 || (a.is_i32(0) && width == 1), ERR_DTYPE, "mrec_push_rows_to_peers: the modulo transform is for int32 keys");
+  if (n == 0) return OK;
+  MREC_LAUNCH(push_rows_to_peers_kernel, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<uint32_t>(0), width,
+              a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, mod, cap_rows, a.ptr<int32_t>(6));
+  return check_launch("push_rows_to_peers");
+}
+
+// in : payload[K] i32 (K may be 0), payload_ptrs[G] i64, flag_ptrs[G] i64, epoch[1] i32 (incremented)   out: dummy[1]
+MREC_API int mrec_peer_signal(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                              void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 5) return fail(ERR_NPARAM, "mrec_peer_signal: expected 5 params, got %d", a.nparam);
+  MREC_REQUIRE(a.is_i32(0) && a.is_i64(1) && a.is_i64(2) && a.is_i32(3), ERR_DTYPE, "mrec_peer_signal: dtype mismatch");
+  const int world = (int)a.numel(2);
+  MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks, ERR_SHAPE, "mrec_peer_signal: G out of range");
+  MREC_LAUNCH(peer_signal_kernel, 1, 256, 0, a.stream, a.ptr<int32_t>(0), (int)a.numel(0), a.ptr<int64_t>(1),
+              a.ptr<int64_t>(2), world, a.ptr<int32_t>(3));
+  return check_launch("peer_signal");
+}
+
+// in : flags[G] i32 (local slots written by the peers), epoch[1] i32, optional limit_log2[1] i32 (spin limit in
+//      cycles = 2^limit; default ~4 s)                                       out: err[1] i32 (bit 0 = time-out)
+MREC_API int mrec_peer_wait(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                            void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 3 && a.nparam != 4) return fail(ERR_NPARAM, "mrec_peer_wait: expected 3 or 4 params, got %d", a.nparam);
+  const int o = a.nparam - 1;                       // err is the last param
+  MREC_REQUIRE(a.is_i32(0) && a.is_i32(1) && a.is_i32(o) && a.is_i32(2), ERR_DTYPE, "mrec_peer_wait: int32 expected");
+  const int world = (int)a.numel(0);
+  MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks, ERR_SHAPE, "mrec_peer_wait: G out of range");
+  // ~4 s at 2 GHz: a dead peer raises err instead of hanging the GPU
+  MREC_LAUNCH(peer_wait_kernel, 1, 32, 0, a.stream, a.ptr<int32_t>(0), world, a.ptr<int32_t>(1), a.ptr<int32_t>(o),
+              a.nparam == 4 ? a.ptr<int32_t>(2) : (int32_t*)nullptr, 8000000000ll);
+  return check_launch("peer_wait");
 }

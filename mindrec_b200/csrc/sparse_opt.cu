@@ -194,12 +194,16 @@ __global__ void __launch_bounds__(kSegThreads, 3)
 segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __restrict__ mask,
                     const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
                     const int32_t* __restrict__ seg_start, int64_t n, int64_t n_tiles, Vec* __restrict__ part,
-                    Vec* __restrict__ gsum, int32_t* __restrict__ long_list, int32_t* __restrict__ long_count) {
+                    Vec* __restrict__ gsum, int32_t* __restrict__ long_list, int32_t* __restrict__ long_count,
+                    const int32_t* __restrict__ n_valid) {
+  // n_valid (optional): only the first *n_valid sorted positions are real, the rest is padding of a static buffer
+  if (n_valid) n = min(n, (int64_t)n_valid[0]);
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t j = gid / cpr;
   if (j >= n_tiles) return;
   const int c = (int)(gid - j * cpr);
   const int64_t pos0 = j * kSegTile;
+  if (pos0 >= n) return;
   const int64_t pos1 = min(n, pos0 + kSegTile);
 
   int cur = seg_of[pos0];
@@ -271,8 +275,11 @@ template <typename Vec, typename Sink>
 __global__ void __launch_bounds__(kSegThreads)
 rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                    int64_t n, const Vec* __restrict__ gsum, const Vec* __restrict__ part,
-                   const int32_t* __restrict__ long_list, const int32_t* __restrict__ long_count, Sink sink) {
+                   const int32_t* __restrict__ long_list, const int32_t* __restrict__ long_count, Sink sink,
+                   const int32_t* __restrict__ n_valid) {
   __shared__ Vec s_part[kSegThreads];
+  if (n_valid) n = min(n, (int64_t)n_valid[0]);
+  if (n <= 0) return;
   const int gi = threadIdx.x / cpr;
   const int c = threadIdx.x - gi * cpr;
   const int groups = kSegThreads / cpr;
@@ -358,7 +365,7 @@ struct NoSink {};
 template <typename Vec, typename GT, typename Sink>
 static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const int32_t* perm,
                         const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws,
-                        size_t ws_bytes, Sink sink, Vec* out, cudaStream_t stream) {
+                        size_t ws_bytes, Sink sink, Vec* out, cudaStream_t stream, const int32_t* n_valid) {
   if (n == 0) return OK;
   constexpr bool kStandalone = std::is_same<Sink, NoSink>::value;
   const SegWorkspace W = seg_ws(n, dim, !kStandalone);
@@ -377,10 +384,10 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
   cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
   if (mask) {
     MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
-                seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count);
+                seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count, n_valid);
   } else {
     MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, false>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
-                seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count);
+                seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count, n_valid);
   }
   const int groups = kSegThreads / cpr;
   const int row_blocks = grid_for(cdiv(n, groups), 8);
@@ -388,11 +395,11 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
     if (n_tiles > 1) {
       StoreSink<Vec> store{gsum, cpr};
       MREC_LAUNCH((rows_update_kernel<Vec, StoreSink<Vec>>), kChainBlocks + row_blocks, kSegThreads, 0, stream,
-                  cpr, seg_of, seg_start, n, gsum, part, long_list, long_count, store);
+                  cpr, seg_of, seg_start, n, gsum, part, long_list, long_count, store, n_valid);
     }
   } else {
     MREC_LAUNCH((rows_update_kernel<Vec, Sink>), kChainBlocks + row_blocks, kSegThreads, 0, stream, cpr, seg_of,
-                seg_start, n, gsum, part, long_list, long_count, sink);
+                seg_start, n, gsum, part, long_list, long_count, sink, n_valid);
   }
   return check_launch("segment_sum");
 }
@@ -401,12 +408,12 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
 template <typename Vec, typename Sink>
 static int run_segsum(const void* g, bool g16, int dim, int div, const float* mask, const int32_t* perm,
                       const int32_t* seg_start, const int32_t* seg_of, int64_t n, void* ws, size_t ws_bytes,
-                      Sink sink, cudaStream_t stream, Vec* out = nullptr) {
+                      Sink sink, cudaStream_t stream, Vec* out = nullptr, const int32_t* n_valid = nullptr) {
   if (g16)
     return run_segsum_t<Vec, __half, Sink>(reinterpret_cast<const __half*>(g), dim, div, mask, perm, seg_start,
-                                           seg_of, n, ws, ws_bytes, sink, out, stream);
+                                           seg_of, n, ws, ws_bytes, sink, out, stream, n_valid);
   return run_segsum_t<Vec, float, Sink>(reinterpret_cast<const float*>(g), dim, div, mask, perm, seg_start,
-                                        seg_of, n, ws, ws_bytes, sink, out, stream);
+                                        seg_of, n, ws, ws_bytes, sink, out, stream, n_valid);
 }
 
 // ---- dense optimizers (MLP parameters, Wide_b: SURVEY a5/a7) ----
@@ -546,7 +553,18 @@ static int parse_seg_args(const Aot& a, int b, int dim, bool has_uniq, SegArgs* 
 MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_t** shapes,
                                    const char** dtypes, void* stream, void* /*extra*/) {
   Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
-  MREC_CHECK_NPARAM(a, 12);
+  // optional input 10: n_valid[1] i32 (device-side count of real sorted positions; outputs shift by one)
+  const bool has_nv = (a.nparam == 13);
+  if (a.nparam != 12 && a.nparam != 13)
+    return fail(ERR_NPARAM, "mrec_sparse_lazy_adam: expected 12 or 13 params, got %d", a.nparam);
+  for (int i = 0; i < a.nparam; ++i)
+    if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "mrec_sparse_lazy_adam: param %d is null", i);
+  const int32_t* n_valid = nullptr;
+  if (has_nv) {
+    MREC_REQUIRE(a.is_i32(10) && a.numel(10) >= 1, ERR_DTYPE, "mrec_sparse_lazy_adam: n_valid must be int32[1]");
+    n_valid = a.ptr<int32_t>(10);
+  }
+  const int ws_i = has_nv ? 12 : 11;
   MREC_REQUIRE(a.is_f32(0) && a.is_f32(1) && a.is_f32(2) && a.is_f32(3), ERR_DTYPE,
                "mrec_sparse_lazy_adam: w/m/v/hyper must be float32");
   MREC_REQUIRE(a.numel(3) >= kHyperLen, ERR_SHAPE, "mrec_sparse_lazy_adam: hyper needs %d floats", kHyperLen);
@@ -557,8 +575,8 @@ MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_
   SegArgs s;
   int rc = parse_seg_args(a, 4, dim, true, &s, "mrec_sparse_lazy_adam");
   if (rc) return rc;
-  const size_t ws_bytes = (size_t)a.numel(11);
-  void* ws = a.params[11];
+  const size_t ws_bytes = (size_t)a.numel(ws_i);
+  void* ws = a.params[ws_i];
   const float* hyper = a.ptr<float>(3);
   if (dim % 4 == 0) {
     MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(2, 16), ERR_ALIGN,
@@ -568,21 +586,21 @@ MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_
     if (s.uniq64) {
       LazyAdamSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                          (const int64_t*)s.uniq, hyper, vocab, cpr};
-      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
     }
     LazyAdamSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                        (const int32_t*)s.uniq, hyper, vocab, cpr};
-    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_lazy_adam: D too large");
   if (s.uniq64) {
     LazyAdamSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                       (const int64_t*)s.uniq, hyper, vocab, dim};
-    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
   }
   LazyAdamSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                     (const int32_t*)s.uniq, hyper, vocab, dim};
-  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
 }
 
 // inputs : w[V,D] accum[V,D] linear[V,D] hyper[8] g[N/div,D] mask[N|0] uniq[N] perm[N] seg_start[N+1] seg_of[N]
@@ -590,7 +608,18 @@ MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_
 MREC_API int mrec_sparse_ftrl(int nparam, void** params, int* ndims, int64_t** shapes,
                               const char** dtypes, void* stream, void* /*extra*/) {
   Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
-  MREC_CHECK_NPARAM(a, 12);
+  // optional input 10: n_valid[1] i32 (device-side count of real sorted positions; outputs shift by one)
+  const bool has_nv = (a.nparam == 13);
+  if (a.nparam != 12 && a.nparam != 13)
+    return fail(ERR_NPARAM, "mrec_sparse_ftrl: expected 12 or 13 params, got %d", a.nparam);
+  for (int i = 0; i < a.nparam; ++i)
+    if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "mrec_sparse_ftrl: param %d is null", i);
+  const int32_t* n_valid = nullptr;
+  if (has_nv) {
+    MREC_REQUIRE(a.is_i32(10) && a.numel(10) >= 1, ERR_DTYPE, "mrec_sparse_ftrl: n_valid must be int32[1]");
+    n_valid = a.ptr<int32_t>(10);
+  }
+  const int ws_i = has_nv ? 12 : 11;
   MREC_REQUIRE(a.is_f32(0) && a.is_f32(1) && a.is_f32(2) && a.is_f32(3), ERR_DTYPE,
                "mrec_sparse_ftrl: w/accum/linear/hyper must be float32");
   MREC_REQUIRE(a.numel(3) >= kHyperLen, ERR_SHAPE, "mrec_sparse_ftrl: hyper needs %d floats", kHyperLen);
@@ -601,8 +630,8 @@ MREC_API int mrec_sparse_ftrl(int nparam, void** params, int* ndims, int64_t** s
   SegArgs s;
   int rc = parse_seg_args(a, 4, dim, true, &s, "mrec_sparse_ftrl");
   if (rc) return rc;
-  const size_t ws_bytes = (size_t)a.numel(11);
-  void* ws = a.params[11];
+  const size_t ws_bytes = (size_t)a.numel(ws_i);
+  void* ws = a.params[ws_i];
   const float* hyper = a.ptr<float>(3);
   if (dim % 4 == 0) {
     MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(2, 16), ERR_ALIGN,
@@ -612,21 +641,21 @@ MREC_API int mrec_sparse_ftrl(int nparam, void** params, int* ndims, int64_t** s
     if (s.uniq64) {
       FtrlSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                      (const int64_t*)s.uniq, hyper, vocab, cpr};
-      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
     }
     FtrlSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
                                    (const int32_t*)s.uniq, hyper, vocab, cpr};
-    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_ftrl: D too large");
   if (s.uniq64) {
     FtrlSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                   (const int64_t*)s.uniq, hyper, vocab, dim};
-    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
   }
   FtrlSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
                                 (const int32_t*)s.uniq, hyper, vocab, dim};
-  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
 }
 
 // Standalone deterministic segment-sum (the UnsortedSegmentSum of SURVEY a4, in sorted-segment order).

@@ -50,11 +50,16 @@ __device__ __forceinline__ KeyT decode_key(typename UKeyOf<KeyT>::type u, uint64
   return (KeyT)(u ^ UKeyOf<KeyT>::sign);
 }
 
+// n_valid (optional, RAW pass of a bounded sort only): entries at i >= *n_valid are padding of a statically
+// sized buffer and are read as out-of-range (they sort last and form the segment every consumer skips).
 template <typename KeyT, bool RAW>
-__device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys, int64_t i,
-                                                                uint64_t bound) {
+__device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys, int64_t i, uint64_t bound,
+                                                                const int32_t* n_valid = nullptr) {
   using U = typename UKeyOf<KeyT>::type;
-  if (RAW) return encode_key<KeyT>(reinterpret_cast<const KeyT*>(keys)[i], bound);
+  if (RAW) {
+    if (n_valid && i >= (int64_t)n_valid[0]) return (U)bound;
+    return encode_key<KeyT>(reinterpret_cast<const KeyT*>(keys)[i], bound);
+  }
   return reinterpret_cast<const U*>(keys)[i];
 }
 
@@ -62,7 +67,7 @@ __device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys
 template <typename KeyT, bool RAW>
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, int radix, uint64_t bound,
-                  int tiles_per_block, uint32_t* __restrict__ hist) {
+                  int tiles_per_block, uint32_t* __restrict__ hist, const int32_t* __restrict__ n_valid) {
   __shared__ uint32_t s_hist[MAX_RADIX];
   const int RADIX = radix;
   for (int d = threadIdx.x; d < RADIX; d += RS_THREADS) s_hist[d] = 0;
@@ -70,7 +75,7 @@ radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, int radix
   const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
   const int64_t end = min(n, begin + (int64_t)tiles_per_block * RS_TILE);
   for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
-    const auto k = load_key<KeyT, RAW>(keys, i, bound);
+    const auto k = load_key<KeyT, RAW>(keys, i, bound, n_valid);
     atomicAdd(&s_hist[(uint32_t)(k >> shift) & (RADIX - 1)], 1u);
   }
   __syncthreads();
@@ -129,7 +134,7 @@ radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
                      typename UKeyOf<KeyT>::type* __restrict__ keys_out, int32_t* __restrict__ vals_out,
                      int64_t n, int shift, int radix, uint64_t bound, int tiles_per_block,
                      const uint32_t* __restrict__ hist, int n_blocks, uint32_t* __restrict__ hist_next,
-                     int next_shift) {
+                     int next_shift, const int32_t* __restrict__ n_valid) {
   using U = typename UKeyOf<KeyT>::type;
   __shared__ uint32_t s_cnt[RS_WARPS][MAX_RADIX];
   __shared__ uint32_t s_base[MAX_RADIX];
@@ -172,7 +177,7 @@ radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
     for (int i = 0; i < RS_ITEMS; ++i) {
       const int64_t idx = tile0 + warp * (RS_ITEMS * 32) + i * 32 + lane;
       if (idx < n) {
-        key[i] = load_key<KeyT, RAW>(keys_in, idx, bound);
+        key[i] = load_key<KeyT, RAW>(keys_in, idx, bound, n_valid);
         val[i] = RAW ? (int32_t)idx : vals_in[idx];
         dig[i] = (uint32_t)(key[i] >> shift) & (RADIX - 1);
       } else {
@@ -379,7 +384,7 @@ int key_bits_for_bound(uint64_t bound) {
 template <typename KeyT>
 int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t* inverse,
                   int32_t* count, int32_t* perm, int32_t* seg_start, int32_t* seg_of, void* ws,
-                  size_t ws_bytes, cudaStream_t stream) {
+                  size_t ws_bytes, cudaStream_t stream, const int32_t* n_valid) {
   using U = typename UKeyOf<KeyT>::type;
   const int key_bits = bound ? key_bits_for_bound(bound) : 8 * (int)sizeof(KeyT);
   const SortPlan p = make_plan(n, sizeof(KeyT), key_bits);
@@ -416,17 +421,17 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
     if (more) cudaMemsetAsync(hn, 0, hist_bytes, stream);
     if (pass == 0) {
       MREC_LAUNCH((radix_hist_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
-                  bound, p.tiles_per_block, h);
+                  bound, p.tiles_per_block, h, n_valid);
       MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, h, p.n_blocks, radix);
       MREC_LAUNCH((radix_scatter_kernel<KeyT, true>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
-                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits);
+                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits, n_valid);
     } else {
       if (!kFuseNextHist)
         MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
-                    bound, p.tiles_per_block, h);
+                    bound, p.tiles_per_block, h, nullptr);
       MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, h, p.n_blocks, radix);
       MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
-                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits);
+                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits, nullptr);
     }
     kin = kout;
     vin = vout;
@@ -440,9 +445,9 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
 }
 
 template int unique_sorted<int32_t>(const int32_t*, int64_t, uint64_t, int32_t*, int32_t*, int32_t*,
-                                    int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+                                    int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t, const int32_t*);
 template int unique_sorted<int64_t>(const int64_t*, int64_t, uint64_t, int64_t*, int32_t*, int32_t*,
-                                    int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+                                    int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t, const int32_t*);
 
 // ---- first-occurrence order (upstream CPU Unique) ----
 // Segments are re-ranked by their first position perm[seg_start[u]] (stable sort => minimum).
@@ -497,7 +502,7 @@ int unique_first(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t
   int32_t* scratch = reinterpret_cast<int32_t*>(w + o); o += arr;
   KeyT* uniq_asc = reinterpret_cast<KeyT*>(w + o);
   int rc = unique_sorted<KeyT>(ids, n, bound, uniq_asc, inverse, count, perm, seg_start, seg_of, ws1,
-                               ws1_b, stream);
+                               ws1_b, stream, nullptr);
   if (rc != OK || n == 0) return rc;
   const int grid = (int)cdiv(n, 256);
   MREC_LAUNCH(first_pos_kernel, grid, 256, 0, stream, perm, seg_start, count, first_pos, n);
@@ -508,7 +513,7 @@ int unique_first(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_t
   // second sort's throw-away outputs.
   rc = unique_sorted<int32_t>(first_pos, n, (uint64_t)n, /*uniq*/ seg_of, /*inverse*/ remap,
                               /*count*/ scratch, /*perm*/ order, /*seg_start*/ seg_start,
-                              /*seg_of*/ perm, ws2, ws2_b, stream);
+                              /*seg_of*/ perm, ws2, ws2_b, stream, nullptr);
   if (rc != OK) return rc;
   MREC_LAUNCH(reorder_first_kernel<KeyT>, grid, 256, 0, stream, order, count, uniq_asc, uniq, remap, n);
   MREC_LAUNCH(remap_inverse_kernel, grid, 256, 0, stream, inverse, remap, n);
@@ -536,7 +541,9 @@ MREC_API size_t mrec_unique_first_workspace_bytes(int64_t n, int key_bytes) {
 // outputs: uniq[N] (ids dtype), inverse[N] i32, count[1] i32, perm[N] i32, seg_start[N+1] i32,
 //          seg_of[N] i32, workspace[bytes] uint8|int8
 static int unique_entry(const Aot& a, bool bounded) {
-  const int n_in = bounded ? 2 : 1;
+  // bounded: optional third input n_valid[1] i32 (entries at i >= n_valid are padding of a static buffer)
+  const bool has_nv = bounded && a.nparam == 10;
+  const int n_in = bounded ? (has_nv ? 3 : 2) : 1;
   if (a.nparam != n_in + 7)
     return fail(ERR_NPARAM, "mrec_unique%s: expected %d params, got %d", bounded ? "_bounded" : "",
                 n_in + 7, a.nparam);
@@ -553,19 +560,24 @@ static int unique_entry(const Aot& a, bool bounded) {
                    a.numel(o + 4) >= n + 1 && a.numel(o + 5) >= n,
                ERR_SHAPE, "mrec_unique: outputs must be padded to N (seg_start to N+1)");
   uint64_t bound = 0;
+  const int32_t* n_valid = nullptr;
   if (bounded) {
     MREC_REQUIRE(a.ndims[1] >= 1 && a.dim(1, 0) > 0, ERR_SHAPE, "mrec_unique_bounded: bad table shape");
     bound = (uint64_t)a.dim(1, 0);
     if (a.is_i32(0)) MREC_REQUIRE(bound < 0x7fffffffull, ERR_SHAPE, "mrec_unique_bounded: V too large for int32 ids");
+    if (has_nv) {
+      MREC_REQUIRE(a.is_i32(2) && a.numel(2) >= 1, ERR_DTYPE, "mrec_unique_bounded: n_valid must be int32[1]");
+      n_valid = a.ptr<int32_t>(2);
+    }
   }
   const size_t ws_bytes = (size_t)a.numel(o + 6);
   if (a.is_i32(0))
     return unique_sorted<int32_t>(a.ptr<int32_t>(0), n, bound, a.ptr<int32_t>(o), a.ptr<int32_t>(o + 1),
                                   a.ptr<int32_t>(o + 2), a.ptr<int32_t>(o + 3), a.ptr<int32_t>(o + 4),
-                                  a.ptr<int32_t>(o + 5), a.params[o + 6], ws_bytes, a.stream);
+                                  a.ptr<int32_t>(o + 5), a.params[o + 6], ws_bytes, a.stream, n_valid);
   return unique_sorted<int64_t>(a.ptr<int64_t>(0), n, bound, a.ptr<int64_t>(o), a.ptr<int32_t>(o + 1),
                                 a.ptr<int32_t>(o + 2), a.ptr<int32_t>(o + 3), a.ptr<int32_t>(o + 4),
-                                a.ptr<int32_t>(o + 5), a.params[o + 6], ws_bytes, a.stream);
+                                a.ptr<int32_t>(o + 5), a.params[o + 6], ws_bytes, a.stream, n_valid);
 }
 
 MREC_API int mrec_unique(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,

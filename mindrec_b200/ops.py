@@ -110,7 +110,7 @@ class UniqueResult:
         return v
 
 
-def unique(ids, table_like=None, result=None, ws_tag="unique"):
+def unique(ids, table_like=None, result=None, ws_tag="unique", n_valid=None):
     """Ascending unique + inverse + stable sort permutation + segment map.
 
     With `table_like` (any tensor whose dim 0 is the table's row count V) only ceil(log2(V+1)) key bits
@@ -125,8 +125,10 @@ def unique(ids, table_like=None, result=None, ws_tag="unique"):
     ws = _ws(ws_tag, nbytes, flat.device)
     if table_like is None:
         _lib.aot_call("mrec_unique", [flat] + result.outputs() + [ws])
-    else:
+    elif n_valid is None:
         _lib.aot_call("mrec_unique_bounded", [flat, table_like] + result.outputs() + [ws])
+    else:
+        _lib.aot_call("mrec_unique_bounded", [flat, table_like, n_valid] + result.outputs() + [ws])
     return result
 
 
@@ -174,12 +176,14 @@ def segment_sum(g, mask, uq, dim=None, out=None):
     return out
 
 
-def sparse_lazy_adam(w, m, v, hyper, g, mask, uq):
-    """Fused segment-sum + LazyAdam row update on the rows named by uq.uniq (in place)."""
+def sparse_lazy_adam(w, m, v, hyper, g, mask, uq, n_valid=None):
+    """Fused segment-sum + LazyAdam row update on the rows named by uq.uniq (in place).
+    n_valid (device int32[1]): only the first n_valid sorted positions are real (static inbox)."""
     dim = w.shape[1] if w.dim() == 2 else 1
     mask = _empty_mask(w.device) if mask is None else mask.reshape(-1)
+    nv = [] if n_valid is None else [n_valid]
     _lib.aot_call("mrec_sparse_lazy_adam", [w, m, v, hyper, g, mask, uq.uniq, uq.perm, uq.seg_start,
-                                            uq.seg_of, _dummy(w.device), _opt_ws(uq.n, dim, w.device)])
+                                            uq.seg_of] + nv + [_dummy(w.device), _opt_ws(uq.n, dim, w.device)])
 
 
 def adam_rowsparse_dense_equiv(w, m, v, hyper, g, mask, uq, row_flags):
@@ -191,12 +195,13 @@ def adam_rowsparse_dense_equiv(w, m, v, hyper, g, mask, uq, row_flags):
                                           _opt_ws(uq.n, dim, w.device)])
 
 
-def sparse_ftrl(w, accum, linear, hyper, g, mask, uq):
+def sparse_ftrl(w, accum, linear, hyper, g, mask, uq, n_valid=None):
     """Fused segment-sum + FTRL row update on the rows named by uq.uniq (in place)."""
     dim = w.shape[1] if w.dim() == 2 else 1
     mask = _empty_mask(w.device) if mask is None else mask.reshape(-1)
+    nv = [] if n_valid is None else [n_valid]
     _lib.aot_call("mrec_sparse_ftrl", [w, accum, linear, hyper, g, mask, uq.uniq, uq.perm, uq.seg_start,
-                                       uq.seg_of, _dummy(w.device), _opt_ws(uq.n, dim, w.device)])
+                                       uq.seg_of] + nv + [_dummy(w.device), _opt_ws(uq.n, dim, w.device)])
 
 
 def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, loss_scale=1.0, l2=0.0, device="cuda"):
@@ -304,3 +309,24 @@ def sigmoid_xent(a, b, label, sens, out=None, half=False):
 def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
     """Owner-side gather fused with the NVLink peer store of every row into its requester's landing buffer."""
     _lib.aot_call("mrec_gather_to_peers", [table, rows, peer_ptrs, dst_off, src_off, _dummy(table.device)])
+
+
+def shard_offsets(bounds_all, ctrl, dst_off, src_off, inbox_off, n_r):
+    _lib.aot_call("mrec_shard_offsets", [bounds_all, ctrl, dst_off, src_off, inbox_off, n_r])
+
+
+def push_rows_to_peers(rows, my_bounds, inbox_off, peer_ptrs, cap_like, mod_like, err):
+    _lib.aot_call("mrec_push_rows_to_peers", [rows, my_bounds, inbox_off, peer_ptrs, cap_like, mod_like, err])
+
+
+def peer_signal(payload, payload_ptrs, flag_ptrs, epoch):
+    _lib.aot_call("mrec_peer_signal", [payload, payload_ptrs, flag_ptrs, epoch, _dummy(epoch.device)])
+
+
+def peer_wait(flags, epoch, err, max_cycles_log2=None):
+    """Spin (bounded) until every flag slot reached epoch; a time-out sets bit 0 of err instead of hanging."""
+    if max_cycles_log2 is None:
+        _lib.aot_call("mrec_peer_wait", [flags, epoch, err])
+    else:
+        lim = torch.tensor([max_cycles_log2], dtype=torch.int32, device=flags.device)
+        _lib.aot_call("mrec_peer_wait", [flags, epoch, lim, err])

@@ -1,0 +1,371 @@
+"""Device-driven exchange for row-sharded tables: no host-side sizes, so the whole step is CUDA-graph capturable.
+
+Same sharding as mindrec_b200.sharded (owner = key mod G, owner-major remap, one dedup per batch), but every
+transfer is a peer store over NVLink into CUDA-IPC inboxes at offsets computed ON THE DEVICE from the all-ranks
+bucket-bounds matrix, and every phase boundary is a signal / wait pair of flag kernels (bounded spin):
+
+    plan     shard_remap -> unique -> shard_bounds                      (local)
+    publish  bounds row -> every peer's matrix                 signal 0 | wait 0
+    keys     shard_offsets; uniq % R -> owners' key inboxes    signal 1 | wait 1
+    serve    gather fused with peer stores into requesters' landing buffers (deep + wide)
+                                                               signal 2 | wait 2
+    expand   gather_masked / gather_reduce from the landing buffers by the inverse index
+    ...      DenseLayers forward / loss / backward ...
+    grads    segment_sum per unique key -> owners' gradient inboxes (deep + wide)
+                                                               signal 3 | wait 3
+    update   owner: unique over the key inbox (static capacity, device-side valid count) -> fused FTRL / LazyAdam
+
+`PeerRank` holds one rank's state and phase methods.  `EmulatedPeerGroup` runs G ranks inside ONE process on ONE
+GPU in phase-major order (tests: all of the offset / inbox logic without a multi-GPU box);
+`PeerShardedTables` is the multi-process form (one rank per GPU, buffers shared with CUDA IPC) and plugs into
+sharded.ShardedWideDeepStep.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .sharded import ShardPlan, ShardedWideDeepStep, _RawCuda
+
+N_PHASES = 4
+_PEER_BUFFERS = ("ball", "keys_in", "land_deep", "land_wide", "grad_in", "gwide_in", "flags")
+
+
+class PeerRank:
+    """State and phases of one rank.  `alloc(name, shape, dtype)` returns the rank's peer-writable buffers."""
+
+    def __init__(self, rank, world, vocab_size, emb_dim, n_lookups, device, alloc, seed=1, sens=1024.0,
+                 init_std=0.01, cap_rows=None):
+        self.rank, self.world = rank, world
+        self.plan = ShardPlan(vocab_size, world)
+        self.dim, self.n = emb_dim, n_lookups
+        self.device = torch.device(device)
+        g, r, dev = world, self.plan.rows_per_rank, self.device
+        self.cap = int(cap_rows or n_lookups)          # rows an inbox / landing buffer can hold
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000 + rank)
+        self.wide = torch.empty((r, 1), dtype=torch.float32, device=dev).normal_(0, init_std, generator=gen)
+        self.deep = torch.empty((r, emb_dim), dtype=torch.float32, device=dev).normal_(0, init_std, generator=gen)
+        self.acc, self.lin = torch.ones_like(self.wide), torch.zeros_like(self.wide)
+        self.m, self.v = torch.zeros_like(self.deep), torch.zeros_like(self.deep)
+        self.adam_hyper = ops.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * world, device=dev)
+        self.ftrl_hyper = ops.ftrl_hyper(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens * world, device=dev)
+        # peer-writable buffers
+        i32, f32 = torch.int32, torch.float32
+        self.buf = {
+            "ball": alloc("ball", (g * (g + 1),), i32), "keys_in": alloc("keys_in", (self.cap,), i32),
+            "land_deep": alloc("land_deep", (self.cap, emb_dim), f32), "land_wide": alloc("land_wide", (self.cap, 1), f32),
+            "grad_in": alloc("grad_in", (self.cap, emb_dim), f32), "gwide_in": alloc("gwide_in", (self.cap, 1), f32),
+            "flags": alloc("flags", (N_PHASES * g,), i32),
+        }
+        self.buf["ball"].zero_()
+        self.buf["flags"].zero_()
+        self.buf["keys_in"].zero_()
+        # local state
+        self.ctrl = torch.tensor([rank, world], dtype=i32, device=dev)
+        self.epoch = [torch.zeros(1, dtype=i32, device=dev) for _ in range(N_PHASES)]
+        self.err = torch.zeros(1, dtype=i32, device=dev)
+        self.bounds = torch.zeros(g + 1, dtype=i32, device=dev)
+        self.dst_off = torch.zeros(g, dtype=i32, device=dev)
+        self.src_off = torch.zeros(g + 1, dtype=i32, device=dev)
+        self.inbox_off = torch.zeros(g, dtype=i32, device=dev)
+        self.n_r = torch.zeros(1, dtype=i32, device=dev)
+        self.edges = (torch.arange(g + 1, device=dev, dtype=i32) * r)
+        self.key = torch.empty(n_lookups, dtype=i32, device=dev)
+        self.uq = ops.UniqueResult(n_lookups, i32, dev)
+        self.uq_owner = ops.UniqueResult(self.cap, i32, dev)
+        self.gs_deep = torch.empty((n_lookups, emb_dim), dtype=f32, device=dev)
+        self.gs_wide = torch.empty((n_lookups, 1), dtype=f32, device=dev)
+        self._bound_like = torch.empty((g * r, 0), device=dev)
+        self._vocab_like = torch.empty((vocab_size, 0), device=dev)
+        self._owners_like = torch.empty((g, r, 0), device=dev)
+        self._cap_like = torch.empty((self.cap, 0), device=dev)
+        self._mod_rows = torch.empty((r, 0), device=dev)
+        self._mod_none = torch.empty((0, 0), device=dev)
+        self._no_payload = torch.empty(0, dtype=i32, device=dev)
+        self.flag_views = [self.buf["flags"][ph * g:(ph + 1) * g] for ph in range(N_PHASES)]
+        self.ptrs = None
+        self._wts = None
+
+    def connect(self, base_ptrs):
+        """base_ptrs[name][s] = address of rank s's buffer `name` as mapped in THIS process."""
+        g, me, dev = self.world, self.rank, self.device
+        t = lambda lst: torch.tensor(lst, dtype=torch.int64, device=dev)
+        self.ptrs = {
+            "ball_row": t([base_ptrs["ball"][s] + me * (g + 1) * 4 for s in range(g)]),
+            "keys_in": t(base_ptrs["keys_in"]), "land_deep": t(base_ptrs["land_deep"]),
+            "land_wide": t(base_ptrs["land_wide"]), "grad_in": t(base_ptrs["grad_in"]),
+            "gwide_in": t(base_ptrs["gwide_in"]),
+            "flag": [t([base_ptrs["flags"][s] + (ph * g + me) * 4 for s in range(g)]) for ph in range(N_PHASES)],
+            "none": t([0] * g),
+        }
+
+    # ---- phase boundaries ----------------------------------------------------------------------------
+    def signal(self, phase, payload=None, payload_ptrs=None):
+        ops.peer_signal(self._no_payload if payload is None else payload,
+                        self.ptrs["none"] if payload_ptrs is None else payload_ptrs,
+                        self.ptrs["flag"][phase], self.epoch[phase])
+
+    def wait(self, phase):
+        ops.peer_wait(self.flag_views[phase], self.epoch[phase], self.err)
+
+    # ---- phases --------------------------------------------------------------------------------------
+    def p_plan_publish(self, ids):
+        ops.shard_remap(ids.reshape(-1), self._vocab_like, self._owners_like, out=self.key)
+        ops.unique(self.key, table_like=self._bound_like, result=self.uq, ws_tag="unique_peer_plan")
+        ops.shard_bounds(self.uq.uniq, self.uq.count, self.edges, out=self.bounds)
+        self.signal(0, self.bounds, self.ptrs["ball_row"])
+
+    def p_keys(self):
+        ops.shard_offsets(self.buf["ball"], self.ctrl, self.dst_off, self.src_off, self.inbox_off, self.n_r)
+        ops.push_rows_to_peers(self.uq.uniq, self.bounds, self.inbox_off, self.ptrs["keys_in"], self._cap_like,
+                               self._mod_rows, self.err)
+        self.signal(1)
+
+    def p_serve(self):
+        ops.gather_to_peers(self.deep, self.buf["keys_in"], self.ptrs["land_deep"], self.dst_off, self.src_off)
+        ops.gather_to_peers(self.wide, self.buf["keys_in"], self.ptrs["land_wide"], self.dst_off, self.src_off)
+        self.signal(2)
+
+    def p_expand(self, ids_shape, wts, wide_bias, deep_out, wide_out):
+        inverse = self.uq.inverse.view(ids_shape)
+        ops.gather_masked(self.buf["land_deep"], inverse, wts, out=deep_out)
+        ops.gather_reduce(self.buf["land_wide"], inverse, wts, wide_bias, out=wide_out)
+        self._wts = wts
+
+    def p_grads(self, delta, gx):
+        mask = self._wts.reshape(-1)
+        ops.segment_sum(gx.view(self.n, self.dim), mask, self.uq, dim=self.dim, out=self.gs_deep)
+        ops.segment_sum(delta, mask, self.uq, dim=1, out=self.gs_wide)
+        ops.push_rows_to_peers(self.gs_deep, self.bounds, self.inbox_off, self.ptrs["grad_in"], self._cap_like,
+                               self._mod_none, self.err)
+        ops.push_rows_to_peers(self.gs_wide, self.bounds, self.inbox_off, self.ptrs["gwide_in"], self._cap_like,
+                               self._mod_none, self.err)
+        self.signal(3)
+
+    def p_update(self):
+        uq2 = ops.unique(self.buf["keys_in"], table_like=self.deep, result=self.uq_owner, ws_tag="unique_peer_owner",
+                         n_valid=self.n_r)
+        ops.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, self.buf["gwide_in"], None, uq2, n_valid=self.n_r)
+        ops.adam_begin_step(self.adam_hyper)
+        ops.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, self.buf["grad_in"], None, uq2,
+                             n_valid=self.n_r)
+
+
+class EmulatedPeerGroup:
+    """G ranks in one process on one GPU, phases run in phase-major order (every signal of a phase is issued
+    before any wait of that phase, so the wait kernels never spin).  Test vehicle for the protocol's data flow."""
+
+    def __init__(self, world, vocab_size, emb_dim, n_lookups, device, seed=1, sens=1024.0):
+        def alloc(name, shape, dtype):
+            return torch.empty(shape, dtype=dtype, device=device)
+        self.ranks = [PeerRank(r, world, vocab_size, emb_dim, n_lookups, device, alloc, seed=seed, sens=sens)
+                      for r in range(world)]
+        base = {name: [rk.buf[name].data_ptr() for rk in self.ranks] for name in _PEER_BUFFERS}
+        for rk in self.ranks:
+            rk.connect(base)
+
+    def forward(self, ids_list, wts_list, bias, deep_outs, wide_outs):
+        for rk, ids in zip(self.ranks, ids_list):
+            rk.p_plan_publish(ids)
+        for rk in self.ranks:
+            rk.wait(0)
+            rk.p_keys()
+        for rk in self.ranks:
+            rk.wait(1)
+            rk.p_serve()
+        for rk, ids, wts, do, wo in zip(self.ranks, ids_list, wts_list, deep_outs, wide_outs):
+            rk.wait(2)
+            rk.p_expand(ids.shape, wts, bias, do, wo)
+
+    def backward(self, deltas, gxs):
+        for rk, d, g in zip(self.ranks, deltas, gxs):
+            rk.p_grads(d, g)
+        for rk in self.ranks:
+            rk.wait(3)
+            rk.p_update()
+
+    def full_tables(self):
+        g = len(self.ranks)
+        v = self.ranks[0].plan.vocab_size
+        r = self.ranks[0].plan.rows_per_rank
+        wide = torch.stack([rk.wide for rk in self.ranks], 1).reshape(r * g, 1)[:v]
+        deep = torch.stack([rk.deep for rk in self.ranks], 1).reshape(r * g, -1)[:v]
+        return wide, deep
+
+
+class _IpcArena:
+    """cudaMalloc'ed buffers exported to the other ranks of the node with CUDA IPC."""
+
+    def __init__(self, group):
+        self.group = group
+        self.lib = _lib.lib()
+        self.lib.mrec_peer_alloc.restype = ctypes.c_void_p
+        self.lib.mrec_peer_alloc.argtypes = [ctypes.c_size_t]
+        self.lib.mrec_ipc_open_handle.restype = ctypes.c_void_p
+        self.lib.mrec_ipc_open_handle.argtypes = [ctypes.c_char_p]
+        self.lib.mrec_ipc_get_handle.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        self.local = {}
+
+    def alloc(self, device):
+        def _alloc(name, shape, dtype):
+            nbytes = 1
+            for d in shape:
+                nbytes *= d
+            nbytes = max(nbytes * 4, 256)
+            ptr = self.lib.mrec_peer_alloc(nbytes)
+            if not ptr:
+                raise RuntimeError("mrec_peer_alloc failed: " + _lib.last_error())
+            h = ctypes.create_string_buffer(64)
+            if self.lib.mrec_ipc_get_handle(ctypes.c_void_p(ptr), h) != 0:
+                raise RuntimeError("mrec_ipc_get_handle failed: " + _lib.last_error())
+            self.local[name] = (ptr, h.raw)
+            typestr = "<i4" if dtype == torch.int32 else "<f4"
+            return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)
+        return _alloc
+
+    def exchange(self):
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: h for k, (_, h) in self.local.items()}, group=self.group)
+        base = {}
+        for name, (ptr, _) in self.local.items():
+            lst = []
+            for r in range(world):
+                if r == rank:
+                    lst.append(ptr)
+                else:
+                    p = self.lib.mrec_ipc_open_handle(gathered[r][name])
+                    if not p:
+                        raise RuntimeError("mrec_ipc_open_handle failed: " + _lib.last_error())
+                    lst.append(p)
+            base[name] = lst
+        return base
+
+
+class PeerShardedTables:
+    """Multi-process form: drop-in for sharded.ShardedWideDeepTables inside sharded.ShardedWideDeepStep
+    (`plan_batch` / `lookup` / `update` / `gather_full`), with nothing read back to the host."""
+
+    def __init__(self, vocab_size, emb_dim, n_lookups, device, group=None, seed=1, sens=1024.0):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        self.cuda = True
+        self.plan_stream = None
+        arena = _IpcArena(group)
+        self.rk = PeerRank(self.rank, self.world, vocab_size, emb_dim, n_lookups, device, arena.alloc(device),
+                           seed=seed, sens=sens)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        self.rk.connect(arena.exchange())
+        dist.barrier(group=group)
+        self.plan = self.rk.plan
+        self.dim = emb_dim
+        self._ids = None
+
+    # sharded.ShardedWideDeepStep drives these three; the "plan" is implicit in device state
+    def plan_batch(self, ids, ahead=False):
+        rk = self.rk
+        rk.p_plan_publish(ids)
+        rk.wait(0)
+        rk.p_keys()
+        rk.wait(1)
+        return _DevicePlan(ids)
+
+    def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
+        rk = self.rk
+        rk.p_serve()
+        rk.wait(2)
+        rk.p_expand(plan.ids.shape, wts, wide_bias, deep_out, wide_out)
+        return wide_out, deep_out
+
+    def update(self, delta, gx):
+        rk = self.rk
+        rk.p_grads(delta, gx)
+        rk.wait(3)
+        rk.p_update()
+
+    @property
+    def wide(self):
+        return self.rk.wide
+
+    @property
+    def deep(self):
+        return self.rk.deep
+
+    def error_flags(self):
+        """bit 0: a peer wait timed out; bit 1: an inbox overflowed (host read — call outside the hot loop)."""
+        return int(self.rk.err.item())
+
+    def gather_full(self):
+        g, r, v = self.world, self.plan.rows_per_rank, self.plan.vocab_size
+        wl = [torch.empty_like(self.rk.wide) for _ in range(g)]
+        dl = [torch.empty_like(self.rk.deep) for _ in range(g)]
+        dist.all_gather(wl, self.rk.wide, group=self.group)
+        dist.all_gather(dl, self.rk.deep, group=self.group)
+        return (torch.stack(wl, 1).reshape(r * g, 1)[:v], torch.stack(dl, 1).reshape(r * g, self.dim)[:v])
+
+
+class _DevicePlan:
+    __slots__ = ("ids",)
+
+    def __init__(self, ids):
+        self.ids = ids
+
+
+class PeerShardedWideDeepStep(ShardedWideDeepStep):
+    """Wide&Deep step over PeerShardedTables.  Nothing in the step depends on a host-side size, so `capture`
+    records plan -> exchange -> DenseLayers -> gradient exchange -> fused row updates as ONE CUDA graph; the mean
+    all-reduce of the DenseLayer gradients and the dense Adam stay eager behind it (NCCL in a captured graph hung
+    on this stack), i.e. a step costs one graph launch + one collective + two kernel launches of host time."""
+
+    def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
+                 use_mixed_precision=True, group=None, graph=True):
+        super().__init__(batch_size, vocab_size, emb_dim, hidden, device, seed=seed, sens=sens, fields=fields,
+                         use_mixed_precision=use_mixed_precision, group=group, graph_dense=False,
+                         tables_factory=lambda: PeerShardedTables(vocab_size, emb_dim, batch_size * fields, device,
+                                                                  group=group, seed=seed, sens=sens))
+        self._graph_step = graph
+        self._whole = None
+        self._loss = None
+
+    def _sparse_and_dense(self):
+        ids, wts, label = self._slots[0]
+        t = self.tables
+        plan = t.plan_batch(ids)
+        t.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
+        self._io["label"].copy_(label)
+        loss, delta, gx = self._dense_segment()
+        t.update(delta, gx)
+        return loss
+
+    def capture(self, ids, wts, label, warmup=3):
+        self._slots = [tuple(t.clone() for t in (ids, wts, label))]
+        self._ensure_io(ids)
+        for _ in range(warmup):
+            self._loss = self._sparse_and_dense()
+            self._dense_update()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if self._graph_step:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loss = self._sparse_and_dense()
+            self._whole = g
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        return self._slots[0]
+
+    def replay(self, ids=None, wts=None, label=None, next_batch=None):
+        if ids is not None:
+            for d, s in zip(self._slots[0], (ids, wts, label)):
+                d.copy_(s, non_blocking=True)
+        if self._whole is not None:
+            self._whole.replay()
+        else:
+            self._loss = self._sparse_and_dense()
+        self._dense_update()
+        return self._loss, self._loss

@@ -371,7 +371,7 @@ class ShardedWideDeepStep:
     is already resident when it is needed and the launch pipeline never drains."""
 
     def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
-                 use_mixed_precision=True, group=None, kernels=_cuda_ops, graph_dense=True):
+                 use_mixed_precision=True, group=None, kernels=_cuda_ops, graph_dense=True, tables_factory=None):
         from .nn import DenseStack
         self.k = kernels
         self.group = group
@@ -380,8 +380,9 @@ class ShardedWideDeepStep:
         self.sens = float(sens)
         self.fields, self.emb_dim = fields, emb_dim
         self.mixed = use_mixed_precision
-        self.tables = ShardedWideDeepTables(vocab_size, emb_dim, device, group=group, seed=seed, sens=sens,
-                                            kernels=kernels)
+        self.tables = (tables_factory() if tables_factory is not None else
+                       ShardedWideDeepTables(vocab_size, emb_dim, device, group=group, seed=seed, sens=sens,
+                                             kernels=kernels))
         gen = torch.Generator(device=device)
         gen.manual_seed(seed)                      # identical DenseLayer replicas on every rank
         dims = [fields * emb_dim] + list(hidden) + [1]

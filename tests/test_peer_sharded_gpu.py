@@ -1,0 +1,156 @@
+"""Device-driven sharded exchange (peer_sharded.py): G emulated ranks on ONE GPU vs the oracle on the full tables,
+plus the static-capacity (`n_valid`) forms of the dedup and of the fused row updates it relies on."""
+import numpy as np
+import pytest
+import torch
+
+from mindrec_b200 import ops, peer_sharded
+from oracle import ref_numpy as ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _group_inputs(world, vocab, b, f, dim, cuda, seed):
+    rng = np.random.default_rng(seed)
+    ids = [rng.integers(0, vocab, size=(b, f)).astype(np.int32) for _ in range(world)]
+    for r in range(world):                       # hot keys shared by every rank, and duplicates inside a rank
+        ids[r][:, 0] = rng.integers(0, 7, size=b)
+        ids[r][::3, 1] = ids[r][::3, 2]
+    wts = [(rng.random((b, f)) < 0.9).astype(np.float32) for _ in range(world)]
+    delta = [rng.standard_normal((b, 1)).astype(np.float32) for _ in range(world)]
+    gx = [rng.standard_normal((b, f * dim)).astype(np.float32) for _ in range(world)]
+    to = lambda lst: [torch.from_numpy(x).to(cuda) for x in lst]
+    return ids, wts, delta, gx, to(ids), to(wts), to(delta), to(gx)
+
+
+@pytest.mark.parametrize("world,vocab", [(1, 257), (2, 1000), (3, 1000), (8, 4099)])
+def test_emulated_ranks_match_oracle_on_full_tables(cuda, world, vocab):
+    b, f, dim, sens = 48, 5, 16, 1024.0
+    grp = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, cuda, seed=5, sens=sens)
+    bias = torch.tensor([0.25], dtype=torch.float32, device=cuda)
+    state = dict(w_wide=None)
+    for step in range(3):                        # three steps: the inboxes and flags are re-used across steps
+        ids, wts, delta, gx, ids_t, wts_t, delta_t, gx_t = _group_inputs(world, vocab, b, f, dim, cuda, 10 + step)
+        wide0, deep0 = (t.cpu().numpy().astype(np.float64) for t in grp.full_tables())
+        if step == 0:
+            acc, lin = np.ones_like(wide0), np.zeros_like(wide0)
+            m, v = np.zeros_like(deep0), np.zeros_like(deep0)
+            adam = ref.AdamState(3.5e-4, eps=1e-8)
+            ftrl = ref.FtrlState(5e-2, l1=1e-8, l2=1e-8)
+        deep_outs = [torch.empty((b, f * dim), dtype=torch.float32, device=cuda) for _ in range(world)]
+        wide_outs = [torch.empty((b, 1), dtype=torch.float32, device=cuda) for _ in range(world)]
+        grp.forward(ids_t, wts_t, bias, deep_outs, wide_outs)
+        for r in range(world):
+            want = (deep0[ids[r]] * wts[r][..., None]).reshape(b, f * dim)
+            assert np.array_equal(deep_outs[r].cpu().numpy(), want.astype(np.float32))      # copies x {0,1}: exact
+            want_w = (wide0[ids[r], 0] * wts[r]).sum(1, keepdims=True) + 0.25
+            np.testing.assert_allclose(wide_outs[r].cpu().numpy(), want_w, rtol=1e-5, atol=1e-7)
+        grp.backward(delta_t, gx_t)
+        torch.cuda.synchronize()
+        for rk in grp.ranks:
+            assert int(rk.err.item()) == 0
+        # oracle: one table, the concatenated global batch, gradients divided by sens * G
+        ids_cat = np.concatenate(ids).reshape(-1)
+        mask_cat = np.concatenate(wts).reshape(-1).astype(np.float64)
+        g_deep = np.concatenate(gx).reshape(-1, dim).astype(np.float64) * mask_cat[:, None] / (sens * world)
+        g_wide = np.repeat(np.concatenate(delta).astype(np.float64), f, axis=0) * mask_cat[:, None] / (sens * world)
+        uniq, inverse = np.unique(ids_cat, return_inverse=True)
+        gs_deep = np.zeros((uniq.size, dim))
+        np.add.at(gs_deep, inverse, g_deep)
+        gs_wide = np.zeros((uniq.size, 1))
+        np.add.at(gs_wide, inverse, g_wide)
+        adam.begin_step()
+        ref.lazy_adam_sparse(deep0, m, v, uniq, gs_deep, adam)
+        ref.ftrl_sparse(wide0, acc, lin, uniq, gs_wide, ftrl)
+        wide1, deep1 = (t.cpu().numpy() for t in grp.full_tables())
+        np.testing.assert_allclose(deep1, deep0, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(wide1, wide0, rtol=1e-5, atol=1e-7)
+
+
+def test_offsets_cover_every_inbox_exactly_once(cuda):
+    """inbox_off / dst_off / src_off derived on the device from the bounds matrix tile each inbox without gaps."""
+    world = 4
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(0, 9, size=(world, world))            # sizes[s][o]: rank s's bucket for owner o
+    ball = np.zeros((world, world + 1), dtype=np.int32)
+    ball[:, 1:] = np.cumsum(sizes, 1)
+    ball_t = torch.from_numpy(ball.reshape(-1)).to(cuda)
+    for me in range(world):
+        ctrl = torch.tensor([me, world], dtype=torch.int32, device=cuda)
+        dst, src = torch.zeros(world, dtype=torch.int32, device=cuda), torch.zeros(world + 1, dtype=torch.int32, device=cuda)
+        inbox, n_r = torch.zeros(world, dtype=torch.int32, device=cuda), torch.zeros(1, dtype=torch.int32, device=cuda)
+        ops.shard_offsets(ball_t, ctrl, dst, src, inbox, n_r)
+        assert dst.tolist() == ball[:, me].tolist()
+        assert src.tolist() == [0] + np.cumsum(sizes[:, me]).tolist()
+        assert int(n_r) == int(sizes[:, me].sum())
+        assert inbox.tolist() == [int(sizes[:me, o].sum()) for o in range(world)]
+
+
+def test_inbox_overflow_raises_flag_not_a_fault(cuda):
+    rows = torch.arange(40, dtype=torch.int32, device=cuda)
+    bounds = torch.tensor([0, 40], dtype=torch.int32, device=cuda)
+    inbox_off = torch.zeros(1, dtype=torch.int32, device=cuda)
+    inbox = torch.full((16,), -1, dtype=torch.int32, device=cuda)
+    guard = torch.full((64,), -7, dtype=torch.int32, device=cuda)
+    ptrs = torch.tensor([inbox.data_ptr()], dtype=torch.int64, device=cuda)
+    err = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ops.push_rows_to_peers(rows, bounds, inbox_off, ptrs, torch.empty((16, 0), device=cuda), torch.empty((0, 0), device=cuda), err)
+    assert int(err) == 2
+    assert inbox.tolist() == list(range(16))
+    assert (guard == -7).all()
+
+
+def test_wait_times_out_with_error_bit(cuda):
+    flags = torch.zeros(2, dtype=torch.int32, device=cuda)
+    flags[0] = 5
+    epoch = torch.tensor([5], dtype=torch.int32, device=cuda)
+    err = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ops.peer_wait(flags[:1], epoch, err)
+    assert int(err) == 0
+    ops.peer_wait(flags, epoch, err, max_cycles_log2=24)          # rank 1 never signals: ~10 ms bounded spin
+    assert int(err) == 1
+
+
+@pytest.mark.parametrize("n_valid", [0, 1, 37, 1000])
+def test_unique_with_device_valid_count(cuda, n_valid):
+    cap, vocab = 1000, 300
+    rng = np.random.default_rng(n_valid)
+    ids = rng.integers(0, vocab, size=cap).astype(np.int32)
+    ids_t = torch.from_numpy(ids).to(cuda)
+    nv = torch.tensor([n_valid], dtype=torch.int32, device=cuda)
+    uq = ops.unique(ids_t, table_like=torch.empty((vocab, 0), device=cuda), n_valid=nv)
+    # padding sorts last as ONE out-of-range segment (key == vocab), which the row updates skip
+    want = np.unique(np.concatenate([ids[:n_valid], np.full(cap - n_valid, vocab, dtype=np.int32)]))
+    assert int(uq.count) == want.size
+    assert np.array_equal(uq.uniq[:want.size].cpu().numpy(), want)
+    inv = uq.inverse.cpu().numpy()[:n_valid]
+    assert np.array_equal(want[inv], ids[:n_valid])
+
+
+@pytest.mark.parametrize("dim", [1, 16])
+def test_row_updates_with_device_valid_count_ignore_the_padding(cuda, dim):
+    cap, vocab, n_valid = 512, 200, 131
+    rng = np.random.default_rng(dim)
+    ids = rng.integers(0, vocab, size=cap).astype(np.int32)
+    g = rng.standard_normal((cap, dim)).astype(np.float32)
+    nv = torch.tensor([n_valid], dtype=torch.int32, device=cuda)
+    like = torch.empty((vocab, 0), device=cuda)
+
+    def run(ids_np, g_np, n_valid_t):
+        torch.manual_seed(0)
+        w = torch.randn((vocab, dim), device=cuda)
+        m, v = torch.zeros_like(w), torch.zeros_like(w)
+        acc, lin = torch.ones_like(w), torch.zeros_like(w)
+        w2 = w.clone()
+        ids_t, g_t = torch.from_numpy(ids_np).to(cuda), torch.from_numpy(g_np).to(cuda)
+        uq = ops.unique(ids_t, table_like=like, n_valid=n_valid_t)
+        ah = ops.adam_hyper(1e-2, device=cuda)
+        ops.adam_begin_step(ah)
+        ops.sparse_lazy_adam(w, m, v, ah, g_t, None, uq, n_valid=n_valid_t)
+        ops.sparse_ftrl(w2, acc, lin, ops.ftrl_hyper(5e-2, l1=1e-3, l2=1e-3, device=cuda), g_t, None, uq, n_valid=n_valid_t)
+        return [t.cpu().numpy() for t in (w, m, v, w2, acc, lin)]
+
+    got = run(ids, g, nv)                                  # padded inbox + device-side count
+    want = run(ids[:n_valid].copy(), g[:n_valid].copy(), None)   # the exact-size call
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
