@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--vocab-scale", type=float, default=1.0, help="shrink the Kaggle cardinalities (debug)")
     ap.add_argument("--alpha", type=float, default=1.05)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default=os.environ.get("MREC_BENCH_EXCHANGE", "device"), choices=["nccl", "device"],
+                    help="N>1: nccl = all-to-all with host-side split sizes; device = device-driven peer stores, "
+                         "whole step in one CUDA graph")
     ap.add_argument("--cpu-sample-batch", type=int, default=2000)
     ap.add_argument("--cpu-vocab", type=int, default=4000000)
     return ap.parse_args()
@@ -122,7 +125,8 @@ def workload_config(args, n_gpus):
         "global_batch": args.batch * n_gpus, "batch_per_gpu": args.batch, "fields": FIELDS, "emb_dim": EMB,
         "vocab_rows": synth.vocab_size(cards), "zipf_alpha": args.alpha, "mlp": [FIELDS * EMB] + list(HIDDEN) + [1],
         "mlp_dtype": "fp16 (use_mixed_precision)", "loss_scale": 1024,
-        "parallelism": "single" if n_gpus == 1 else "row-sharded embeddings (a2a) + data-parallel MLP x%d" % n_gpus,
+        "parallelism": "single" if n_gpus == 1 else "row-sharded embeddings (%s) + data-parallel MLP x%d" % (
+            "device-driven NVLink peer stores, step in one CUDA graph" if args.exchange == "device" else "a2a", n_gpus),
         "l2": "per-step working set (>= 0.8 GB of table rows, activations and gradients) exceeds the 126 MB L2; "
               "batches rotate over a ring of 8",
     }
@@ -265,8 +269,12 @@ def run_ours(args):
         model = cells.WideDeepModel(cfg, device=dev)
         step = cells.TrainStepWrap(cells.NetWithLossClass(model, cfg), sens=1024.0, sparse=True, lazy_adam=True)
     else:
-        from mindrec_b200 import sharded
-        step = sharded.build_sharded_wide_deep(b, vocab, EMB, HIDDEN, dev, seed=1)
+        if args.exchange == "device":
+            from mindrec_b200 import peer_sharded
+            step = peer_sharded.PeerShardedWideDeepStep(b, vocab, EMB, HIDDEN, dev, seed=1)
+        else:
+            from mindrec_b200 import sharded
+            step = sharded.build_sharded_wide_deep(b, vocab, EMB, HIDDEN, dev, seed=1)
 
     ring = 8
     gen = synth.CriteoSynth(b, cards=cards, alpha=args.alpha, seed=20260101, rank=rank)

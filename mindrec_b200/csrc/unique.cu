@@ -50,14 +50,19 @@ __device__ __forceinline__ KeyT decode_key(typename UKeyOf<KeyT>::type u, uint64
   return (KeyT)(u ^ UKeyOf<KeyT>::sign);
 }
 
-// n_valid (optional, RAW pass of a bounded sort only): entries at i >= *n_valid are padding of a statically
-// sized buffer and are read as out-of-range (they sort last and form the segment every consumer skips).
+// n_valid (optional): the input is a statically sized buffer of which only the first *n_valid entries are
+// real (device-side count).  Every kernel of the sort then works on n_eff = min(n, *n_valid): CTAs past the valid
+// prefix exit at once, so the cost follows the valid count, not the capacity; outputs past n_eff are not written.
+__device__ __forceinline__ int64_t eff_n(int64_t n, const int32_t* n_valid) {
+  if (!n_valid) return n;
+  const int64_t v = n_valid[0];
+  return v < 0 ? 0 : (v < n ? v : n);
+}
+
 template <typename KeyT, bool RAW>
-__device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys, int64_t i, uint64_t bound,
-                                                                const int32_t* n_valid = nullptr) {
+__device__ __forceinline__ typename UKeyOf<KeyT>::type load_key(const void* keys, int64_t i, uint64_t bound) {
   using U = typename UKeyOf<KeyT>::type;
   if (RAW) {
-    if (n_valid && i >= (int64_t)n_valid[0]) return (U)bound;
     return encode_key<KeyT>(reinterpret_cast<const KeyT*>(keys)[i], bound);
   }
   return reinterpret_cast<const U*>(keys)[i];
@@ -70,12 +75,13 @@ radix_hist_kernel(const void* __restrict__ keys, int64_t n, int shift, int radix
                   int tiles_per_block, uint32_t* __restrict__ hist, const int32_t* __restrict__ n_valid) {
   __shared__ uint32_t s_hist[MAX_RADIX];
   const int RADIX = radix;
+  n = eff_n(n, n_valid);
   for (int d = threadIdx.x; d < RADIX; d += RS_THREADS) s_hist[d] = 0;
   __syncthreads();
   const int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
   const int64_t end = min(n, begin + (int64_t)tiles_per_block * RS_TILE);
   for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
-    const auto k = load_key<KeyT, RAW>(keys, i, bound, n_valid);
+    const auto k = load_key<KeyT, RAW>(keys, i, bound);
     atomicAdd(&s_hist[(uint32_t)(k >> shift) & (RADIX - 1)], 1u);
   }
   __syncthreads();
@@ -142,6 +148,8 @@ radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
   const int RADIX = radix;
   const int rbits = __ffs(radix) - 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  n = eff_n(n, n_valid);
+  if ((int64_t)blockIdx.x * tiles_per_block * RS_TILE >= n) return;
   const uint32_t lt_mask = (1u << lane) - 1u;
   {
     // exclusive scan of the digit totals (<= 512 entries, 2 per thread) -> digit base
@@ -177,7 +185,7 @@ radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
     for (int i = 0; i < RS_ITEMS; ++i) {
       const int64_t idx = tile0 + warp * (RS_ITEMS * 32) + i * 32 + lane;
       if (idx < n) {
-        key[i] = load_key<KeyT, RAW>(keys_in, idx, bound, n_valid);
+        key[i] = load_key<KeyT, RAW>(keys_in, idx, bound);
         val[i] = RAW ? (int32_t)idx : vals_in[idx];
         dig[i] = (uint32_t)(key[i] >> shift) & (RADIX - 1);
       } else {
@@ -232,8 +240,14 @@ radix_scatter_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
 // ---- unique from sorted keys ----
 template <typename UKey>
 __global__ void __launch_bounds__(RS_THREADS)
-seg_count_kernel(const UKey* __restrict__ sorted, int64_t n, uint32_t* __restrict__ tile_heads) {
+seg_count_kernel(const UKey* __restrict__ sorted, int64_t n, uint32_t* __restrict__ tile_heads,
+                 const int32_t* __restrict__ n_valid) {
   __shared__ uint32_t s_warp[RS_WARPS];
+  n = eff_n(n, n_valid);
+  if ((int64_t)blockIdx.x * RS_TILE >= n) {
+    if (threadIdx.x == 0) tile_heads[blockIdx.x] = 0;
+    return;
+  }
   const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)threadIdx.x * RS_ITEMS;
   uint32_t c = 0;
 #pragma unroll
@@ -255,9 +269,10 @@ seg_count_kernel(const UKey* __restrict__ sorted, int64_t n, uint32_t* __restric
 // single block: exclusive scan of tile_heads (in place), total -> count[0] and seg_start[total] = n
 __global__ void __launch_bounds__(1024)
 seg_scan_kernel(uint32_t* __restrict__ tile_heads, int n_tiles, int32_t* __restrict__ count,
-                int32_t* __restrict__ seg_start, int64_t n) {
+                int32_t* __restrict__ seg_start, int64_t n, const int32_t* __restrict__ n_valid) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
+  n = eff_n(n, n_valid);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
   __syncthreads();
@@ -301,9 +316,11 @@ seg_emit_kernel(const typename UKeyOf<KeyT>::type* __restrict__ sorted,
                 const int32_t* __restrict__ perm, int64_t n, uint64_t bound,
                 const uint32_t* __restrict__ tile_offset, KeyT* __restrict__ uniq,
                 int32_t* __restrict__ inverse, int32_t* __restrict__ seg_start,
-                int32_t* __restrict__ seg_of) {
+                int32_t* __restrict__ seg_of, const int32_t* __restrict__ n_valid) {
   __shared__ uint32_t s_warp[RS_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  n = eff_n(n, n_valid);
+  if ((int64_t)blockIdx.x * RS_TILE >= n) return;
   const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)tid * RS_ITEMS;
   uint32_t head[RS_ITEMS];
   uint32_t c = 0;
@@ -428,19 +445,19 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
     } else {
       if (!kFuseNextHist)
         MREC_LAUNCH((radix_hist_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, n, shift, radix,
-                    bound, p.tiles_per_block, h, nullptr);
+                    bound, p.tiles_per_block, h, n_valid);
       MREC_LAUNCH(radix_scan_kernel, scan_grid, 1024, 0, stream, h, p.n_blocks, radix);
       MREC_LAUNCH((radix_scatter_kernel<KeyT, false>), p.n_blocks, RS_THREADS, 0, stream, kin, vin, kout,
-                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits, nullptr);
+                  vout, n, shift, radix, bound, p.tiles_per_block, h, p.n_blocks, hn, shift + p.digit_bits, n_valid);
     }
     kin = kout;
     vin = vout;
   }
   const U* sorted = reinterpret_cast<const U*>(kin);
-  MREC_LAUNCH(seg_count_kernel<U>, p.n_tiles, RS_THREADS, 0, stream, sorted, n, tiles);
-  MREC_LAUNCH(seg_scan_kernel, 1, 1024, 0, stream, tiles, p.n_tiles, count, seg_start, n);
+  MREC_LAUNCH(seg_count_kernel<U>, p.n_tiles, RS_THREADS, 0, stream, sorted, n, tiles, n_valid);
+  MREC_LAUNCH(seg_scan_kernel, 1, 1024, 0, stream, tiles, p.n_tiles, count, seg_start, n, n_valid);
   MREC_LAUNCH(seg_emit_kernel<KeyT>, p.n_tiles, RS_THREADS, 0, stream, sorted, perm, n, bound, tiles,
-              uniq, inverse, seg_start, seg_of);
+              uniq, inverse, seg_start, seg_of, n_valid);
   return check_launch("unique_sorted");
 }
 

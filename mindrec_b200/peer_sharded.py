@@ -144,13 +144,25 @@ class PeerRank:
                                self._mod_none, self.err)
         self.signal(3)
 
-    def p_update(self):
-        uq2 = ops.unique(self.buf["keys_in"], table_like=self.deep, result=self.uq_owner, ws_tag="unique_peer_owner",
-                         n_valid=self.n_r)
-        ops.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, self.buf["gwide_in"], None, uq2, n_valid=self.n_r)
+    def p_owner_dedup(self):
+        """The same row can be asked for by several ranks: dedup the key inbox (needs only the keys, so callers
+        run it on a side stream underneath the DenseLayer segment).  Work follows n_r, not the capacity."""
+        ops.unique(self.buf["keys_in"], table_like=self.deep, result=self.uq_owner, ws_tag="unique_peer_owner",
+                   n_valid=self.n_r)
+
+    def p_update_wide(self):
+        ops.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, self.buf["gwide_in"], None, self.uq_owner,
+                        n_valid=self.n_r)
+
+    def p_update_deep(self):
         ops.adam_begin_step(self.adam_hyper)
-        ops.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, self.buf["grad_in"], None, uq2,
+        ops.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, self.buf["grad_in"], None, self.uq_owner,
                              n_valid=self.n_r)
+
+    def p_update(self):
+        self.p_owner_dedup()
+        self.p_update_wide()
+        self.p_update_deep()
 
 
 class EmulatedPeerGroup:
@@ -255,6 +267,8 @@ class PeerShardedTables:
         self.device = torch.device(device)
         self.cuda = True
         self.plan_stream = None
+        self.owner_stream = torch.cuda.Stream(device=self.device)
+        self._side_open = False
         arena = _IpcArena(group)
         self.rk = PeerRank(self.rank, self.world, vocab_size, emb_dim, n_lookups, device, arena.alloc(device),
                            seed=seed, sens=sens)
@@ -273,6 +287,11 @@ class PeerShardedTables:
         rk.wait(0)
         rk.p_keys()
         rk.wait(1)
+        # owner-side dedup of the key inbox: forked (a parallel branch when captured) under serve / DenseLayers
+        self.owner_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.owner_stream):
+            rk.p_owner_dedup()
+        self._side_open = True
         return _DevicePlan(ids)
 
     def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
@@ -286,7 +305,19 @@ class PeerShardedTables:
         rk = self.rk
         rk.p_grads(delta, gx)
         rk.wait(3)
-        rk.p_update()
+        main = torch.cuda.current_stream()
+        self.join_side()
+        self.owner_stream.wait_stream(main)
+        with torch.cuda.stream(self.owner_stream):       # latency-bound FTRL beside the LazyAdam rows
+            rk.p_update_wide()
+        rk.p_update_deep()
+        main.wait_stream(self.owner_stream)
+
+    def join_side(self):
+        """Join the forked dedup branch (a captured graph must end with every branch joined)."""
+        if self._side_open:
+            torch.cuda.current_stream().wait_stream(self.owner_stream)
+            self._side_open = False
 
     @property
     def wide(self):
@@ -329,43 +360,81 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
                          tables_factory=lambda: PeerShardedTables(vocab_size, emb_dim, batch_size * fields, device,
                                                                   group=group, seed=seed, sens=sens))
         self._graph_step = graph
-        self._whole = None
+        self._graphs = None
         self._loss = None
+        self._bwd = None
+        self._dense_stream = torch.cuda.Stream(device=self.device)
+        self._stage_stream = torch.cuda.Stream(device=self.device)
+        self._stage = None
+        self._staged_for = None
 
-    def _sparse_and_dense(self):
+    # the step in two fixed-shape halves; the DenseLayer mean all-reduce + Adam run between them on a side stream
+    def _forward_half(self):
         ids, wts, label = self._slots[0]
         t = self.tables
         plan = t.plan_batch(ids)
         t.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
         self._io["label"].copy_(label)
         loss, delta, gx = self._dense_segment()
-        t.update(delta, gx)
+        t.join_side()
+        self._bwd = (delta, gx)
         return loss
+
+    def _backward_half(self):
+        self.tables.update(*self._bwd)
+
+    def _one_step(self):
+        main = torch.cuda.current_stream()
+        main.wait_stream(self._dense_stream)                 # last step's dense Adam wrote the weights
+        if self._graphs is not None:
+            self._graphs[0].replay()
+        else:
+            self._loss = self._forward_half()
+        self._dense_stream.wait_stream(main)
+        with torch.cuda.stream(self._dense_stream):          # NCCL + dense Adam under the gradient exchange
+            self._dense_update()
+        if self._graphs is not None:
+            self._graphs[1].replay()
+        else:
+            self._backward_half()
+        return self._loss
 
     def capture(self, ids, wts, label, warmup=3):
         self._slots = [tuple(t.clone() for t in (ids, wts, label))]
+        self._stage = tuple(torch.empty_like(t) for t in self._slots[0])
         self._ensure_io(ids)
         for _ in range(warmup):
-            self._loss = self._sparse_and_dense()
-            self._dense_update()
+            self._one_step()
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         if self._graph_step:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._loss = self._sparse_and_dense()
-            self._whole = g
+            # capture executes nothing: both halves are recorded back to back, then a real step is replayed
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._loss = self._forward_half()
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._backward_half()
+            self._graphs = (ga, gb)
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
         return self._slots[0]
 
     def replay(self, ids=None, wts=None, label=None, next_batch=None):
+        main = torch.cuda.current_stream()
         if ids is not None:
-            for d, s in zip(self._slots[0], (ids, wts, label)):
-                d.copy_(s, non_blocking=True)
-        if self._whole is not None:
-            self._whole.replay()
-        else:
-            self._loss = self._sparse_and_dense()
-        self._dense_update()
-        return self._loss, self._loss
+            if self._staged_for is not None and self._staged_for is ids:
+                main.wait_stream(self._stage_stream)         # staged one step ahead: a device-local copy
+                for d, s in zip(self._slots[0], self._stage):
+                    d.copy_(s, non_blocking=True)
+            else:
+                for d, s in zip(self._slots[0], (ids, wts, label)):
+                    d.copy_(s, non_blocking=True)
+        self._staged_for = None
+        if next_batch is not None and not next_batch[0].is_cuda:
+            self._stage_stream.wait_stream(main)             # the staging buffers were just consumed
+            with torch.cuda.stream(self._stage_stream):
+                for d, s in zip(self._stage, next_batch):
+                    d.copy_(s, non_blocking=True)
+            self._staged_for = next_batch[0]
+        loss = self._one_step()
+        return loss, loss

@@ -119,12 +119,12 @@ def test_unique_with_device_valid_count(cuda, n_valid):
     ids_t = torch.from_numpy(ids).to(cuda)
     nv = torch.tensor([n_valid], dtype=torch.int32, device=cuda)
     uq = ops.unique(ids_t, table_like=torch.empty((vocab, 0), device=cuda), n_valid=nv)
-    # padding sorts last as ONE out-of-range segment (key == vocab), which the row updates skip
-    want = np.unique(np.concatenate([ids[:n_valid], np.full(cap - n_valid, vocab, dtype=np.int32)]))
+    want = np.unique(ids[:n_valid])                    # the padding past n_valid is never looked at
     assert int(uq.count) == want.size
     assert np.array_equal(uq.uniq[:want.size].cpu().numpy(), want)
     inv = uq.inverse.cpu().numpy()[:n_valid]
     assert np.array_equal(want[inv], ids[:n_valid])
+    assert int(uq.seg_start[want.size]) == n_valid
 
 
 @pytest.mark.parametrize("dim", [1, 16])
