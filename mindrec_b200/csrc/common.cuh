@@ -139,6 +139,7 @@ __device__ __forceinline__ void reg_fence(float4& v) {
 __device__ __forceinline__ void reg_fence(float& v) { asm volatile("" : "+f"(v)); }
 __device__ __forceinline__ void reg_fence(uint2& v) { asm volatile("" : "+r"(v.x), "+r"(v.y)); }
 __device__ __forceinline__ void reg_fence(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void reg_fence(uint4& v) { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace mrec {
@@ -107,44 +109,69 @@ __device__ __forceinline__ void ftrl_elem(float& w, float& a, float& lin, float 
 }
 
 // ---- per-segment sinks ----
+// A sink owns the per-row state of an optimizer.  The row pass drives it in three steps so that the loads of
+// several rows can be in flight together: row_of(seg) (one index load), load(offset, state) (unconditional loads
+// of the state chunks; the caller clamps the offset of skipped rows to a valid one), finish(offset, state, gsum)
+// (math + stores).  apply() is the one-row form used by the chain paths.
+template <typename T> struct State3 { T a, b, c; };
+struct State0 {};
+
 template <typename Vec, typename IdT> struct LazyAdamSink;
 template <typename IdT>
 struct LazyAdamSink<float4, IdT> {
   static constexpr bool kApplyComplete = true;
+  using State = State3<float4>;
   float4* w; float4* m; float4* v;
   const IdT* uniq;
   const float* hyper;
   int64_t vocab;
   int cpr;
-  __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
-    const int64_t row = (int64_t)uniq[seg];
-    if ((uint64_t)row >= (uint64_t)vocab) return;  // out-of-range ids carry no row
+  __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
+  __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
+  __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = m[o]; s.c = v[o]; }
+  __device__ __forceinline__ void fence(State& s) const { reg_fence(s.a); reg_fence(s.b); reg_fence(s.c); }
+  __device__ __forceinline__ void finish(int64_t o, State& s, const float4& gs) const {
     const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6], sc = hyper[7];
     const float l2 = hyper[8];
-    const int64_t o = row * cpr + c;
-    float4 W = w[o], M = m[o], V = v[o];
+    float4 W = s.a, M = s.b, V = s.c;
     adam_elem(W.x, M.x, V.x, fmaf(l2, W.x, gs.x * sc), b1, b2, eps, lr_t);
     adam_elem(W.y, M.y, V.y, fmaf(l2, W.y, gs.y * sc), b1, b2, eps, lr_t);
     adam_elem(W.z, M.z, V.z, fmaf(l2, W.z, gs.z * sc), b1, b2, eps, lr_t);
     adam_elem(W.w, M.w, V.w, fmaf(l2, W.w, gs.w * sc), b1, b2, eps, lr_t);
     w[o] = W; m[o] = M; v[o] = V;
   }
+  __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
+    const int64_t row = row_of(seg);
+    if (!in_range(row)) return;                    // out-of-range ids carry no row
+    State s;
+    load(row * cpr + c, s);
+    finish(row * cpr + c, s, gs);
+  }
 };
 template <typename IdT>
 struct LazyAdamSink<float, IdT> {
   static constexpr bool kApplyComplete = true;
+  using State = State3<float>;
   float* w; float* m; float* v;
   const IdT* uniq;
   const float* hyper;
   int64_t vocab;
   int cpr;
-  __device__ __forceinline__ void apply(int seg, int c, const float& gs) const {
-    const int64_t row = (int64_t)uniq[seg];
-    if ((uint64_t)row >= (uint64_t)vocab) return;
-    const int64_t o = row * cpr + c;
-    float W = w[o], M = m[o], V = v[o];
+  __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
+  __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
+  __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = m[o]; s.c = v[o]; }
+  __device__ __forceinline__ void fence(State& s) const { reg_fence(s.a); reg_fence(s.b); reg_fence(s.c); }
+  __device__ __forceinline__ void finish(int64_t o, State& s, const float& gs) const {
+    float W = s.a, M = s.b, V = s.c;
     adam_elem(W, M, V, fmaf(hyper[8], W, gs * hyper[7]), hyper[1], hyper[2], hyper[3], hyper[6]);
     w[o] = W; m[o] = M; v[o] = V;
+  }
+  __device__ __forceinline__ void apply(int seg, int c, const float& gs) const {
+    const int64_t row = row_of(seg);
+    if (!in_range(row)) return;
+    State s;
+    load(row * cpr + c, s);
+    finish(row * cpr + c, s, gs);
   }
 };
 
@@ -152,39 +179,57 @@ template <typename Vec, typename IdT> struct FtrlSink;
 template <typename IdT>
 struct FtrlSink<float4, IdT> {
   static constexpr bool kApplyComplete = true;
+  using State = State3<float4>;
   float4* w; float4* acc; float4* lin;
   const IdT* uniq;
   const float* hyper;
   int64_t vocab;
   int cpr;
-  __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
-    const int64_t row = (int64_t)uniq[seg];
-    if ((uint64_t)row >= (uint64_t)vocab) return;
+  __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
+  __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
+  __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = acc[o]; s.c = lin[o]; }
+  __device__ __forceinline__ void fence(State& s) const { reg_fence(s.a); reg_fence(s.b); reg_fence(s.c); }
+  __device__ __forceinline__ void finish(int64_t o, State& s, const float4& gs) const {
     const float lr = hyper[0], l1 = hyper[1], l2 = hyper[2], p = hyper[3], sc = hyper[4];
-    const int64_t o = row * cpr + c;
-    float4 W = w[o], A = acc[o], L = lin[o];
+    float4 W = s.a, A = s.b, L = s.c;
     ftrl_elem(W.x, A.x, L.x, gs.x * sc, lr, l1, l2, p);
     ftrl_elem(W.y, A.y, L.y, gs.y * sc, lr, l1, l2, p);
     ftrl_elem(W.z, A.z, L.z, gs.z * sc, lr, l1, l2, p);
     ftrl_elem(W.w, A.w, L.w, gs.w * sc, lr, l1, l2, p);
     w[o] = W; acc[o] = A; lin[o] = L;
   }
+  __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
+    const int64_t row = row_of(seg);
+    if (!in_range(row)) return;
+    State s;
+    load(row * cpr + c, s);
+    finish(row * cpr + c, s, gs);
+  }
 };
 template <typename IdT>
 struct FtrlSink<float, IdT> {
   static constexpr bool kApplyComplete = true;
+  using State = State3<float>;
   float* w; float* acc; float* lin;
   const IdT* uniq;
   const float* hyper;
   int64_t vocab;
   int cpr;
-  __device__ __forceinline__ void apply(int seg, int c, const float& gs) const {
-    const int64_t row = (int64_t)uniq[seg];
-    if ((uint64_t)row >= (uint64_t)vocab) return;
-    const int64_t o = row * cpr + c;
-    float W = w[o], A = acc[o], L = lin[o];
+  __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
+  __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
+  __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = acc[o]; s.c = lin[o]; }
+  __device__ __forceinline__ void fence(State& s) const { reg_fence(s.a); reg_fence(s.b); reg_fence(s.c); }
+  __device__ __forceinline__ void finish(int64_t o, State& s, const float& gs) const {
+    float W = s.a, A = s.b, L = s.c;
     ftrl_elem(W, A, L, gs * hyper[4], hyper[0], hyper[1], hyper[2], hyper[3]);
     w[o] = W; acc[o] = A; lin[o] = L;
+  }
+  __device__ __forceinline__ void apply(int seg, int c, const float& gs) const {
+    const int64_t row = row_of(seg);
+    if (!in_range(row)) return;
+    State s;
+    load(row * cpr + c, s);
+    finish(row * cpr + c, s, gs);
   }
 };
 
@@ -259,6 +304,111 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
   }
 }
 
+
+// ---- kernel A, staged form: rows through shared memory with cp.async --------------------------------------
+// The register-resident walks above keep a thread alive for 32 positions with only a handful of row loads in
+// flight behind a perm -> row dependent chain (ncu r1g: 33 % warps active, 34 % of DRAM peak).  Here a CTA owns
+// P consecutive sorted positions: (1) perm / seg_of of the range go to shared memory, (2) EVERY 16-byte chunk of
+// the P gradient rows is requested at once with cp.async (LDGSTS: no registers, no scoreboard, the whole range
+// in flight), (3) the segmented sums are then walked out of shared memory, one thread per (32-position tile,
+// float4 chunk), in exactly the order and with exactly the outputs of segsum_tiles_kernel (bit-identical).
+// Many small CTAs per SM overlap one CTA's walk with the others' loads.
+template <typename GT>
+__device__ __forceinline__ float4 seg_smem_f4(const GT* row, int c);
+template <>
+__device__ __forceinline__ float4 seg_smem_f4<float>(const float* row, int c) {
+  return reinterpret_cast<const float4*>(row)[c];
+}
+template <>
+__device__ __forceinline__ float4 seg_smem_f4<__half>(const __half* row, int c) {
+  const uint2 u = reinterpret_cast<const uint2*>(row)[c];
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename GT, bool HAS_MASK>
+__global__ void __launch_bounds__(kSegThreads)
+segsum_stage_kernel(const GT* __restrict__ g, int dim, int div, const float* __restrict__ mask,
+                    const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
+                    const int32_t* __restrict__ seg_start, int64_t n64, int P, float4* __restrict__ part,
+                    float4* __restrict__ gsum, int32_t* __restrict__ long_list, int32_t* __restrict__ long_count,
+                    const int32_t* __restrict__ n_valid) {
+  extern __shared__ uint4 seg_smem[];
+  int n = (int)n64;
+  if (n_valid) n = min(n, n_valid[0]);
+  const int pos0 = blockIdx.x * P;
+  if (pos0 >= n) return;
+  const int cnt = min(P, n - pos0);
+  const int row_bytes = dim * (int)sizeof(GT);
+  char* s_rows = reinterpret_cast<char*>(seg_smem);
+  int32_t* s_perm = reinterpret_cast<int32_t*>(s_rows + (size_t)P * row_bytes);
+  int32_t* s_seg = s_perm + P;
+  float* s_mask = reinterpret_cast<float*>(s_seg + P);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < cnt; i += kSegThreads) {
+    s_perm[i] = perm[pos0 + i];
+    s_seg[i] = seg_of[pos0 + i];
+  }
+  __syncthreads();
+  const int cpr16 = row_bytes >> 4;
+  const uint32_t s_base = smem_u32(s_rows);
+  for (int q = tid; q < cnt * cpr16; q += kSegThreads) {
+    const int r = q / cpr16;
+    const int c = q - r * cpr16;
+    const int p = s_perm[r];
+    const int64_t grow = (div == 1) ? (int64_t)p : (int64_t)(p / div);
+    const char* src = reinterpret_cast<const char*>(g) + (grow * cpr16 + c) * 16;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + (uint32_t)q * 16u), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < cnt; i += kSegThreads) s_mask[i] = HAS_MASK ? __ldg(mask + s_perm[i]) : 1.f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int cpr = dim >> 2;
+  const int tiles = (cnt + kSegTile - 1) / kSegTile;
+  for (int t = tid; t < tiles * cpr; t += kSegThreads) {
+    const int tl = t / cpr;
+    const int c = t - tl * cpr;
+    const int j = pos0 / kSegTile + tl;              // global tile index (P is a multiple of kSegTile)
+    const int l0 = tl * kSegTile;
+    const int l1 = min(cnt, l0 + kSegTile);
+    int cur = s_seg[l0];
+    bool enters;
+    if (l0 > 0) enters = (s_seg[l0 - 1] == cur);
+    else enters = (pos0 > 0) && (seg_of[pos0 - 1] == cur);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int l = l0; l < l1; ++l) {
+      const int sg = s_seg[l];
+      if (sg != cur) {
+        if (enters) part[(int64_t)(j * 2 + 0) * cpr + c] = acc;
+        else gsum[(int64_t)cur * cpr + c] = acc;
+        cur = sg;
+        enters = false;
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float4 v = seg_smem_f4<GT>(reinterpret_cast<const GT*>(s_rows + (size_t)l * row_bytes), c);
+      f4_fma(acc, v, s_mask[l]);
+    }
+    bool leaves = false;
+    if (pos0 + l1 < n) leaves = ((l1 < cnt) ? s_seg[l1] : seg_of[pos0 + l1]) == cur;
+    if (enters) {
+      part[(int64_t)(j * 2 + 0) * cpr + c] = acc;
+    } else if (leaves) {
+      part[(int64_t)(j * 2 + 1) * cpr + c] = acc;
+      if (c == 0) {
+        const int j_last = (seg_start[cur + 1] - 1) / kSegTile;
+        if (j_last - j > kLongChain) long_list[atomicAdd(long_count, 1)] = cur;
+      }
+    } else {
+      gsum[(int64_t)cur * cpr + c] = acc;
+    }
+  }
+}
+
 // ---- kernel B: finish every segment and hand its sum to the sink -------------------------------------
 // A segment [s, e) of the sorted order is "complete" when it lies inside one tile (its sum is already in
 // gsum), else it is a chain of partials: slot 1 of tile s/32, then slot 0 of every following tile up to
@@ -271,8 +421,8 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
 // Sink::kApplyComplete = false (plain segment-sum into gsum) skips rows whose sum is already stored.
 constexpr int kChainBlocks = 64;
 
-template <typename Vec, typename Sink>
-__global__ void __launch_bounds__(kSegThreads)
+template <typename Vec, typename Sink, int ROWS>
+__global__ void __launch_bounds__(kSegThreads, (sizeof(Vec) == 16 ? (ROWS == 2 ? 3 : 4) : 4))
 rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                    int64_t n, const Vec* __restrict__ gsum, const Vec* __restrict__ part,
                    const int32_t* __restrict__ long_list, const int32_t* __restrict__ long_count, Sink sink,
@@ -318,15 +468,50 @@ rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* _
   if (gi >= groups) return;
   const int n_seg = seg_of[n - 1] + 1;  // U: segment id of the last sorted position + 1
   const int64_t n_groups = (int64_t)(gridDim.x - kChainBlocks) * groups;
-  for (int64_t u = (int64_t)(blockIdx.x - kChainBlocks) * groups + gi; u < n_seg; u += n_groups) {
-    const int64_t j0 = seg_start[u] / kSegTile;
-    const int64_t j1 = ((int64_t)seg_start[u + 1] - 1) / kSegTile;
-    if (j0 == j1) {
-      if (Sink::kApplyComplete) sink.apply((int)u, c, gsum[u * cpr + c]);
-    } else if (j1 - j0 <= kLongChain) {
-      Vec acc = part[(j0 * 2 + 1) * cpr + c];
-      for (int64_t jj = j0 + 1; jj <= j1; ++jj) VOps<Vec>::add(acc, part[(jj * 2) * cpr + c]);
-      sink.apply((int)u, c, acc);
+  // ROWS rows per thread and iteration: the index loads of all of them, then all their state / gsum chunk loads,
+  // are issued before any is used (ncu r1h: with one row at a time the chain seg_start -> uniq -> state left
+  // ~16 bytes in flight per thread and 26 % issue activity).  Rows past the end are clamped and discarded.
+  for (int64_t u0 = (int64_t)(blockIdx.x - kChainBlocks) * groups + gi; u0 < n_seg; u0 += ROWS * n_groups) {
+    int s0[ROWS], s1[ROWS];
+    int64_t row[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      const int uc = (int)min(u0 + k * n_groups, (int64_t)n_seg - 1);
+      s0[k] = seg_start[uc];
+      s1[k] = seg_start[uc + 1];
+      row[k] = sink.row_of(uc);
+    }
+    Vec gs[ROWS];
+    typename Sink::State st[ROWS];
+    int64_t off[ROWS];
+    bool ok[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      const int64_t u = u0 + k * n_groups;
+      const int uc = (int)min(u, (int64_t)n_seg - 1);
+      ok[k] = (u < n_seg) && sink.in_range(row[k]);
+      off[k] = (ok[k] ? row[k] : 0) * cpr + c;
+      if (Sink::kApplyComplete) gs[k] = gsum[(int64_t)uc * cpr + c];
+      sink.load(off[k], st[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      if (Sink::kApplyComplete) reg_fence(gs[k]);
+      sink.fence(st[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      const int64_t u = u0 + k * n_groups;
+      if (u >= n_seg) continue;
+      const int64_t j0 = s0[k] / kSegTile;
+      const int64_t j1 = ((int64_t)s1[k] - 1) / kSegTile;
+      if (j0 == j1) {
+        if (Sink::kApplyComplete && ok[k]) sink.finish(off[k], st[k], gs[k]);
+      } else if (j1 - j0 <= kLongChain) {
+        Vec acc = part[(j0 * 2 + 1) * cpr + c];
+        for (int64_t jj = j0 + 1; jj <= j1; ++jj) VOps<Vec>::add(acc, part[(jj * 2) * cpr + c]);
+        if (ok[k]) sink.finish(off[k], st[k], acc);
+      }
     }
   }
 }
@@ -335,8 +520,14 @@ rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* _
 template <typename Vec>
 struct StoreSink {
   static constexpr bool kApplyComplete = false;
+  using State = State0;
   Vec* out;
   int cpr;
+  __device__ __forceinline__ int64_t row_of(int seg) const { return seg; }
+  __device__ __forceinline__ bool in_range(int64_t) const { return true; }
+  __device__ __forceinline__ void load(int64_t, State&) const {}
+  __device__ __forceinline__ void fence(State&) const {}
+  __device__ __forceinline__ void finish(int64_t o, State&, const Vec& gs) const { out[o] = gs; }
   __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const { out[(int64_t)seg * cpr + c] = gs; }
 };
 
@@ -382,7 +573,31 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
   const int64_t n_tiles = cdiv(n, kSegTile);
   const int grid = (int)cdiv(n_tiles * cpr, kSegThreads);
   cudaMemsetAsync(long_count, 0, sizeof(int32_t), stream);
-  if (mask) {
+  // MREC_SEG_MODE: -1 (default) staged cp.async kernel | 0 register tile walk
+  const char* seg_env = getenv("MREC_SEG_MODE");
+  const int seg_batch = seg_env ? atoi(seg_env) : -1;
+  const int row_bytes = dim * (int)sizeof(GT);
+  int stage_p = 0;                                  // positions per CTA of the staged kernel (0: not applicable)
+  if (std::is_same<Vec, float4>::value && seg_batch < 0 && row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+      n < ((int64_t)1 << 31)) {
+    const char* pe = getenv("MREC_SEG_P");
+    stage_p = pe ? atoi(pe) : 128;
+    while (stage_p > 32 && (size_t)stage_p * (row_bytes + 12) > 40 * 1024) stage_p >>= 1;
+    if ((size_t)stage_p * (row_bytes + 12) > 40 * 1024) stage_p = 0;
+  }
+  if (stage_p) {
+    if constexpr (std::is_same<Vec, float4>::value) {
+      const size_t smem = (size_t)stage_p * (row_bytes + 12);
+      const int grid_s = (int)cdiv(n, stage_p);
+      if (mask) {
+        MREC_LAUNCH((segsum_stage_kernel<GT, true>), grid_s, kSegThreads, smem, stream, g, dim, div, mask, perm, seg_of,
+                    seg_start, n, stage_p, part, gsum, long_list, long_count, n_valid);
+      } else {
+        MREC_LAUNCH((segsum_stage_kernel<GT, false>), grid_s, kSegThreads, smem, stream, g, dim, div, mask, perm, seg_of,
+                    seg_start, n, stage_p, part, gsum, long_list, long_count, n_valid);
+      }
+    }
+  } else if (mask) {
     MREC_LAUNCH((segsum_tiles_kernel<Vec, GT, true>), grid, kSegThreads, 0, stream, g, cpr, div, mask, perm,
                 seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count, n_valid);
   } else {
@@ -390,16 +605,32 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
                 seg_of, seg_start, n, n_tiles, part, gsum, long_list, long_count, n_valid);
   }
   const int groups = kSegThreads / cpr;
-  const int row_blocks = grid_for(cdiv(n, groups), 8);
+  int row_blocks = grid_for(cdiv(n, groups), 8);
   if constexpr (kStandalone) {
     if (n_tiles > 1) {
       StoreSink<Vec> store{gsum, cpr};
-      MREC_LAUNCH((rows_update_kernel<Vec, StoreSink<Vec>>), kChainBlocks + row_blocks, kSegThreads, 0, stream,
+      MREC_LAUNCH((rows_update_kernel<Vec, StoreSink<Vec>, 1>), kChainBlocks + row_blocks, kSegThreads, 0, stream,
                   cpr, seg_of, seg_start, n, gsum, part, long_list, long_count, store, n_valid);
     }
   } else {
-    MREC_LAUNCH((rows_update_kernel<Vec, Sink>), kChainBlocks + row_blocks, kSegThreads, 0, stream, cpr, seg_of,
-                seg_start, n, gsum, part, long_list, long_count, sink, n_valid);
+    // MREC_ROWS_R: rows in flight per thread of the row pass (1 default | 2).  Measured r1h (U = 243 k rows of
+    // 320 B x {w, m, v}): 1 row x 8 CTAs/SM 0.170 ms, 2 rows x 3/SM 0.176, 4 rows x 2/SM 0.182 — the pass is
+    // not bound by loads in flight but by DRAM efficiency on random 320-byte read-modify-write rows.
+    const char* re = getenv("MREC_ROWS_R");
+    const int rows_r = re ? atoi(re) : 1;
+    const bool v4 = sizeof(Vec) == 16;
+    const char* pse = getenv("MREC_ROWS_PER_SM");
+    const int per_sm_env = pse ? atoi(pse) : 0;
+#define MREC_ROWS(R, PER_SM)                                                                                     \
+  do {                                                                                                           \
+    row_blocks = (int)std::min<int64_t>(cdiv(n, (int64_t)groups * R), (int64_t)kNumSMs * (per_sm_env ? per_sm_env : PER_SM)); \
+    if (row_blocks < 1) row_blocks = 1;                                                                          \
+    MREC_LAUNCH((rows_update_kernel<Vec, Sink, R>), kChainBlocks + row_blocks, kSegThreads, 0, stream, cpr, seg_of, \
+                seg_start, n, gsum, part, long_list, long_count, sink, n_valid);                                 \
+  } while (0)
+    if (rows_r == 2) MREC_ROWS(2, (v4 ? 3 : 4));
+    else MREC_ROWS(1, 8);
+#undef MREC_ROWS
   }
   return check_launch("segment_sum");
 }

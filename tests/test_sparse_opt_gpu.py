@@ -170,14 +170,15 @@ def test_dense_adam_and_ftrl_match_oracle(cuda):
     np.testing.assert_allclose(da.cpu().numpy(), acc, rtol=RTOL)
 
 
-@pytest.mark.parametrize("dim", [80, 6])
-def test_fp16_gradient_rows_equal_cast_then_fp32(cuda, dim):
-    """fp16 gradient rows fuse the Cast-to-fp32 of the DenseLayer bprop: same bits as casting first."""
+@pytest.mark.parametrize("dim,b,use_mask", [(80, 300, True), (6, 300, True), (80, 64, False), (16, 1, True), (8, 937, True)])
+def test_fp16_gradient_rows_equal_cast_then_fp32(cuda, dim, b, use_mask):
+    """fp16 gradient rows fuse the Cast-to-fp32 of the DenseLayer bprop: same bits as casting first
+    (D % 8 == 0 takes the 16-byte-chunk tile walk, other widths the generic one)."""
     rng = np.random.default_rng(21 + dim)
-    vocab, b, f = 3000, 300, 39
+    vocab, f = 3000, 39
     ids = torch.from_numpy(_zipf_ids(rng, b, f, vocab)).to(cuda)
     g16 = torch.from_numpy(rng.standard_normal((b * f, dim)).astype(np.float16)).to(cuda)
-    mask = torch.from_numpy(rng.random(b * f).astype(np.float32)).to(cuda)
+    mask = torch.from_numpy(rng.random(b * f).astype(np.float32)).to(cuda) if use_mask else None
     w0 = torch.from_numpy((rng.standard_normal((vocab, dim)) * 0.01).astype(np.float32)).to(cuda)
     uq = ops.unique(ids, table_like=w0)
     a = ops.segment_sum(g16, mask, uq, dim=dim).clone()
