@@ -161,6 +161,27 @@ int mrec_ftrl_dense(MREC_AOT_ARGS);
  *   out: logit[B], loss[1] (mean), delta[B] = sens*(sigmoid(logit)-label)/B, delta16[B] f16 | numel 0, delta_sum[1] */
 int mrec_sigmoid_xent(MREC_AOT_ARGS);
 
+/* ---- a7 DenseLayer backward glue ------------------------------------------------------------------------
+ * ReluGrad + BiasAddGrad of one DenseLayer (wide_and_deep.py:72-133 bprop; deepfm.py:150-170;
+ * deep_and_cross.py:161-200) in one pass, deterministic fp32 column sums:
+ *   in : g[B,N] f16|f32, y[B,N] same dtype | numel 0 (no mask: plain BiasAddGrad)
+ *   out: gz[B,N] = g * (y > 0) (may be g's own buffer; not written without a mask), gb[N] f32, workspace uint8
+ * The workspace (mrec_relu_bwd_bias_workspace_bytes(N)) holds ticket counters: zero-fill it once; every launch
+ * leaves them at zero. */
+int mrec_relu_bwd_bias(MREC_AOT_ARGS);
+size_t mrec_relu_bwd_bias_workspace_bytes(int64_t n_cols);
+
+/* The one-unit output DenseLayer (the logit head: wide_and_deep.py:293-297 dense_layer_5; deepfm.py:215;
+ * deep_and_cross.py:309) without skinny library GEMMs:
+ *   mrec_dense_head_fwd  in : h[B,K] f16|f32, w[K] same dtype, bias[1] same dtype        out: out[B] f32
+ *   mrec_dense_head_bwd  in : delta[B] f16|f32, h[B,K], w[K] (same dtype), relu_like[0|1] (numel 1: mask with h > 0)
+ *                        out: gh[B,K] = (delta x w) * mask, gw[K] f32 = delta^T h, gb_head[1] f32 = sum(delta),
+ *                             gb_prev[K] f32 | numel 0 = column sums of gh (previous layer's BiasAddGrad), workspace
+ * Workspace: mrec_dense_head_workspace_bytes(K), zero-filled once (self-resetting ticket counters). */
+int mrec_dense_head_fwd(MREC_AOT_ARGS);
+int mrec_dense_head_bwd(MREC_AOT_ARGS);
+size_t mrec_dense_head_workspace_bytes(int64_t k_dim);
+
 /* ---- K7 FM second-order interaction -------------------------------------------------------------
  * Replaces Square/ReduceSum/Sub x6 of models/deepfm/src/deepfm.py:222-228 and their autodiff.
  *   fwd  in : vx[B,F,D] f32 (already multiplied by the mask)      out: fm[B]|[B,1] f32

@@ -104,6 +104,7 @@ class WideDeepModel:
             self.wide_b.data.normal_(0.0, 0.01, generator=gen)
         self._wide_out = None
         self._deep_in = None
+        self._wide_stream = None
         self.defer_add = False       # set by NetWithLossClass: `out = wide_out + deep_out` happens in mrec_sigmoid_xent
 
     def trainable_params(self):
@@ -120,13 +121,20 @@ class WideDeepModel:
             # fp16 when the DenseLayers run in mixed precision: the Cast is fused into the gather store
             self._deep_in = torch.empty((b, f * d), device=self.device,
                                         dtype=torch.float16 if self.config.use_mixed_precision else torch.float32)
-        # wide_and_deep.py:300,303,305-306: gather(dim 1) * mask, ReduceSum(axis 1) + Wide_b
-        ops.gather_reduce(self.wide_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
-                          self.wide_b.data, out=self._wide_out)
+        # wide_and_deep.py:300,303,305-306: gather(dim 1) * mask, ReduceSum(axis 1) + Wide_b.  The wide term is
+        # needed only by the loss: it runs on its own stream (a parallel graph branch) beside the deep path.
+        main = torch.cuda.current_stream()
+        if self._wide_stream is None:
+            self._wide_stream = torch.cuda.Stream(device=self.device)
+        self._wide_stream.wait_stream(main)
+        with torch.cuda.stream(self._wide_stream):
+            ops.gather_reduce(self.wide_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
+                              self.wide_b.data, out=self._wide_out)
         # wide_and_deep.py:302,308-309: gather(dim D) * mask -> [B, F*D]
         ops.gather_masked(self.deep_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
                           out=self._deep_in)
         deep_out = self.dense.forward(self._deep_in)       # :310-314
+        main.wait_stream(self._wide_stream)
         self.wide_out, self.deep_out = self._wide_out, deep_out
         if self.defer_add:                                  # :315 is fused into the loss kernel
             return None, self.embedding_table

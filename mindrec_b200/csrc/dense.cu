@@ -1,0 +1,455 @@
+// DenseLayer backward glue — ReLU gradient mask fused with BiasAddGrad.
+//
+// Replaces, per DenseLayer of models/wide_deep/src/wide_and_deep.py:72-133 (bprop of BiasAdd + ReLU, also
+// deepfm.py:150-170 and deep_and_cross.py:161-200):  gz = g * (y > 0)  (ReluGrad) and  gb = sum_b gz[b, :]
+// (BiasAddGrad).  As separate library ops these were an element-wise kernel, a ones-vector GEMM on 8 CTAs
+// (13.5 us per layer, ncu r1g) and a cast; here one pass reads g and y once, writes gz in place and leaves the
+// fp32 column sums in the flat gradient buffer.
+//
+// Grid (row blocks, column tiles); a CTA is tx column chunks (16 bytes each) x ty row lanes.  Column sums are
+// reduced lane -> CTA -> grid in a fixed order (per-CTA partials in a workspace; the last CTA of a column tile,
+// found with a ticket counter, adds them up in row-block order), so the result is bit-reproducible.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace mrec {
+
+constexpr int kDenseThreads = 256;
+constexpr int kDenseMaxRowBlocks = 64;
+
+template <typename T> struct DChunk;
+template <> struct DChunk<__half> {
+  static constexpr int kVec = 8;
+  using Raw = uint4;
+  static __device__ __forceinline__ void acc(float (&a)[8], Raw& g, const Raw& y, bool mask) {
+    __half2* gh = reinterpret_cast<__half2*>(&g);
+    const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 gf = __half22float2(gh[k]);
+      if (mask) {
+        const float2 yf = __half22float2(yh[k]);
+        if (!(yf.x > 0.f)) gf.x = 0.f;
+        if (!(yf.y > 0.f)) gf.y = 0.f;
+        gh[k] = __floats2half2_rn(gf.x, gf.y);   // exact: a kept value is unchanged, a dropped one is +0
+      }
+      a[2 * k] += gf.x;
+      a[2 * k + 1] += gf.y;
+    }
+  }
+};
+template <> struct DChunk<float> {
+  static constexpr int kVec = 4;
+  using Raw = float4;
+  static __device__ __forceinline__ void acc(float (&a)[4], Raw& g, const Raw& y, bool mask) {
+    if (mask) {
+      if (!(y.x > 0.f)) g.x = 0.f;
+      if (!(y.y > 0.f)) g.y = 0.f;
+      if (!(y.z > 0.f)) g.z = 0.f;
+      if (!(y.w > 0.f)) g.w = 0.f;
+    }
+    a[0] += g.x; a[1] += g.y; a[2] += g.z; a[3] += g.w;
+  }
+};
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+__device__ __forceinline__ void from_f(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f(__half& d, float v) { d = __float2half_rn(v); }
+
+// VEC = true: 16-byte chunks (n_cols % kVec == 0, 16-byte aligned rows); VEC = false: one column per thread.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kDenseThreads)
+relu_bwd_bias_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restrict__ gz, int64_t rows, int n_cols,
+                     int rows_per_cta, float* __restrict__ partial, unsigned* __restrict__ counters,
+                     float* __restrict__ gb) {
+  constexpr int V = VEC ? DChunk<T>::kVec : 1;
+  __shared__ float s_red[kDenseThreads * V];
+  __shared__ bool s_last;
+  const int tx = threadIdx.x, ty = threadIdx.y, ntx = blockDim.x, nty = blockDim.y;
+  const int chunks = n_cols / V;
+  const int ch = blockIdx.y * ntx + tx;
+  const bool active = ch < chunks;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + rows_per_cta);
+  const bool mask = (y != nullptr);
+  float a[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) a[k] = 0.f;
+
+  if (active) {
+    if constexpr (VEC) {
+      using Raw = typename DChunk<T>::Raw;
+      const Raw* g4 = reinterpret_cast<const Raw*>(g);
+      const Raw* y4 = reinterpret_cast<const Raw*>(y);
+      Raw* z4 = reinterpret_cast<Raw*>(gz);
+      constexpr int U = 4;                               // rows in flight per thread
+      for (int64_t r = r0 + ty; r < r1; r += (int64_t)U * nty) {
+        Raw gv[U], yv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t rr = min(r + (int64_t)u * nty, r1 - 1);   // clamped: loads stay unconditional
+          gv[u] = g4[rr * chunks + ch];
+          yv[u] = mask ? y4[rr * chunks + ch] : gv[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t rr = r + (int64_t)u * nty;
+          if (rr < r1) {
+            DChunk<T>::acc(a, gv[u], yv[u], mask);
+            if (mask && z4) z4[rr * chunks + ch] = gv[u];
+          }
+        }
+      }
+    } else {
+      for (int64_t r = r0 + ty; r < r1; r += nty) {
+        float v = to_f(g[r * n_cols + ch]);
+        if (mask) {
+          if (!(to_f(y[r * n_cols + ch]) > 0.f)) v = 0.f;
+          if (gz) from_f(gz[r * n_cols + ch], v);
+        }
+        a[0] += v;
+      }
+    }
+  }
+  // lanes -> CTA, in lane order
+  const int slot = (ty * ntx + tx) * V;
+#pragma unroll
+  for (int k = 0; k < V; ++k) s_red[slot + k] = a[k];
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = s_red[tx * V + k];
+      for (int l = 1; l < nty; ++l) t += s_red[(l * ntx + tx) * V + k];
+      partial[(int64_t)blockIdx.x * n_cols + ch * V + k] = t;
+    }
+  }
+  // CTA -> grid: the last CTA of this column tile adds the row-block partials in row-block order
+  __threadfence();
+  __syncthreads();
+  if (tx == 0 && ty == 0) s_last = (atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    float t = 0.f;
+    if (active)
+      for (int rb = ty; rb < (int)gridDim.x; rb += nty) t += __ldcg(&partial[(int64_t)rb * n_cols + ch * V + k]);
+    s_red[slot + k] = t;
+  }
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = s_red[tx * V + k];
+      for (int l = 1; l < nty; ++l) t += s_red[(l * ntx + tx) * V + k];
+      gb[ch * V + k] = t;
+    }
+  }
+  if (tx == 0 && ty == 0) counters[blockIdx.y] = 0;      // self-resetting: the workspace is reusable as is
+}
+
+
+// ---- output DenseLayer with one unit (the logit head: wide_and_deep.py:293-297 dense_layer_5, deepfm.py:215,
+// deep_and_cross.py:309) -------------------------------------------------------------------------------------
+// As library GEMMs the N = 1 layer is three skinny calls (GEMV forward, GEMV weight gradient, rank-1 input
+// gradient: 8-CTA kernels of 5-13 us each, ncu r1g).  Forward: one warp per row.  Backward: the pass above with
+// the incoming gradient generated on the fly, g[b,k] = delta[b] * w[k], so ONE kernel emits the input gradient
+// already masked by the previous layer's ReLU, that layer's BiasAddGrad, this layer's weight gradient
+// gw[k] = sum_b delta[b] * h[b,k] and its bias gradient sum_b delta[b].
+template <typename T>
+__global__ void __launch_bounds__(256)
+dense_head_fwd_kernel(const T* __restrict__ h, const T* __restrict__ w, const T* __restrict__ bias, int64_t rows,
+                      int k_dim, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const T* hr = h + row * k_dim;
+  float acc = 0.f;
+  for (int k = lane; k < k_dim; k += 32) acc = fmaf(to_f(hr[k]), to_f(w[k]), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc + to_f(bias[0]);
+}
+
+template <>
+__global__ void __launch_bounds__(256)
+dense_head_fwd_kernel<__half>(const __half* __restrict__ h, const __half* __restrict__ w,
+                              const __half* __restrict__ bias, int64_t rows, int k_dim, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const __half* hr = h + row * k_dim;
+  float acc = 0.f;
+  if ((k_dim & 7) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    for (int c = lane; c < (k_dim >> 3); c += 32) {
+      const uint4 hv = reinterpret_cast<const uint4*>(hr)[c];
+      const uint4 wv = reinterpret_cast<const uint4*>(w)[c];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+      const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = __half22float2(h2[q]), b = __half22float2(w2[q]);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+      }
+    }
+  } else {
+    for (int k = lane; k < k_dim; k += 32) acc = fmaf(__half2float(hr[k]), __half2float(w[k]), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc + __half2float(bias[0]);
+}
+
+// One column per thread (K is small: the head's fan-in), rows split over ty lanes and row blocks exactly as in
+// relu_bwd_bias_kernel.  partial holds three planes per row block: [gb_prev | gw | sum(delta) in column 0].
+template <typename T, bool MASK>
+__global__ void __launch_bounds__(kDenseThreads)
+dense_head_bwd_kernel(const T* __restrict__ delta, const T* __restrict__ h, const T* __restrict__ w, T* __restrict__ gh,
+                      int64_t rows, int k_dim, int rows_per_cta, float* __restrict__ partial,
+                      unsigned* __restrict__ counters, float* __restrict__ gb_prev, float* __restrict__ gw,
+                      float* __restrict__ gb_head) {
+  __shared__ float s_red[3][kDenseThreads];
+  __shared__ bool s_last;
+  const int tx = threadIdx.x, ty = threadIdx.y, ntx = blockDim.x, nty = blockDim.y;
+  const int col = blockIdx.y * ntx + tx;
+  const bool active = col < k_dim;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + rows_per_cta);
+  const float wv = active ? to_f(w[col]) : 0.f;
+  float a_gb = 0.f, a_gw = 0.f, a_d = 0.f;
+  if (active) {
+    constexpr int U = 4;
+    for (int64_t r = r0 + ty; r < r1; r += (int64_t)U * nty) {
+      float d[U], hv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t rr = min(r + (int64_t)u * nty, r1 - 1);
+        d[u] = to_f(delta[rr]);
+        hv[u] = to_f(h[rr * k_dim + col]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t rr = r + (int64_t)u * nty;
+        if (rr < r1) {
+          T gq;
+          from_f(gq, d[u] * wv);                         // the rank-1 GEMM's rounding (one product per element)
+          float gv = to_f(gq);
+          if (MASK && !(hv[u] > 0.f)) { gv = 0.f; from_f(gq, 0.f); }
+          gh[rr * k_dim + col] = gq;
+          a_gb += gv;
+          a_gw = fmaf(d[u], hv[u], a_gw);
+          a_d += d[u];
+        }
+      }
+    }
+  }
+  const int slot = ty * ntx + tx;
+  s_red[0][slot] = a_gb; s_red[1][slot] = a_gw; s_red[2][slot] = a_d;
+  __syncthreads();
+  const int64_t plane = (int64_t)gridDim.x * k_dim;
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float t = s_red[q][tx];
+      for (int l = 1; l < nty; ++l) t += s_red[q][l * ntx + tx];
+      partial[q * plane + (int64_t)blockIdx.x * k_dim + col] = t;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tx == 0 && ty == 0) s_last = (atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float t = 0.f;
+    if (active)
+      for (int rb = ty; rb < (int)gridDim.x; rb += nty) t += __ldcg(&partial[q * plane + (int64_t)rb * k_dim + col]);
+    s_red[q][slot] = t;
+  }
+  __syncthreads();
+  if (ty == 0 && active) {
+    float t[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      t[q] = s_red[q][tx];
+      for (int l = 1; l < nty; ++l) t[q] += s_red[q][l * ntx + tx];
+    }
+    if (gb_prev) gb_prev[col] = t[0];
+    gw[col] = t[1];
+    if (col == 0) gb_head[0] = t[2];
+  }
+  if (tx == 0 && ty == 0) counters[blockIdx.y] = 0;
+}
+
+struct DensePlan {
+  int ntx, nty, col_tiles, row_blocks, rows_per_cta;
+  bool vec;
+};
+
+static DensePlan dense_plan(int64_t rows, int n_cols, int elem_bytes, bool aligned) {
+  DensePlan p;
+  const int v = 16 / elem_bytes;
+  p.vec = aligned && (n_cols % v == 0);
+  const int chunks = p.vec ? n_cols / v : n_cols;
+  int ntx = 1;
+  while (ntx < chunks && ntx < 16) ntx <<= 1;
+  p.ntx = ntx;
+  p.nty = kDenseThreads / ntx;
+  p.col_tiles = (int)cdiv(chunks, ntx);
+  int rb = (int)cdiv(2 * kNumSMs, p.col_tiles);
+  if (rb > kDenseMaxRowBlocks) rb = kDenseMaxRowBlocks;
+  const int64_t by_rows = cdiv(rows, p.nty);
+  if (rb > by_rows) rb = (int)by_rows;
+  if (rb < 1) rb = 1;
+  p.rows_per_cta = (int)cdiv(rows, rb);
+  p.row_blocks = (int)cdiv(rows, p.rows_per_cta);
+  return p;
+}
+
+}  // namespace mrec
+
+using namespace mrec;
+
+// Plain-C helper: workspace for mrec_relu_bwd_bias.  The caller zero-fills it ONCE (ticket counters); every
+// launch leaves the counters at zero again.
+MREC_API size_t mrec_relu_bwd_bias_workspace_bytes(int64_t n_cols) {
+  return (size_t)kDenseMaxRowBlocks * (size_t)(n_cols > 0 ? n_cols : 1) * sizeof(float) + 4096 * sizeof(unsigned);
+}
+
+// in : g[B,N] f16|f32, y[B,N] same dtype | numel 0 (no mask: plain BiasAddGrad)
+// out: gz[B,N] same dtype (may be the same buffer as g; numel 0 with no mask), gb[N] f32, workspace uint8
+MREC_API int mrec_relu_bwd_bias(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 5) return fail(ERR_NPARAM, "mrec_relu_bwd_bias: expected 5 params, got %d", a.nparam);
+  const bool half = a.is(0, "float16");
+  MREC_REQUIRE(half || a.is_f32(0), ERR_DTYPE, "mrec_relu_bwd_bias: g must be float16 or float32");
+  MREC_REQUIRE(a.ndims[0] == 2, ERR_SHAPE, "mrec_relu_bwd_bias: g must be [B, N]");
+  const int64_t rows = a.dim(0, 0), n_cols = a.dim(0, 1);
+  const bool mask = a.numel(1) > 0;
+  MREC_REQUIRE(!mask || (a.numel(1) == rows * n_cols && a.is(1, half ? "float16" : "float32")), ERR_SHAPE,
+               "mrec_relu_bwd_bias: y must match g (or be empty)");
+  MREC_REQUIRE(a.numel(2) == 0 || (a.numel(2) == rows * n_cols && a.is(2, half ? "float16" : "float32")), ERR_SHAPE,
+               "mrec_relu_bwd_bias: gz must match g (or be empty)");
+  MREC_REQUIRE(!mask || a.numel(2) > 0, ERR_SHAPE, "mrec_relu_bwd_bias: gz is required with a mask");
+  MREC_REQUIRE(a.is_f32(3) && a.numel(3) == n_cols, ERR_SHAPE, "mrec_relu_bwd_bias: gb must be float32[N]");
+  MREC_REQUIRE(n_cols < ((int64_t)1 << 31), ERR_SHAPE, "mrec_relu_bwd_bias: N too large");
+  const size_t need = mrec_relu_bwd_bias_workspace_bytes(n_cols);
+  if ((size_t)a.numel(4) < need)
+    return fail(ERR_WORKSPACE, "mrec_relu_bwd_bias: workspace %lld bytes < required %zu", (long long)a.numel(4), need);
+  if (n_cols == 0) return OK;
+  if (rows == 0) {
+    cudaMemsetAsync(a.params[3], 0, (size_t)n_cols * sizeof(float), a.stream);
+    return OK;
+  }
+  for (int i : {0, 3, 4})
+    if (!a.params[i]) return fail(ERR_NULL, "mrec_relu_bwd_bias: param %d is null", i);
+  const int eb = half ? 2 : 4;
+  bool aligned = reinterpret_cast<uintptr_t>(a.params[0]) % 16 == 0 && (n_cols * eb) % 16 == 0;
+  if (mask) aligned = aligned && reinterpret_cast<uintptr_t>(a.params[1]) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(a.params[2]) % 16 == 0;
+  const DensePlan p = dense_plan(rows, (int)n_cols, eb, aligned);
+  MREC_REQUIRE(p.col_tiles <= 4096, ERR_SHAPE, "mrec_relu_bwd_bias: too many column tiles");
+  float* partial = reinterpret_cast<float*>(a.params[4]);
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.params[4]) +
+                                                   (size_t)kDenseMaxRowBlocks * n_cols * sizeof(float));
+  const dim3 grid(p.row_blocks, p.col_tiles), block(p.ntx, p.nty);
+  const void* y = mask ? a.params[1] : nullptr;
+  void* gz = a.numel(2) ? a.params[2] : nullptr;
+#define MREC_DENSE(T, V)                                                                                      \
+  MREC_LAUNCH((relu_bwd_bias_kernel<T, V>), grid, block, 0, a.stream, reinterpret_cast<const T*>(a.params[0]), \
+              reinterpret_cast<const T*>(y), reinterpret_cast<T*>(gz), rows, (int)n_cols, p.rows_per_cta,     \
+              partial, counters, a.ptr<float>(3))
+  if (half) { if (p.vec) MREC_DENSE(__half, true); else MREC_DENSE(__half, false); }
+  else      { if (p.vec) MREC_DENSE(float, true); else MREC_DENSE(float, false); }
+#undef MREC_DENSE
+  return check_launch("relu_bwd_bias");
+}
+
+// Plain-C helper: workspace of mrec_dense_head_bwd (zero-fill once, self-resetting like the one above).
+MREC_API size_t mrec_dense_head_workspace_bytes(int64_t k_dim) {
+  return 3 * (size_t)kDenseMaxRowBlocks * (size_t)(k_dim > 0 ? k_dim : 1) * sizeof(float) + 4096 * sizeof(unsigned);
+}
+
+// in : h[B,K] f16|f32, w[K]|[K,1] same dtype, bias[1] same dtype           out: out[B]|[B,1] f32
+MREC_API int mrec_dense_head_fwd(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                 void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 4) return fail(ERR_NPARAM, "mrec_dense_head_fwd: expected 4 params, got %d", a.nparam);
+  const bool half = a.is(0, "float16");
+  MREC_REQUIRE((half || a.is_f32(0)) && a.is(1, half ? "float16" : "float32") && a.is(2, half ? "float16" : "float32") &&
+                   a.is_f32(3), ERR_DTYPE, "mrec_dense_head_fwd: h/w/bias f16|f32 (same), out f32");
+  MREC_REQUIRE(a.ndims[0] == 2, ERR_SHAPE, "mrec_dense_head_fwd: h must be [B, K]");
+  const int64_t rows = a.dim(0, 0), k = a.dim(0, 1);
+  MREC_REQUIRE(a.numel(1) == k && a.numel(2) >= 1 && a.numel(3) == rows && k < ((int64_t)1 << 31), ERR_SHAPE,
+               "mrec_dense_head_fwd: shape mismatch");
+  if (rows == 0) return OK;
+  for (int i = 0; i < 4; ++i)
+    if (!a.params[i]) return fail(ERR_NULL, "mrec_dense_head_fwd: param %d is null", i);
+  const int grid = (int)cdiv(rows * 32, 256);
+  if (half)
+    MREC_LAUNCH(dense_head_fwd_kernel<__half>, grid, 256, 0, a.stream, a.ptr<__half>(0), a.ptr<__half>(1),
+                a.ptr<__half>(2), rows, (int)k, a.ptr<float>(3));
+  else
+    MREC_LAUNCH(dense_head_fwd_kernel<float>, grid, 256, 0, a.stream, a.ptr<float>(0), a.ptr<float>(1),
+                a.ptr<float>(2), rows, (int)k, a.ptr<float>(3));
+  return check_launch("dense_head_fwd");
+}
+
+// in : delta[B]|[B,1] f16|f32, h[B,K] same dtype (the head's input = previous layer's output), w[K]|[K,1] same dtype,
+//      relu_like[0|1] (numel 1: mask the input gradient with h > 0, i.e. the previous layer ends in ReLU)
+// out: gh[B,K] same dtype, gw[K]|[K,1] f32, gb_head[1] f32, gb_prev[K] f32 | numel 0, workspace uint8
+MREC_API int mrec_dense_head_bwd(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                 void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 9) return fail(ERR_NPARAM, "mrec_dense_head_bwd: expected 9 params, got %d", a.nparam);
+  const bool half = a.is(0, "float16");
+  const char* dt = half ? "float16" : "float32";
+  MREC_REQUIRE((half || a.is_f32(0)) && a.is(1, dt) && a.is(2, dt) && a.is(4, dt) && a.is_f32(5) && a.is_f32(6) &&
+                   a.is_f32(7), ERR_DTYPE, "mrec_dense_head_bwd: delta/h/w/gh f16|f32 (same), gw/gb f32");
+  MREC_REQUIRE(a.ndims[1] == 2, ERR_SHAPE, "mrec_dense_head_bwd: h must be [B, K]");
+  const int64_t rows = a.dim(1, 0), k = a.dim(1, 1);
+  MREC_REQUIRE(a.numel(0) == rows && a.numel(2) == k && a.numel(4) == rows * k && a.numel(5) == k && a.numel(6) >= 1 &&
+                   (a.numel(7) == 0 || a.numel(7) == k) && k < ((int64_t)1 << 31), ERR_SHAPE,
+               "mrec_dense_head_bwd: shape mismatch");
+  const size_t need = mrec_dense_head_workspace_bytes(k);
+  if ((size_t)a.numel(8) < need)
+    return fail(ERR_WORKSPACE, "mrec_dense_head_bwd: workspace %lld bytes < required %zu", (long long)a.numel(8), need);
+  if (k == 0) return OK;
+  if (rows == 0) {
+    cudaMemsetAsync(a.params[5], 0, (size_t)k * sizeof(float), a.stream);
+    cudaMemsetAsync(a.params[6], 0, sizeof(float), a.stream);
+    if (a.numel(7)) cudaMemsetAsync(a.params[7], 0, (size_t)k * sizeof(float), a.stream);
+    return OK;
+  }
+  for (int i : {0, 1, 2, 4, 5, 6, 8})
+    if (!a.params[i]) return fail(ERR_NULL, "mrec_dense_head_bwd: param %d is null", i);
+  int ntx = 1;
+  while (ntx < k && ntx < 128) ntx <<= 1;
+  const int nty = kDenseThreads / ntx;
+  const int col_tiles = (int)cdiv(k, ntx);
+  MREC_REQUIRE(col_tiles <= 4096, ERR_SHAPE, "mrec_dense_head_bwd: K too large");
+  int rb = (int)cdiv(2 * kNumSMs, col_tiles);
+  if (rb > kDenseMaxRowBlocks) rb = kDenseMaxRowBlocks;
+  if (rb > cdiv(rows, nty)) rb = (int)cdiv(rows, nty);
+  if (rb < 1) rb = 1;
+  const int rows_per_cta = (int)cdiv(rows, rb);
+  const int row_blocks = (int)cdiv(rows, rows_per_cta);
+  float* partial = reinterpret_cast<float*>(a.params[8]);
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.params[8]) +
+                                                   3 * (size_t)kDenseMaxRowBlocks * k * sizeof(float));
+  const dim3 grid(row_blocks, col_tiles), block(ntx, nty);
+  const bool mask = a.numel(3) > 0;
+  float* gb_prev = a.numel(7) ? a.ptr<float>(7) : nullptr;
+#define MREC_HEAD(T, M)                                                                                          \
+  MREC_LAUNCH((dense_head_bwd_kernel<T, M>), grid, block, 0, a.stream, a.ptr<T>(0), a.ptr<T>(1), a.ptr<T>(2),     \
+              a.ptr<T>(4), rows, (int)k, rows_per_cta, partial, counters, gb_prev, a.ptr<float>(5), a.ptr<float>(6))
+  if (half) { if (mask) MREC_HEAD(__half, true); else MREC_HEAD(__half, false); }
+  else      { if (mask) MREC_HEAD(float, true); else MREC_HEAD(float, false); }
+#undef MREC_HEAD
+  return check_launch("dense_head_bwd");
+}

@@ -19,18 +19,33 @@ sigmoid_xent_kernel(const float* __restrict__ a, const float* __restrict__ b2, c
   __shared__ float s_l[32], s_d[32];
   const float k = scale[0] / (float)batch;
   float acc_l = 0.f, acc_d = 0.f;
-  for (int64_t i = threadIdx.x; i < batch; i += blockDim.x) {
-    const float x = a[i] + (b2 ? b2[i] : 0.f);
-    const float z = label[i];
-    const float e = __expf(-fabsf(x));
-    acc_l += fmaxf(x, 0.f) - x * z + log1pf(e);
-    // sigmoid(x) without overflow: x >= 0 -> 1/(1+e), x < 0 -> e/(1+e)
-    const float sg = (x >= 0.f ? 1.f : e) / (1.f + e);
-    const float d = (sg - z) * k;
-    if (logit) logit[i] = x;
-    delta[i] = d;
-    if (delta16) delta16[i] = __float2half_rn(d);
-    acc_d += d;
+  // 8 elements per thread and round, loads first: the walk is latency bound (one CTA, fixed summation order)
+  constexpr int U = 8;
+  for (int64_t base = threadIdx.x; base < batch; base += (int64_t)U * blockDim.x) {
+    float xa[U], xb[U], zl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = min(base + (int64_t)u * blockDim.x, batch - 1);
+      xa[u] = a[i];
+      xb[u] = b2 ? b2[i] : 0.f;
+      zl[u] = label[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i >= batch) break;
+      const float x = xa[u] + xb[u];
+      const float z = zl[u];
+      const float e = __expf(-fabsf(x));
+      acc_l += fmaxf(x, 0.f) - x * z + log1pf(e);
+      // sigmoid(x) without overflow: x >= 0 -> 1/(1+e), x < 0 -> e/(1+e)
+      const float sg = (x >= 0.f ? 1.f : e) / (1.f + e);
+      const float d = (sg - z) * k;
+      if (logit) logit[i] = x;
+      delta[i] = d;
+      if (delta16) delta16[i] = __float2half_rn(d);
+      acc_d += d;
+    }
   }
   acc_l = warp_sum(acc_l);
   acc_d = warp_sum(acc_d);

@@ -248,11 +248,28 @@ class DenseStack:
         self._acts = None
         self._flat16 = None
         self._ones = None
+        self._mm_f32 = None
+        self._head = False
 
     def _ones16(self, b):
         if self._ones is None or self._ones.shape[1] != b:
             self._ones = torch.ones((1, b), dtype=torch.float16, device=self.flat.device)
         return self._ones
+
+    def _wgrad(self, h_in, g, out):
+        """gw = h_in^T g for fp16 operands, fp32 accumulate.  With out_dtype the GEMM writes fp32 straight into the
+        flat gradient buffer; older torch builds round to fp16 and cast."""
+        if self._mm_f32 is None:
+            try:
+                torch.mm(h_in.t(), g, out_dtype=torch.float32, out=out)
+                self._mm_f32 = True
+                return
+            except (TypeError, RuntimeError):
+                self._mm_f32 = False
+        if self._mm_f32:
+            torch.mm(h_in.t(), g, out_dtype=torch.float32, out=out)
+        else:
+            out.copy_(torch.mm(h_in.t(), g))
 
     def refresh_half(self):
         """fp16 shadow of the weights (the per-layer Cast(weight, float16) of the reference, done once
@@ -272,6 +289,9 @@ class DenseStack:
         Returns the stack output in fp32."""
         nl = len(self.weights)
         acts = [x]
+        # a one-unit output layer without activation runs as mrec_dense_head_fwd / _bwd instead of skinny GEMMs
+        head = x.is_cuda and self.dims[-1] == 1 and not self.last_activation
+        self._head = head
         if self.convert_dtype:
             self.refresh_half()
             h = x if x.dtype == torch.float16 else x.half()
@@ -279,14 +299,19 @@ class DenseStack:
             for i in range(nl):
                 if i + 1 < nl or self.last_activation:
                     h = torch._addmm_activation(self.b16[i], h, self.w16[i], use_gelu=False)
+                elif head:
+                    h = ops.dense_head_fwd(h, self.w16[i].view(-1), self.b16[i])
                 else:
                     h = torch.addmm(self.b16[i], h, self.w16[i])
                 acts.append(h)
             self._acts = acts
-            return h.float()
+            return h if head else h.float()
         h = x
         for i, (w, b) in enumerate(zip(self.weights, self.biases)):
-            a = torch.addmm(b, h, w)
+            if head and i + 1 == nl:
+                a = ops.dense_head_fwd(h, w.view(-1), b)
+            else:
+                a = torch.addmm(b, h, w)
             if i + 1 < nl or self.last_activation:
                 a = torch.relu_(a)
             h = a
@@ -300,17 +325,33 @@ class DenseStack:
         acts = self._acts
         nl = len(self.weights)
         g = g_out.half() if (self.convert_dtype and g_out.dtype != torch.float16) else g_out
+        fused = g.is_cuda          # CUDA: ReluGrad + BiasAddGrad in one mrec_relu_bwd_bias pass, fp32 sums in place
+        premasked = False
         for i in range(nl - 1, -1, -1):
             h_in, h_out = acts[i], acts[i + 1]
-            if i + 1 < nl or self.last_activation:
+            if fused and self._head and i + 1 == nl:
+                # output unit: rank-1 input gradient, weight / bias gradients and the previous layer's
+                # ReluGrad + BiasAddGrad in one kernel
+                w = self.w16[i] if self.convert_dtype else self.weights[i]
+                g = ops.dense_head_bwd(g, h_in, w.view(-1), i > 0, self.gw[i].view(-1), self.gb[i],
+                                       self.gb[i - 1] if i > 0 else None)
+                premasked = True
+                continue
+            masked = i + 1 < nl or self.last_activation
+            if premasked:
+                premasked = False
+            elif fused:
+                g = ops.relu_bwd_bias(g, h_out if masked else None, self.gb[i])
+            elif masked:
                 g = torch.ops.aten.threshold_backward(g, h_out, 0)
             if self.convert_dtype:
-                self.gw[i].copy_(torch.mm(h_in.t(), g))
-                # BiasAddGrad as a GEMV on the tensor cores (fp32 accumulate, fp16 result like the fp16 op)
-                self.gb[i].copy_(torch.mm(self._ones16(g.shape[0]), g).view(-1))
+                self._wgrad(h_in, g, self.gw[i])
+                if not fused:
+                    self.gb[i].copy_(torch.mm(self._ones16(g.shape[0]), g).view(-1))
                 g = torch.mm(g, self.w16[i].t())
             else:
                 torch.mm(h_in.t(), g, out=self.gw[i])
-                torch.sum(g, 0, out=self.gb[i])
+                if not fused:
+                    torch.sum(g, 0, out=self.gb[i])
                 g = torch.mm(g, self.weights[i].t())
         return g

@@ -306,6 +306,79 @@ def sigmoid_xent(a, b, label, sens, out=None, half=False):
     return out
 
 
+_dense_ws = {}
+
+
+def relu_bwd_bias(g, y, gb, out=None):
+    """gz = g * (y > 0) written over g (or into `out`), gb[N] = column sums of gz in fp32 (ReluGrad + BiasAddGrad of a
+    DenseLayer in one pass).  y=None: plain BiasAddGrad, g untouched.  Returns gz."""
+    n_cols = g.shape[1]
+    key = (g.device, n_cols)
+    ws = _dense_ws.get(key)
+    if ws is None:
+        lib = _lib.lib()
+        lib.mrec_relu_bwd_bias_workspace_bytes.restype = ctypes.c_size_t
+        lib.mrec_relu_bwd_bias_workspace_bytes.argtypes = [ctypes.c_int64]
+        ws = _dense_ws[key] = torch.zeros(lib.mrec_relu_bwd_bias_workspace_bytes(n_cols), dtype=torch.uint8, device=g.device)
+    gz = g if out is None else out
+    if y is None:
+        _lib.aot_call("mrec_relu_bwd_bias", [g, _empty_like_dtype(g), _empty_like_dtype(g), gb, ws])
+        return g
+    _lib.aot_call("mrec_relu_bwd_bias", [g, y, gz, gb, ws])
+    return gz
+
+
+def dense_head_fwd(h, w, bias, out=None):
+    """out[b] = sum_k h[b,k] * w[k] + bias  (the one-unit output DenseLayer; fp32 accumulate and result)."""
+    if out is None:
+        out = torch.empty((h.shape[0], 1), dtype=torch.float32, device=h.device)
+    _lib.aot_call("mrec_dense_head_fwd", [h, w, bias, out])
+    return out
+
+
+_head_ws = {}
+
+
+def dense_head_bwd(delta, h, w, masked, gw, gb_head, gb_prev=None, out=None):
+    """Backward of the one-unit output layer fused with the previous layer's ReluGrad + BiasAddGrad:
+    gh = (delta x w) * (h > 0 if masked), gw = delta^T h, gb_head = sum(delta), gb_prev = column sums of gh."""
+    k = h.shape[1]
+    key = (h.device, k)
+    ws = _head_ws.get(key)
+    if ws is None:
+        lib = _lib.lib()
+        lib.mrec_dense_head_workspace_bytes.restype = ctypes.c_size_t
+        lib.mrec_dense_head_workspace_bytes.argtypes = [ctypes.c_int64]
+        ws = _head_ws[key] = torch.zeros(lib.mrec_dense_head_workspace_bytes(k), dtype=torch.uint8, device=h.device)
+    if out is None:
+        out = torch.empty_like(h)
+    flag = _relu_flag(h.device) if masked else _empty_mask(h.device)
+    _lib.aot_call("mrec_dense_head_bwd", [delta, h, w, flag, out, gw, gb_head,
+                                          gb_prev if gb_prev is not None else _empty_mask(h.device), ws])
+    return out
+
+
+_relu_flags = {}
+
+
+def _relu_flag(device):
+    f = _relu_flags.get(device)
+    if f is None:
+        f = _relu_flags[device] = torch.ones(1, dtype=torch.float32, device=device)
+    return f
+
+
+_empties = {}
+
+
+def _empty_like_dtype(t):
+    key = (t.device, t.dtype)
+    e = _empties.get(key)
+    if e is None:
+        e = _empties[key] = torch.empty((0, 0), dtype=t.dtype, device=t.device)
+    return e
+
+
 def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
     """Owner-side gather fused with the NVLink peer store of every row into its requester's landing buffer."""
     _lib.aot_call("mrec_gather_to_peers", [table, rows, peer_ptrs, dst_off, src_off, _dummy(table.device)])
