@@ -7,15 +7,17 @@
 // fp32 column sums in the flat gradient buffer.
 //
 // Grid (row blocks, column tiles); a CTA is tx column chunks (16 bytes each) x ty row lanes.  Column sums are
-// reduced lane -> CTA -> grid in a fixed order (per-CTA partials in a workspace; the last CTA of a column tile,
-// found with a ticket counter, adds them up in row-block order), so the result is bit-reproducible.
+// reduced lane -> CTA -> grid in a fixed order: per-CTA partials go to a workspace and colsum_finish_kernel adds
+// them per column (a "last CTA adds them up" ticket variant cost 15-20 us of serial tail per call, r1i kbench),
+// so the result is bit-reproducible.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
 namespace mrec {
 
 constexpr int kDenseThreads = 256;
-constexpr int kDenseMaxRowBlocks = 64;
+constexpr int kDenseMaxRowBlocks = 256;   // row blocks per column tile (partials the last CTA adds up)
+constexpr int kDenseTargetCtas = 8 * kNumSMs;
 
 template <typename T> struct DChunk;
 template <> struct DChunk<__half> {
@@ -61,11 +63,9 @@ __device__ __forceinline__ void from_f(__half& d, float v) { d = __float2half_rn
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kDenseThreads)
 relu_bwd_bias_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restrict__ gz, int64_t rows, int n_cols,
-                     int rows_per_cta, float* __restrict__ partial, unsigned* __restrict__ counters,
-                     float* __restrict__ gb) {
+                     int rows_per_cta, float* __restrict__ partial) {
   constexpr int V = VEC ? DChunk<T>::kVec : 1;
   __shared__ float s_red[kDenseThreads * V];
-  __shared__ bool s_last;
   const int tx = threadIdx.x, ty = threadIdx.y, ntx = blockDim.x, nty = blockDim.y;
   const int chunks = n_cols / V;
   const int ch = blockIdx.y * ntx + tx;
@@ -125,32 +125,38 @@ relu_bwd_bias_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __rest
       partial[(int64_t)blockIdx.x * n_cols + ch * V + k] = t;
     }
   }
-  // CTA -> grid: the last CTA of this column tile adds the row-block partials in row-block order
-  __threadfence();
-  __syncthreads();
-  if (tx == 0 && ty == 0) s_last = (atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    float t = 0.f;
-    if (active)
-      for (int rb = ty; rb < (int)gridDim.x; rb += nty) t += __ldcg(&partial[(int64_t)rb * n_cols + ch * V + k]);
-    s_red[slot + k] = t;
-  }
-  __syncthreads();
-  if (ty == 0 && active) {
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float t = s_red[tx * V + k];
-      for (int l = 1; l < nty; ++l) t += s_red[(l * ntx + tx) * V + k];
-      gb[ch * V + k] = t;
-    }
-  }
-  if (tx == 0 && ty == 0) counters[blockIdx.y] = 0;      // self-resetting: the workspace is reusable as is
 }
 
+// partial[plane][rb][n_cols] -> out[plane][n_cols]: CTA = 32 columns x 8 row-block lanes, fixed order.
+struct ColsumOut { float* p[3]; int n[3]; };
+
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ partial, int row_blocks, int n_cols, ColsumOut out) {
+  __shared__ float s_red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int plane = blockIdx.y;
+  const int col = blockIdx.x * 32 + tx;
+  const int n_out = out.n[plane];                 // columns of this plane that are wanted (1 for the sum(delta) plane)
+  const float* src = partial + (int64_t)plane * row_blocks * n_cols;
+  float t = 0.f;
+  if (col < n_out) {
+    int rb = ty;
+    for (; rb + 24 < row_blocks; rb += 32) {     // four independent loads per round
+      const float v0 = __ldcg(src + (int64_t)rb * n_cols + col), v1 = __ldcg(src + (int64_t)(rb + 8) * n_cols + col);
+      const float v2 = __ldcg(src + (int64_t)(rb + 16) * n_cols + col), v3 = __ldcg(src + (int64_t)(rb + 24) * n_cols + col);
+      t += v0; t += v1; t += v2; t += v3;
+    }
+    for (; rb < row_blocks; rb += 8) t += __ldcg(src + (int64_t)rb * n_cols + col);
+  }
+  s_red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && col < n_out) {
+    float r = s_red[0][tx];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) r += s_red[l][tx];
+    out.p[plane][col] = r;
+  }
+}
 
 // ---- output DenseLayer with one unit (the logit head: wide_and_deep.py:293-297 dense_layer_5, deepfm.py:215,
 // deep_and_cross.py:309) -------------------------------------------------------------------------------------
@@ -202,87 +208,93 @@ dense_head_fwd_kernel<__half>(const __half* __restrict__ h, const __half* __rest
   if (lane == 0) out[row] = acc + __half2float(bias[0]);
 }
 
-// One column per thread (K is small: the head's fan-in), rows split over ty lanes and row blocks exactly as in
-// relu_bwd_bias_kernel.  partial holds three planes per row block: [gb_prev | gw | sum(delta) in column 0].
-template <typename T, bool MASK>
+// Same grid / reduction scheme as relu_bwd_bias_kernel (16-byte column chunks when VEC, else one column per
+// thread).  partial holds three planes per row block: [gb_prev | gw | sum(delta) in column 0].
+template <typename T, bool VEC, bool MASK>
 __global__ void __launch_bounds__(kDenseThreads)
 dense_head_bwd_kernel(const T* __restrict__ delta, const T* __restrict__ h, const T* __restrict__ w, T* __restrict__ gh,
-                      int64_t rows, int k_dim, int rows_per_cta, float* __restrict__ partial,
-                      unsigned* __restrict__ counters, float* __restrict__ gb_prev, float* __restrict__ gw,
-                      float* __restrict__ gb_head) {
-  __shared__ float s_red[3][kDenseThreads];
-  __shared__ bool s_last;
+                      int64_t rows, int k_dim, int rows_per_cta, float* __restrict__ partial) {
+  constexpr int V = VEC ? DChunk<T>::kVec : 1;
+  __shared__ float s_red[2][kDenseThreads * V];
+  __shared__ float s_d[kDenseThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, ntx = blockDim.x, nty = blockDim.y;
-  const int col = blockIdx.y * ntx + tx;
-  const bool active = col < k_dim;
+  const int chunks = k_dim / V;
+  const int ch = blockIdx.y * ntx + tx;
+  const bool active = ch < chunks;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(rows, r0 + rows_per_cta);
-  const float wv = active ? to_f(w[col]) : 0.f;
-  float a_gb = 0.f, a_gw = 0.f, a_d = 0.f;
+  float wv[V], a_gb[V], a_gw[V];
+  float a_d = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    wv[k] = active ? to_f(w[ch * V + k]) : 0.f;
+    a_gb[k] = 0.f;
+    a_gw[k] = 0.f;
+  }
   if (active) {
     constexpr int U = 4;
     for (int64_t r = r0 + ty; r < r1; r += (int64_t)U * nty) {
-      float d[U], hv[U];
+      float d[U];
+      alignas(16) T hv[U][V];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t rr = min(r + (int64_t)u * nty, r1 - 1);
         d[u] = to_f(delta[rr]);
-        hv[u] = to_f(h[rr * k_dim + col]);
+        if constexpr (VEC) {
+          using Raw = typename DChunk<T>::Raw;
+          *reinterpret_cast<Raw*>(hv[u]) = reinterpret_cast<const Raw*>(h)[rr * chunks + ch];
+        } else {
+          hv[u][0] = h[rr * k_dim + ch];
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t rr = r + (int64_t)u * nty;
         if (rr < r1) {
-          T gq;
-          from_f(gq, d[u] * wv);                         // the rank-1 GEMM's rounding (one product per element)
-          float gv = to_f(gq);
-          if (MASK && !(hv[u] > 0.f)) { gv = 0.f; from_f(gq, 0.f); }
-          gh[rr * k_dim + col] = gq;
-          a_gb += gv;
-          a_gw = fmaf(d[u], hv[u], a_gw);
+          alignas(16) T gq[V];
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            const float hf = to_f(hv[u][k]);
+            from_f(gq[k], d[u] * wv[k]);                   // the rank-1 GEMM's rounding (one product per element)
+            if (MASK && !(hf > 0.f)) from_f(gq[k], 0.f);
+            a_gb[k] += to_f(gq[k]);
+            a_gw[k] = fmaf(d[u], hf, a_gw[k]);
+          }
+          if constexpr (VEC) {
+            using Raw = typename DChunk<T>::Raw;
+            reinterpret_cast<Raw*>(gh)[rr * chunks + ch] = *reinterpret_cast<const Raw*>(gq);
+          } else {
+            gh[rr * k_dim + ch] = gq[0];
+          }
           a_d += d[u];
         }
       }
     }
   }
-  const int slot = ty * ntx + tx;
-  s_red[0][slot] = a_gb; s_red[1][slot] = a_gw; s_red[2][slot] = a_d;
+  const int lin = ty * ntx + tx;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    s_red[0][lin * V + k] = a_gb[k];
+    s_red[1][lin * V + k] = a_gw[k];
+  }
+  s_d[lin] = a_d;
   __syncthreads();
   const int64_t plane = (int64_t)gridDim.x * k_dim;
   if (ty == 0 && active) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      float t = s_red[q][tx];
-      for (int l = 1; l < nty; ++l) t += s_red[q][l * ntx + tx];
-      partial[q * plane + (int64_t)blockIdx.x * k_dim + col] = t;
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float t = s_red[q][tx * V + k];
+        for (int l = 1; l < nty; ++l) t += s_red[q][(l * ntx + tx) * V + k];
+        partial[q * plane + (int64_t)blockIdx.x * k_dim + ch * V + k] = t;
+      }
+    if (ch == 0) {
+      float t = s_d[0];
+      for (int l = 1; l < nty; ++l) t += s_d[l * ntx];
+      partial[2 * plane + (int64_t)blockIdx.x * k_dim] = t;   // plane 2, column 0
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (tx == 0 && ty == 0) s_last = (atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    float t = 0.f;
-    if (active)
-      for (int rb = ty; rb < (int)gridDim.x; rb += nty) t += __ldcg(&partial[q * plane + (int64_t)rb * k_dim + col]);
-    s_red[q][slot] = t;
-  }
-  __syncthreads();
-  if (ty == 0 && active) {
-    float t[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      t[q] = s_red[q][tx];
-      for (int l = 1; l < nty; ++l) t[q] += s_red[q][l * ntx + tx];
-    }
-    if (gb_prev) gb_prev[col] = t[0];
-    gw[col] = t[1];
-    if (col == 0) gb_head[0] = t[2];
-  }
-  if (tx == 0 && ty == 0) counters[blockIdx.y] = 0;
 }
 
 struct DensePlan {
@@ -300,9 +312,10 @@ static DensePlan dense_plan(int64_t rows, int n_cols, int elem_bytes, bool align
   p.ntx = ntx;
   p.nty = kDenseThreads / ntx;
   p.col_tiles = (int)cdiv(chunks, ntx);
-  int rb = (int)cdiv(2 * kNumSMs, p.col_tiles);
+  // ~8 CTAs per SM (r1i: 128-296 CTAs ran at half the memory rate), but at least 4 rows per lane
+  int rb = (int)cdiv(kDenseTargetCtas, p.col_tiles);
   if (rb > kDenseMaxRowBlocks) rb = kDenseMaxRowBlocks;
-  const int64_t by_rows = cdiv(rows, p.nty);
+  const int64_t by_rows = cdiv(rows, (int64_t)p.nty * 4);
   if (rb > by_rows) rb = (int)by_rows;
   if (rb < 1) rb = 1;
   p.rows_per_cta = (int)cdiv(rows, rb);
@@ -314,10 +327,9 @@ static DensePlan dense_plan(int64_t rows, int n_cols, int elem_bytes, bool align
 
 using namespace mrec;
 
-// Plain-C helper: workspace for mrec_relu_bwd_bias.  The caller zero-fills it ONCE (ticket counters); every
-// launch leaves the counters at zero again.
+// Plain-C helper: workspace for mrec_relu_bwd_bias (per-row-block partial column sums; no initialisation needed).
 MREC_API size_t mrec_relu_bwd_bias_workspace_bytes(int64_t n_cols) {
-  return (size_t)kDenseMaxRowBlocks * (size_t)(n_cols > 0 ? n_cols : 1) * sizeof(float) + 4096 * sizeof(unsigned);
+  return (size_t)kDenseMaxRowBlocks * (size_t)(n_cols > 0 ? n_cols : 1) * sizeof(float);
 }
 
 // in : g[B,N] f16|f32, y[B,N] same dtype | numel 0 (no mask: plain BiasAddGrad)
@@ -355,24 +367,25 @@ MREC_API int mrec_relu_bwd_bias(int nparam, void** params, int* ndims, int64_t**
   const DensePlan p = dense_plan(rows, (int)n_cols, eb, aligned);
   MREC_REQUIRE(p.col_tiles <= 4096, ERR_SHAPE, "mrec_relu_bwd_bias: too many column tiles");
   float* partial = reinterpret_cast<float*>(a.params[4]);
-  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.params[4]) +
-                                                   (size_t)kDenseMaxRowBlocks * n_cols * sizeof(float));
   const dim3 grid(p.row_blocks, p.col_tiles), block(p.ntx, p.nty);
   const void* y = mask ? a.params[1] : nullptr;
   void* gz = a.numel(2) ? a.params[2] : nullptr;
 #define MREC_DENSE(T, V)                                                                                      \
   MREC_LAUNCH((relu_bwd_bias_kernel<T, V>), grid, block, 0, a.stream, reinterpret_cast<const T*>(a.params[0]), \
               reinterpret_cast<const T*>(y), reinterpret_cast<T*>(gz), rows, (int)n_cols, p.rows_per_cta,     \
-              partial, counters, a.ptr<float>(3))
+              partial)
   if (half) { if (p.vec) MREC_DENSE(__half, true); else MREC_DENSE(__half, false); }
   else      { if (p.vec) MREC_DENSE(float, true); else MREC_DENSE(float, false); }
 #undef MREC_DENSE
+  ColsumOut co{{a.ptr<float>(3), nullptr, nullptr}, {(int)n_cols, 0, 0}};
+  MREC_LAUNCH(colsum_finish_kernel, dim3((unsigned)cdiv(n_cols, 32), 1), dim3(32, 8), 0, a.stream, partial, p.row_blocks,
+              (int)n_cols, co);
   return check_launch("relu_bwd_bias");
 }
 
-// Plain-C helper: workspace of mrec_dense_head_bwd (zero-fill once, self-resetting like the one above).
+// Plain-C helper: workspace of mrec_dense_head_bwd (three planes of partials; no initialisation needed).
 MREC_API size_t mrec_dense_head_workspace_bytes(int64_t k_dim) {
-  return 3 * (size_t)kDenseMaxRowBlocks * (size_t)(k_dim > 0 ? k_dim : 1) * sizeof(float) + 4096 * sizeof(unsigned);
+  return 3 * (size_t)kDenseMaxRowBlocks * (size_t)(k_dim > 0 ? k_dim : 1) * sizeof(float);
 }
 
 // in : h[B,K] f16|f32, w[K]|[K,1] same dtype, bias[1] same dtype           out: out[B]|[B,1] f32
@@ -428,28 +441,28 @@ MREC_API int mrec_dense_head_bwd(int nparam, void** params, int* ndims, int64_t*
   }
   for (int i : {0, 1, 2, 4, 5, 6, 8})
     if (!a.params[i]) return fail(ERR_NULL, "mrec_dense_head_bwd: param %d is null", i);
-  int ntx = 1;
-  while (ntx < k && ntx < 128) ntx <<= 1;
-  const int nty = kDenseThreads / ntx;
-  const int col_tiles = (int)cdiv(k, ntx);
-  MREC_REQUIRE(col_tiles <= 4096, ERR_SHAPE, "mrec_dense_head_bwd: K too large");
-  int rb = (int)cdiv(2 * kNumSMs, col_tiles);
-  if (rb > kDenseMaxRowBlocks) rb = kDenseMaxRowBlocks;
-  if (rb > cdiv(rows, nty)) rb = (int)cdiv(rows, nty);
-  if (rb < 1) rb = 1;
-  const int rows_per_cta = (int)cdiv(rows, rb);
-  const int row_blocks = (int)cdiv(rows, rows_per_cta);
+  const int eb = half ? 2 : 4;
+  const bool aligned = reinterpret_cast<uintptr_t>(a.params[1]) % 16 == 0 && reinterpret_cast<uintptr_t>(a.params[4]) % 16 == 0 &&
+                       (k * eb) % 16 == 0;
+  const DensePlan p = dense_plan(rows, (int)k, eb, aligned);
+  MREC_REQUIRE(p.col_tiles <= 4096, ERR_SHAPE, "mrec_dense_head_bwd: K too large");
   float* partial = reinterpret_cast<float*>(a.params[8]);
-  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.params[8]) +
-                                                   3 * (size_t)kDenseMaxRowBlocks * k * sizeof(float));
-  const dim3 grid(row_blocks, col_tiles), block(ntx, nty);
+  const dim3 grid(p.row_blocks, p.col_tiles), block(p.ntx, p.nty);
   const bool mask = a.numel(3) > 0;
   float* gb_prev = a.numel(7) ? a.ptr<float>(7) : nullptr;
-#define MREC_HEAD(T, M)                                                                                          \
-  MREC_LAUNCH((dense_head_bwd_kernel<T, M>), grid, block, 0, a.stream, a.ptr<T>(0), a.ptr<T>(1), a.ptr<T>(2),     \
-              a.ptr<T>(4), rows, (int)k, rows_per_cta, partial, counters, gb_prev, a.ptr<float>(5), a.ptr<float>(6))
-  if (half) { if (mask) MREC_HEAD(__half, true); else MREC_HEAD(__half, false); }
-  else      { if (mask) MREC_HEAD(float, true); else MREC_HEAD(float, false); }
+#define MREC_HEAD(T, V, M)                                                                                       \
+  MREC_LAUNCH((dense_head_bwd_kernel<T, V, M>), grid, block, 0, a.stream, a.ptr<T>(0), a.ptr<T>(1), a.ptr<T>(2),  \
+              a.ptr<T>(4), rows, (int)k, p.rows_per_cta, partial)
+  if (half) {
+    if (p.vec) { if (mask) MREC_HEAD(__half, true, true); else MREC_HEAD(__half, true, false); }
+    else       { if (mask) MREC_HEAD(__half, false, true); else MREC_HEAD(__half, false, false); }
+  } else {
+    if (p.vec) { if (mask) MREC_HEAD(float, true, true); else MREC_HEAD(float, true, false); }
+    else       { if (mask) MREC_HEAD(float, false, true); else MREC_HEAD(float, false, false); }
+  }
 #undef MREC_HEAD
+  // planes: 0 = previous layer's BiasAddGrad (optional), 1 = gw, 2 = sum(delta) in column 0
+  ColsumOut co{{gb_prev, a.ptr<float>(5), a.ptr<float>(6)}, {gb_prev ? (int)k : 0, (int)k, 1}};
+  MREC_LAUNCH(colsum_finish_kernel, dim3((unsigned)cdiv(k, 32), 3), dim3(32, 8), 0, a.stream, partial, p.row_blocks, (int)k, co);
   return check_launch("dense_head_bwd");
 }

@@ -90,6 +90,8 @@ def main():
     a = ap.parse_args()
     global GRAPH
     GRAPH = not a.eager
+    if a.what == "dense":
+        return dense_bench(a.batch)
     b, f, d, v = a.batch, 39, a.dim, a.vocab
     n = b * f
     ids = zipf_ids(b, f, v)
@@ -158,6 +160,29 @@ def main():
         hyper = ops.ftrl_hyper(5e-2, 1e-8, 1e-8, loss_scale=1024.0)
         ms = timeit(lambda: ops.sparse_ftrl(wt, acc, lin, hyper, g, mask, res))
         report("segsum+ftrl D=1 U=%d" % u, ms, u * 28 + n * 8)
+
+
+def dense_bench(b=16000):
+    """DenseLayer glue kernels at config-2 shapes (fp16)."""
+    for n in (1024, 512, 256, 128):
+        g = torch.randn((b, n), device="cuda").half()
+        y = torch.relu(torch.randn((b, n), device="cuda")).half()
+        gb = torch.empty(n, device="cuda")
+        report("relu_bwd_bias fp16 N=%d" % n, timeit(lambda: ops.relu_bwd_bias(g, y, gb)), b * n * 6)
+    k = 128
+    h = torch.relu(torch.randn((b, k), device="cuda")).half()
+    w = torch.randn(k, device="cuda").half()
+    bias = torch.zeros(1, device="cuda").half()
+    d16 = (torch.randn((b, 1), device="cuda") * 0.01).half()
+    out = torch.empty((b, 1), device="cuda")
+    report("dense_head_fwd K=128", timeit(lambda: ops.dense_head_fwd(h, w, bias, out=out)), b * k * 2 + b * 4)
+    gw, gbh, gbp, gh = torch.empty(k, device="cuda"), torch.empty(1, device="cuda"), torch.empty(k, device="cuda"), torch.empty_like(h)
+    report("dense_head_bwd K=128", timeit(lambda: ops.dense_head_bwd(d16, h, w, True, gw, gbh, gbp, out=gh)), b * k * 4 + b * 2)
+    a = torch.randn((b, 1), device="cuda")
+    lab = (torch.rand((b, 1), device="cuda") < 0.25).float()
+    sens = torch.tensor([1024.0], device="cuda")
+    o = ops.sigmoid_xent(a, a, lab, sens, half=True)
+    report("sigmoid_xent B=%d" % b, timeit(lambda: ops.sigmoid_xent(a, a, lab, sens, out=o)), b * 26)
 
 
 def interaction():
