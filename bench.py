@@ -377,6 +377,15 @@ def run_ours(args):
     if world == 1:
         roofline = measure_dominant_op(step, devb[:4], b)
 
+    exch_err = 0
+    if world > 1 and hasattr(step.tables, "error_flags"):
+        # device-driven exchange: bit 0 = a peer wait timed out, bit 1 = an inbox overflowed (either voids the run)
+        t = torch.tensor([step.tables.error_flags()], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exch_err = int(t.item())
+        if exch_err:
+            raise SystemExit("bench.py: sharded exchange raised error flags %d (1 = wait time-out, 2 = inbox overflow)" % exch_err)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -127,12 +127,13 @@ relu_bwd_bias_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __rest
   }
 }
 
-// partial[plane][rb][n_cols] -> out[plane][n_cols]: CTA = 32 columns x 8 row-block lanes, fixed order.
+// partial[plane][rb][n_cols] -> out[plane][n_cols]: CTA = 32 columns x 32 row-block lanes, fixed order.
 struct ColsumOut { float* p[3]; int n[3]; };
+constexpr int kFinishLanes = 32;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kFinishLanes)
 colsum_finish_kernel(const float* __restrict__ partial, int row_blocks, int n_cols, ColsumOut out) {
-  __shared__ float s_red[8][33];
+  __shared__ float s_red[kFinishLanes][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int plane = blockIdx.y;
   const int col = blockIdx.x * 32 + tx;
@@ -141,19 +142,21 @@ colsum_finish_kernel(const float* __restrict__ partial, int row_blocks, int n_co
   float t = 0.f;
   if (col < n_out) {
     int rb = ty;
-    for (; rb + 24 < row_blocks; rb += 32) {     // four independent loads per round
-      const float v0 = __ldcg(src + (int64_t)rb * n_cols + col), v1 = __ldcg(src + (int64_t)(rb + 8) * n_cols + col);
-      const float v2 = __ldcg(src + (int64_t)(rb + 16) * n_cols + col), v3 = __ldcg(src + (int64_t)(rb + 24) * n_cols + col);
+    for (; rb + 3 * kFinishLanes < row_blocks; rb += 4 * kFinishLanes) {     // four independent loads per round
+      const float v0 = __ldcg(src + (int64_t)rb * n_cols + col);
+      const float v1 = __ldcg(src + (int64_t)(rb + kFinishLanes) * n_cols + col);
+      const float v2 = __ldcg(src + (int64_t)(rb + 2 * kFinishLanes) * n_cols + col);
+      const float v3 = __ldcg(src + (int64_t)(rb + 3 * kFinishLanes) * n_cols + col);
       t += v0; t += v1; t += v2; t += v3;
     }
-    for (; rb < row_blocks; rb += 8) t += __ldcg(src + (int64_t)rb * n_cols + col);
+    for (; rb < row_blocks; rb += kFinishLanes) t += __ldcg(src + (int64_t)rb * n_cols + col);
   }
   s_red[ty][tx] = t;
   __syncthreads();
   if (ty == 0 && col < n_out) {
     float r = s_red[0][tx];
 #pragma unroll
-    for (int l = 1; l < 8; ++l) r += s_red[l][tx];
+    for (int l = 1; l < kFinishLanes; ++l) r += s_red[l][tx];
     out.p[plane][col] = r;
   }
 }
@@ -378,7 +381,7 @@ MREC_API int mrec_relu_bwd_bias(int nparam, void** params, int* ndims, int64_t**
   else      { if (p.vec) MREC_DENSE(float, true); else MREC_DENSE(float, false); }
 #undef MREC_DENSE
   ColsumOut co{{a.ptr<float>(3), nullptr, nullptr}, {(int)n_cols, 0, 0}};
-  MREC_LAUNCH(colsum_finish_kernel, dim3((unsigned)cdiv(n_cols, 32), 1), dim3(32, 8), 0, a.stream, partial, p.row_blocks,
+  MREC_LAUNCH(colsum_finish_kernel, dim3((unsigned)cdiv(n_cols, 32), 1), dim3(32, kFinishLanes), 0, a.stream, partial, p.row_blocks,
               (int)n_cols, co);
   return check_launch("relu_bwd_bias");
 }
@@ -463,6 +466,6 @@ MREC_API int mrec_dense_head_bwd(int nparam, void** params, int* ndims, int64_t*
 #undef MREC_HEAD
   // planes: 0 = previous layer's BiasAddGrad (optional), 1 = gw, 2 = sum(delta) in column 0
   ColsumOut co{{gb_prev, a.ptr<float>(5), a.ptr<float>(6)}, {gb_prev ? (int)k : 0, (int)k, 1}};
-  MREC_LAUNCH(colsum_finish_kernel, dim3((unsigned)cdiv(k, 32), 3), dim3(32, 8), 0, a.stream, partial, p.row_blocks, (int)k, co);
+  MREC_LAUNCH(colsum_finish_kernel, dim3((unsigned)cdiv(k, 32), 3), dim3(32, kFinishLanes), 0, a.stream, partial, p.row_blocks, (int)k, co);
   return check_launch("dense_head_bwd");
 }
