@@ -79,3 +79,56 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.lib()
+
+
+def test_every_aot_entry_rejects_an_empty_argument_pack(built_lib):
+    """Every aot symbol of the header validates nparam before touching CUDA (error 1), never crashes."""
+    helpers = ("_workspace_bytes", "mrec_version", "mrec_last_error", "mrec_launch_count", "mrec_peer_alloc",
+               "mrec_peer_free", "mrec_ipc_")
+    for sym in _declared_symbols():
+        if any(h in sym for h in helpers):
+            continue
+        rc = _lib.aot_call_raw(sym, [], [], [])
+        assert rc == 1, "%s returned %d for nparam = 0" % (sym, rc)
+        assert _lib.last_error()
+
+
+def test_dense_glue_validation_without_gpu(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    lib.mrec_relu_bwd_bias_workspace_bytes.restype = ctypes.c_size_t
+    lib.mrec_relu_bwd_bias_workspace_bytes.argtypes = [ctypes.c_int64]
+    ws = lib.mrec_relu_bwd_bias_workspace_bytes(1024)
+    assert ws >= 1024 * 4
+    # g int32: dtype error
+    rc = _lib.aot_call_raw("mrec_relu_bwd_bias", [16, 32, 48, 64, 80], [(4, 8), (4, 8), (4, 8), (8,), (ws,)],
+                           ["int32", "int32", "int32", "float32", "uint8"])
+    assert rc == 2
+    # y of another shape
+    rc = _lib.aot_call_raw("mrec_relu_bwd_bias", [16, 32, 48, 64, 80], [(4, 8), (4, 4), (4, 8), (8,), (ws,)],
+                           ["float16", "float16", "float16", "float32", "uint8"])
+    assert rc == 3
+    # workspace too small
+    rc = _lib.aot_call_raw("mrec_relu_bwd_bias", [16, 32, 48, 64, 80], [(4, 8), (4, 8), (4, 8), (8,), (16,)],
+                           ["float16", "float16", "float16", "float32", "uint8"])
+    assert rc == 7
+    # head: w of the wrong length
+    rc = _lib.aot_call_raw("mrec_dense_head_fwd", [16, 32, 48, 64], [(4, 8), (7,), (1,), (4,)],
+                           ["float16", "float16", "float16", "float32"])
+    assert rc == 3
+    rc = _lib.aot_call_raw("mrec_dense_head_fwd", [16, 32, 48, 64], [(4, 8), (8,), (1,), (4,)],
+                           ["float16", "float32", "float16", "float32"])
+    assert rc == 2
+
+
+def test_peer_exchange_validation_without_gpu(built_lib):
+    # shard_offsets: every param int32
+    rc = _lib.aot_call_raw("mrec_shard_offsets", [16] * 6, [(6,), (2,), (2,), (3,), (2,), (1,)],
+                           ["int32", "int32", "float32", "int32", "int32", "int32"])
+    assert rc == 2
+    # push_rows: the modulo transform is for int32 keys only
+    rc = _lib.aot_call_raw("mrec_push_rows_to_peers", [16] * 7, [(8, 4), (3,), (2,), (2,), (8, 0), (5, 0), (1,)],
+                           ["float32", "int32", "int32", "int64", "float32", "float32", "int32"])
+    assert rc == 2
+    # more ranks than the kernels support
+    rc = _lib.aot_call_raw("mrec_peer_wait", [16, 32, 48], [(4096,), (1,), (1,)], ["int32", "int32", "int32"])
+    assert rc == 3
