@@ -207,14 +207,18 @@ size_t mrec_cross_workspace_bytes(int64_t layers, int dp);
  * mrec_gather and updated with mrec_sparse_lazy_adam / mrec_sparse_ftrl on slot indices.
  * Framework-owned state, passed on every call and mutated in place:
  *   tkeys[C] i64 (-1 empty, -2 erased; C a power of two >= 8, 64-byte aligned), meta[C] i64
- *   ((sightings << 32) | last_step), state[8] i32 {resident, step, tombstones, overflow, occupied, ...},
+ *   ((sightings << 32) | last_step), state[8] i32 {resident, step, tombstones, overflow, occupied, erase-log
+ *   entries, erase-log overflow, -},
  *   cfg[2] i32 {permit_filter_value, evict_filter_value}.
  * Probe entry points:   in : keys[N] i32|i64, tkeys, meta, state, cfg
  *   mrec_hash_find            MapTensorGet(insert_default_value=False)   out: slots[N] i32 (C = default row)
  *   mrec_hash_find_or_insert  MapTensorGet(True): a key becomes resident on its permit-th sighting
  *                             (one sighting per key per call)             out: slots[N], new_slots[N], new_count[1]
  *   mrec_hash_insert          MapTensorPut / import_data                  out: slots[N], new_slots[N], new_count[1]
- *   mrec_hash_erase           MapTensorErase                              out: slots[N]                       */
+ *   mrec_hash_erase           MapTensorErase                              out: slots[N] [, erase_log[L] i64]
+ * erase_log (optional, also on mrec_hash_evict): every removed key is appended at state[5]++; state[6] is raised
+ * when the log is full.  Together with mrec_hash_export(since) it gives the incremental export of
+ * RELEASE.md:18 / README.md:213-214 (keys changed since a step + keys erased since then).              */
 int mrec_hash_find(MREC_AOT_ARGS);
 int mrec_hash_find_or_insert(MREC_AOT_ARGS);
 int mrec_hash_insert(MREC_AOT_ARGS);
@@ -226,9 +230,10 @@ int mrec_hash_init_rows(MREC_AOT_ARGS);
 /*   in : arena[C+1,D], slots[N], values[N,D]     out: dummy[1]     (put / import: arena[slots[i]] = values[i]) */
 int mrec_hash_scatter_rows(MREC_AOT_ARGS);
 /* Eviction sweep: erase every key not looked up for more than evict_filter_value calls.
- *   in : tkeys, meta, state, cfg                  out: dummy[1]                                               */
+ *   in : tkeys, meta, state, cfg                  out: dummy[1] [, erase_log[L] i64]                          */
 int mrec_hash_evict(MREC_AOT_ARGS);
-/* get_keys / export_data:  in : tkeys, meta, state, cfg   out: keys_out[C] i64, slots_out[C] i32, count[1] i32 */
+/* get_keys / export_data:  in : tkeys, meta, state, cfg [, since[1] i32: only keys looked up / put after that step]
+ *                          out: keys_out[C] i64, slots_out[C] i32, count[1] i32                               */
 int mrec_hash_export(MREC_AOT_ARGS);
 
 #ifdef __cplusplus

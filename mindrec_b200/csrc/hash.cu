@@ -28,7 +28,17 @@ namespace mrec {
 constexpr long long kEmpty = -1;
 constexpr long long kErased = -2;
 constexpr int kHashThreads = 256;
-enum { ST_SIZE = 0, ST_STEP = 1, ST_TOMB = 2, ST_OVERFLOW = 3, ST_OCC = 4, ST_LEN = 8 };
+enum { ST_SIZE = 0, ST_STEP = 1, ST_TOMB = 2, ST_OVERFLOW = 3, ST_OCC = 4, ST_LOGN = 5, ST_LOGOVF = 6, ST_LEN = 8 };
+
+// Erase log (incremental export): every key removed by erase / evict is appended to a
+// caller-owned int64 buffer; state[ST_LOGN] counts the appends, state[ST_LOGOVF] is raised when one did not fit
+// (the next incremental export must then be a full one).
+__device__ __forceinline__ void log_erased(long long key, long long* log, int64_t log_cap, int32_t* state) {
+  if (!log) return;
+  const int i = atomicAdd(&state[ST_LOGN], 1);
+  if (i < log_cap) log[i] = key;
+  else state[ST_LOGOVF] = 1;
+}
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // murmur3 finaliser
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(kHashThreads)
 hash_probe_kernel(const KeyT* __restrict__ keys_in, int64_t n, long long* __restrict__ keys,
                   unsigned long long* __restrict__ meta, int32_t* __restrict__ state, int64_t capacity,
                   const int32_t* __restrict__ cfg, int32_t* __restrict__ slots, int32_t* __restrict__ new_slots,
-                  int32_t* __restrict__ new_count) {
+                  int32_t* __restrict__ new_count, long long* __restrict__ erase_log, int64_t log_cap) {
   const int permit = cfg[0];  // MapParameter(permit_filter_value): device scalar like every other "attr"
   const int lane = threadIdx.x & 31;
   const int lt = lane & 7;      // lane in tile
@@ -158,6 +168,7 @@ hash_probe_kernel(const KeyT* __restrict__ keys_in, int64_t n, long long* __rest
           atomicAdd(&state[ST_TOMB], 1);
           atomicSub(&state[ST_OCC], 1);
           if ((uint32_t)(mo >> 32) >= (uint32_t)permit) atomicSub(&state[ST_SIZE], 1);
+          log_erased(key, erase_log, log_cap, state);
         }
         out_slot = result;
       } else if (MODE == 0) {
@@ -250,7 +261,7 @@ hash_scatter_rows_kernel(float* __restrict__ arena, int64_t capacity, int dim, c
 // eviction: every resident or candidate key not looked up for more than `evict_after` steps is erased
 __global__ void __launch_bounds__(256)
 hash_evict_kernel(long long* __restrict__ keys, unsigned long long* __restrict__ meta, int32_t* __restrict__ state,
-                  int64_t capacity, const int32_t* __restrict__ cfg) {
+                  int64_t capacity, const int32_t* __restrict__ cfg, long long* __restrict__ erase_log, int64_t log_cap) {
   const int permit = cfg[0], evict_after = cfg[1];
   const int step = state[ST_STEP];
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < capacity;
@@ -265,6 +276,7 @@ hash_evict_kernel(long long* __restrict__ keys, unsigned long long* __restrict__
       atomicAdd(&state[ST_TOMB], 1);
       atomicSub(&state[ST_OCC], 1);
       if ((uint32_t)(mo >> 32) >= (uint32_t)permit) atomicSub(&state[ST_SIZE], 1);
+      log_erased(k, erase_log, log_cap, state);
     }
   }
 }
@@ -272,14 +284,18 @@ hash_evict_kernel(long long* __restrict__ keys, unsigned long long* __restrict__
 // export: resident (key, slot) pairs, compacted (order unspecified); values follow with mrec_gather(arena, slots)
 __global__ void __launch_bounds__(256)
 hash_export_kernel(const long long* __restrict__ keys, const unsigned long long* __restrict__ meta,
-                   int64_t capacity, const int32_t* __restrict__ cfg, long long* __restrict__ keys_out,
-                   int32_t* __restrict__ slots_out, int32_t* __restrict__ count) {
+                   int64_t capacity, const int32_t* __restrict__ cfg, const int32_t* __restrict__ since,
+                   long long* __restrict__ keys_out, int32_t* __restrict__ slots_out, int32_t* __restrict__ count) {
   const int permit = cfg[0];
+  const bool incremental = since != nullptr;       // only keys looked up / put after step since[0]
+  const int since_step = incremental ? since[0] : 0;
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < capacity;
        s += (int64_t)gridDim.x * blockDim.x) {
     const long long k = keys[s];
     if (k == kEmpty || k == kErased) continue;
-    if ((uint32_t)(meta[s] >> 32) < (uint32_t)permit) continue;
+    const unsigned long long mo = meta[s];
+    if ((uint32_t)(mo >> 32) < (uint32_t)permit) continue;
+    if (incremental && (int)(uint32_t)mo <= since_step) continue;
     const int idx = atomicAdd(count, 1);
     keys_out[idx] = k;
     slots_out[idx] = (int32_t)s;
@@ -303,7 +319,9 @@ static int probe_entry(const Aot& a, const char* who, bool has_new) {
   // inputs : keys_in[N] i32|i64, table_keys[C] i64, meta[C] i64, state[8] i32, permit[1] i32
   // outputs: slots[N] i32, (new_slots[N] i32, new_count[1] i32)
   const int expect = has_new ? 8 : 6;
-  if (a.nparam != expect) return fail(ERR_NPARAM, "%s: expected %d params, got %d", who, expect, a.nparam);
+  const bool with_log = (MODE == 3) && a.nparam == expect + 1;     // erase: optional trailing erase_log[L] i64
+  if (a.nparam != expect && !with_log)
+    return fail(ERR_NPARAM, "%s: expected %d params, got %d", who, expect, a.nparam);
   for (int i = 0; i < a.nparam; ++i)
     if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "%s: param %d is null", who, i);
   MREC_REQUIRE(a.is_i32(0) || a.is_i64(0), ERR_DTYPE, "%s: keys must be int32|int64", who);
@@ -320,17 +338,24 @@ static int probe_entry(const Aot& a, const char* who, bool has_new) {
     new_slots = a.ptr<int32_t>(6);
     new_count = a.ptr<int32_t>(7);
   }
+  long long* erase_log = nullptr;
+  int64_t log_cap = 0;
+  if (with_log) {
+    MREC_REQUIRE(a.is_i64(6), ERR_DTYPE, "%s: erase_log must be int64", who);
+    erase_log = a.ptr<long long>(6);
+    log_cap = a.numel(6);
+  }
   MREC_LAUNCH(hash_begin_kernel, 1, 32, 0, a.stream, a.ptr<int32_t>(3), new_count, (MODE == 1 || MODE == 2) ? 1 : 0);
   if (n == 0) return check_launch(who);
   const int grid = (int)cdiv(n, kHashThreads);
   if (a.is_i32(0)) {
     MREC_LAUNCH((hash_probe_kernel<int32_t, MODE>), grid, kHashThreads, 0, a.stream, a.ptr<int32_t>(0), n,
                 a.ptr<long long>(1), a.ptr<unsigned long long>(2), a.ptr<int32_t>(3), capacity,
-                a.ptr<int32_t>(4), a.ptr<int32_t>(5), new_slots, new_count);
+                a.ptr<int32_t>(4), a.ptr<int32_t>(5), new_slots, new_count, erase_log, log_cap);
   } else {
     MREC_LAUNCH((hash_probe_kernel<int64_t, MODE>), grid, kHashThreads, 0, a.stream, a.ptr<int64_t>(0), n,
                 a.ptr<long long>(1), a.ptr<unsigned long long>(2), a.ptr<int32_t>(3), capacity,
-                a.ptr<int32_t>(4), a.ptr<int32_t>(5), new_slots, new_count);
+                a.ptr<int32_t>(4), a.ptr<int32_t>(5), new_slots, new_count, erase_log, log_cap);
   }
   return check_launch(who);
 }
@@ -401,34 +426,50 @@ MREC_API int mrec_hash_scatter_rows(MREC_AOT_SIG) {
   return check_launch("hash_scatter_rows");
 }
 
-// eviction sweep: in tkeys[C] meta[C] state[8] cfg[2]     out: dummy[1]
+// eviction sweep: in tkeys[C] meta[C] state[8] cfg[2]     out: dummy[1] [, erase_log[L] i64]
 MREC_API int mrec_hash_evict(MREC_AOT_SIG) {
   MREC_AOT_PACK;
-  MREC_CHECK_NPARAM(a, 5);
+  if (a.nparam != 5 && a.nparam != 6) return fail(ERR_NPARAM, "mrec_hash_evict: expected 5 or 6 params, got %d", a.nparam);
+  long long* erase_log = nullptr;
+  int64_t log_cap = 0;
+  if (a.nparam == 6) {
+    MREC_REQUIRE(a.is_i64(5), ERR_DTYPE, "mrec_hash_evict: erase_log must be int64");
+    erase_log = a.ptr<long long>(5);
+    log_cap = a.numel(5);
+  }
   int64_t capacity;
   int rc = table_args(a, 0, 1, 2, &capacity, "mrec_hash_evict");
   if (rc) return rc;
   MREC_REQUIRE(a.is_i32(3) && a.numel(3) >= 2, ERR_DTYPE, "mrec_hash_evict: cfg must be int32[2]");
   MREC_LAUNCH(hash_evict_kernel, grid_for(cdiv(capacity, 256), 8), 256, 0, a.stream, a.ptr<long long>(0),
-              a.ptr<unsigned long long>(1), a.ptr<int32_t>(2), capacity, a.ptr<int32_t>(3));
+              a.ptr<unsigned long long>(1), a.ptr<int32_t>(2), capacity, a.ptr<int32_t>(3), erase_log, log_cap);
   return check_launch("hash_evict");
 }
 
-// export_data / get_keys: in tkeys[C] meta[C] state[8] cfg[2]     out: keys_out[C] i64, slots_out[C] i32, count[1] i32
-// (values follow with mrec_gather(arena, slots_out); order of the pairs is unspecified)
+// export_data / get_keys: in tkeys[C] meta[C] state[8] cfg[2] [, since[1] i32]
+//                          out: keys_out[C] i64, slots_out[C] i32, count[1] i32
+// (values follow with mrec_gather(arena, slots_out); order of the pairs is unspecified).  With `since` only the
+// resident keys looked up or put after step since[0] are exported (incremental export; the erased keys of the
+// same interval are in the erase log of mrec_hash_erase / mrec_hash_evict).
 MREC_API int mrec_hash_export(MREC_AOT_SIG) {
   MREC_AOT_PACK;
-  MREC_CHECK_NPARAM(a, 7);
+  if (a.nparam != 7 && a.nparam != 8) return fail(ERR_NPARAM, "mrec_hash_export: expected 7 or 8 params, got %d", a.nparam);
+  const int o = a.nparam - 3;                       // first output
   int64_t capacity;
   int rc = table_args(a, 0, 1, 2, &capacity, "mrec_hash_export");
   if (rc) return rc;
-  MREC_REQUIRE(a.is_i32(3) && a.is_i64(4) && a.is_i32(5) && a.is_i32(6), ERR_DTYPE,
+  MREC_REQUIRE(a.is_i32(3) && a.is_i64(o) && a.is_i32(o + 1) && a.is_i32(o + 2), ERR_DTYPE,
                "mrec_hash_export: cfg int32, keys_out int64, slots_out/count int32");
-  MREC_REQUIRE(a.numel(4) >= capacity && a.numel(5) >= capacity && a.numel(6) >= 1, ERR_SHAPE,
+  const int32_t* since = nullptr;
+  if (a.nparam == 8) {
+    MREC_REQUIRE(a.is_i32(4) && a.numel(4) >= 1, ERR_DTYPE, "mrec_hash_export: since must be int32[1]");
+    since = a.ptr<int32_t>(4);
+  }
+  MREC_REQUIRE(a.numel(o) >= capacity && a.numel(o + 1) >= capacity && a.numel(o + 2) >= 1, ERR_SHAPE,
                "mrec_hash_export: outputs must be padded to C");
-  cudaMemsetAsync(a.params[6], 0, sizeof(int32_t), a.stream);
+  cudaMemsetAsync(a.params[o + 2], 0, sizeof(int32_t), a.stream);
   MREC_LAUNCH(hash_export_kernel, grid_for(cdiv(capacity, 256), 8), 256, 0, a.stream, a.ptr<long long>(0),
-              a.ptr<unsigned long long>(1), capacity, a.ptr<int32_t>(3), a.ptr<long long>(4), a.ptr<int32_t>(5),
-              a.ptr<int32_t>(6));
+              a.ptr<unsigned long long>(1), capacity, a.ptr<int32_t>(3), since, a.ptr<long long>(o), a.ptr<int32_t>(o + 1),
+              a.ptr<int32_t>(o + 2));
   return check_launch("hash_export");
 }

@@ -81,6 +81,9 @@ class MapParameter:
         self._sigma = torch.tensor([sigma], dtype=torch.float32, device=dev)
         self._arenas = []          # sibling [C+1, D'] arenas, initialised from their own default row
         self._scratch = {}
+        # incremental export: keys removed since the last export, and the step of that export
+        self._erase_log = torch.empty(max(1024, min(c, 1 << 20)), dtype=torch.int64, device=dev)
+        self._exported_at = torch.zeros(1, dtype=torch.int32, device=dev)
         if key_tensor is not None:
             self.put(key_tensor, value_tensor)
 
@@ -148,20 +151,21 @@ class MapParameter:
         """MapTensorErase."""
         flat = key.reshape(-1)
         slots, _, _ = self._bufs(flat.numel())
-        _lib.aot_call("mrec_hash_erase", [flat] + self._table() + [slots])
+        _lib.aot_call("mrec_hash_erase", [flat] + self._table() + [slots, self._erase_log])
         return self
 
     def evict(self):
         """Erase keys not looked up for more than evict_filter_value calls (README.md:182-183)."""
-        _lib.aot_call("mrec_hash_evict", self._table() + [ops._dummy(self.device)])
+        _lib.aot_call("mrec_hash_evict", self._table() + [ops._dummy(self.device), self._erase_log])
         return self
 
-    def _export(self):
+    def _export(self, since=None):
         c = self.capacity
         keys_out = torch.empty(c, dtype=torch.int64, device=self.device)
         slots_out = torch.empty(c, dtype=torch.int32, device=self.device)
         count = torch.zeros(1, dtype=torch.int32, device=self.device)
-        _lib.aot_call("mrec_hash_export", self._table() + [keys_out, slots_out, count])
+        _lib.aot_call("mrec_hash_export", self._table() + ([since] if since is not None else []) +
+                      [keys_out, slots_out, count])
         n = int(count.item())
         order = torch.argsort(keys_out[:n])  # deterministic presentation order
         return keys_out[:n][order], slots_out[:n][order]
@@ -176,16 +180,44 @@ class MapParameter:
         k, s = self._export()
         return k.to(self.key_dtype), ops.gather(self.values, s.contiguous())
 
+    STATUS_NORMAL, STATUS_MODIFIED, STATUS_ERASED = 0, 1, 2
+
     def export_data(self, incremental=False):
-        """(keys, values, statuses); statuses are all 0 (= unchanged/normal): incremental export needs a
-        per-slot dirty bit that this round does not track."""
-        if incremental:
-            raise NotImplementedError("incremental export is listed as 'next' (SURVEY 8f rank 1)")
-        k, v = self.get_data()
-        return k, v, torch.zeros(k.numel(), dtype=torch.int32, device=self.device)
+        """(keys, values, statuses).  Full export: every resident key, status 0.  incremental=True: only what
+        changed since the previous export_data call — keys looked up / put since then (status 1, current values)
+        and keys erased or evicted since then that are not resident again (status 2, zero values).  If the erase
+        log overflowed in between, the export falls back to a full one (all statuses 0: replace the replica)."""
+        st = self.state.tolist()
+        log_n, log_ovf = st[5], st[6]
+        if incremental and not log_ovf:
+            k, s = self._export(since=self._exported_at)
+            v = ops.gather(self.values, s.contiguous())
+            status = torch.full((k.numel(),), self.STATUS_MODIFIED, dtype=torch.int32, device=self.device)
+            if log_n:
+                gone = torch.unique(self._erase_log[:log_n])
+                # a key erased and inserted again since the last export is simply "modified"
+                still = self.lookup_slots(gone.to(self.key_dtype), insert_default_value=False) == self.capacity
+                gone = gone[still]
+                k = torch.cat([k, gone])
+                v = torch.cat([v, torch.zeros((gone.numel(), self.dim), dtype=torch.float32, device=self.device)])
+                status = torch.cat([status, torch.full((gone.numel(),), self.STATUS_ERASED, dtype=torch.int32,
+                                                       device=self.device)])
+        else:
+            k, v = self.get_data()
+            status = torch.zeros(k.numel(), dtype=torch.int32, device=self.device)
+        self._exported_at.copy_(self.state[1:2])
+        self.state[5:7] = 0
+        return k.to(self.key_dtype), v, status
 
     def import_data(self, data):
+        """Apply a full or incremental export: erase the status-2 keys, put the rest."""
         keys, values = data[0], data[1]
+        if len(data) > 2 and data[2] is not None and bool((data[2] == self.STATUS_ERASED).any()):
+            gone = data[2] == self.STATUS_ERASED
+            self.erase(keys[gone].contiguous())
+            keys, values = keys[~gone].contiguous(), values[~gone].contiguous()
+        if keys.numel() == 0:
+            return self
         return self.put(keys, values)
 
     def __getitem__(self, key):

@@ -145,3 +145,73 @@ def test_lazy_adam_on_map_parameter_by_slot(cuda):
     R.lazy_adam_sparse(w_ref, m_ref, v_ref, uniq, R.segment_sum(g.cpu().numpy(), inverse, uniq.size), st)
     np.testing.assert_allclose(mp.values.cpu().numpy(), w_ref, rtol=1e-5, atol=1e-7)
     assert torch.equal(mp.values[mp.capacity], w0[mp.capacity])   # default row untouched
+
+
+def _sorted_data(mp):
+    k, v = mp.get_data()
+    order = torch.argsort(k)
+    return k[order].cpu().numpy(), v[order].cpu().numpy()
+
+
+@pytest.mark.parametrize("kdt", [torch.int32, torch.int64])
+def test_incremental_export_replays_onto_a_replica(cuda, kdt):
+    """Full export, then two rounds of put / touch / erase / evict, each shipped as an incremental export:
+    the replica ends bit-identical and the statuses name exactly the changed and the erased keys."""
+    rng = np.random.default_rng(3)
+    src = H.MapParameter(key_dtype=kdt, value_shape=8, capacity=1 << 12, default_value="zeros", device=cuda,
+                         evict_filter_value=3)
+    rep = H.MapParameter(key_dtype=kdt, value_shape=8, capacity=1 << 12, default_value="zeros", device=cuda)
+    t = lambda a, dt=kdt: torch.as_tensor(a, dtype=dt, device=cuda)
+    keys0 = rng.choice(100000, size=600, replace=False)
+    src.put(t(keys0), torch.from_numpy(rng.standard_normal((600, 8)).astype(np.float32)).to(cuda))
+    k, v, st = src.export_data()
+    assert int(st.sum()) == 0 and k.numel() == 600
+    rep.import_data((k, v, st))
+    for a, b in zip(_sorted_data(src), _sorted_data(rep)):
+        assert np.array_equal(a, b)
+
+    # round 1: overwrite 50 old keys, add 40 new ones, erase 30, erase-and-reinsert 5
+    over, new = keys0[:50], np.arange(200000, 200040)
+    gone, back = keys0[100:130], keys0[130:135]
+    src.put(t(over), torch.full((50, 8), 2.5, device=cuda))
+    src.put(t(new), torch.full((40, 8), -1.0, device=cuda))
+    src.erase(t(gone))
+    src.erase(t(back))
+    src.put(t(back), torch.full((5, 8), 9.0, device=cuda))
+    k, v, st = src.export_data(incremental=True)
+    got_mod = set(k[st == H.MapParameter.STATUS_MODIFIED].tolist())
+    got_gone = set(k[st == H.MapParameter.STATUS_ERASED].tolist())
+    assert got_mod == set(over.tolist()) | set(new.tolist()) | set(back.tolist())
+    assert got_gone == set(gone.tolist())
+    rep.import_data((k, v, st))
+    for a, b in zip(_sorted_data(src), _sorted_data(rep)):
+        assert np.array_equal(a, b)
+
+    # round 2: only 20 keys are looked up for four steps; everything else falls to the eviction filter
+    alive = keys0[200:220]
+    for _ in range(5):
+        src.get(t(alive))
+    src.evict()
+    assert len(src) == 20
+    k, v, st = src.export_data(incremental=True)
+    assert set(k[st == H.MapParameter.STATUS_MODIFIED].tolist()) == set(alive.tolist())
+    assert int((st == H.MapParameter.STATUS_ERASED).sum()) == len(rep) - 20
+    rep.import_data((k, v, st))
+    for a, b in zip(_sorted_data(src), _sorted_data(rep)):
+        assert np.array_equal(a, b)
+    # nothing happened since: the next incremental export is empty
+    k, v, st = src.export_data(incremental=True)
+    assert k.numel() == 0
+
+
+def test_incremental_export_falls_back_to_full_when_the_erase_log_overflows(cuda):
+    mp = H.MapParameter(key_dtype=torch.int64, value_shape=4, capacity=1 << 12, default_value="zeros", device=cuda)
+    mp._erase_log = torch.empty(8, dtype=torch.int64, device=cuda)           # tiny log
+    keys = torch.arange(100, dtype=torch.int64, device=cuda)
+    mp.put(keys, torch.ones((100, 4), device=cuda))
+    mp.export_data()
+    mp.erase(keys[:50].contiguous())
+    k, v, st = mp.export_data(incremental=True)
+    assert int(st.sum()) == 0 and k.numel() == 50                            # a full export of what is left
+    k, v, st = mp.export_data(incremental=True)
+    assert k.numel() == 0
