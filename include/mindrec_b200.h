@@ -100,13 +100,21 @@ int mrec_gather_to_peers(MREC_AOT_ARGS);
  * B[s][o] = start of rank s's bucket for owner o among its sorted unique keys (B[s][G] = U_s):
  *   mrec_shard_offsets       in : bounds_all[G*(G+1)] i32, ctrl[2] i32 {rank, G}
  *                            out: dst_off[G], src_off[G+1], inbox_off[G], n_r[1]  (all i32)
- *   mrec_push_rows_to_peers  in : rows[cap,W] f32|i32, my_bounds[G+1], inbox_off[G], peer_ptrs[G] i64,
- *                                 cap_like[cap_rows,..], mod_like[M,..] (M > 0: int32 keys are sent as key % M)
+ *   mrec_push_rows_to_peers  in : rows[cap,W] f32|i32|i64, my_bounds[G+1], inbox_off[G], peer_ptrs[G] i64,
+ *                                 cap_like[cap_rows,..], mod_like[M,..] (M > 0: integer keys are sent as key % M)
  *                            out: err[1] i32 (bit 1: an inbox overflowed)
  *   mrec_peer_signal         in : payload[K] i32, payload_ptrs[G] i64, flag_ptrs[G] i64, epoch[1] i32 (+1)  out: dummy[1]
  *   mrec_peer_wait           in : flags[G] i32, epoch[1] i32 [, limit_log2[1] i32: spin limit 2^limit cycles, default ~4 s]
  *                            out: err[1] i32 (bit 0: time-out) */
 int mrec_shard_offsets(MREC_AOT_ARGS);
+/* Hash-table (MapParameter) sharding, SURVEY 8e: owner = hash(key) mod G, every rank owns an independent table.
+ *   mrec_shard_remap_hash    in : keys[N] i32|i64, owners_like[G,..], bits_like[B,..] (keys live in [0, 2^B))
+ *                            out: keys'[N] i64 = owner << B | key (reserved / out-of-range keys -> G << B, dropped
+ *                                 by mrec_unique_bounded with bound G << B); the owner gets key' % 2^B back
+ *   mrec_fill_tail           in : n_valid[1] i32, value[1]            out: buf[cap] i32|i64 (buf[i >= n_valid] = value:
+ *                                 blanks the stale tail of a static key inbox with the reserved key -1) */
+int mrec_shard_remap_hash(MREC_AOT_ARGS);
+int mrec_fill_tail(MREC_AOT_ARGS);
 int mrec_push_rows_to_peers(MREC_AOT_ARGS);
 int mrec_peer_signal(MREC_AOT_ARGS);
 int mrec_peer_wait(MREC_AOT_ARGS);

@@ -169,19 +169,21 @@ __global__ void shard_offsets_kernel(const int32_t* __restrict__ ball, const int
   }
 }
 
-// rows[u, :] (4-byte elements, `width` per row) of my buckets -> owner o's inbox row inbox_off[o] + (u - B[me][o]).
-// transform_mod > 0: the element is an int32 owner-major key and is sent as key % transform_mod (local row id).
+// rows[u, :] (`width` elements of 4 or 8 bytes per row) of my buckets -> owner o's inbox row
+// inbox_off[o] + (u - B[me][o]).  transform_mod > 0: the element is an owner-major integer key and is sent as
+// key % transform_mod (the owner's local row id, or the original hash key).
+template <typename E>
 __global__ void __launch_bounds__(256)
-push_rows_to_peers_kernel(const uint32_t* __restrict__ rows, int width, const int32_t* __restrict__ my_bounds,
+push_rows_to_peers_kernel(const E* __restrict__ rows, int width, const int32_t* __restrict__ my_bounds,
                           const int32_t* __restrict__ inbox_off, const int64_t* __restrict__ peer_ptrs, int world,
-                          int transform_mod, int64_t cap_rows, int32_t* __restrict__ err) {
+                          int64_t transform_mod, int64_t cap_rows, int32_t* __restrict__ err) {
   __shared__ int32_t s_b[kPeerMaxRanks + 1];
   __shared__ int32_t s_off[kPeerMaxRanks];
-  __shared__ uint32_t* s_ptr[kPeerMaxRanks];
+  __shared__ E* s_ptr[kPeerMaxRanks];
   if (threadIdx.x <= world) s_b[threadIdx.x] = my_bounds[threadIdx.x];
   if (threadIdx.x < world) {
     s_off[threadIdx.x] = inbox_off[threadIdx.x];
-    s_ptr[threadIdx.x] = reinterpret_cast<uint32_t*>(peer_ptrs[threadIdx.x]);
+    s_ptr[threadIdx.x] = reinterpret_cast<E*>(peer_ptrs[threadIdx.x]);
   }
   __syncthreads();
   const int64_t total = (int64_t)s_b[world] * width;
@@ -195,10 +197,40 @@ push_rows_to_peers_kernel(const uint32_t* __restrict__ rows, int width, const in
       if (err) atomicOr(err, 2);
       continue;
     }
-    uint32_t v = rows[e];
-    if (transform_mod > 0) v = (uint32_t)((int32_t)v % transform_mod);
+    E v = rows[e];
+    if (transform_mod > 0) v = (E)((int64_t)v % transform_mod);
     s_ptr[o][drow * width + c] = v;
   }
+}
+
+// owner-major key of a hash-table key: key' = owner << bits | key with owner = (mix64(key) >> 40) mod G (high hash
+// bits: the table itself indexes its slots with the low ones).  Reserved (-1, -2), negative and >= 2^bits keys map
+// to G << bits, which the bounded dedup drops.
+__device__ __forceinline__ uint64_t peer_mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+template <typename KeyT>
+__global__ void shard_remap_hash_kernel(const KeyT* __restrict__ keys, int64_t* __restrict__ out, int64_t n, int world,
+                                        int bits) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = (int64_t)keys[i];
+    const bool ok = k >= 0 && (k >> bits) == 0;
+    const int64_t owner = (int64_t)((peer_mix64((uint64_t)k) >> 40) % (uint64_t)world);
+    out[i] = ok ? ((owner << bits) | k) : ((int64_t)world << bits);
+  }
+}
+
+// buf[i] = value for i >= *n_valid (the stale tail of a statically sized inbox)
+template <typename E>
+__global__ void fill_tail_kernel(E* __restrict__ buf, int64_t n, const int32_t* __restrict__ n_valid, const E* __restrict__ value) {
+  const int64_t first = max(0, n_valid[0]);
+  const E v = value[0];
+  for (int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = v;
 }
 
 // payload[K] -> every peer's payload slot, then (after a system fence) epoch -> every peer's flag slot.
@@ -253,14 +285,15 @@ MREC_API int mrec_shard_offsets(int nparam, void** params, int* ndims, int64_t**
   return check_launch("shard_offsets");
 }
 
-// in : rows[U_cap, W] f32|i32 (first B[me][G] rows valid), my_bounds[G+1] i32, inbox_off[G] i32, peer_ptrs[G] i64,
+// in : rows[U_cap, W] f32|i32|i64 (first B[me][G] rows valid), my_bounds[G+1] i32, inbox_off[G] i32, peer_ptrs[G] i64,
 //      cap_like[cap_rows, 0..] (shape carrier: capacity of every inbox in rows), mod_like[M, 0..] (M > 0 and rows
 //      int32: send rows % M; numel-0 tensor with M = 0 rows: no transform)         out: err[1] i32 (bit 1 = overflow)
 MREC_API int mrec_push_rows_to_peers(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
                                      void* stream, void* /*extra*/) {
   Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
   if (a.nparam != 7) return fail(ERR_NPARAM, "mrec_push_rows_to_peers: expected 7 params, got %d", a.nparam);
-  MREC_REQUIRE(a.is_f32(0) || a.is_i32(0), ERR_DTYPE, "mrec_push_rows_to_peers: rows must be 4-byte (f32|i32)");
+  const bool wide = a.is_i64(0);
+  MREC_REQUIRE(a.is_f32(0) || a.is_i32(0) || wide, ERR_DTYPE, "mrec_push_rows_to_peers: rows must be f32|i32|i64");
   MREC_REQUIRE(a.is_i32(1) && a.is_i32(2) && a.is_i64(3) && a.is_i32(6), ERR_DTYPE,
                "mrec_push_rows_to_peers: bounds/inbox_off/err int32, peer_ptrs int64");
   const int world = (int)a.numel(3);
@@ -269,11 +302,20 @@ MREC_API int mrec_push_rows_to_peers(int nparam, void** params, int* ndims, int6
   const int64_t n = a.ndims[0] >= 2 ? a.dim(0, 0) : a.numel(0);
   const int width = a.ndims[0] >= 2 ? (int)(a.numel(0) / (n > 0 ? n : 1)) : 1;
   const int64_t cap_rows = a.dim(4, 0);
-  const int mod = (int)a.dim(5, 0);
-  MREC_REQUIRE(mod == 0 || (a.is_i32(0) && width == 1), ERR_DTYPE, "mrec_push_rows_to_peers: the modulo transform is for int32 keys");
+  const int64_t mod = a.dim(5, 0);
+  MREC_REQUIRE(mod == 0 || ((a.is_i32(0) || wide) && width == 1), ERR_DTYPE,
+               "mrec_push_rows_to_peers: the modulo transform is for integer keys");
   if (n == 0) return OK;
-  MREC_LAUNCH(push_rows_to_peers_kernel, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<uint32_t>(0), width,
-              a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, mod, cap_rows, a.ptr<int32_t>(6));
+  if (wide) {
+    MREC_LAUNCH(push_rows_to_peers_kernel<int64_t>, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<int64_t>(0),
+                width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, mod, cap_rows, a.ptr<int32_t>(6));
+  } else if (a.is_i32(0)) {
+    MREC_LAUNCH(push_rows_to_peers_kernel<int32_t>, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<int32_t>(0),
+                width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, mod, cap_rows, a.ptr<int32_t>(6));
+  } else {
+    MREC_LAUNCH(push_rows_to_peers_kernel<uint32_t>, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<uint32_t>(0),
+                width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, (int64_t)0, cap_rows, a.ptr<int32_t>(6));
+  }
   return check_launch("push_rows_to_peers");
 }
 
@@ -304,4 +346,47 @@ MREC_API int mrec_peer_wait(int nparam, void** params, int* ndims, int64_t** sha
   MREC_LAUNCH(peer_wait_kernel, 1, 32, 0, a.stream, a.ptr<int32_t>(0), world, a.ptr<int32_t>(1), a.ptr<int32_t>(o),
               a.nparam == 4 ? a.ptr<int32_t>(2) : (int32_t*)nullptr, 8000000000ll);
   return check_launch("peer_wait");
+}
+
+// in : keys[N] i32|i64, owners_like[G, ..] (dim 0 = ranks), bits_like[B, ..] (dim 0 = key bits, B + log2 G < 63)
+// out: keys'[N] i64 = owner << B | key
+MREC_API int mrec_shard_remap_hash(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                   void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 4) return fail(ERR_NPARAM, "mrec_shard_remap_hash: expected 4 params, got %d", a.nparam);
+  MREC_REQUIRE((a.is_i32(0) || a.is_i64(0)) && a.is_i64(3), ERR_DTYPE, "mrec_shard_remap_hash: keys i32|i64, out i64");
+  MREC_REQUIRE(a.ndims[1] >= 1 && a.ndims[2] >= 1, ERR_SHAPE, "mrec_shard_remap_hash: owners_like[G,..], bits_like[B,..]");
+  const int64_t n = a.numel(0);
+  const int world = (int)a.dim(1, 0), bits = (int)a.dim(2, 0);
+  MREC_REQUIRE(a.numel(3) == n, ERR_SHAPE, "mrec_shard_remap_hash: out must match keys");
+  MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks && bits >= 1 && bits <= 56, ERR_SHAPE,
+               "mrec_shard_remap_hash: G in [1, 64], key bits in [1, 56]");
+  if (n == 0) return OK;
+  if (!a.params[0] || !a.params[3]) return fail(ERR_NULL, "mrec_shard_remap_hash: null keys/out");
+  if (a.is_i32(0))
+    MREC_LAUNCH(shard_remap_hash_kernel<int32_t>, grid_for(cdiv(n, 256), 8), 256, 0, a.stream, a.ptr<int32_t>(0),
+                a.ptr<int64_t>(3), n, world, bits);
+  else
+    MREC_LAUNCH(shard_remap_hash_kernel<int64_t>, grid_for(cdiv(n, 256), 8), 256, 0, a.stream, a.ptr<int64_t>(0),
+                a.ptr<int64_t>(3), n, world, bits);
+  return check_launch("shard_remap_hash");
+}
+
+// in : n_valid[1] i32, value[1] (dtype of buf)     out: buf[cap] i32|i64 — buf[i] = value for i >= n_valid
+MREC_API int mrec_fill_tail(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                            void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 3) return fail(ERR_NPARAM, "mrec_fill_tail: expected 3 params, got %d", a.nparam);
+  MREC_REQUIRE(a.is_i32(0) && (a.is_i32(2) || a.is_i64(2)) && strcmp(a.dtypes[1], a.dtypes[2]) == 0, ERR_DTYPE,
+               "mrec_fill_tail: n_valid int32, value and buf the same integer dtype");
+  MREC_REQUIRE(a.numel(0) >= 1 && a.numel(1) >= 1, ERR_SHAPE, "mrec_fill_tail: n_valid[1], value[1]");
+  const int64_t n = a.numel(2);
+  if (n == 0) return OK;
+  if (a.is_i32(2))
+    MREC_LAUNCH(fill_tail_kernel<int32_t>, grid_for(cdiv(n, 256), 4), 256, 0, a.stream, a.ptr<int32_t>(2), n, a.ptr<int32_t>(0),
+                a.ptr<int32_t>(1));
+  else
+    MREC_LAUNCH(fill_tail_kernel<int64_t>, grid_for(cdiv(n, 256), 4), 256, 0, a.stream, a.ptr<int64_t>(2), n, a.ptr<int32_t>(0),
+                a.ptr<int64_t>(1));
+  return check_launch("fill_tail");
 }

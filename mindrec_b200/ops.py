@@ -388,6 +388,20 @@ def shard_offsets(bounds_all, ctrl, dst_off, src_off, inbox_off, n_r):
     _lib.aot_call("mrec_shard_offsets", [bounds_all, ctrl, dst_off, src_off, inbox_off, n_r])
 
 
+def shard_remap_hash(keys, owners_like, bits_like, out=None):
+    """key -> (owner << B) | key with owner = hash(key) mod G (G, B = dim 0 of the two shape carriers)."""
+    if out is None:
+        out = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+    _lib.aot_call("mrec_shard_remap_hash", [keys, owners_like, bits_like, out])
+    return out
+
+
+def fill_tail(buf, n_valid, value):
+    """buf[i] = value for i >= n_valid (device-side count)."""
+    _lib.aot_call("mrec_fill_tail", [n_valid, value, buf])
+    return buf
+
+
 def push_rows_to_peers(rows, my_bounds, inbox_off, peer_ptrs, cap_like, mod_like, err):
     _lib.aot_call("mrec_push_rows_to_peers", [rows, my_bounds, inbox_off, peer_ptrs, cap_like, mod_like, err])
 

@@ -207,6 +207,195 @@ class EmulatedPeerGroup:
         return wide, deep
 
 
+_HASH_BUFFERS = ("ball", "keys_in", "land", "grad_in", "flags")
+
+
+class PeerHashRank:
+    """One rank of a MapParameter sharded by owner = hash(key) mod G: every rank owns an independent
+    open-addressing table (mindrec_b200.hash.MapParameter) plus LazyAdam moments addressed by slot.
+
+    Same four-phase exchange as PeerRank; what differs is the key handling: keys are int64 in [0, 2^key_bits),
+    made owner-major as owner << key_bits | key (mrec_shard_remap_hash) so one bounded sort dedups and buckets
+    them; the owner gets the ORIGINAL key back (key' % 2^key_bits), runs find-or-insert on its table (admission /
+    eviction counters live there), initialises rows of new keys (Philox keyed by the key, so a key's first row does
+    not depend on G) and serves rows by slot.  The stale tail of the static key inbox is blanked with the
+    reserved key -1 so that it cannot touch the table."""
+
+    def __init__(self, rank, world, emb_dim, n_lookups, device, alloc, key_bits=40, capacity=1 << 16, seed=0,
+                 learning_rate=1e-3, loss_scale=1.0, permit_filter_value=1, evict_filter_value=None, cap_rows=None):
+        from . import hash as _hash
+        self.rank, self.world, self.dim, self.n = rank, world, emb_dim, n_lookups
+        self.bits = int(key_bits)
+        if world << self.bits >= 1 << 62:
+            raise ValueError("key_bits + log2(world) must stay below 62")
+        self.device = torch.device(device)
+        dev, g = self.device, world
+        self.cap = int(cap_rows or n_lookups)
+        self.table = _hash.MapParameter(key_dtype=torch.int64, value_shape=emb_dim, default_value="normal",
+                                        permit_filter_value=permit_filter_value,
+                                        evict_filter_value=evict_filter_value or _hash.MAX_SIZE, capacity=capacity,
+                                        device=dev, seed=seed)
+        self.m, self.v = self.table.add_arena(0.0), self.table.add_arena(0.0)
+        self.hyper = ops.adam_hyper(learning_rate, loss_scale=loss_scale, device=dev)
+        i32, i64, f32 = torch.int32, torch.int64, torch.float32
+        self.buf = {"ball": alloc("ball", (g * (g + 1),), i32), "keys_in": alloc("keys_in", (self.cap,), i64),
+                    "land": alloc("land", (self.cap, emb_dim), f32), "grad_in": alloc("grad_in", (self.cap, emb_dim), f32),
+                    "flags": alloc("flags", (N_PHASES * g,), i32)}
+        self.buf["ball"].zero_()
+        self.buf["flags"].zero_()
+        self.buf["keys_in"].fill_(-1)
+        self.ctrl = torch.tensor([rank, world], dtype=i32, device=dev)
+        self.epoch = [torch.zeros(1, dtype=i32, device=dev) for _ in range(N_PHASES)]
+        self.err = torch.zeros(1, dtype=i32, device=dev)
+        self.bounds = torch.zeros(g + 1, dtype=i32, device=dev)
+        self.dst_off = torch.zeros(g, dtype=i32, device=dev)
+        self.src_off = torch.zeros(g + 1, dtype=i32, device=dev)
+        self.inbox_off = torch.zeros(g, dtype=i32, device=dev)
+        self.n_r = torch.zeros(1, dtype=i32, device=dev)
+        self.edges = torch.arange(g + 1, device=dev, dtype=i64) << self.bits
+        self.key = torch.empty(n_lookups, dtype=i64, device=dev)
+        self.uq = ops.UniqueResult(n_lookups, i64, dev)
+        self.uq_owner = ops.UniqueResult(self.cap, i32, dev)
+        self.gs = torch.empty((n_lookups, emb_dim), dtype=f32, device=dev)
+        self._bound_like = torch.empty((g << self.bits, 0), device=dev)
+        self._owners_like = torch.empty((g, 0), device=dev)
+        self._bits_like = torch.empty((self.bits, 0), device=dev)
+        self._mod_keys = torch.empty((1 << self.bits, 0), device=dev)
+        self._mod_none = torch.empty((0, 0), device=dev)
+        self._cap_like = torch.empty((self.cap, 0), device=dev)
+        self._slot_like = torch.empty((self.table.capacity, 0), device=dev)      # slot C (default row) is out of range
+        self._minus_one = torch.tensor([-1], dtype=i64, device=dev)
+        self._no_payload = torch.empty(0, dtype=i32, device=dev)
+        self.flag_views = [self.buf["flags"][ph * g:(ph + 1) * g] for ph in range(N_PHASES)]
+        self.slots = None
+        self.ptrs = None
+
+    def connect(self, base_ptrs):
+        g, me, dev = self.world, self.rank, self.device
+        t = lambda lst: torch.tensor(lst, dtype=torch.int64, device=dev)
+        self.ptrs = {"ball_row": t([base_ptrs["ball"][s] + me * (g + 1) * 4 for s in range(g)]),
+                     "keys_in": t(base_ptrs["keys_in"]), "land": t(base_ptrs["land"]), "grad_in": t(base_ptrs["grad_in"]),
+                     "flag": [t([base_ptrs["flags"][s] + (ph * g + me) * 4 for s in range(g)]) for ph in range(N_PHASES)],
+                     "none": t([0] * g)}
+
+    signal = PeerRank.signal
+    wait = PeerRank.wait
+
+    def p_plan_publish(self, keys):
+        ops.shard_remap_hash(keys.reshape(-1), self._owners_like, self._bits_like, out=self.key)
+        ops.unique(self.key, table_like=self._bound_like, result=self.uq, ws_tag="unique_peerhash_plan")
+        ops.shard_bounds(self.uq.uniq, self.uq.count, self.edges, out=self.bounds)
+        self.signal(0, self.bounds, self.ptrs["ball_row"])
+
+    def p_keys(self):
+        ops.shard_offsets(self.buf["ball"], self.ctrl, self.dst_off, self.src_off, self.inbox_off, self.n_r)
+        ops.push_rows_to_peers(self.uq.uniq, self.bounds, self.inbox_off, self.ptrs["keys_in"], self._cap_like,
+                               self._mod_keys, self.err)
+        self.signal(1)
+
+    def p_serve(self):
+        ops.fill_tail(self.buf["keys_in"], self.n_r, self._minus_one)
+        self.slots = self.table.lookup_slots(self.buf["keys_in"], insert_default_value=True)
+        ops.gather_to_peers(self.table.values, self.slots, self.ptrs["land"], self.dst_off, self.src_off)
+        self.signal(2)
+
+    def p_expand(self, out):
+        """out[..., D] = rows of the looked-up keys (keys.shape + (D,))."""
+        ops.gather(self.buf["land"], self.uq.inverse, out=out.view(self.n, self.dim))
+
+    def p_grads(self, g_out):
+        ops.segment_sum(g_out.reshape(self.n, self.dim), None, self.uq, dim=self.dim, out=self.gs)
+        ops.push_rows_to_peers(self.gs, self.bounds, self.inbox_off, self.ptrs["grad_in"], self._cap_like,
+                               self._mod_none, self.err)
+        self.signal(3)
+
+    def p_update(self):
+        c = self.table.capacity
+        uq2 = ops.unique(self.slots, table_like=self._slot_like, result=self.uq_owner, ws_tag="unique_peerhash_owner",
+                         n_valid=self.n_r)
+        ops.adam_begin_step(self.hyper)
+        ops.sparse_lazy_adam(self.table.values[:c], self.m[:c], self.v[:c], self.hyper, self.buf["grad_in"], None, uq2,
+                             n_valid=self.n_r)
+
+
+class EmulatedPeerHashGroup:
+    """G PeerHashRank on one GPU in phase-major order (tests)."""
+
+    def __init__(self, world, emb_dim, n_lookups, device, **kw):
+        def alloc(name, shape, dtype):
+            return torch.empty(shape, dtype=dtype, device=device)
+        self.ranks = [PeerHashRank(r, world, emb_dim, n_lookups, device, alloc, **kw) for r in range(world)]
+        base = {name: [rk.buf[name].data_ptr() for rk in self.ranks] for name in _HASH_BUFFERS}
+        for rk in self.ranks:
+            rk.connect(base)
+
+    def forward(self, keys_list, outs):
+        for rk, keys in zip(self.ranks, keys_list):
+            rk.p_plan_publish(keys)
+        for rk in self.ranks:
+            rk.wait(0)
+            rk.p_keys()
+        for rk in self.ranks:
+            rk.wait(1)
+            rk.p_serve()
+        for rk, out in zip(self.ranks, outs):
+            rk.wait(2)
+            rk.p_expand(out)
+
+    def backward(self, grads):
+        for rk, g in zip(self.ranks, grads):
+            rk.p_grads(g)
+        for rk in self.ranks:
+            rk.wait(3)
+            rk.p_update()
+
+    def get_data(self):
+        """All (key, row) pairs of the G tables, sorted by key."""
+        ks, vs = zip(*[rk.table.get_data() for rk in self.ranks])
+        k, v = torch.cat(ks), torch.cat(vs)
+        order = torch.argsort(k)
+        return k[order], v[order]
+
+
+class PeerShardedHashEmbedding:
+    """Multi-process form of PeerHashRank (one rank per GPU, CUDA-IPC inboxes): `lookup(keys)` returns the rows,
+    `update(g_out)` applies LazyAdam to the owners' rows.  Mirrors HashEmbeddingLookup(sparse=True) + LazyAdam on a
+    MapParameter (mindspore_rec/ops/embedding.py:85-206, wide_and_deep.py:415-422) under row sharding."""
+
+    def __init__(self, emb_dim, n_lookups, device, group=None, **kw):
+        self.group = group
+        arena = _IpcArena(group)
+        self.rk = PeerHashRank(dist.get_rank(group), dist.get_world_size(group), emb_dim, n_lookups, device,
+                               arena.alloc(device), **kw)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        self.rk.connect(arena.exchange())
+        dist.barrier(group=group)
+        self.dim = emb_dim
+
+    def lookup(self, keys, out=None):
+        rk = self.rk
+        if out is None:
+            out = torch.empty(tuple(keys.shape) + (self.dim,), dtype=torch.float32, device=keys.device)
+        rk.p_plan_publish(keys)
+        rk.wait(0)
+        rk.p_keys()
+        rk.wait(1)
+        rk.p_serve()
+        rk.wait(2)
+        rk.p_expand(out)
+        return out
+
+    def update(self, g_out):
+        rk = self.rk
+        rk.p_grads(g_out)
+        rk.wait(3)
+        rk.p_update()
+
+    def error_flags(self):
+        return int(self.rk.err.item()) | (4 if self.rk.table.overflowed else 0)
+
+
 class _IpcArena:
     """cudaMalloc'ed buffers exported to the other ranks of the node with CUDA IPC."""
 
@@ -225,7 +414,7 @@ class _IpcArena:
             nbytes = 1
             for d in shape:
                 nbytes *= d
-            nbytes = max(nbytes * 4, 256)
+            nbytes = max(nbytes * (8 if dtype == torch.int64 else 4), 256)
             ptr = self.lib.mrec_peer_alloc(nbytes)
             if not ptr:
                 raise RuntimeError("mrec_peer_alloc failed: " + _lib.last_error())
@@ -233,7 +422,7 @@ class _IpcArena:
             if self.lib.mrec_ipc_get_handle(ctypes.c_void_p(ptr), h) != 0:
                 raise RuntimeError("mrec_ipc_get_handle failed: " + _lib.last_error())
             self.local[name] = (ptr, h.raw)
-            typestr = "<i4" if dtype == torch.int32 else "<f4"
+            typestr = {torch.int32: "<i4", torch.int64: "<i8"}.get(dtype, "<f4")
             return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)
         return _alloc
 

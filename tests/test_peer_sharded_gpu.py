@@ -154,3 +154,69 @@ def test_row_updates_with_device_valid_count_ignore_the_padding(cuda, dim):
     want = run(ids[:n_valid].copy(), g[:n_valid].copy(), None)   # the exact-size call
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_emulated_hash_sharding_matches_one_table(cuda, world):
+    """MapParameter sharded by hash(key) mod G: rows are bit-identical to ONE table fed the same keys
+    (a key's initial row is keyed by the key, not by its slot or owner), and after LazyAdam the union of the G
+    tables equals the single table."""
+    from mindrec_b200 import hash as H
+    dim, n, bits = 16, 400, 40
+    rng = np.random.default_rng(world)
+    grp = peer_sharded.EmulatedPeerHashGroup(world, dim, n, cuda, key_bits=bits, capacity=1 << 12, seed=7,
+                                             learning_rate=1e-2)
+    one = H.MapParameter(key_dtype=torch.int64, value_shape=dim, default_value="normal", capacity=1 << 14,
+                         device=cuda, seed=7)
+    m1, v1 = one.add_arena(0.0), one.add_arena(0.0)
+    hyper = ops.adam_hyper(1e-2, device=cuda)
+    pool = rng.integers(0, 1 << bits, size=3000)
+    for step in range(3):
+        keys = [rng.choice(pool[: 1000 * (step + 1)], size=n) for _ in range(world)]        # new keys every step
+        for k in keys:
+            k[:20] = pool[:20]                                                              # shared across ranks
+        grads = [rng.standard_normal((n, dim)).astype(np.float32) for _ in range(world)]
+        keys_t = [torch.from_numpy(k).to(cuda) for k in keys]
+        outs = [torch.empty((n, dim), device=cuda) for _ in range(world)]
+        grp.forward(keys_t, outs)
+        all_keys = torch.cat(keys_t)
+        slots = one.lookup_slots(all_keys).clone()
+        want = ops.gather(one.values, slots).view(world, n, dim)
+        for r in range(world):
+            if step == 0:                            # fresh rows: bit-identical (initialisation keyed by the key)
+                assert torch.equal(outs[r], want[r])
+            else:                                    # updated rows: the gradient sums associate differently
+                torch.testing.assert_close(outs[r], want[r], rtol=1e-5, atol=1e-7)
+        grp.backward([torch.from_numpy(g).to(cuda) for g in grads])
+        ops.adam_begin_step(hyper)
+        uq = ops.unique(slots, table_like=torch.empty((one.capacity, 0), device=cuda))
+        c = one.capacity
+        ops.sparse_lazy_adam(one.values[:c], m1[:c], v1[:c], hyper, torch.from_numpy(np.concatenate(grads)).to(cuda), None, uq)
+        torch.cuda.synchronize()
+        for rk in grp.ranks:
+            assert int(rk.err.item()) == 0 and not rk.table.overflowed
+        k_sh, v_sh = grp.get_data()
+        k_1, v_1 = one.get_data()
+        order = torch.argsort(k_1)
+        assert torch.equal(k_sh, k_1[order])
+        torch.testing.assert_close(v_sh, v_1[order], rtol=1e-5, atol=1e-7)
+    assert sum(len(rk.table) for rk in grp.ranks) == len(one)
+    if world > 1:                                   # the owner function spreads the keys
+        sizes = [len(rk.table) for rk in grp.ranks]
+        assert min(sizes) > 0.5 * len(one) / world
+
+
+def test_shard_remap_hash_and_fill_tail(cuda):
+    g, bits = 4, 20
+    keys = torch.tensor([0, 5, (1 << bits) - 1, 1 << bits, -1, -2, -7, 123456], dtype=torch.int64, device=cuda)
+    out = ops.shard_remap_hash(keys, torch.empty((g, 0), device=cuda), torch.empty((bits, 0), device=cuda)).tolist()
+    for k, o in zip(keys.tolist(), out):
+        if 0 <= k < (1 << bits):
+            assert o & ((1 << bits) - 1) == k and 0 <= (o >> bits) < g
+        else:
+            assert o == g << bits
+    k32 = keys[:3].to(torch.int32)
+    assert ops.shard_remap_hash(k32, torch.empty((g, 0), device=cuda), torch.empty((bits, 0), device=cuda)).tolist() == out[:3]
+    buf = torch.arange(10, dtype=torch.int64, device=cuda)
+    ops.fill_tail(buf, torch.tensor([4], dtype=torch.int32, device=cuda), torch.tensor([-1], dtype=torch.int64, device=cuda))
+    assert buf.tolist() == [0, 1, 2, 3] + [-1] * 6
