@@ -4,7 +4,8 @@
 
 G ranks look up and LazyAdam-update rank-specific int64 keys through peer_sharded.PeerShardedHashEmbedding
 (owner = hash(key) mod G, device-driven exchange over CUDA-IPC peer memory) for 3 steps; rank 0 replays all ranks'
-keys and gradients on ONE MapParameter and the union of the G tables must equal it.
+keys and gradients on ONE MapParameter and the union of the G tables must equal it (1e-5 relative; the gradients
+are kept positive so that per-key sums do not cancel — a cancelling fp32 sum has no 1e-5 relative meaning).
 """
 import os
 import sys
@@ -26,7 +27,7 @@ def main():
     emb = peer_sharded.PeerShardedHashEmbedding(dim, n, dev, key_bits=bits, capacity=1 << 17, seed=11, learning_rate=1e-2)
     rng = np.random.default_rng(5)                       # same stream on every rank: everybody knows all batches
     pool = rng.integers(0, 1 << bits, size=60000)
-    batches = [[(rng.choice(pool[: 20000 * (s + 1)], size=n), rng.standard_normal((n, dim)).astype(np.float32))
+    batches = [[(rng.choice(pool[: 20000 * (s + 1)], size=n), (np.abs(rng.standard_normal((n, dim))) + 0.5).astype(np.float32))
                 for _ in range(world)] for s in range(steps)]
     outs = []
     for s in range(steps):
