@@ -147,6 +147,11 @@ int mrec_sparse_ftrl(MREC_AOT_ARGS);
  *   in : g mask perm seg_start seg_of     out: gsum[N,D] f32 (rows >= count untouched),
  *        workspace[mrec_segment_sum_workspace_bytes(N, D)]                                        */
 int mrec_segment_sum(MREC_AOT_ARGS);
+/* Dense gradient of a non-sparse Gather (bprop = UnsortedSegmentSum into [V,D]; the multitable model,
+ * models/wide_and_deep_multitable/src/wide_and_deep.py:291-346, looks one table up from several inputs):
+ *   in : g[N/div,D] f32|f16, mask[N|0], uniq[N], perm[N], seg_start[N+1], seg_of[N]
+ *   out: table[V,D] f32 with table[uniq[u]] += segment sum (accumulates over calls; no atomics), workspace */
+int mrec_segment_sum_scatter_add(MREC_AOT_ARGS);
 /* nn.Adam (not Lazy) with a RowTensor gradient = dense-equivalent update of the WHOLE table (every
  * row's moments decay; wide_and_deep.py:435-437 when sparse=True on one device):
  *   in : w m v hyper[16] g mask uniq perm seg_start seg_of row_flags[V] u8 (zero on entry and exit)

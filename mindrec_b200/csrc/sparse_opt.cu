@@ -233,6 +233,35 @@ struct FtrlSink<float, IdT> {
   }
 };
 
+// Dense-gradient accumulation (UnsortedSegmentSum into a [V, D] gradient table, the bprop of a non-sparse
+// `Gather`): table[uniq[seg]] += sum.  Rows of one call are distinct, so there are no atomics and the result is
+// deterministic; several calls (several inputs looking up the same table) accumulate in call order.
+template <typename Vec, typename IdT>
+struct ScatterAddSink {
+  static constexpr bool kApplyComplete = true;
+  struct State { Vec a; };
+  Vec* table;
+  const IdT* uniq;
+  int64_t vocab;
+  int cpr;
+  __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
+  __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
+  __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = table[o]; }
+  __device__ __forceinline__ void fence(State& s) const { reg_fence(s.a); }
+  __device__ __forceinline__ void finish(int64_t o, State& s, const Vec& gs) const {
+    Vec t = s.a;
+    VOps<Vec>::add(t, gs);
+    table[o] = t;
+  }
+  __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const {
+    const int64_t row = row_of(seg);
+    if (!in_range(row)) return;
+    State s;
+    load(row * cpr + c, s);
+    finish(row * cpr + c, s, gs);
+  }
+};
+
 // ---- kernel A: walk tiles ----
 template <typename Vec, typename GT, bool HAS_MASK>
 __global__ void __launch_bounds__(kSegThreads, 3)
@@ -912,6 +941,43 @@ MREC_API int mrec_segment_sum(int nparam, void** params, int* ndims, int64_t** s
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_segment_sum: D too large");
   return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, a.params[6],
                            ws_bytes, NoSink{}, a.stream, a.ptr<float>(5));
+}
+
+
+// Dense gradient of a (non-sparse) Gather, accumulated: table[uniq[u], :] += sum of segment u.
+// inputs : g[N/div,D] mask[N|0] uniq[N] perm[N] seg_start[N+1] seg_of[N]
+// outputs: table[V,D] f32 (accumulated in place), workspace[mrec_sparse_opt_workspace_bytes]
+MREC_API int mrec_segment_sum_scatter_add(int nparam, void** params, int* ndims, int64_t** shapes,
+                                          const char** dtypes, void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 8);
+  MREC_REQUIRE(a.is_f32(6), ERR_DTYPE, "mrec_segment_sum_scatter_add: table must be float32");
+  const int64_t vocab = a.dim(6, 0);
+  const int dim = a.ndims[6] >= 2 ? (int)a.dim(6, 1) : 1;
+  SegArgs s;
+  int rc = parse_seg_args(a, 0, dim, true, &s, "mrec_segment_sum_scatter_add");
+  if (rc) return rc;
+  const size_t ws_bytes = (size_t)a.numel(7);
+  void* ws = a.params[7];
+  if (s.n == 0 || vocab == 0) return OK;
+  if (dim % 4 == 0) {
+    MREC_REQUIRE(a.aligned(6, 16), ERR_ALIGN, "mrec_segment_sum_scatter_add: table must be 16-byte aligned");
+    MREC_REQUIRE(dim / 4 <= kSegThreads, ERR_DIM, "mrec_segment_sum_scatter_add: D too large");
+    const int cpr = dim / 4;
+    if (s.uniq64) {
+      ScatterAddSink<float4, int64_t> sink{a.ptr<float4>(6), reinterpret_cast<const int64_t*>(s.uniq), vocab, cpr};
+      return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+    }
+    ScatterAddSink<float4, int32_t> sink{a.ptr<float4>(6), reinterpret_cast<const int32_t*>(s.uniq), vocab, cpr};
+    return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  }
+  MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_segment_sum_scatter_add: D too large");
+  if (s.uniq64) {
+    ScatterAddSink<float, int64_t> sink{a.ptr<float>(6), reinterpret_cast<const int64_t*>(s.uniq), vocab, dim};
+    return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
+  }
+  ScatterAddSink<float, int32_t> sink{a.ptr<float>(6), reinterpret_cast<const int32_t*>(s.uniq), vocab, dim};
+  return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream);
 }
 
 

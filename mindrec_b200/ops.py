@@ -176,6 +176,15 @@ def segment_sum(g, mask, uq, dim=None, out=None):
     return out
 
 
+def segment_sum_scatter_add(table, g, mask, uq):
+    """table[uq.uniq[u]] += segment sum u (dense gradient of a non-sparse Gather; accumulates over calls)."""
+    dim = table.shape[1] if table.dim() == 2 else 1
+    mask = _empty_mask(table.device) if mask is None else mask.reshape(-1)
+    _lib.aot_call("mrec_segment_sum_scatter_add", [g, mask, uq.uniq, uq.perm, uq.seg_start, uq.seg_of, table,
+                                                   _opt_ws(uq.n, dim, table.device)])
+    return table
+
+
 def sparse_lazy_adam(w, m, v, hyper, g, mask, uq, n_valid=None):
     """Fused segment-sum + LazyAdam row update on the rows named by uq.uniq (in place).
     n_valid (device int32[1]): only the first n_valid sorted positions are real (static inbox)."""

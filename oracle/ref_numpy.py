@@ -529,3 +529,97 @@ def gather_pool(table, ids, mask):
     — models/wide_and_deep_multitable/src/wide_and_deep.py:301-307."""
     e = gather(table, ids).astype(np.float64) * np.asarray(mask, dtype=np.float64)[..., None]
     return e.mean(axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# a15  Wide&Deep multitable (models/wide_and_deep_multitable/src/wide_and_deep.py)
+# ------------------------------------------------------------------------------------------------
+class MultitableOracle:
+    """models/wide_and_deep_multitable/src/wide_and_deep.py:271-427 (forward), :431-480 (loss), :495-600 (step),
+    DenseLayers in fp32 arithmetic.  `deep` / `wide` are dicts of float32 arrays under the reference's parameter
+    names (wide vectors [V,1]); every `P.Gather` has a dense gradient, so every parameter takes a dense optimizer
+    step: FTRL(lr, l1=l2=5e-4, initial_accum=0.1) on the "wide" names (wide_bias included), Adam(lr, eps=1e-6) on
+    the rest.  multi: list of six (ids [B,S], mask [B,S])."""
+
+    def __init__(self, deep, wide, mlp_w, mlp_b, adam_lr=3e-3, ftrl_lr=0.1, sens=1000.0):
+        self.deep = {k: v.astype(F32).copy() for k, v in deep.items()}
+        self.wide = {k: v.astype(F32).copy() for k, v in wide.items()}
+        self.mlp_w = [w.astype(F32).copy() for w in mlp_w]
+        self.mlp_b = [b.astype(F32).copy() for b in mlp_b]
+        self.sens = sens
+        self.adam = AdamState(adam_lr, eps=1e-6, loss_scale=sens)
+        self.ftrl = FtrlState(ftrl_lr, l1=5e-4, l2=5e-4, loss_scale=sens)
+        z = np.zeros_like
+        self.mv = {k: (z(v), z(v)) for k, v in self.deep.items()}
+        self.mv_w = [(z(w), z(w)) for w in self.mlp_w]
+        self.mv_b = [(z(b), z(b)) for b in self.mlp_b]
+        self.al = {k: (np.full_like(v, 0.1), z(v)) for k, v in self.wide.items()}
+
+    def forward(self, continue_val, indicator_id, emb_128_id, emb_64_single_id, multi):
+        b = continue_val.shape[0]
+        d, w = self.deep, self.wide
+        cv = continue_val.astype(np.float64)
+        parts = [cv, gather(d["emb64_indicator"], indicator_id).reshape(b, -1),
+                 gather(d["emb128_embedding"], emb_128_id).reshape(b, -1),
+                 gather(d["emb64_single"], emb_64_single_id).reshape(b, -1)]
+        parts += [gather_pool(d["emb64_multi"], ids, m) for ids, m in multi]
+        x = np.concatenate([p.astype(np.float64) for p in parts], axis=1)
+        deep_out, acts = _mlp_forward(x, self.mlp_w, self.mlp_b)
+        ones = lambda ids: np.ones(ids.shape)
+        wide = (cv * w["wide_continue_w"].astype(np.float64)[None, :]).sum(1, keepdims=True)
+        wide = wide + gather_reduce(w["wide_indicator_w"], indicator_id, ones(indicator_id))
+        wide = wide + gather_reduce(w["wide_emb128_w"], emb_128_id, ones(emb_128_id))
+        wide = wide + gather_reduce(w["wide_emb64_single_w"], emb_64_single_id, ones(emb_64_single_id))
+        for ids, m in multi:
+            wide = wide + gather_reduce(w["wide_emb64_multi_w"], ids, m)
+        wide = wide + w["wide_bias"].astype(np.float64)
+        return wide + deep_out, acts
+
+    def step(self, label, continue_val, indicator_id, emb_128_id, emb_64_single_id, multi):
+        b = continue_val.shape[0]
+        d, w = self.deep, self.wide
+        logit, acts = self.forward(continue_val, indicator_id, emb_128_id, emb_64_single_id, multi)
+        label = np.asarray(label, dtype=np.float64).reshape(-1, 1)
+        loss = sigmoid_xent(logit, label).mean()
+        delta = self.sens * (sigmoid(logit) - label) / b
+        gx, gw, gb = _mlp_backward(delta, acts, self.mlp_w)
+        nf = continue_val.shape[1]
+        gd = {}
+        o = nf
+        n = indicator_id.shape[1] * 64
+        gd["emb64_indicator"] = _scatter_rows(d["emb64_indicator"].shape, indicator_id, gx[:, o:o + n].reshape(-1, 64),
+                                              np.ones(indicator_id.size)); o += n
+        n = emb_128_id.shape[1] * 128
+        gd["emb128_embedding"] = _scatter_rows(d["emb128_embedding"].shape, emb_128_id, gx[:, o:o + n].reshape(-1, 128),
+                                               np.ones(emb_128_id.size)); o += n
+        n = emb_64_single_id.shape[1] * 64
+        gd["emb64_single"] = _scatter_rows(d["emb64_single"].shape, emb_64_single_id, gx[:, o:o + n].reshape(-1, 64),
+                                           np.ones(emb_64_single_id.size)); o += n
+        gd["emb64_multi"] = np.zeros(d["emb64_multi"].shape)
+        for ids, m in multi:
+            s = ids.shape[1]
+            gd["emb64_multi"] += _scatter_rows(d["emb64_multi"].shape, ids, gx[:, o:o + 64],
+                                               np.asarray(m, dtype=np.float64) / s, div=s)
+            o += 64
+        gwd = {"wide_continue_w": (delta * continue_val.astype(np.float64)).sum(0),
+               "wide_bias": np.array([delta.sum()]),
+               "wide_indicator_w": _scatter_rows(w["wide_indicator_w"].shape, indicator_id, delta,
+                                                 np.ones(indicator_id.size), div=indicator_id.shape[1]),
+               "wide_emb128_w": _scatter_rows(w["wide_emb128_w"].shape, emb_128_id, delta, np.ones(emb_128_id.size),
+                                              div=emb_128_id.shape[1]),
+               "wide_emb64_single_w": _scatter_rows(w["wide_emb64_single_w"].shape, emb_64_single_id, delta,
+                                                    np.ones(emb_64_single_id.size), div=emb_64_single_id.shape[1]),
+               "wide_emb64_multi_w": np.zeros(w["wide_emb64_multi_w"].shape)}
+        for ids, m in multi:
+            gwd["wide_emb64_multi_w"] += _scatter_rows(w["wide_emb64_multi_w"].shape, ids, delta, m, div=ids.shape[1])
+        for k in w:
+            acc, lin = self.al[k]
+            ftrl_dense(w[k], acc, lin, gwd[k].reshape(w[k].shape), self.ftrl)
+        self.adam.begin_step()
+        for k in d:
+            mm, vv = self.mv[k]
+            adam_dense(d[k], mm, vv, gd[k], self.adam)
+        for i in range(len(self.mlp_w)):
+            adam_dense(self.mlp_w[i], self.mv_w[i][0], self.mv_w[i][1], gw[i], self.adam)
+            adam_dense(self.mlp_b[i], self.mv_b[i][0], self.mv_b[i][1], gb[i], self.adam)
+        return F32(loss)
