@@ -297,6 +297,7 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     step.capture(*devb[0], warmup=3)
     per_step_launches = (_lib.launch_count() - launches0) // 4  # 3 warm-up steps + 1 captured
+    per_step_launches = getattr(step, "launches_per_step", per_step_launches)   # counted while capturing, if offered
 
     def barrier():
         if world > 1:

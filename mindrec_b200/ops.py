@@ -86,17 +86,35 @@ def gather_pool(table, ids, mask, out=None, oob_flag=None):
 # K2 unique
 # ------------------------------------------------------------------------------------------------
 class UniqueResult:
-    """Outputs of mrec_unique (all padded to N; `count` is a device scalar)."""
-    __slots__ = ("uniq", "inverse", "count", "perm", "seg_start", "seg_of", "n")
+    """Outputs of mrec_unique (all padded to N; `count` is a device scalar).  packed=True (int32 keys) carves all
+    of them out of ONE buffer (`flat`), so a whole result can be copied with a single device copy."""
+    __slots__ = ("uniq", "inverse", "count", "perm", "seg_start", "seg_of", "n", "flat")
 
-    def __init__(self, n, dtype, device):
+    def __init__(self, n, dtype, device, packed=False):
         self.n = n
+        self.flat = None
+        if packed and dtype == torch.int32:
+            a = (n + 3) // 4 * 4                              # every field starts 16-byte aligned
+            b = (n + 1 + 3) // 4 * 4
+            self.flat = torch.zeros(4 * a + b + 4, dtype=torch.int32, device=device)
+            f = self.flat
+            self.uniq, self.inverse, self.perm, self.seg_of = f[0:n], f[a:a + n], f[2 * a:2 * a + n], f[3 * a:3 * a + n]
+            self.seg_start = f[4 * a:4 * a + n + 1]
+            self.count = f[4 * a + b:4 * a + b + 1]
+            return
         self.uniq = torch.empty(n, dtype=dtype, device=device)
         self.inverse = torch.empty(n, dtype=torch.int32, device=device)
         self.count = torch.zeros(1, dtype=torch.int32, device=device)
         self.perm = torch.empty(n, dtype=torch.int32, device=device)
         self.seg_start = torch.empty(n + 1, dtype=torch.int32, device=device)
         self.seg_of = torch.empty(n, dtype=torch.int32, device=device)
+
+    def copy_from(self, other):
+        if self.flat is not None and other.flat is not None and self.flat.numel() == other.flat.numel():
+            self.flat.copy_(other.flat)
+        else:
+            for d, s_ in zip(self.outputs(), other.outputs()):
+                d.copy_(s_)
 
     def outputs(self):
         return [self.uniq, self.inverse, self.count, self.perm, self.seg_start, self.seg_of]
@@ -105,6 +123,7 @@ class UniqueResult:
         """A view of these buffers for a dedup of n <= self.n keys (data-dependent sizes without reallocation)."""
         v = UniqueResult.__new__(UniqueResult)
         v.n = n
+        v.flat = None
         v.uniq, v.inverse, v.count = self.uniq[:n], self.inverse[:n], self.count
         v.perm, v.seg_start, v.seg_of = self.perm[:n], self.seg_start[:n + 1], self.seg_of[:n]
         return v

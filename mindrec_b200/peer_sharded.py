@@ -73,7 +73,11 @@ class PeerRank:
         self.n_r = torch.zeros(1, dtype=i32, device=dev)
         self.edges = (torch.arange(g + 1, device=dev, dtype=i32) * r)
         self.key = torch.empty(n_lookups, dtype=i32, device=dev)
-        self.uq = ops.UniqueResult(n_lookups, i32, dev)
+        self.uq = ops.UniqueResult(n_lookups, i32, dev, packed=True)
+        # the NEXT batch's local plan (remap + dedup + bounds), computed one step ahead under the DenseLayers
+        self.key_n = torch.empty(n_lookups, dtype=i32, device=dev)
+        self.uq_n = ops.UniqueResult(n_lookups, i32, dev, packed=True)
+        self.bounds_n = torch.zeros(g + 1, dtype=i32, device=dev)
         self.uq_owner = ops.UniqueResult(self.cap, i32, dev)
         self.gs_deep = torch.empty((n_lookups, emb_dim), dtype=f32, device=dev)
         self.gs_wide = torch.empty((n_lookups, 1), dtype=f32, device=dev)
@@ -111,11 +115,24 @@ class PeerRank:
         ops.peer_wait(self.flag_views[phase], self.epoch[phase], self.err)
 
     # ---- phases --------------------------------------------------------------------------------------
-    def p_plan_publish(self, ids):
-        ops.shard_remap(ids.reshape(-1), self._vocab_like, self._owners_like, out=self.key)
-        ops.unique(self.key, table_like=self._bound_like, result=self.uq, ws_tag="unique_peer_plan")
-        ops.shard_bounds(self.uq.uniq, self.uq.count, self.edges, out=self.bounds)
+    def p_plan_local(self, ids, nxt=False):
+        """The rank-local part of the plan: owner-major remap, dedup, bucket bounds.  nxt=True writes the look-ahead
+        buffers (p_adopt moves them in at the start of the next step)."""
+        key, uq, bounds = (self.key_n, self.uq_n, self.bounds_n) if nxt else (self.key, self.uq, self.bounds)
+        ops.shard_remap(ids.reshape(-1), self._vocab_like, self._owners_like, out=key)
+        ops.unique(key, table_like=self._bound_like, result=uq, ws_tag="unique_peer_plan_next" if nxt else "unique_peer_plan")
+        ops.shard_bounds(uq.uniq, uq.count, self.edges, out=bounds)
+
+    def p_adopt(self):
+        self.uq.copy_from(self.uq_n)
+        self.bounds.copy_(self.bounds_n)
+
+    def p_publish(self):
         self.signal(0, self.bounds, self.ptrs["ball_row"])
+
+    def p_plan_publish(self, ids):
+        self.p_plan_local(ids)
+        self.p_publish()
 
     def p_keys(self):
         ops.shard_offsets(self.buf["ball"], self.ctrl, self.dst_off, self.src_off, self.inbox_off, self.n_r)
@@ -470,9 +487,14 @@ class PeerShardedTables:
         self._ids = None
 
     # sharded.ShardedWideDeepStep drives these three; the "plan" is implicit in device state
-    def plan_batch(self, ids, ahead=False):
+    def plan_batch(self, ids, ahead=False, adopt=False):
+        """adopt=True: the local plan of this batch was computed one step ahead (plan_next_local)."""
         rk = self.rk
-        rk.p_plan_publish(ids)
+        if adopt:
+            rk.p_adopt()
+            rk.p_publish()
+        else:
+            rk.p_plan_publish(ids)
         rk.wait(0)
         rk.p_keys()
         rk.wait(1)
@@ -482,6 +504,9 @@ class PeerShardedTables:
             rk.p_owner_dedup()
         self._side_open = True
         return _DevicePlan(ids)
+
+    def plan_next_local(self, ids):
+        self.rk.p_plan_local(ids, nxt=True)
 
     def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
         rk = self.rk
@@ -538,9 +563,10 @@ class _DevicePlan:
 
 class PeerShardedWideDeepStep(ShardedWideDeepStep):
     """Wide&Deep step over PeerShardedTables.  Nothing in the step depends on a host-side size, so `capture`
-    records plan -> exchange -> DenseLayers -> gradient exchange -> fused row updates as ONE CUDA graph; the mean
-    all-reduce of the DenseLayer gradients and the dense Adam stay eager behind it (NCCL in a captured graph hung
-    on this stack), i.e. a step costs one graph launch + one collective + two kernel launches of host time."""
+    records plan -> exchange -> DenseLayers -> gradient exchange -> fused row updates as three CUDA graphs; the mean
+    all-reduce of the DenseLayer gradients and the dense Adam stay eager between them (NCCL in a captured graph
+    hung on this stack), i.e. a step costs three graph launches + one collective + two kernel launches of host
+    time."""
 
     def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
                  use_mixed_precision=True, group=None, graph=True):
@@ -554,76 +580,112 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         self._bwd = None
         self._dense_stream = torch.cuda.Stream(device=self.device)
         self._stage_stream = torch.cuda.Stream(device=self.device)
+        self._plan_stream = torch.cuda.Stream(device=self.device)
         self._stage = None
         self._staged_for = None
 
-    # the step in two fixed-shape halves; the DenseLayer mean all-reduce + Adam run between them on a side stream
-    def _forward_half(self):
-        ids, wts, label = self._slots[0]
+    # The step in three fixed-shape pieces:
+    #   A1  plan (inline, or adopted from the look-ahead buffers) -> key / row exchange -> expand
+    #   A2  DenseLayers forward / loss / backward, with the NEXT batch's local plan (remap + dedup + bounds) on a
+    #       forked branch underneath — the plan never sits on the critical path in steady state
+    #   B   gradient exchange -> fused row updates
+    # Between A1 and A2 the host makes the stream wait for the staged copy of the next batch (it overlaps A1);
+    # between A2 and B it launches the DenseLayer mean all-reduce + Adam on a side stream (they overlap B).
+    def _a1(self, adopt):
+        ids, wts, _ = self._slots[0]
         t = self.tables
-        plan = t.plan_batch(ids)
+        plan = t.plan_batch(ids, adopt=adopt)
         t.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
-        self._io["label"].copy_(label)
-        loss, delta, gx = self._dense_segment()
         t.join_side()
+
+    def _a2(self):
+        main = torch.cuda.current_stream()
+        self._plan_stream.wait_stream(main)
+        with torch.cuda.stream(self._plan_stream):
+            self.tables.plan_next_local(self._stage[0])
+        self._io["label"].copy_(self._slots[0][2])
+        loss, delta, gx = self._dense_segment()
+        main.wait_stream(self._plan_stream)
         self._bwd = (delta, gx)
         return loss
 
-    def _backward_half(self):
+    def _b(self):
         self.tables.update(*self._bwd)
 
-    def _one_step(self):
+    def _one_step(self, adopt=False):
         main = torch.cuda.current_stream()
+        g = self._graphs
         main.wait_stream(self._dense_stream)                 # last step's dense Adam wrote the weights
-        if self._graphs is not None:
-            self._graphs[0].replay()
+        if g is not None:
+            g["a1_adopt" if adopt else "a1_inline"].replay()
         else:
-            self._loss = self._forward_half()
+            self._a1(adopt)
+        main.wait_stream(self._stage_stream)                 # the next batch is on the device (copied under A1)
+        if g is not None:
+            g["a2"].replay()
+        else:
+            self._loss = self._a2()
         self._dense_stream.wait_stream(main)
         with torch.cuda.stream(self._dense_stream):          # NCCL + dense Adam under the gradient exchange
             self._dense_update()
-        if self._graphs is not None:
-            self._graphs[1].replay()
+        if g is not None:
+            g["b"].replay()
         else:
-            self._backward_half()
+            self._b()
         return self._loss
 
     def capture(self, ids, wts, label, warmup=3):
         self._slots = [tuple(t.clone() for t in (ids, wts, label))]
-        self._stage = tuple(torch.empty_like(t) for t in self._slots[0])
+        self._stage = tuple(t.clone() for t in self._slots[0])
         self._ensure_io(ids)
         for _ in range(warmup):
             self._one_step()
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         if self._graph_step:
-            # capture executes nothing: both halves are recorded back to back, then a real step is replayed
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
-                self._loss = self._forward_half()
-            with torch.cuda.graph(gb, pool=ga.pool()):
-                self._backward_half()
-            self._graphs = (ga, gb)
+            # capture executes nothing: the pieces are recorded back to back, real steps are replayed afterwards
+            graphs, pool = {}, None
+            self.launches_per_step = 2                       # the eager dense Adam pair (begin_step + adam_dense)
+            for name, fn in (("a1_inline", lambda: self._a1(False)), ("a1_adopt", lambda: self._a1(True)),
+                             ("a2", self._a2), ("b", self._b)):
+                gr = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(gr, pool=pool):
+                    out = fn()
+                if name != "a1_inline":                      # steady state replays a1_adopt + a2 + b
+                    self.launches_per_step += _lib.launch_count() - n0
+                if name == "a2":
+                    self._loss = out
+                pool = pool or gr.pool()
+                graphs[name] = gr
+            self._graphs = graphs
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
+        self._staged_for = None
         return self._slots[0]
 
     def replay(self, ids=None, wts=None, label=None, next_batch=None):
+        """One step on (ids, wts, label).  next_batch (host-pinned or device tensors): staged on a copy stream during
+        this step AND planned (dedup + bucket bounds) underneath this step's DenseLayers; pass the same tensors as
+        the next call's batch to use both."""
         main = torch.cuda.current_stream()
+        adopt = False
         if ids is not None:
             if self._staged_for is not None and self._staged_for is ids:
-                main.wait_stream(self._stage_stream)         # staged one step ahead: a device-local copy
-                for d, s in zip(self._slots[0], self._stage):
+                for d, s in zip(self._slots[0], self._stage):        # staged (and planned) one step ahead
                     d.copy_(s, non_blocking=True)
+                adopt = True
             else:
                 for d, s in zip(self._slots[0], (ids, wts, label)):
                     d.copy_(s, non_blocking=True)
         self._staged_for = None
-        if next_batch is not None and not next_batch[0].is_cuda:
-            self._stage_stream.wait_stream(main)             # the staging buffers were just consumed
+        if next_batch is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)                                  # the staging buffers have been consumed
+            self._stage_stream.wait_event(ev)
             with torch.cuda.stream(self._stage_stream):
                 for d, s in zip(self._stage, next_batch):
                     d.copy_(s, non_blocking=True)
             self._staged_for = next_batch[0]
-        loss = self._one_step()
+        loss = self._one_step(adopt)
         return loss, loss

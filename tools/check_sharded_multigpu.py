@@ -26,7 +26,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    vocab, dim, b, hidden, steps = 50021, 16, 512, (64, 32), 3
+    vocab, dim, b, hidden, steps = 50021, 16, 512, (64, 32), 5
     if MODE == "nccl":
         step = sharded.ShardedWideDeepStep(b, vocab, dim, hidden, dev, seed=3, use_mixed_precision=False,
                                            graph_dense=False)
@@ -41,8 +41,9 @@ def main():
         batches = [[bs[0], bs[0]] + bs[1:] for bs in batches]
         steps += 1
     losses = []
+    dev_batches = [tuple(torch.from_numpy(x).to(dev) for x in batches[rank][s]) for s in range(steps)]
     for s in range(steps):
-        ids, wts, label = (torch.from_numpy(x).to(dev) for x in batches[rank][s])
+        ids, wts, label = dev_batches[s]
         if MODE == "device-graph":
             if s == 0:
                 step.capture(ids, wts, label, warmup=2)
@@ -50,7 +51,9 @@ def main():
             if s == 1:
                 losses += [float("nan")] * 2
                 continue
-            losses.append(float(step.replay(ids, wts, label)[0]))
+            # the next batch is handed over too: staged and planned (dedup + bounds) underneath this step
+            nxt = dev_batches[s + 1] if s + 1 < steps else None
+            losses.append(float(step.replay(ids, wts, label, next_batch=nxt)[0]))
         else:
             losses.append(float(step(ids, wts, label)[0]))
     if MODE != "nccl":
