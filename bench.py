@@ -378,6 +378,24 @@ def run_ours(args):
     if world == 1:
         roofline = measure_dominant_op(step, devb[:4], b)
 
+    exchange = None
+    if world > 1 and hasattr(step.tables, "rk"):
+        # NVLink traffic of the last step, from the device-side plan (a2a bytes = remote unique keys x
+        # (key + row) forward and x row backward; rows are D deep floats + 1 wide float)
+        rk = step.tables.rk
+        bnd = rk.bounds.tolist()
+        n_u, own = bnd[world], bnd[rank + 1] - bnd[rank]
+        n_r = int(rk.n_r.item())
+        row_b = (EMB + 1) * 4
+        out_b = (n_u - own) * 4 + (n_r - own) * row_b + (n_u - own) * row_b     # keys out, rows served out, grads out
+        t_b = torch.tensor([float(out_b), float(n_u), float(n_r)], device=dev)
+        dist.all_reduce(t_b, op=dist.ReduceOp.SUM)
+        out_b, n_u_avg, n_r_avg = (float(x) / world for x in t_b.tolist())
+        exchange = {"unique_keys_per_rank": int(n_u_avg), "rows_owned_per_rank": int(n_r_avg),
+                    "nvlink_bytes_out_per_rank_per_step": int(out_b),
+                    "avg_gbs_per_direction_over_step": round(out_b / (ms * 1e-3) / 1e9, 1), "nvlink_peak_gbs_per_direction": 900,
+                    "note": "peer stores (keys, rows, gradients) leaving one GPU in one step / step time; the "
+                            "exchange is latency- and dedup-bound, not link-bound"}
     exch_err = 0
     if world > 1 and hasattr(step.tables, "error_flags"):
         # device-driven exchange: bit 0 = a peer wait timed out, bit 1 = an inbox overflowed (either voids the run)
@@ -406,7 +424,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(per_step_launches * args.steps),
         "gpu_launches_per_step": int(per_step_launches),
-        "roofline": roofline, "cpu_baseline": cb, "breakdown_ms": breakdown, "final_loss": final_loss,
+        "roofline": roofline, "cpu_baseline": cb, "breakdown_ms": breakdown, "exchange": exchange, "final_loss": final_loss,
         "lib": _lib.version(),
     }
     print(json.dumps(line), flush=True)

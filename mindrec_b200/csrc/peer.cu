@@ -10,6 +10,7 @@
 // the requester's dedup placed its s-th bucket, so the landing buffer is the same [U, D] array an all-to-all
 // would have produced.  Completion is published by the stream-ordered barrier collective that follows.
 #include "common.cuh"
+#include <type_traits>
 
 namespace mrec {
 
@@ -198,7 +199,9 @@ push_rows_to_peers_kernel(const E* __restrict__ rows, int width, const int32_t* 
       continue;
     }
     E v = rows[e];
-    if (transform_mod > 0) v = (E)((int64_t)v % transform_mod);
+    if constexpr (std::is_integral<E>::value) {
+      if (transform_mod > 0) v = (E)((int64_t)v % transform_mod);
+    }
     s_ptr[o][drow * width + c] = v;
   }
 }
@@ -312,6 +315,11 @@ MREC_API int mrec_push_rows_to_peers(int nparam, void** params, int* ndims, int6
   } else if (a.is_i32(0)) {
     MREC_LAUNCH(push_rows_to_peers_kernel<int32_t>, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<int32_t>(0),
                 width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, mod, cap_rows, a.ptr<int32_t>(6));
+  } else if (width % 4 == 0 && reinterpret_cast<uintptr_t>(a.params[0]) % 16 == 0) {
+    // float rows of a multiple of 16 bytes: one 16-byte NVLink store per thread (the inboxes are 256-byte aligned
+    // cudaMalloc allocations, so row starts stay 16-byte aligned)
+    MREC_LAUNCH(push_rows_to_peers_kernel<uint4>, grid_for(cdiv(n * (width / 4), 1024), 8), 256, 0, a.stream, a.ptr<uint4>(0),
+                width / 4, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, (int64_t)0, cap_rows, a.ptr<int32_t>(6));
   } else {
     MREC_LAUNCH(push_rows_to_peers_kernel<uint32_t>, grid_for(cdiv(n * width, 1024), 8), 256, 0, a.stream, a.ptr<uint32_t>(0),
                 width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, (int64_t)0, cap_rows, a.ptr<int32_t>(6));
