@@ -278,10 +278,16 @@ def run_ours(args):
         model = cells.WideDeepModel(cfg, device=dev)
         step = cells.TrainStepWrap(cells.NetWithLossClass(model, cfg), sens=1024.0, sparse=True, lazy_adam=True)
     else:
+        step = None
         if args.exchange == "device":
             from mindrec_b200 import peer_sharded
-            step = peer_sharded.PeerShardedWideDeepStep(b, vocab, EMB, HIDDEN, dev, seed=1)
-        else:
+            try:
+                step = peer_sharded.PeerShardedWideDeepStep(b, vocab, EMB, HIDDEN, dev, seed=1)
+            except peer_sharded.PeerMemoryUnavailable as exc:      # raised on every rank together
+                if rank == 0:
+                    print("bench.py: %s -> falling back to the NCCL exchange" % (exc,), file=sys.stderr)
+                args.exchange = "nccl"
+        if step is None:
             from mindrec_b200 import sharded
             step = sharded.build_sharded_wide_deep(b, vocab, EMB, HIDDEN, dev, seed=1)
 

@@ -104,7 +104,7 @@ int mrec_gather_to_peers(MREC_AOT_ARGS);
  *                                 cap_like[cap_rows,..], mod_like[M,..] (M > 0: integer keys are sent as key % M)
  *                            out: err[1] i32 (bit 1: an inbox overflowed)
  *   mrec_peer_signal         in : payload[K] i32, payload_ptrs[G] i64, flag_ptrs[G] i64, epoch[1] i32 (+1)  out: dummy[1]
- *   mrec_peer_wait           in : flags[G] i32, epoch[1] i32 [, limit_log2[1] i32: spin limit 2^limit cycles, default ~4 s]
+ *   mrec_peer_wait           in : flags[G] i32, epoch[1] i32 [, limit_log2[1] i32: spin limit 2^limit cycles, default 2^35 (~17 s)]
  *                            out: err[1] i32 (bit 0: time-out) */
 int mrec_shard_offsets(MREC_AOT_ARGS);
 /* Hash-table (MapParameter) sharding, SURVEY 8e: owner = hash(key) mod G, every rank owns an independent table.

@@ -350,9 +350,10 @@ MREC_API int mrec_peer_wait(int nparam, void** params, int* ndims, int64_t** sha
   MREC_REQUIRE(a.is_i32(0) && a.is_i32(1) && a.is_i32(o) && a.is_i32(2), ERR_DTYPE, "mrec_peer_wait: int32 expected");
   const int world = (int)a.numel(0);
   MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks, ERR_SHAPE, "mrec_peer_wait: G out of range");
-  // ~4 s at 2 GHz: a dead peer raises err instead of hanging the GPU
+  // ~17 s at 2 GHz (first steps on a cold box can be seconds apart between ranks): a dead peer raises err instead
+  // of hanging the GPU
   MREC_LAUNCH(peer_wait_kernel, 1, 32, 0, a.stream, a.ptr<int32_t>(0), world, a.ptr<int32_t>(1), a.ptr<int32_t>(o),
-              a.nparam == 4 ? a.ptr<int32_t>(2) : (int32_t*)nullptr, 8000000000ll);
+              a.nparam == 4 ? a.ptr<int32_t>(2) : (int32_t*)nullptr, 1ll << 35);
   return check_launch("peer_wait");
 }
 

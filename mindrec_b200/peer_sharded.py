@@ -382,12 +382,9 @@ class PeerShardedHashEmbedding:
     def __init__(self, emb_dim, n_lookups, device, group=None, **kw):
         self.group = group
         arena = _IpcArena(group)
-        self.rk = PeerHashRank(dist.get_rank(group), dist.get_world_size(group), emb_dim, n_lookups, device,
-                               arena.alloc(device), **kw)
-        torch.cuda.synchronize()
-        dist.barrier(group=group)
-        self.rk.connect(arena.exchange())
-        dist.barrier(group=group)
+        self.rk = _connect_collectively(
+            lambda: PeerHashRank(dist.get_rank(group), dist.get_world_size(group), emb_dim, n_lookups, device,
+                                 arena.alloc(device), **kw), arena, group, torch.device(device))
         self.dim = emb_dim
 
     def lookup(self, keys, out=None):
@@ -411,6 +408,39 @@ class PeerShardedHashEmbedding:
 
     def error_flags(self):
         return int(self.rk.err.item()) | (4 if self.rk.table.overflowed else 0)
+
+
+class PeerMemoryUnavailable(RuntimeError):
+    """CUDA-IPC peer memory could not be set up on SOME rank; raised on EVERY rank (collectively agreed), so callers
+    can fall back to the NCCL exchange without dead-locking."""
+
+
+def _all_ok(ok, group, device):
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
+
+
+def _connect_collectively(make_rank, arena, group, device):
+    """Allocate + export on every rank, agree, open the peers' handles, agree again."""
+    rk, err = None, None
+    try:
+        rk = make_rank()
+        torch.cuda.synchronize()
+    except Exception as exc:                                   # noqa: BLE001 - reported through the collective
+        err = exc
+    if not _all_ok(err is None, group, device):
+        raise PeerMemoryUnavailable("peer buffer allocation / export failed on a rank: %s" % (err,))
+    base = None
+    try:
+        base = arena.exchange()
+    except Exception as exc:                                   # noqa: BLE001
+        err = exc
+    if not _all_ok(err is None, group, device):
+        raise PeerMemoryUnavailable("opening the peers' IPC handles failed on a rank: %s" % (err,))
+    rk.connect(base)
+    dist.barrier(group=group)
+    return rk
 
 
 class _IpcArena:
@@ -476,12 +506,9 @@ class PeerShardedTables:
         self.owner_stream = torch.cuda.Stream(device=self.device)
         self._side_open = False
         arena = _IpcArena(group)
-        self.rk = PeerRank(self.rank, self.world, vocab_size, emb_dim, n_lookups, device, arena.alloc(device),
-                           seed=seed, sens=sens)
-        torch.cuda.synchronize()
-        dist.barrier(group=group)
-        self.rk.connect(arena.exchange())
-        dist.barrier(group=group)
+        self.rk = _connect_collectively(
+            lambda: PeerRank(self.rank, self.world, vocab_size, emb_dim, n_lookups, device, arena.alloc(device),
+                             seed=seed, sens=sens), arena, group, self.device)
         self.plan = self.rk.plan
         self.dim = emb_dim
         self._ids = None
