@@ -77,7 +77,8 @@ int mrec_gather_pool(MREC_AOT_ARGS);
 int mrec_unique(MREC_AOT_ARGS);
 /* Same, second input table_like[V,...]: only ceil(log2(V+1)) key bits are sorted; ids outside [0,V)
  * collapse onto the value V (they form the last segment, which the optimizers skip).  Optional third input
- * n_valid[1] i32: entries at i >= n_valid are padding and are read as out of range.            */
+ * n_valid[1] i32 (device-side count): only ids[0 .. n_valid) exist — the dedup works on that prefix (its cost
+ * follows n_valid, not N), seg_start[count] = n_valid, outputs past the prefix are not written.           */
 int mrec_unique_bounded(MREC_AOT_ARGS);
 /* First-occurrence order = upstream CPU Unique kernel (BASELINE config 1 runs device_target=CPU).
  *   in : ids[N]   out: uniq[N], inverse[N] i32, count[1] i32, workspace[mrec_unique_first_workspace_bytes] */
