@@ -129,6 +129,22 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
   return r;
 }
 
+// ---- 256-bit accesses (sm_100: LDG.E.256 / STG.E.256), L2 evict-first: for rows that are read-modify-written
+// once and not needed again soon (optimizer state), so they do not push reusable lines out of the L2 ----
+struct alignas(32) F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ld256_evict_first(const F8* p) {
+  F8 r;
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256_evict_first(F8* p, const F8& v) {
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.lo.x),
+               "f"(v.lo.y), "f"(v.lo.z), "f"(v.lo.w), "f"(v.hi.x), "f"(v.hi.y), "f"(v.hi.z), "f"(v.hi.w)
+               : "memory");
+}
+
 // Scheduling fence: an empty volatile asm that "rewrites" the registers of a loaded value.  Volatile asms keep
 // their program order, so placing these after a batch of (volatile) loads forces every load of the batch to
 // be issued before the first use of any of them — without it nvcc interleaves load/use pairs to save
@@ -139,6 +155,9 @@ __device__ __forceinline__ void reg_fence(float4& v) {
 __device__ __forceinline__ void reg_fence(float& v) { asm volatile("" : "+f"(v)); }
 __device__ __forceinline__ void reg_fence(uint2& v) { asm volatile("" : "+r"(v.x), "+r"(v.y)); }
 __device__ __forceinline__ void reg_fence(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void reg_fence(F8& v) {
+  asm volatile("" : "+f"(v.lo.x), "+f"(v.lo.y), "+f"(v.lo.z), "+f"(v.lo.w), "+f"(v.hi.x), "+f"(v.hi.y), "+f"(v.hi.z), "+f"(v.hi.w));
+}
 __device__ __forceinline__ void reg_fence(uint4& v) { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -67,6 +67,13 @@ template <> struct VOps<float4> {
     return make_float4(a.x, a.y, b.x, b.y);
   }
 };
+template <> struct VOps<F8> {
+  static __device__ __forceinline__ F8 zero() { F8 z; z.lo = make_float4(0.f, 0.f, 0.f, 0.f); z.hi = z.lo; return z; }
+  static __device__ __forceinline__ void add(F8& a, const F8& x) {
+    a.lo.x += x.lo.x; a.lo.y += x.lo.y; a.lo.z += x.lo.z; a.lo.w += x.lo.w;
+    a.hi.x += x.hi.x; a.hi.y += x.hi.y; a.hi.z += x.hi.z; a.hi.w += x.hi.w;
+  }
+};
 template <> struct VOps<float> {
   static __device__ __forceinline__ float zero() { return 0.f; }
   static __device__ __forceinline__ void fma(float& a, const float& x, float s) { a = fmaf(x, s, a); }
@@ -143,6 +150,45 @@ struct LazyAdamSink<float4, IdT> {
   __device__ __forceinline__ void apply(int seg, int c, const float4& gs) const {
     const int64_t row = row_of(seg);
     if (!in_range(row)) return;                    // out-of-range ids carry no row
+    State s;
+    load(row * cpr + c, s);
+    finish(row * cpr + c, s, gs);
+  }
+};
+// 32-byte form of the LazyAdam row update: D/8 threads per row, LDG.256 / STG.256 with L2 evict-first on w, m, v
+// (each touched once per step), so the L2 keeps gsum and the hot Zipf rows instead.  Same per-element math.
+template <typename IdT>
+struct LazyAdamSink<F8, IdT> {
+  static constexpr bool kApplyComplete = true;
+  using State = State3<F8>;
+  F8* w; F8* m; F8* v;
+  const IdT* uniq;
+  const float* hyper;
+  int64_t vocab;
+  int cpr;
+  __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
+  __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
+  __device__ __forceinline__ void load(int64_t o, State& s) const {
+    s.a = ld256_evict_first(w + o); s.b = ld256_evict_first(m + o); s.c = ld256_evict_first(v + o);
+  }
+  __device__ __forceinline__ void fence(State& s) const { reg_fence(s.a); reg_fence(s.b); reg_fence(s.c); }
+  __device__ __forceinline__ void finish(int64_t o, State& s, const F8& gs) const {
+    const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6], sc = hyper[7];
+    const float l2 = hyper[8];
+    F8 W = s.a, M = s.b, V = s.c;
+    adam_elem(W.lo.x, M.lo.x, V.lo.x, fmaf(l2, W.lo.x, gs.lo.x * sc), b1, b2, eps, lr_t);
+    adam_elem(W.lo.y, M.lo.y, V.lo.y, fmaf(l2, W.lo.y, gs.lo.y * sc), b1, b2, eps, lr_t);
+    adam_elem(W.lo.z, M.lo.z, V.lo.z, fmaf(l2, W.lo.z, gs.lo.z * sc), b1, b2, eps, lr_t);
+    adam_elem(W.lo.w, M.lo.w, V.lo.w, fmaf(l2, W.lo.w, gs.lo.w * sc), b1, b2, eps, lr_t);
+    adam_elem(W.hi.x, M.hi.x, V.hi.x, fmaf(l2, W.hi.x, gs.hi.x * sc), b1, b2, eps, lr_t);
+    adam_elem(W.hi.y, M.hi.y, V.hi.y, fmaf(l2, W.hi.y, gs.hi.y * sc), b1, b2, eps, lr_t);
+    adam_elem(W.hi.z, M.hi.z, V.hi.z, fmaf(l2, W.hi.z, gs.hi.z * sc), b1, b2, eps, lr_t);
+    adam_elem(W.hi.w, M.hi.w, V.hi.w, fmaf(l2, W.hi.w, gs.hi.w * sc), b1, b2, eps, lr_t);
+    st256_evict_first(w + o, W); st256_evict_first(m + o, M); st256_evict_first(v + o, V);
+  }
+  __device__ __forceinline__ void apply(int seg, int c, const F8& gs) const {
+    const int64_t row = row_of(seg);
+    if (!in_range(row)) return;
     State s;
     load(row * cpr + c, s);
     finish(row * cpr + c, s, gs);
@@ -451,7 +497,7 @@ segsum_stage_kernel(const GT* __restrict__ g, int dim, int div, const float* __r
 constexpr int kChainBlocks = 64;
 
 template <typename Vec, typename Sink, int ROWS>
-__global__ void __launch_bounds__(kSegThreads, (sizeof(Vec) == 16 ? (ROWS == 2 ? 3 : 4) : 4))
+__global__ void __launch_bounds__(kSegThreads, (sizeof(Vec) == 16 ? (ROWS == 2 ? 3 : 4) : (sizeof(Vec) == 32 ? 3 : 4)))
 rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                    int64_t n, const Vec* __restrict__ gsum, const Vec* __restrict__ part,
                    const int32_t* __restrict__ long_list, const int32_t* __restrict__ long_count, Sink sink,
@@ -579,6 +625,8 @@ size_t sparse_opt_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim, tr
 size_t segment_sum_workspace_bytes(int64_t n, int dim) { return seg_ws(n, dim, false).total; }
 
 struct NoSink {};
+template <typename S> struct IsLazyAdamF4 { static constexpr bool value = false; using Id = int; };
+template <typename IdT> struct IsLazyAdamF4<LazyAdamSink<float4, IdT>> { static constexpr bool value = true; using Id = IdT; };
 
 // Sink = NoSink: stand-alone segment sum into `out`; otherwise the sums go to the workspace and the sink
 // (optimizer update) is applied per unique row.  Two launches: tile walk, then finish + sink.
@@ -657,7 +705,28 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
     MREC_LAUNCH((rows_update_kernel<Vec, Sink, R>), kChainBlocks + row_blocks, kSegThreads, 0, stream, cpr, seg_of, \
                 seg_start, n, gsum, part, long_list, long_count, sink, n_valid);                                 \
   } while (0)
-    if (rows_r == 2) MREC_ROWS(2, (v4 ? 3 : 4));
+    bool done256 = false;
+    if constexpr (IsLazyAdamF4<Sink>::value) {
+      // MREC_ROWS_256 (default on): 32-byte accesses with L2 evict-first for the LazyAdam rows when D % 8 == 0
+      const char* e256 = getenv("MREC_ROWS_256");
+      const bool want = e256 ? atoi(e256) != 0 : true;
+      const bool al = ((reinterpret_cast<uintptr_t>(sink.w) | reinterpret_cast<uintptr_t>(sink.m) |
+                        reinterpret_cast<uintptr_t>(sink.v) | reinterpret_cast<uintptr_t>(gsum) |
+                        reinterpret_cast<uintptr_t>(part)) % 32) == 0;
+      if (want && al && dim % 8 == 0) {
+        using S8 = LazyAdamSink<F8, typename IsLazyAdamF4<Sink>::Id>;
+        const int cpr8 = dim / 8, groups8 = kSegThreads / cpr8;
+        S8 s8{reinterpret_cast<F8*>(sink.w), reinterpret_cast<F8*>(sink.m), reinterpret_cast<F8*>(sink.v), sink.uniq,
+              sink.hyper, sink.vocab, cpr8};
+        int rb8 = (int)std::min<int64_t>(cdiv(n, (int64_t)groups8), (int64_t)kNumSMs * (per_sm_env ? per_sm_env : 8));
+        if (rb8 < 1) rb8 = 1;
+        MREC_LAUNCH((rows_update_kernel<F8, S8, 1>), kChainBlocks + rb8, kSegThreads, 0, stream, cpr8, seg_of, seg_start, n,
+                    reinterpret_cast<const F8*>(gsum), reinterpret_cast<const F8*>(part), long_list, long_count, s8, n_valid);
+        done256 = true;
+      }
+    }
+    if (done256) {
+    } else if (rows_r == 2) MREC_ROWS(2, (v4 ? 3 : 4));
     else MREC_ROWS(1, 8);
 #undef MREC_ROWS
   }
