@@ -80,5 +80,58 @@ def main():
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
+MT_SHAPES = dict(batch=40, continue_fields=8, n_indicator=2, n_emb128=3, n_emb64_single=2, multi_slots=(3, 5, 2, 4, 1, 6),
+                 emb_128_size=120, emb64_single_size=90, emb64_multi_size=60, indicator_size=16, hidden=(24, 16))
+
+
+def multitable():
+    """Wide&Deep multitable cell: two training steps of the oracle (python make_golden.py multitable)."""
+    c = MT_SHAPES
+    rng = np.random.default_rng(20260102)
+    n = lambda *shape: (rng.standard_normal(shape) * 0.01).astype(np.float32)
+    deep = {"emb128_embedding": n(c["emb_128_size"], 128), "emb64_single": n(c["emb64_single_size"], 64),
+            "emb64_multi": n(c["emb64_multi_size"], 64), "emb64_indicator": n(c["indicator_size"], 64)}
+    wide = {"wide_continue_w": n(c["continue_fields"]), "wide_emb128_w": n(c["emb_128_size"], 1),
+            "wide_emb64_single_w": n(c["emb64_single_size"], 1), "wide_emb64_multi_w": n(c["emb64_multi_size"], 1),
+            "wide_indicator_w": n(c["indicator_size"], 1), "wide_bias": n(1)}
+    din = c["continue_fields"] + c["n_indicator"] * 64 + c["n_emb128"] * 128 + c["n_emb64_single"] * 64 + 6 * 64
+    dims = [din] + list(c["hidden"]) + [1]
+    mlp_w = [(rng.standard_normal((dims[i], dims[i + 1])) * 0.1).astype(np.float32) for i in range(len(dims) - 1)]
+    mlp_b = [(rng.standard_normal(dims[i + 1]) * 0.01).astype(np.float32) for i in range(len(dims) - 1)]
+    out = {}
+    for k, v in list(deep.items()) + list(wide.items()):
+        out["init_" + k] = v
+    for i, (a, b_) in enumerate(zip(mlp_w, mlp_b)):
+        out["mlp_w%d" % i], out["mlp_b%d" % i] = a, b_
+    orc = R.MultitableOracle(deep, wide, mlp_w, mlp_b)
+    b = c["batch"]
+    losses = []
+    for step in range(2):
+        cont = rng.random((b, c["continue_fields"])).astype(np.float32)
+        ind = rng.integers(0, c["indicator_size"], size=(b, c["n_indicator"])).astype(np.int32)
+        e128 = rng.integers(0, c["emb_128_size"], size=(b, c["n_emb128"])).astype(np.int32)
+        e64 = rng.integers(0, c["emb64_single_size"], size=(b, c["n_emb64_single"])).astype(np.int32)
+        multi = [(rng.integers(0, 25, size=(b, s)).astype(np.int32), (rng.random((b, s)) < 0.7).astype(np.float32))
+                 for s in c["multi_slots"]]
+        label = (rng.random(b) < 0.25).astype(np.float32)
+        if step == 0:
+            out["logit0"] = orc.forward(cont, ind, e128, e64, multi)[0].astype(np.float32)
+        losses.append(orc.step(label, cont, ind, e128, e64, multi))
+        out.update({"label%d" % step: label, "cont%d" % step: cont, "ind%d" % step: ind, "e128_%d" % step: e128,
+                    "e64_%d" % step: e64})
+        for k, (ids, m) in enumerate(multi):
+            out["multi_ids%d_%d" % (step, k)], out["multi_mask%d_%d" % (step, k)] = ids, m
+    out["loss"] = np.array(losses, np.float32)
+    for k, v in list(orc.deep.items()) + list(orc.wide.items()):
+        out["final_" + k] = v
+    out["final_mlp_w0"] = orc.mlp_w[0]
+    np.savez_compressed(os.path.join(HERE, "multitable_steps.npz"), **out)
+    print("wrote multitable_steps.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "multitable":
+        multitable()
+    else:
+        main()
+        multitable()

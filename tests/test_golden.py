@@ -66,3 +66,33 @@ def test_oracle_reproduces_wide_deep_steps_fixture():
             np.testing.assert_allclose(ld, z["%s_loss_d" % mode][i], rtol=1e-6)
         np.testing.assert_allclose(orc.wd, z["%s_deep" % mode], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(orc.ww, z["%s_wide" % mode], rtol=1e-6, atol=1e-9)
+
+
+def _multitable_fixture():
+    sys_path = os.path.join(G, "make_golden.py")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", sys_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return np.load(os.path.join(G, "multitable_steps.npz")), mod.MT_SHAPES
+
+
+DEEP_NAMES = ("emb128_embedding", "emb64_single", "emb64_multi", "emb64_indicator")
+WIDE_NAMES = ("wide_continue_w", "wide_emb128_w", "wide_emb64_single_w", "wide_emb64_multi_w", "wide_indicator_w", "wide_bias")
+
+
+def test_oracle_reproduces_multitable_fixture():
+    z, c = _multitable_fixture()
+    n_layers = len(c["hidden"]) + 1
+    orc = R.MultitableOracle({k: z["init_" + k] for k in DEEP_NAMES}, {k: z["init_" + k] for k in WIDE_NAMES},
+                             [z["mlp_w%d" % i] for i in range(n_layers)], [z["mlp_b%d" % i] for i in range(n_layers)])
+    for step in range(2):
+        multi = [(z["multi_ids%d_%d" % (step, k)], z["multi_mask%d_%d" % (step, k)]) for k in range(6)]
+        args = (z["cont%d" % step], z["ind%d" % step], z["e128_%d" % step], z["e64_%d" % step], multi)
+        if step == 0:
+            np.testing.assert_allclose(orc.forward(*args)[0], z["logit0"], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(orc.step(z["label%d" % step], *args), z["loss"][step], rtol=1e-6)
+    for k in DEEP_NAMES:
+        np.testing.assert_allclose(orc.deep[k], z["final_" + k], rtol=1e-6, atol=1e-9)
+    for k in WIDE_NAMES:
+        np.testing.assert_allclose(orc.wide[k], z["final_" + k], rtol=1e-6, atol=1e-9)

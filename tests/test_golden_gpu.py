@@ -82,3 +82,38 @@ def test_wide_deep_steps_against_fixture(cuda, mode):
                      (model.dense.weights[0], "%s_mlp_w0" % mode)):
         ref = z[key]
         np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-4, atol=2e-5 * np.abs(ref).max())
+
+
+def test_multitable_steps_against_fixture(cuda):
+    """The CUDA multitable cell against bytes that travel with the repository (tests/golden/multitable_steps.npz)."""
+    import importlib.util
+    from mindrec_b200 import multitable as MT
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    c = mod.MT_SHAPES
+    z = np.load(os.path.join(G, "multitable_steps.npz"))
+    cfg = MT.MultitableConfig(batch_size=c["batch"], n_indicator=c["n_indicator"], n_emb128=c["n_emb128"],
+                              n_emb64_single=c["n_emb64_single"], multi_slots=c["multi_slots"],
+                              continue_field_size=c["continue_fields"], emb_128_size=c["emb_128_size"],
+                              emb64_single_size=c["emb64_single_size"], emb64_multi_size=c["emb64_multi_size"],
+                              indicator_size=c["indicator_size"], deep_dim_list=c["hidden"], use_mixed_precision=False)
+    model = MT.MultitableWideDeepModel(cfg, device=cuda)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    for k, v in list(model.deep_tables().items()) + list(model.wide_tables().items()):
+        v.copy_(t(z["init_" + k]).view(v.shape))
+    for i, (w, b) in enumerate(zip(model.dense.weights, model.dense.biases)):
+        w.copy_(t(z["mlp_w%d" % i]))
+        b.copy_(t(z["mlp_b%d" % i]))
+    step = MT.TrainStepWrap(MT.NetWithLossClass(model, cfg), cfg, sens=1000.0)
+    for s in range(2):
+        args = (t(z["cont%d" % s]), t(z["ind%d" % s]), t(z["e128_%d" % s]), t(z["e64_%d" % s]),
+                [t(z["multi_ids%d_%d" % (s, k)]) for k in range(6)], [t(z["multi_mask%d_%d" % (s, k)]) for k in range(6)])
+        if s == 0:
+            np.testing.assert_allclose(model(*args).cpu().numpy(), z["logit0"], rtol=1e-5, atol=1e-6)
+        loss, _ = step(t(z["label%d" % s]), *args)
+        np.testing.assert_allclose(float(loss), z["loss"][s], rtol=1e-5)
+    for k, v in list(model.deep_tables().items()) + list(model.wide_tables().items()):
+        np.testing.assert_allclose(v.cpu().numpy().reshape(z["final_" + k].shape), z["final_" + k], rtol=2e-4, atol=2e-6,
+                                   err_msg=k)
+    np.testing.assert_allclose(model.dense.weights[0].cpu().numpy(), z["final_mlp_w0"], rtol=2e-4, atol=2e-6)
