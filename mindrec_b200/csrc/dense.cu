@@ -11,6 +11,7 @@
 // them per column (a "last CTA adds them up" ticket variant cost 15-20 us of serial tail per call, r1i kbench),
 // so the result is bit-reproducible.
 #include "common.cuh"
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 namespace mrec {
@@ -316,7 +317,8 @@ static DensePlan dense_plan(int64_t rows, int n_cols, int elem_bytes, bool align
   p.nty = kDenseThreads / ntx;
   p.col_tiles = (int)cdiv(chunks, ntx);
   // ~8 CTAs per SM (r1i: 128-296 CTAs ran at half the memory rate), but at least 4 rows per lane
-  int rb = (int)cdiv(kDenseTargetCtas, p.col_tiles);
+  static const int per_sm = [] { const char* e = getenv("MREC_DENSE_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  int rb = (int)cdiv(per_sm > 0 ? per_sm * kNumSMs : kDenseTargetCtas, p.col_tiles);
   if (rb > kDenseMaxRowBlocks) rb = kDenseMaxRowBlocks;
   const int64_t by_rows = cdiv(rows, (int64_t)p.nty * 4);
   if (rb > by_rows) rb = (int)by_rows;
