@@ -132,3 +132,15 @@ def test_peer_exchange_validation_without_gpu(built_lib):
     # more ranks than the kernels support
     rc = _lib.aot_call_raw("mrec_peer_wait", [16, 32, 48], [(4096,), (1,), (1,)], ["int32", "int32", "int32"])
     assert rc == 3
+
+
+def test_every_exported_mrec_symbol_is_declared_in_the_header(built_lib):
+    """The reverse direction: nothing is exported that include/mindrec_b200.h does not document."""
+    import shutil
+    import subprocess
+    if shutil.which("nm") is None:
+        pytest.skip("binutils nm not available")
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T mrec_" in l}
+    assert exported, "no mrec_* symbols exported?"
+    assert not (exported - set(_declared_symbols())), sorted(exported - set(_declared_symbols()))
