@@ -238,7 +238,7 @@ def measure_dominant_op(step, batches, b, reps=10):
     except Exception:
         pass
     return {"kernel": "mrec_sparse_lazy_adam = segsum_stage_kernel<__half> + "
-                      "rows_update_kernel<float4,LazyAdamSink> (2 launches, timed as one op)",
+                      "rows_update_kernel<F8,LazyAdamSink> (256-bit rows; 2 launches, timed as one op)",
             "bound": "hbm", "achieved": round(gbs, 1), "peak": peak,
             "peak_source": "MEASURED_PEAKS.json (measured)" if how == "measured" else "fallback 6650",
             "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": traffic, "algorithmic_bytes": alg,
