@@ -144,3 +144,17 @@ def test_every_exported_mrec_symbol_is_declared_in_the_header(built_lib):
     exported = {l.split()[-1] for l in out.splitlines() if " T mrec_" in l}
     assert exported, "no mrec_* symbols exported?"
     assert not (exported - set(_declared_symbols())), sorted(exported - set(_declared_symbols()))
+
+
+def test_c_harness_compiles_against_the_header_and_runs(built_lib, tmp_path):
+    """The boundary is usable from plain C: tests/c/abi_harness.c includes include/mindrec_b200.h (C99), dlopens the
+    library and checks the documented error codes — no Python, no torch in that process."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "abi_harness")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_harness.c"), "-ldl", "-o", exe], check=True)
+    r = subprocess.run([exe, built_lib], capture_output=True, text=True)
+    assert r.returncode == 0 and "ABI HARNESS OK" in r.stdout, r.stdout + r.stderr
