@@ -318,13 +318,23 @@ def run_ours(args):
     sampler.start()
     w0 = max(3, args.warmup)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # per-step spread (p10/p50/p90)
     e0.record()
     for i in range(w0, w0 + args.steps):
         step.replay(*devb[i % ring], next_batch=devb[(i + 1) % ring])
+        marks[i - w0].record()
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    step_ms = None
+    try:
+        edges = [e0] + marks
+        per = sorted(edges[j].elapsed_time(edges[j + 1]) for j in range(args.steps))
+        pick = lambda q: round(per[min(len(per) - 1, int(q * len(per)))], 4)
+        step_ms = {"p10": pick(0.10), "p50": pick(0.50), "p90": pick(0.90), "rank": rank}
+    except Exception:                                      # the spread is informative only
+        step_ms = None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -423,7 +433,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "step_ms": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": b * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
