@@ -623,3 +623,47 @@ class MultitableOracle:
             adam_dense(self.mlp_w[i], self.mv_w[i][0], self.mv_w[i][1], gw[i], self.adam)
             adam_dense(self.mlp_b[i], self.mv_b[i][0], self.mv_b[i][1], gb[i], self.adam)
         return F32(loss)
+
+
+# ------------------------------------------------------------------------------------------------
+# 8e  row-sharded exchange: index arithmetic of the device-driven protocol (mindrec_b200/peer_sharded.py)
+# ------------------------------------------------------------------------------------------------
+def shard_exchange_offsets(bounds_all, me):
+    """bounds_all[s, :] = bucket bounds of rank s's sorted unique keys (bucket o = keys owned by rank o).
+    Returns what mrec_shard_offsets computes on rank `me`:
+      dst_off[s]   where rank s wants my rows in ITS landing buffer   = bounds_all[s, me]
+      src_off[s]   where rank s's requests start in MY key inbox      = sum_{t<s} |bucket(t -> me)|   (src_off[G] = n_r)
+      inbox_off[o] where MY bucket for owner o starts in o's inbox    = sum_{t<me} |bucket(t -> o)|
+    The reference reaches the same layout with AllGather / ReduceScatter over a contiguous row split
+    (models/wide_deep/src/wide_and_deep.py:232-249); this is its all-to-all form."""
+    b = np.asarray(bounds_all, dtype=np.int64)
+    g = b.shape[0]
+    size = b[:, 1:] - b[:, :-1]                        # size[s, o]
+    dst_off = b[:, me].copy()
+    src_off = np.concatenate([[0], np.cumsum(size[:, me])])
+    inbox_off = np.array([size[:me, o].sum() for o in range(g)], dtype=np.int64)
+    return dst_off, src_off, inbox_off, int(src_off[-1])
+
+
+def shard_exchange_simulate(keys_per_rank, world, rows_per_rank):
+    """Full forward exchange on the host for G ranks: per-rank sorted unique owner-major keys -> key inboxes ->
+    (owner, local row) served back into landing buffers.  Returns (inboxes, landings) where landing[s][u] is the
+    (owner, local_row) pair that arrived for rank s's u-th unique key — it must name that very key."""
+    uniq = [np.unique(np.asarray(k, dtype=np.int64)) for k in keys_per_rank]                 # owner-major, sorted
+    edges = np.arange(world + 1) * rows_per_rank
+    bounds = np.stack([np.searchsorted(u, edges, side="left") for u in uniq])
+    inbox = [np.full(sum(int(bounds[s, o + 1] - bounds[s, o]) for s in range(world)), -1, dtype=np.int64)
+             for o in range(world)]
+    for me in range(world):
+        _, _, inbox_off, _ = shard_exchange_offsets(bounds, me)
+        for o in range(world):
+            seg = uniq[me][bounds[me, o]:bounds[me, o + 1]] % rows_per_rank                    # local rows
+            inbox[o][inbox_off[o]:inbox_off[o] + seg.size] = seg
+    landing = [np.full((u.size, 2), -1, dtype=np.int64) for u in uniq]
+    for me in range(world):
+        dst_off, src_off, _, n_r = shard_exchange_offsets(bounds, me)
+        assert n_r == inbox[me].size
+        for s in range(world):
+            rows = inbox[me][src_off[s]:src_off[s + 1]]
+            landing[s][dst_off[s]:dst_off[s] + rows.size] = np.stack([np.full(rows.size, me), rows], 1)
+    return uniq, inbox, landing
