@@ -334,6 +334,8 @@ def sigmoid_xent(a, b, label, sens, out=None, half=False):
     return out
 
 
+# Workspaces of the DenseLayer glue kernels are cached per (device, width): calls that share a width must be
+# stream-ordered (they are: one DenseStack runs its layers on one stream).
 _dense_ws = {}
 
 
