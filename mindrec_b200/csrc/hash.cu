@@ -325,7 +325,7 @@ static int probe_entry(const Aot& a, const char* who, bool has_new) {
   for (int i = 0; i < a.nparam; ++i)
     if (!a.params[i] && a.numel(i) > 0) return fail(ERR_NULL, "%s: param %d is null", who, i);
   MREC_REQUIRE(a.is_i32(0) || a.is_i64(0), ERR_DTYPE, "%s: keys must be int32|int64", who);
-  int64_t capacity;
+  int64_t capacity = 0;
   int rc = table_args(a, 1, 2, 3, &capacity, who);
   if (rc) return rc;
   MREC_REQUIRE(a.is_i32(4) && a.numel(4) >= 2, ERR_DTYPE, "%s: params must be int32[2] = {permit, evict_after}", who);
@@ -437,7 +437,7 @@ MREC_API int mrec_hash_evict(MREC_AOT_SIG) {
     erase_log = a.ptr<long long>(5);
     log_cap = a.numel(5);
   }
-  int64_t capacity;
+  int64_t capacity = 0;
   int rc = table_args(a, 0, 1, 2, &capacity, "mrec_hash_evict");
   if (rc) return rc;
   MREC_REQUIRE(a.is_i32(3) && a.numel(3) >= 2, ERR_DTYPE, "mrec_hash_evict: cfg must be int32[2]");
@@ -455,7 +455,7 @@ MREC_API int mrec_hash_export(MREC_AOT_SIG) {
   MREC_AOT_PACK;
   if (a.nparam != 7 && a.nparam != 8) return fail(ERR_NPARAM, "mrec_hash_export: expected 7 or 8 params, got %d", a.nparam);
   const int o = a.nparam - 3;                       // first output
-  int64_t capacity;
+  int64_t capacity = 0;
   int rc = table_args(a, 0, 1, 2, &capacity, "mrec_hash_export");
   if (rc) return rc;
   MREC_REQUIRE(a.is_i32(3) && a.is_i64(o) && a.is_i32(o + 1) && a.is_i32(o + 2), ERR_DTYPE,
