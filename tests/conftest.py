@@ -26,3 +26,13 @@ def cuda(built_lib):
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _seed_torch_per_test(request):
+    """Every test starts from a torch RNG state derived from its own id (CPU and CUDA generators): a draw does not
+    depend on which tests ran before it, so a test that passes once passes always, whatever is added around it."""
+    import zlib
+    import torch
+    torch.manual_seed(zlib.crc32(request.node.nodeid.encode()) & 0x7fffffff)
+    yield
