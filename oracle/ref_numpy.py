@@ -283,6 +283,8 @@ class MapParameterModel:
         self.seen = {}       # key -> number of steps in which it was looked up
         self.last = {}       # key -> last step it was looked up
         self.step = 0
+        self._touched = set()   # keys looked up / put since the last export (incremental export, ASSUMPTIONS)
+        self._erased = set()    # keys erased / evicted since the last export
 
     def get(self, keys, insert_default_value=True):
         """MapTensorGet: one sighting per distinct key per call; a key becomes resident on its
@@ -296,6 +298,7 @@ class MapParameterModel:
                 touched.add(k)
                 self.seen[k] = self.seen.get(k, 0) + 1
                 self.last[k] = self.step
+                self._touched.add(k)
                 if k not in self.rows and insert_default_value and self.seen[k] >= self.permit:
                     self.rows[k] = self.default.copy()
             out[i] = self.rows[k] if k in self.rows else self.default
@@ -306,9 +309,12 @@ class MapParameterModel:
             self.rows[k] = v.copy()
             self.last[k] = self.step
             self.seen[k] = max(self.seen.get(k, 0), self.permit)
+            self._touched.add(k)
 
     def erase(self, keys):
         for k in np.asarray(keys).reshape(-1).tolist():
+            if k in self.rows or k in self.seen:
+                self._erased.add(k)
             self.rows.pop(k, None)
             self.seen.pop(k, None)
             self.last.pop(k, None)
@@ -322,6 +328,30 @@ class MapParameterModel:
 
     def keys(self):
         return np.asarray(sorted(self.rows.keys()), dtype=np.int64)
+
+    def export_data(self, incremental=False):
+        """(keys, values, statuses): full = every resident key, status 0; incremental = resident keys looked up or put
+        since the previous export (status 1) + keys erased since then and not resident again (status 2, zero rows)."""
+        if incremental:
+            mod = sorted(k for k in self._touched if k in self.rows)
+            gone = sorted(k for k in self._erased if k not in self.rows)
+            keys = np.asarray(mod + gone, dtype=np.int64)
+            vals = np.stack([self.rows[k] for k in mod] + [np.zeros(self.dim, F32)] * len(gone)) if keys.size \
+                else np.zeros((0, self.dim), F32)
+            status = np.asarray([1] * len(mod) + [2] * len(gone), dtype=np.int32)
+        else:
+            keys = self.keys()
+            vals = np.stack([self.rows[k] for k in keys.tolist()]) if keys.size else np.zeros((0, self.dim), F32)
+            status = np.zeros(keys.size, dtype=np.int32)
+        self._touched.clear()
+        self._erased.clear()
+        return keys, vals, status
+
+    def import_data(self, data):
+        keys, vals, status = data
+        gone = status == 2
+        self.erase(keys[gone])
+        self.put(keys[~gone], vals[~gone])
 
 
 # ------------------------------------------------------------------------------------------------

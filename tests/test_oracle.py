@@ -177,3 +177,37 @@ def test_c_port_full_step_agrees_with_numpy_oracle():
         np.testing.assert_allclose(l1, l2, rtol=1e-5)
     np.testing.assert_allclose(cpu.wd, orc.wd, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(cpu.ww, orc.ww, rtol=1e-4, atol=1e-6)
+
+
+def test_map_parameter_model_incremental_export_replays_onto_a_replica():
+    """The dict model's incremental export (status 1 = modified, 2 = erased) reproduces the source on a replica —
+    the semantics tests/test_hash_gpu.py::test_incremental_export_* demand of the CUDA table."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 10_000))
+    def run(seed):
+        rng = np.random.default_rng(seed)
+        src = R.MapParameterModel(4, default_value=0.0, evict_filter_value=3)
+        rep = R.MapParameterModel(4, default_value=0.0)
+        src.put(np.arange(30), rng.standard_normal((30, 4)).astype(np.float32))
+        rep.import_data(src.export_data())
+        for _ in range(4):
+            op = rng.integers(0, 4)
+            ks = rng.choice(60, size=rng.integers(1, 12), replace=False)
+            if op == 0:
+                src.put(ks, rng.standard_normal((ks.size, 4)).astype(np.float32))
+            elif op == 1:
+                src.get(ks)
+            elif op == 2:
+                src.erase(ks)
+            else:
+                src.evict()
+            if rng.random() < 0.5:
+                rep.import_data(src.export_data(incremental=True))
+        rep.import_data(src.export_data(incremental=True))
+        assert sorted(src.rows) == sorted(rep.rows)
+        for k in src.rows:
+            assert np.array_equal(src.rows[k], rep.rows[k])
+        assert src.export_data(incremental=True)[0].size == 0
+    run()
