@@ -1,0 +1,80 @@
+"""The device-driven exchange protocol (peer_sharded.PeerRank / EmulatedPeerGroup) driven on the CPU with stand-in
+kernels (tests/fake_peer_ops.py): phase order, buffer wiring and the pointer tables of `connect` are the real
+product code; G emulated ranks must equal the oracle on the full tables (same check as the GPU emulation test)."""
+import numpy as np
+import pytest
+import torch
+
+from mindrec_b200 import peer_sharded
+from oracle import ref_numpy as R
+from tests import fake_peer_ops
+
+
+@pytest.fixture()
+def cpu_ops(monkeypatch):
+    monkeypatch.setattr(peer_sharded, "ops", fake_peer_ops)
+    return fake_peer_ops
+
+
+@pytest.mark.parametrize("world,vocab", [(1, 53), (2, 200), (3, 101), (4, 64)])
+def test_emulated_ranks_on_cpu_match_oracle_on_full_tables(cpu_ops, world, vocab):
+    b, f, dim, sens = 12, 4, 8, 1024.0
+    grp = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, "cpu", seed=5, sens=sens)
+    bias = torch.tensor([0.25], dtype=torch.float32)
+    rng = np.random.default_rng(world)
+    for step in range(3):
+        ids = [rng.integers(0, vocab, size=(b, f)).astype(np.int32) for _ in range(world)]
+        for r in range(world):
+            ids[r][:, 0] = rng.integers(0, 5, size=b)                  # keys shared by every rank
+        wts = [(rng.random((b, f)) < 0.9).astype(np.float32) for _ in range(world)]
+        delta = [rng.standard_normal((b, 1)).astype(np.float32) for _ in range(world)]
+        gx = [rng.standard_normal((b, f * dim)).astype(np.float32) for _ in range(world)]
+        wide0, deep0 = (t.numpy().astype(np.float64) for t in grp.full_tables())
+        if step == 0:
+            acc, lin = np.ones_like(wide0), np.zeros_like(wide0)
+            m, v = np.zeros_like(deep0), np.zeros_like(deep0)
+            adam, ftrl = R.AdamState(3.5e-4, eps=1e-8), R.FtrlState(5e-2, l1=1e-8, l2=1e-8)
+        t = lambda lst: [torch.from_numpy(x) for x in lst]
+        deep_outs = [torch.empty((b, f * dim)) for _ in range(world)]
+        wide_outs = [torch.empty((b, 1)) for _ in range(world)]
+        grp.forward(t(ids), t(wts), bias, deep_outs, wide_outs)
+        for r in range(world):
+            want = (deep0[ids[r]] * wts[r][..., None]).reshape(b, f * dim).astype(np.float32)
+            assert np.array_equal(deep_outs[r].numpy(), want)
+            want_w = (wide0[ids[r], 0] * wts[r]).sum(1, keepdims=True) + 0.25
+            np.testing.assert_allclose(wide_outs[r].numpy(), want_w, rtol=1e-5, atol=1e-7)
+        grp.backward(t(delta), t(gx))
+        for rk in grp.ranks:
+            assert int(rk.err) == 0                                     # no wait saw a missing signal, no overflow
+        ids_cat = np.concatenate(ids).reshape(-1)
+        mask_cat = np.concatenate(wts).reshape(-1).astype(np.float64)
+        g_deep = np.concatenate(gx).reshape(-1, dim).astype(np.float64) * mask_cat[:, None] / (sens * world)
+        g_wide = np.repeat(np.concatenate(delta).astype(np.float64), f, axis=0) * mask_cat[:, None] / (sens * world)
+        uniq, inverse = np.unique(ids_cat, return_inverse=True)
+        gs_deep, gs_wide = np.zeros((uniq.size, dim)), np.zeros((uniq.size, 1))
+        np.add.at(gs_deep, inverse, g_deep)
+        np.add.at(gs_wide, inverse, g_wide)
+        adam.begin_step()
+        R.lazy_adam_sparse(deep0, m, v, uniq, gs_deep, adam)
+        R.ftrl_sparse(wide0, acc, lin, uniq, gs_wide, ftrl)
+        wide1, deep1 = (t_.numpy() for t_ in grp.full_tables())
+        np.testing.assert_allclose(deep1, deep0, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(wide1, wide0, rtol=1e-5, atol=1e-7)
+
+
+def test_look_ahead_plan_equals_inline_plan_on_cpu(cpu_ops):
+    """p_plan_local(nxt=True) + p_adopt leaves exactly the state of an inline p_plan_local."""
+    vocab, n = 300, 40
+    alloc = lambda name, shape, dtype: torch.zeros(shape, dtype=dtype)
+    a = peer_sharded.PeerRank(1, 3, vocab, 8, n, "cpu", alloc)
+    bk = peer_sharded.PeerRank(1, 3, vocab, 8, n, "cpu", alloc)
+    ids = torch.from_numpy(np.random.default_rng(0).integers(-2, vocab + 3, size=n).astype(np.int32))
+    a.p_plan_local(ids)
+    bk.p_plan_local(ids, nxt=True)
+    bk.p_adopt()
+    u = int(a.uq.count)
+    assert int(bk.uq.count) == u
+    for fa, fb, k in ((a.uq.uniq, bk.uq.uniq, u), (a.uq.inverse, bk.uq.inverse, n), (a.uq.perm, bk.uq.perm, n),
+                      (a.uq.seg_of, bk.uq.seg_of, n), (a.uq.seg_start, bk.uq.seg_start, u + 1)):
+        assert torch.equal(fa[:k], fb[:k])
+    assert torch.equal(a.bounds, bk.bounds)
