@@ -104,8 +104,8 @@ def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
     g = peer_ptrs.numel()
     r = _np(rows)
     for s in range(g):
-        lo, hi = int(src_off[s]), int(src_off[s + 1])
-        for j in range(hi - lo):
+        lo, hi = int(src_off[s]), min(int(src_off[s + 1]), r.size)      # like the kernel: never past the inbox
+        for j in range(max(0, hi - lo)):
             dst = _at(int(peer_ptrs[s]) + (int(dst_off[s]) + j) * d * 4, d, ctypes.c_float, np.float32)
             row = int(r[lo + j])
             dst[:] = t[row] if 0 <= row < t.shape[0] else 0.0
@@ -181,3 +181,83 @@ def sparse_ftrl(w, accum, linear, hyper, g, mask, uq, n_valid=None):
     h = _np(hyper)
     st = types.SimpleNamespace(lr=float(h[0]), l1=float(h[1]), l2=float(h[2]), lr_power=float(h[3]), grad_scale=h[4])
     R.ftrl_sparse(_np(w), _np(accum), _np(linear), _np(uq.uniq)[:u], gsum, st)
+
+
+# ---- hash-sharded variant (PeerHashRank) -------------------------------------------------------------------------
+def shard_remap_hash(keys, owners_like, bits_like, out=None):
+    """Any owner function works for the protocol; the stand-in uses key mod G (the CUDA kernel uses high mix64 bits)."""
+    g, bits = owners_like.shape[0], bits_like.shape[0]
+    k = _np(keys).astype(np.int64).reshape(-1)
+    ok = (k >= 0) & ((k >> bits) == 0)
+    res = np.where(ok, ((k % g) << bits) | k, g << bits)
+    if out is None:
+        out = torch.empty(keys.shape, dtype=torch.int64)
+    out.copy_(torch.from_numpy(res).view(out.shape))
+    return out
+
+
+def fill_tail(buf, n_valid, value):
+    _np(buf)[max(0, int(n_valid[0])):] = _np(value)[0]
+    return buf
+
+
+def gather(table, ids, out=None, oob_flag=None):
+    t, i = _np(table), _np(ids).reshape(-1).astype(np.int64)
+    ok = (i >= 0) & (i < t.shape[0])
+    res = np.where(ok[:, None], t[np.where(ok, i, 0)], 0.0).astype(F32)
+    if out is None:
+        out = torch.empty(tuple(ids.shape) + (t.shape[1],), dtype=torch.float32)
+    out.copy_(torch.from_numpy(res).view(out.shape))
+    return out
+
+
+class FakeMapParameter:
+    """Slot table with the surface PeerHashRank uses: slots handed out in arrival order, rows initialised by a
+    deterministic function of the KEY (like the CUDA table's Philox-by-key), arenas indexed by slot."""
+
+    def __init__(self, key_dtype=torch.int64, value_shape=1, default_value="normal", permit_filter_value=1,
+                 evict_filter_value=None, capacity=1 << 10, device="cpu", seed=0, **_):
+        self.dim = value_shape if isinstance(value_shape, int) else value_shape[0]
+        self.capacity = capacity
+        self.values = torch.zeros((capacity + 1, self.dim), dtype=torch.float32)
+        self.slot_of = {}
+        self._arenas = []
+        self.seed = seed
+        self.overflowed = False
+
+    def add_arena(self, fill=0.0, dim=None):
+        a = torch.full((self.capacity + 1, dim or self.dim), float(fill), dtype=torch.float32)
+        self._arenas.append(a)
+        return a
+
+    def _init_row(self, key):
+        rng = np.random.default_rng([self.seed, int(key) & 0xffffffff, int(key) >> 32])
+        return (rng.standard_normal(self.dim) * 0.01).astype(F32)
+
+    def lookup_slots(self, key, insert_default_value=True):
+        flat = _np(key).reshape(-1).astype(np.int64)
+        slots = np.full(flat.size, self.capacity, dtype=np.int32)
+        for i, k in enumerate(flat.tolist()):
+            if k < 0:                                   # reserved keys (the blanked inbox tail) read the default row
+                continue
+            s = self.slot_of.get(k)
+            if s is None and insert_default_value:
+                if len(self.slot_of) >= self.capacity:
+                    self.overflowed = True
+                    continue
+                s = self.slot_of[k] = len(self.slot_of)
+                self.values[s] = torch.from_numpy(self._init_row(k))
+                for a in self._arenas:
+                    a[s] = a[self.capacity]
+            if s is not None:
+                slots[i] = s
+        return torch.from_numpy(slots)
+
+    def get_data(self):
+        ks = sorted(self.slot_of)
+        k = torch.tensor(ks, dtype=torch.int64)
+        v = self.values[[self.slot_of[x] for x in ks]] if ks else torch.zeros((0, self.dim))
+        return k, v
+
+    def __len__(self):
+        return len(self.slot_of)

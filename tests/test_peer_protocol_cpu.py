@@ -78,3 +78,56 @@ def test_look_ahead_plan_equals_inline_plan_on_cpu(cpu_ops):
                       (a.uq.seg_of, bk.uq.seg_of, n), (a.uq.seg_start, bk.uq.seg_start, u + 1)):
         assert torch.equal(fa[:k], fb[:k])
     assert torch.equal(a.bounds, bk.bounds)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_emulated_hash_sharding_on_cpu_matches_one_table(cpu_ops, monkeypatch, world):
+    """PeerHashRank's orchestration (owner-major int64 keys, key inbox blanking, serve by slot, update by slot with
+    the device-side valid count) against ONE stand-in table fed the same keys."""
+    from mindrec_b200 import hash as H
+    monkeypatch.setattr(H, "MapParameter", fake_peer_ops.FakeMapParameter)
+    dim, n, bits = 8, 60, 30
+    rng = np.random.default_rng(world)
+    # inboxes sized for the worst case here (every rank's keys on one owner); the default capacity is n per rank
+    grp = peer_sharded.EmulatedPeerHashGroup(world, dim, n, "cpu", key_bits=bits, capacity=1 << 9, seed=7, learning_rate=1e-2,
+                                             cap_rows=world * n)
+    one = fake_peer_ops.FakeMapParameter(value_shape=dim, capacity=1 << 11, seed=7)
+    m1, v1 = one.add_arena(0.0), one.add_arena(0.0)
+    hyper = fake_peer_ops.adam_hyper(1e-2, device="cpu")
+    pool = rng.integers(0, 1 << bits, size=300)
+    for step in range(3):
+        keys = [rng.choice(pool[: 100 * (step + 1)], size=n) for _ in range(world)]
+        for k in keys:
+            k[:6] = pool[:6]                                            # shared across ranks
+        grads = [(np.abs(rng.standard_normal((n, dim))) + 0.5).astype(np.float32) for _ in range(world)]
+        keys_t = [torch.from_numpy(k) for k in keys]
+        outs = [torch.empty((n, dim)) for _ in range(world)]
+        grp.forward(keys_t, outs)
+        slots = one.lookup_slots(torch.cat(keys_t)).clone()
+        want = fake_peer_ops.gather(one.values, slots).view(world, n, dim)
+        for r in range(world):
+            torch.testing.assert_close(outs[r], want[r], rtol=1e-5, atol=1e-8)
+        grp.backward([torch.from_numpy(g) for g in grads])
+        fake_peer_ops.adam_begin_step(hyper)
+        uq = fake_peer_ops.unique(slots, table_like=torch.empty((one.capacity, 0)))
+        c = one.capacity
+        fake_peer_ops.sparse_lazy_adam(one.values[:c], m1[:c], v1[:c], hyper, torch.from_numpy(np.concatenate(grads)), None, uq)
+        for rk in grp.ranks:
+            assert int(rk.err) == 0 and not rk.table.overflowed
+        k_sh, v_sh = grp.get_data()
+        k_1, v_1 = one.get_data()
+        assert torch.equal(k_sh, k_1)
+        torch.testing.assert_close(v_sh, v_1, rtol=1e-5, atol=1e-8)
+    assert sum(len(rk.table) for rk in grp.ranks) == len(one)
+
+
+def test_inbox_overflow_is_flagged_on_cpu(cpu_ops, monkeypatch):
+    """An owner that is sent more keys than its inbox holds raises error bit 2 (bench.py aborts on it) — no stray store."""
+    from mindrec_b200 import hash as H
+    monkeypatch.setattr(H, "MapParameter", fake_peer_ops.FakeMapParameter)
+    world, dim, n = 4, 4, 16
+    grp = peer_sharded.EmulatedPeerHashGroup(world, dim, n, "cpu", key_bits=20, capacity=1 << 8, seed=1)
+    keys = [torch.arange(r * n, (r + 1) * n, dtype=torch.int64) * world for r in range(world)]     # all owned by rank 0
+    outs = [torch.empty((n, dim)) for _ in range(world)]
+    grp.forward(keys, outs)
+    assert any(int(rk.err) & 2 for rk in grp.ranks)
