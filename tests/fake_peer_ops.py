@@ -142,10 +142,10 @@ def gather_reduce(table, ids, mask, bias, out=None, oob_flag=None):
 def _segment_rows(g, mask, uq, dim, n_valid=None):
     n = uq.n if n_valid is None else max(0, min(uq.n, int(n_valid[0])))
     u = int(uq.count[0])
-    rows = _np(g).reshape(-1, dim).astype(np.float64)
+    rows = _np(g).reshape(-1, dim)                     # the padding past n_valid is uninitialised: never cast it
     div = max(1, uq.n // max(1, rows.shape[0])) if rows.shape[0] and uq.n % rows.shape[0] == 0 else 1
     perm, seg_of = _np(uq.perm)[:n].astype(np.int64), _np(uq.seg_of)[:n].astype(np.int64)
-    vals = rows[perm // div]
+    vals = rows[perm // div].astype(np.float64)
     if mask is not None and mask.numel():
         vals = vals * _np(mask).reshape(-1).astype(np.float64)[perm][:, None]
     out = np.zeros((u, dim))
