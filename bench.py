@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--vocab-scale", type=float, default=1.0, help="shrink the Kaggle cardinalities (debug)")
     ap.add_argument("--alpha", type=float, default=1.05)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config-3 / config-4 / config-5 blocks")
     ap.add_argument("--exchange", default=os.environ.get("MREC_BENCH_EXCHANGE", "device"), choices=["nccl", "device"],
                     help="N>1: nccl = all-to-all with host-side split sizes; device = device-driven peer stores, "
                          "whole step in one CUDA graph")
@@ -66,10 +67,33 @@ def scaled_cards(scale):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference path restated in oracle/ (kind = "port"), bounded sample of the same workload
 # --------------------------------------------------------------------------------------------------
+def cpu_config1_run(steps=20, warmup=3):
+    """BASELINE configs[0], faithfully: Wide&Deep, batch 1000, 39 fields, vocab 200 000 (the reference's own
+    cardinality list, models/wide_deep/src/datasets.py:354-379), dim 80, fp32, single process on the host cores."""
+    import numpy as np
+    from mindrec_b200 import synth
+    from oracle import ref_c
+    cores = ref_c.use_all_cores()
+    b, vocab = 1000, 200000
+    model = ref_c.WideDeepCpu(vocab, EMB, hidden=HIDDEN, fields=FIELDS, seed=0)
+    gen = synth.CriteoSynth(b, cards=synth.CARD_REFERENCE, alpha=1.05, seed=20260101, vocab_pad=vocab)
+    batches = [gen.next() for _ in range(4)]
+    for i in range(warmup):
+        model.step(*batches[i % 4])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        model.step(*batches[i % 4])
+    dt = time.perf_counter() - t0
+    return {"value": b * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": 1e3 * dt / steps,
+            "sample": "BASELINE config 1 in full: batch 1000, 39 fields, vocab 200000, dim 80, fp32, %d steps after "
+                      "%d warm-up" % (steps, warmup)}
+
+
 def cpu_baseline_run(args, steps, warmup):
     import numpy as np
     from mindrec_b200 import synth
     from oracle import ref_c
+    ref_c.use_all_cores()            # torchrun exports OMP_NUM_THREADS=1: pin the team to every host core
     cards = scaled_cards(args.vocab_scale)
     full_vocab = synth.vocab_size(cards)
     vocab = min(full_vocab, args.cpu_vocab)
@@ -102,6 +126,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 20))
     warmup = max(1, min(args.warmup, 3))
     cb = cpu_baseline_run(args, steps, warmup)
+    c1 = cpu_config1_run()
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
@@ -110,6 +135,7 @@ def run_reference(args):
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "config1": c1,
         "note": "reference's CPU path as restated in oracle/ (C/OpenMP + numpy BLAS); MindSpore is not installable here",
     }
     print(json.dumps(line), flush=True)
@@ -232,11 +258,13 @@ def measure_dominant_op(step, batches, b, reps=10):
     alg //= k
     peak, how = hbm_peak()
     gbs = alg / ms / 1e6
-    traffic = None
-    try:      # dram__bytes_read + dram__bytes_write of the op's kernels from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic_bytes_per_launch"]
-    except Exception:
-        pass
+    # dram__bytes_read + dram__bytes_write of the op's two kernels, from this round's ncu --set full capture
+    traffic = _traffic("sparse_lazy_adam")
+    if traffic is None:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic_bytes_per_launch"]
+        except Exception:
+            pass
     return {"kernel": "mrec_sparse_lazy_adam = segsum_stage_kernel<__half> + "
                       "rows_update_kernel<F8,LazyAdamSink> (256-bit rows; 2 launches, timed as one op)",
             "bound": "hbm", "achieved": round(gbs, 1), "peak": peak,
@@ -245,6 +273,150 @@ def measure_dominant_op(step, batches, b, reps=10):
             "unique_rows": int(sum(us) / k), "lookups": batches[0][0].numel(), "ms": round(ms, 4),
             "how": "CUDA graph of the op over a ring of %d different batches (inputs > L2, no flush), %d replays "
                    "back to back, CUDA events, mean per call" % (k, reps)}
+
+
+def _traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from this round's `ncu --set full`
+    capture (profiles/r2_traffic.json, written by tools/ncu_metrics.py from the .ncu-rep of the same command)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[name]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def _time_ring(calls, reps=10):
+    """Mean device time (ms) of one call: the calls (each on its own buffers; together larger than the 126 MB L2, so
+    no flush is needed) are captured back to back in one CUDA graph, replayed `reps` times between two CUDA events."""
+    import torch
+    for _ in range(2):
+        for c in calls:
+            c()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for c in calls:
+            c()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * len(calls))
+
+
+def _roof(kernel, alg_bytes, ms, traffic_key=None, **extra):
+    peak, how = hbm_peak()
+    gbs = alg_bytes / ms / 1e6
+    out = {"kernel": kernel, "bound": "hbm", "achieved": round(gbs, 1), "peak": peak,
+           "peak_source": "MEASURED_PEAKS.json (measured)" if how == "measured" else "fallback 6650", "unit": "GB/s",
+           "frac": round(gbs / peak, 4), "traffic": _traffic(traffic_key) if traffic_key else None,
+           "algorithmic_bytes": int(alg_bytes), "ms": round(ms, 4)}
+    out.update(extra)
+    return out
+
+
+def measure_gather(table, zipf_ids):
+    """BASELINE metric "embedding gather HBM GB/s": mrec_gather of the config-2 deep table (33.76 M x 80 fp32),
+    N = 624 000 lookups, algorithmic bytes N*(8D+4).  Two id streams: the step's own Zipf(1.05) ids (most
+    reads hit the L2: ~120 k distinct rows) and ids uniform over the table (every row comes from HBM) — the uniform
+    figure is the honest HBM number.  Ring of 4 id sets, each call writes its own [N, D] output (200 MB)."""
+    import torch
+    from mindrec_b200 import ops
+    dev = table.device
+    v, d = table.shape
+    n = zipf_ids[0].numel()
+    outs = [torch.empty((n, d), dtype=torch.float32, device=dev) for _ in range(2)]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    uni = [torch.randint(0, v, zipf_ids[0].shape, device=dev, dtype=torch.int32, generator=gen) for _ in range(4)]
+    alg = n * (8 * d + 4)
+    res = {}
+    for name, ids in (("zipf", zipf_ids), ("uniform", uni)):
+        calls = [(lambda i=i, t=t: ops.gather(table, t, out=outs[i & 1])) for i, t in enumerate(ids)]
+        ms = _time_ring(calls)
+        res[name] = _roof("gather_rows_kernel (mrec_gather, D=80, %s ids)" % name, alg, ms, "gather_" + name,
+                          lookups=n, distinct_rows=int(torch.unique(ids[0]).numel()))
+    return res
+
+
+def measure_c3(args, dev, steps):
+    """BASELINE configs[2]: Deep&Cross, 6 cross layers, dim 80 (row = 39*80 = 3120 fp32), batch 16384, vocab 200 000,
+    fp32 towers (the reference's convert_dtype=False), Adam on every weight: full training steps through
+    interaction.DeepCrossTrainStep + the cross kernels in isolation (fwd 2*B*D'*4, bwd 3*B*D'*4 algorithmic bytes)."""
+    import torch
+    from mindrec_b200 import interaction, ops, synth
+    b, d, layers, vocab = 16384, EMB, 6, 200000
+    cfg = interaction.DeepCrossConfig(batch_size=b, field_size=FIELDS, vocab_size=vocab, emb_dim=d,
+                                      deep_layer_dim=(1024, 1024), cross_layer_num=layers)
+    model = interaction.DeepCrossModel(cfg, device=dev)
+    step = interaction.DeepCrossTrainStep(interaction.DeepCrossNetWithLoss(model))
+    gen = synth.CriteoSynth(b, cards=synth.CARD_REFERENCE, alpha=args.alpha, seed=20260103, vocab_pad=vocab)
+    batches = [tuple(torch.from_numpy(x).to(dev) for x in gen.next()) for _ in range(4)]
+    for i in range(3):
+        loss = step(*batches[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(*batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    dp = FIELDS * d
+    xs = [torch.randn((b, dp), device=dev) * 0.1 for _ in range(2)]
+    dys = [torch.randn((b, dp), device=dev) * 0.1 for _ in range(2)]
+    ys = [torch.empty((b, dp), device=dev) for _ in range(2)]
+    ps = [torch.empty((b, layers), device=dev) for _ in range(2)]
+    dw, db = torch.empty((layers, dp), device=dev), torch.empty((layers, dp), device=dev)
+    w, bb = model.cross_weight, model.cross_bias
+    fwd = _time_ring([(lambda i=i: ops.cross_fwd(xs[i], w, bb, y=ys[i], p=ps[i])) for i in range(2)])
+    bwd = _time_ring([(lambda i=i: ops.cross_bwd(xs[i], dys[i], w, bb, ps[i], dx=ys[i], dw=dw, db=db)) for i in range(2)])
+    return {"workload": "BASELINE config 3: Deep&Cross, 6 cross layers, dim 80, batch 16384, vocab 200000, fp32, "
+                        "Adam (dense-equivalent) on the table", "samples_per_s": b / (ms * 1e-3), "ms_per_step": ms,
+            "steps": steps, "mode": "eager", "final_loss": float(loss),
+            "cross_fwd": _roof("cross_fwd_kernel (6 layers fused)", 2 * b * dp * 4, fwd, "cross_fwd"),
+            "cross_bwd": _roof("cross_bwd_kernel (6 layers fused)", 3 * b * dp * 4, bwd, "cross_bwd")}
+
+
+def measure_c4(args, dev, steps):
+    """BASELINE configs[3]: DeepFM, FM second order over 39 fields, dim 16, batch 16384, vocab 184 965: full training
+    steps through interaction.DeepFMTrainStep + the FM kernels in isolation (fwd B*F*D*4, bwd 2*B*F*D*4 bytes; a ring
+    of 8 inputs of 41 MB each so that the 126 MB L2 cannot hold them)."""
+    import torch
+    from mindrec_b200 import interaction, ops, synth
+    b, d, vocab = 16384, 16, 184965
+    cfg = interaction.DeepFMConfig(batch_size=b, data_field_size=FIELDS, data_vocab_size=vocab, data_emb_dim=d)
+    model = interaction.DeepFMModel(cfg, device=dev)
+    step = interaction.DeepFMTrainStep(interaction.DeepFMNetWithLoss(model, l2_coef=cfg.l2_coef), lr=cfg.learning_rate,
+                                       eps=cfg.epsilon, loss_scale=cfg.loss_scale)
+    gen = synth.CriteoSynth(b, cards=synth.CARD_REFERENCE, alpha=args.alpha, seed=20260104, vocab_pad=vocab)
+    batches = [tuple(torch.from_numpy(x).to(dev) for x in gen.next()) for _ in range(4)]
+    for i in range(3):
+        loss = step(*batches[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(*batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ring = 8
+    vxs = [torch.randn((b, FIELDS, d), device=dev) * 0.1 for _ in range(ring)]
+    outs = [torch.empty((b, 1), device=dev) for _ in range(ring)]
+    gout = torch.randn((b, 1), device=dev)
+    dvx = [torch.empty((b, FIELDS, d), device=dev) for _ in range(ring)]
+    fwd = _time_ring([(lambda i=i: ops.fm_fwd(vxs[i], out=outs[i])) for i in range(ring)])
+    bwd = _time_ring([(lambda i=i: ops.fm_bwd(vxs[i], gout, out=dvx[i])) for i in range(ring)])
+    vol = b * FIELDS * d * 4
+    return {"workload": "BASELINE config 4: DeepFM, FM second order over 39 fields, dim 16, batch 16384, vocab 184965",
+            "samples_per_s": b / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "mode": "eager",
+            "final_loss": float(loss),
+            "fm_fwd": _roof("fm_fwd_kernel", vol + b * 4, fwd, "fm_fwd"),
+            "fm_bwd": _roof("fm_bwd_kernel", 2 * vol + b * 4, bwd, "fm_bwd")}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -391,8 +563,10 @@ def run_ours(args):
         tot = step.profile.totals()
         step.profile = None
         breakdown = {k: round(statistics.median(v), 4) for k, v in tot.items()}
+    roofline_gather, configs = None, {}
     if world == 1:
         roofline = measure_dominant_op(step, devb[:4], b)
+        roofline_gather = measure_gather(step.model.embedding_table.data, [x[0] for x in devb[:4]])
 
     exchange = None
     if world > 1 and hasattr(step.tables, "rk"):
@@ -430,6 +604,14 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cb_full = cpu_baseline_run(args, steps=8, warmup=2)
         cb = {k: cb_full[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb["config1"] = cpu_config1_run()
+    if world == 1 and not args.no_extra_configs:
+        # the other single-GPU BASELINE configs, measured by the same run (the tables of config 2 are released first)
+        del step, model
+        torch.cuda.empty_cache()
+        n_extra = max(3, min(args.steps, 20))
+        configs["c3"] = measure_c3(args, dev, n_extra)
+        configs["c4"] = measure_c4(args, dev, n_extra)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -440,7 +622,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(per_step_launches * args.steps),
         "gpu_launches_per_step": int(per_step_launches),
-        "roofline": roofline, "cpu_baseline": cb, "breakdown_ms": breakdown, "exchange": exchange, "final_loss": final_loss,
+        "roofline": roofline, "roofline_gather": roofline_gather, "configs": configs, "cpu_baseline": cb, "breakdown_ms": breakdown, "exchange": exchange, "final_loss": final_loss,
         "lib": _lib.version(),
     }
     print(json.dumps(line), flush=True)

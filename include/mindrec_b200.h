@@ -249,6 +249,13 @@ int mrec_hash_evict(MREC_AOT_ARGS);
 /* get_keys / export_data:  in : tkeys, meta, state, cfg [, since[1] i32: only keys looked up / put after that step]
  *                          out: keys_out[C] i64, slots_out[C] i32, count[1] i32                               */
 int mrec_hash_export(MREC_AOT_ARGS);
+/* Growth (upstream's GPUHashTable is a cuco dynamic_map that grows; mindspore_rec/ops/embedding.py:136-144 never sizes
+ * it): rebuild the key -> slot map into a larger table, then move every arena's rows by the slot map.
+ *   mrec_hash_rehash     in : tkeys_old[C], meta_old[C], state[8]
+ *                        out: tkeys_new[C2] (pre-filled with -1), meta_new[C2] (zeros), slot_map[C] i32 (-1 = free slot)
+ *   mrec_hash_move_rows  in : arena_old[C+1,D] f32, slot_map[C] i32         out: arena_new[C2+1,D] f32              */
+int mrec_hash_rehash(MREC_AOT_ARGS);
+int mrec_hash_move_rows(MREC_AOT_ARGS);
 
 #ifdef __cplusplus
 }

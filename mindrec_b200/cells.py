@@ -49,7 +49,7 @@ class WideDeepConfig:
                  deep_layer_dim=(1024, 512, 256, 128), deep_layer_act="relu", keep_prob=1.0,
                  dropout_flag=False, l2_coef=8e-5, emb_init="normal", weight_bias_init=("normal", "normal"),
                  use_mixed_precision=True, sparse=False, dynamic_embedding=False, parameter_server=False,
-                 vocab_cache_size=0, seed=1):
+                 vocab_cache_size=0, seed=1, hash_capacity=1 << 20, hash_auto_grow=True):
         self.batch_size = batch_size
         self.field_size = field_size
         self.vocab_size = vocab_size
@@ -67,6 +67,9 @@ class WideDeepConfig:
         self.parameter_server = parameter_server
         self.vocab_cache_size = vocab_cache_size
         self.seed = seed
+        # dynamic_embedding only: initial slot count of the two MapParameters and whether they grow by themselves
+        self.hash_capacity = hash_capacity
+        self.hash_auto_grow = hash_auto_grow
 
 
 class WideDeepModel:
@@ -77,22 +80,32 @@ class WideDeepModel:
             raise ValueError("only the reference default deep_layer_act='relu' is implemented")
         if config.dropout_flag:
             raise ValueError("dropout_flag=True is not on the benchmarked path (keep_prob 1.0)")
-        if config.dynamic_embedding:
-            raise ValueError("dynamic_embedding=True: build the model with mindrec_b200.hash.HashEmbeddingLookup")
         self.config = config
         self.batch_size = config.batch_size
         self.field_size = config.field_size
         self.emb_dim = config.emb_dim
         self.device = torch.device(device)
+        self.dynamic = bool(config.dynamic_embedding)
         gen = torch.Generator(device=self.device)
         gen.manual_seed(config.seed)
-        self.wide_embeddinglookup = EmbeddingLookup(config.vocab_size, 1, param_init=config.emb_init,
-                                                    sparse=config.sparse, device=self.device,
-                                                    name="wide_embeddinglookup.embedding_table", generator=gen)
-        self.deep_embeddinglookup = EmbeddingLookup(config.vocab_size, config.emb_dim,
-                                                    param_init=config.emb_init, sparse=config.sparse,
-                                                    device=self.device,
-                                                    name="deep_embeddinglookup.embedding_table", generator=gen)
+        if self.dynamic:
+            # wide_and_deep.py:268-274: HashEmbeddingLookup(embedding_size=emb_dim) + HashEmbeddingLookup(embedding_size=1)
+            # over two MapParameters (int32 keys, admitted on first sight, never evicted: the constructor defaults)
+            from .hash import HashEmbeddingLookup
+            kw = dict(param_init=config.emb_init, capacity=config.hash_capacity, device=self.device,
+                      auto_grow=config.hash_auto_grow)
+            self.deep_embeddinglookup = HashEmbeddingLookup(config.emb_dim, seed=config.seed, **kw)
+            self.wide_embeddinglookup = HashEmbeddingLookup(1, seed=config.seed + 1, **kw)
+            self.deep_embeddinglookup.embedding_table.name = "deep_embeddinglookup.embedding_table"
+            self.wide_embeddinglookup.embedding_table.name = "wide_embeddinglookup.embedding_table"
+        else:
+            self.wide_embeddinglookup = EmbeddingLookup(config.vocab_size, 1, param_init=config.emb_init,
+                                                        sparse=config.sparse, device=self.device,
+                                                        name="wide_embeddinglookup.embedding_table", generator=gen)
+            self.deep_embeddinglookup = EmbeddingLookup(config.vocab_size, config.emb_dim,
+                                                        param_init=config.emb_init, sparse=config.sparse,
+                                                        device=self.device,
+                                                        name="deep_embeddinglookup.embedding_table", generator=gen)
         self.embedding_table = self.deep_embeddinglookup.embedding_table
         dims = [self.field_size * self.emb_dim] + list(config.deep_layer_dim) + [1]
         w_init, b_init = config.weight_bias_init
@@ -102,6 +115,7 @@ class WideDeepModel:
         self.wide_b = Parameter(self.dense.extra, name="Wide_b")
         if config.emb_init == "normal":
             self.wide_b.data.normal_(0.0, 0.01, generator=gen)
+        self.slots_w = self.slots_d = None          # dynamic mode: the step's slot indices (the RowTensor indices)
         self._wide_out = None
         self._deep_in = None
         self._wide_stream = None
@@ -126,13 +140,28 @@ class WideDeepModel:
         main = torch.cuda.current_stream()
         if self._wide_stream is None:
             self._wide_stream = torch.cuda.Stream(device=self.device)
+        if self.dynamic:
+            # HashEmbeddingLookup.construct (embedding.py:184-206): key -> slot (find-or-insert; new rows initialised),
+            # then the same fused gathers read the arenas by slot (slot C = the default row of unadmitted keys)
+            wt, dt = self.wide_embeddinglookup, self.deep_embeddinglookup
+            for emb in (wt, dt):
+                if emb.auto_grow:
+                    emb.embedding_table.maybe_grow(id_hldr.numel())
         self._wide_stream.wait_stream(main)
         with torch.cuda.stream(self._wide_stream):
-            ops.gather_reduce(self.wide_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
-                              self.wide_b.data, out=self._wide_out)
+            if self.dynamic:
+                self.slots_w = wt.embedding_table.lookup_slots(id_hldr).view(b, f)
+                ops.gather_reduce(wt.embedding_table.values, self.slots_w, wt_hldr, self.wide_b.data, out=self._wide_out)
+            else:
+                ops.gather_reduce(self.wide_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
+                                  self.wide_b.data, out=self._wide_out)
         # wide_and_deep.py:302,308-309: gather(dim D) * mask -> [B, F*D]
-        ops.gather_masked(self.deep_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
-                          out=self._deep_in)
+        if self.dynamic:
+            self.slots_d = dt.embedding_table.lookup_slots(id_hldr).view(b, f)
+            ops.gather_masked(dt.embedding_table.values, self.slots_d, wt_hldr, out=self._deep_in)
+        else:
+            ops.gather_masked(self.deep_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
+                              out=self._deep_in)
         deep_out = self.dense.forward(self._deep_in)       # :310-314
         main.wait_stream(self._wide_stream)
         self.wide_out, self.deep_out = self._wide_out, deep_out
@@ -176,7 +205,8 @@ class NetWithLossClass:
         if self.no_l2loss:
             deep_loss = wide_loss
         else:
-            l2_loss_v = embedding_table.data.square().sum() / 2
+            tbl = embedding_table.values[:embedding_table.capacity] if net.dynamic else embedding_table.data
+            l2_loss_v = tbl.square().sum() / 2
             deep_loss = wide_loss + self.l2_coef * l2_loss_v
         return wide_loss, deep_loss
 
@@ -196,6 +226,13 @@ class TrainStepWrap:
         self.sens = float(sens)
         network.sens_t.fill_(self.sens)
         self.sparse = sparse
+        self.dynamic = bool(getattr(model, "dynamic", False))
+        if self.dynamic and not dynamic_embedding:
+            raise ValueError("the model was built with dynamic_embedding=True: pass dynamic_embedding=True here too")
+        if self.dynamic and not network.no_l2loss:
+            # the reference's launcher pairs --dynamic_embedding=True with --sparse=True
+            # (scripts/run_dynamic_embed_standalone_train_for_gpu.sh:24-30): no dense l2 gradient on a MapParameter
+            raise ValueError("dynamic_embedding needs sparse=True (no full-table l2 term on a hash table)")
         if lazy_adam is None:
             lazy_adam = (sparse and is_auto_parallel) or (sparse and parameter_server) or dynamic_embedding
         self.lazy_adam = bool(lazy_adam)
@@ -211,6 +248,7 @@ class TrainStepWrap:
             # dense mode: d(deep_loss)/dWd carries l2_coef * Wd on every row (wide_and_deep.py:359-360)
             self.optimizer_d.hyper[8] = network.l2_coef
         self._uq = None
+        self._uq_w = None
         self._graph = None
         self._static = None
         self.profile = None
@@ -231,6 +269,8 @@ class TrainStepWrap:
         rng = self.profile.range if self.profile is not None else _null_range
         b = batch_ids.shape[0]
         n = batch_ids.numel()
+        if self.dynamic:
+            return self._construct_dynamic(batch_ids, batch_wts, label)
         main = torch.cuda.current_stream()
         side = self._side_stream() if self.overlap else main
         if self._uq is None or self._uq.n != n:
@@ -257,6 +297,40 @@ class TrainStepWrap:
         main.wait_stream(side)
         return loss_w, loss_d
 
+    def _construct_dynamic(self, batch_ids, batch_wts, label):
+        """dynamic_embedding=True (wide_and_deep.py:268-274,415-430): the two tables are MapParameters, the sparse
+        gradients are addressed by the slots the forward lookups returned (each table has its own key -> slot map, so
+        each gets its own dedup), LazyAdam / FTRL update rows and sibling-arena state by slot."""
+        model = self.model
+        rng = self.profile.range if self.profile is not None else _null_range
+        n = batch_ids.numel()
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.overlap else main
+        with rng("forward"):
+            loss_w, loss_d = self.network(batch_ids, batch_wts, label)
+        if self._uq is None or self._uq.n != n:
+            self._uq = ops.UniqueResult(n, torch.int32, batch_ids.device)
+            self._uq_w = ops.UniqueResult(n, torch.int32, batch_ids.device)
+        tw, td = model.wide_embeddinglookup.embedding_table, model.deep_embeddinglookup.embedding_table
+        side.wait_stream(main)
+        with torch.cuda.stream(side), rng("unique"):        # under the DenseLayer backward
+            uq_w = ops.unique(model.slots_w, table_like=tw.values[:tw.capacity], result=self._uq_w, ws_tag="unique_wide")
+            uq_d = ops.unique(model.slots_d, table_like=td.values[:td.capacity], result=self._uq)
+        with rng("dense_backward"):
+            delta = self.network.delta
+            seed = self.network.delta16 if self.network.delta16.numel() else delta
+            gx = model.dense.backward(seed)
+            model.dense.extra_grad.copy_(self.network.delta_sum)
+        mask = batch_wts.reshape(-1)
+        main.wait_stream(side)
+        side.wait_stream(main)
+        with torch.cuda.stream(side), rng("ftrl_wide"):
+            self.optimizer_w([RowTensor(model.slots_w, delta, mask, uq_w)])
+        with rng("adam_deep"):
+            self.optimizer_d([RowTensor(model.slots_d, gx.view(n, model.emb_dim), mask, uq_d), model.dense.flat_grad])
+        main.wait_stream(side)
+        return loss_w, loss_d
+
     def _side_stream(self):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.model.device)
@@ -266,6 +340,9 @@ class TrainStepWrap:
     def capture(self, batch_ids, batch_wts, label, warmup=3):
         """Capture construct() on static input buffers.  Afterwards `replay(ids, wts, label)` copies the
         inputs in and launches the graph."""
+        if self.dynamic and (self.model.wide_embeddinglookup.auto_grow or self.model.deep_embeddinglookup.auto_grow):
+            raise RuntimeError("dynamic_embedding with hash_auto_grow=True cannot be captured (growth re-allocates the "
+                               "tables): size hash_capacity up front and set hash_auto_grow=False")
         self._static = (batch_ids.clone(), batch_wts.clone(), label.clone())
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

@@ -302,6 +302,61 @@ hash_export_kernel(const long long* __restrict__ keys, const unsigned long long*
   }
 }
 
+
+// ---- growth: rebuild the key -> slot map into a larger table (upstream's GPUHashTable grows) ----------
+// One thread per OLD slot: a live key (resident or still a candidate) is inserted into the new table with the probe
+// sequence of hash_probe_kernel (groups of 8 slots, linear over groups; a group is left only when all 8 of its slots
+// were seen taken, and slots are never freed during the rebuild, so every later lookup that walks the same sequence
+// finds the key before it meets an EMPTY slot).  Keys of the old table are distinct: a plain CAS per slot suffices.
+// The admission / eviction word travels with the key; slot_map[old] = new slot (or -1) drives mrec_hash_move_rows.
+__global__ void __launch_bounds__(256)
+hash_rehash_kernel(const long long* __restrict__ keys_old, const unsigned long long* __restrict__ meta_old,
+                   int64_t cap_old, long long* __restrict__ keys_new, unsigned long long* __restrict__ meta_new,
+                   int64_t cap_new, int32_t* __restrict__ slot_map, int32_t* __restrict__ state) {
+  const int64_t n_groups = cap_new >> 3;
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap_old; s += (int64_t)gridDim.x * blockDim.x) {
+    const long long k = keys_old[s];
+    if (k == kEmpty || k == kErased) {
+      slot_map[s] = -1;
+      continue;
+    }
+    int64_t g = (int64_t)(mix64((uint64_t)k) & (uint64_t)(n_groups - 1));
+    int32_t placed = -1;
+    for (int64_t probes = 0; probes < n_groups && placed < 0; ++probes) {
+      for (int j = 0; j < 8; ++j) {
+        const int64_t slot = g * 8 + j;
+        if (*reinterpret_cast<volatile long long*>(&keys_new[slot]) != kEmpty) continue;
+        const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(&keys_new[slot]),
+                                                    (unsigned long long)kEmpty, (unsigned long long)k);
+        if (prev == kEmpty) {
+          placed = (int32_t)slot;
+          break;
+        }
+      }
+      g = (g + 1) & (n_groups - 1);
+    }
+    slot_map[s] = placed;
+    if (placed >= 0) meta_new[placed] = meta_old[s];
+    else atomicExch(&state[ST_OVERFLOW], 1);          // cannot happen when cap_new >= cap_old
+  }
+}
+
+__global__ void hash_rehash_finish_kernel(int32_t* state) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) state[ST_TOMB] = 0;   // tombstones do not travel
+}
+
+// arena_new[slot_map[s], :] = arena_old[s, :] for every live slot, and the default row C_old -> C_new
+__global__ void __launch_bounds__(256)
+hash_move_rows_kernel(const float* __restrict__ arena_old, int64_t cap_old, const int32_t* __restrict__ slot_map,
+                      float* __restrict__ arena_new, int64_t cap_new, int dim) {
+  const int64_t total = (cap_old + 1) * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = e / dim;
+    const int64_t dst = (s == cap_old) ? cap_new : (int64_t)slot_map[s];
+    if (dst >= 0) arena_new[dst * dim + (e - s * dim)] = arena_old[e];
+  }
+}
+
 static int table_args(const Aot& a, int ki, int mi, int si, int64_t* capacity, const char* who) {
   MREC_REQUIRE(a.is_i64(ki) && a.is_i64(mi) && a.is_i32(si), ERR_DTYPE,
                "%s: table keys/meta must be int64, state int32", who);
@@ -472,4 +527,41 @@ MREC_API int mrec_hash_export(MREC_AOT_SIG) {
               a.ptr<unsigned long long>(1), capacity, a.ptr<int32_t>(3), since, a.ptr<long long>(o), a.ptr<int32_t>(o + 1),
               a.ptr<int32_t>(o + 2));
   return check_launch("hash_export");
+}
+
+// Growth (rehash into a larger table).  in : tkeys_old[C] meta_old[C] state[8]
+//                                       out: tkeys_new[C2] (pre-filled with -1), meta_new[C2] (zeros), slot_map[C] i32
+// C2 a power of two >= C.  Resident keys, candidates and their admission / eviction words move; tombstones vanish.
+MREC_API int mrec_hash_rehash(MREC_AOT_SIG) {
+  MREC_AOT_PACK;
+  MREC_CHECK_NPARAM(a, 6);
+  int64_t cap_old = 0, cap_new = 0;
+  int rc = table_args(a, 0, 1, 2, &cap_old, "mrec_hash_rehash");
+  if (rc) return rc;
+  MREC_REQUIRE(a.is_i64(3) && a.is_i64(4) && a.is_i32(5), ERR_DTYPE, "mrec_hash_rehash: new keys/meta int64, slot_map int32");
+  cap_new = a.numel(3);
+  MREC_REQUIRE(cap_new >= cap_old && (cap_new & (cap_new - 1)) == 0 && a.numel(4) == cap_new && a.numel(5) >= cap_old,
+               ERR_SHAPE, "mrec_hash_rehash: new capacity must be a power of two >= the old one; slot_map[C]");
+  MREC_REQUIRE(cap_new < ((int64_t)1 << 31) - 1, ERR_SHAPE, "mrec_hash_rehash: capacity must be < 2^31");
+  MREC_REQUIRE(a.aligned(3, 64), ERR_ALIGN, "mrec_hash_rehash: table keys must be 64-byte aligned");
+  MREC_LAUNCH(hash_rehash_kernel, grid_for(cdiv(cap_old, 256), 8), 256, 0, a.stream, a.ptr<long long>(0),
+              a.ptr<unsigned long long>(1), cap_old, a.ptr<long long>(3), a.ptr<unsigned long long>(4), cap_new,
+              a.ptr<int32_t>(5), a.ptr<int32_t>(2));
+  MREC_LAUNCH(hash_rehash_finish_kernel, 1, 32, 0, a.stream, a.ptr<int32_t>(2));
+  return check_launch("hash_rehash");
+}
+
+// in : arena_old[C+1,D] f32, slot_map[C] i32      out: arena_new[C2+1,D] f32 (rows of live slots + the default row)
+MREC_API int mrec_hash_move_rows(MREC_AOT_SIG) {
+  MREC_AOT_PACK;
+  MREC_CHECK_NPARAM(a, 3);
+  MREC_REQUIRE(a.is_f32(0) && a.ndims[0] == 2 && a.is_i32(1) && a.is_f32(2) && a.ndims[2] == 2, ERR_DTYPE,
+               "mrec_hash_move_rows: arenas f32 [C+1,D], slot_map int32");
+  const int64_t cap_old = a.dim(0, 0) - 1, cap_new = a.dim(2, 0) - 1;
+  const int dim = (int)a.dim(0, 1);
+  MREC_REQUIRE(a.dim(2, 1) == dim && a.numel(1) >= cap_old && cap_new >= cap_old, ERR_SHAPE,
+               "mrec_hash_move_rows: arena_new must be [C2+1, D] with C2 >= C; slot_map[C]");
+  MREC_LAUNCH(hash_move_rows_kernel, grid_for(cdiv((cap_old + 1) * dim, 256), 8), 256, 0, a.stream, a.ptr<float>(0),
+              cap_old, a.ptr<int32_t>(1), a.ptr<float>(2), cap_new, dim);
+  return check_launch("hash_move_rows");
 }

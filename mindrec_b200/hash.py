@@ -30,8 +30,10 @@ class MapParameter:
     """MapParameter(key_dtype=int32, value_dtype=float32, value_shape=1, key_tensor=None, value_tensor=None,
     default_value='normal', permit_filter_value=1, evict_filter_value=MAX_SIZE, name=None, requires_grad=True).
 
-    `capacity` (slots, rounded to a power of two) is this implementation's sizing knob: keep the load factor
-    at or below ~0.5.  Sibling arenas (optimizer moments) register through `add_arena`."""
+    `capacity` (slots, rounded to a power of two) is the INITIAL size: `maybe_grow` / `grow` rebuild the table into a
+    larger one (mrec_hash_rehash + mrec_hash_move_rows), as upstream's cuco dynamic_map does, so online training with
+    drifting keys does not end in the overflow flag.  Sibling arenas (optimizer state) register through `add_arena`
+    and are re-read through `arena(i)` after a growth."""
 
     def __init__(self, key_dtype=torch.int32, value_dtype=torch.float32, value_shape=1, key_tensor=None,
                  value_tensor=None, default_value="normal", permit_filter_value=1, evict_filter_value=MAX_SIZE,
@@ -101,10 +103,50 @@ class MapParameter:
         return [self.tkeys, self.meta, self.state, self.cfg]
 
     def add_arena(self, fill=0.0, dim=None):
-        """A sibling arena (e.g. Adam moments): rows of new keys are set to `fill`."""
+        """A sibling arena (e.g. Adam moments): rows of new keys are set to `fill`.  Returns the arena tensor; holders
+        that must survive a growth keep the index `len(self._arenas) - 1` and read `arena(i)` instead."""
         a = torch.full((self.capacity + 1, dim or self.dim), float(fill), dtype=torch.float32, device=self.device)
         self._arenas.append(a)
         return a
+
+    def arena(self, i):
+        return self._arenas[i]
+
+    # ---- growth ------------------------------------------------------------------------------------
+    MAX_LOAD = 0.6
+
+    def grow(self, capacity=None):
+        """Rebuild into `capacity` slots (default 2x): keys, admission / eviction words and the rows of every arena
+        move; tombstones vanish.  Slot indices handed out before the call are invalid afterwards."""
+        c_old = self.capacity
+        c_new = _pow2_at_least(int(capacity or 2 * c_old))
+        if c_new <= c_old:
+            return self
+        dev = self.device
+        tkeys = torch.full((c_new,), EMPTY_KEY, dtype=torch.int64, device=dev)
+        meta = torch.zeros(c_new, dtype=torch.int64, device=dev)
+        slot_map = torch.empty(c_old, dtype=torch.int32, device=dev)
+        _lib.aot_call("mrec_hash_rehash", [self.tkeys, self.meta, self.state, tkeys, meta, slot_map])
+
+        def move(old):
+            new = torch.empty((c_new + 1, old.shape[1]), dtype=torch.float32, device=dev)
+            _lib.aot_call("mrec_hash_move_rows", [old, slot_map, new])
+            return new
+        self.values = move(self.values)
+        self._arenas = [move(a) for a in self._arenas]
+        self.tkeys, self.meta, self.capacity = tkeys, meta, c_new
+        self._scratch = {}
+        self.grown = getattr(self, "grown", 0) + 1
+        return self
+
+    def maybe_grow(self, incoming):
+        """Grow (host-side check: one read of the occupancy counter) so that `incoming` more keys keep the load factor
+        at or below MAX_LOAD.  Call it before a lookup, outside captured graphs."""
+        occupied = int(self.state[4].item())
+        need = (occupied + int(incoming)) / self.MAX_LOAD
+        if need > self.capacity:
+            self.grow(_pow2_at_least(int(need) + 1))
+        return self
 
     def _init_new(self, new_slots, new_count):
         d = ops._dummy(self.device)
@@ -115,8 +157,14 @@ class MapParameter:
                                                   self._sigma, d])
 
     def as_parameter(self):
-        """The value arena as a dense Parameter: optimizers address it by slot index."""
-        return Parameter(self.values, name=self.name or "map_parameter")
+        """The C resident rows of the value arena as a dense Parameter: optimizers address it by slot index.  Row C
+        (the default row every unadmitted / overflowed key reads) is NOT part of it, so a gradient that arrives for
+        slot C is dropped by the bounded dedup instead of moving the default row."""
+        return Parameter(self.values[:self.capacity], name=self.name or "map_parameter")
+
+    def arena_rows(self, arena):
+        """The C slot rows of a sibling arena (same slicing as as_parameter)."""
+        return arena[:self.capacity]
 
     # ---- MapTensor ops ---------------------------------------------------------------------------
     def lookup_slots(self, key, insert_default_value=True):
@@ -240,7 +288,7 @@ class HashEmbeddingLookup:
 
     def __init__(self, embedding_size, key_dtype=torch.int32, param_init="normal", sparse=True, max_norm=None,
                  permit_filter_value=1, evict_filter_value=MAX_SIZE, vocab_cache_size=0, capacity=1 << 20,
-                 device="cuda", seed=0):
+                 device="cuda", seed=0, auto_grow=True):
         if not isinstance(sparse, bool):
             raise TypeError("For 'HashEmbeddingLookup', the type of 'sparse' should be bool, but got %s"
                             % type(sparse).__name__)
@@ -267,6 +315,9 @@ class HashEmbeddingLookup:
                                             device=device, seed=seed)
         self.embedding_table.unique = self.forward_unique
         self.last_slots = None
+        # auto_grow: size the table before every lookup so that it cannot overflow (one host read per call; switch
+        # it off — and size `capacity` up front — to capture lookups in a CUDA graph)
+        self.auto_grow = auto_grow
 
     def __call__(self, indices):
         return self.construct(indices)
@@ -276,6 +327,8 @@ class HashEmbeddingLookup:
         inverse index); the table here resolves duplicates itself (all copies of a key probe to one slot), so
         the keys go straight to find-or-insert and the rows come from one gather by slot — same output."""
         table = self.embedding_table
+        if self.auto_grow:
+            table.maybe_grow(indices.numel())
         slots = table.lookup_slots(indices, insert_default_value=True)
         self.last_slots = slots.view(indices.shape)
         out = ops.gather(table.values, slots).view(tuple(indices.shape) + (self.embedding_size,))

@@ -111,17 +111,42 @@ class EmbeddingLookup:
 # ------------------------------------------------------------------------------------------------
 # optimizers
 # ------------------------------------------------------------------------------------------------
+def _is_map(p):
+    """A mindrec_b200.hash.MapParameter (duck-typed: nn must not import hash)."""
+    return hasattr(p, "tkeys") and hasattr(p, "add_arena")
+
+
 class _Optimizer:
+    """Parameters are `Parameter`s or `MapParameter`s.  On a MapParameter the rows are addressed by SLOT (the
+    RowTensor's indices are the slots returned by the lookup), the state lives in sibling arenas registered with
+    add_arena — so new keys start from fresh state (zeros / initial_accum) and a growth of the table moves it along —
+    and the shared default row (slot C) is outside the updated range (upstream: the MapTensor branch of
+    LazyAdam / FTRL, get(keys) -> row math -> put(keys))."""
+
     def __init__(self, params, loss_scale):
         self.parameters = list(params)
         if not self.parameters:
             raise ValueError("Optimizer got an empty parameter list")
         self.loss_scale = float(loss_scale)
-        self.device = self.parameters[0].data.device
+        p0 = self.parameters[0]
+        self.device = p0.device if _is_map(p0) else p0.data.device
+
+    @staticmethod
+    def _state_arenas(p, fills):
+        first = len(p._arenas)
+        for f in fills:
+            p.add_arena(f)
+        return tuple(range(first, first + len(fills)))
+
+    @staticmethod
+    def _rows(p, arena_ids):
+        """(w, state...) as [C, D] views of the CURRENT arenas of a MapParameter."""
+        c = p.capacity
+        return [p.values[:c]] + [p.arena(i)[:c] for i in arena_ids]
 
     def _dedup(self, p, g):
         if g.uq is None:
-            g.uq = ops.unique(g.indices, table_like=p.data)
+            g.uq = ops.unique(g.indices, table_like=p.values[:p.capacity] if _is_map(p) else p.data)
         return g.uq
 
     def __call__(self, grads):
@@ -147,8 +172,15 @@ class Adam(_Optimizer):
         if use_nesterov or weight_decay != 0.0:
             raise NotImplementedError("use_nesterov / weight_decay are not used on the reference's hot path")
         self.hyper = ops.adam_hyper(learning_rate, beta1, beta2, eps, loss_scale, device=self.device)
-        self.moment1 = [torch.zeros_like(p.data) for p in self.parameters]
-        self.moment2 = [torch.zeros_like(p.data) for p in self.parameters]
+        self.moment1, self.moment2, self._map_state = [], [], {}
+        for i, p in enumerate(self.parameters):
+            if _is_map(p):
+                self._map_state[i] = self._state_arenas(p, (0.0, 0.0))
+                self.moment1.append(None)
+                self.moment2.append(None)
+            else:
+                self.moment1.append(torch.zeros_like(p.data))
+                self.moment2.append(torch.zeros_like(p.data))
 
     def _row_flags(self, p):
         flags = getattr(p, "_row_flags", None)
@@ -159,7 +191,13 @@ class Adam(_Optimizer):
 
     def step(self, grads):
         ops.adam_begin_step(self.hyper)
-        for p, m, v, g in zip(self.parameters, self.moment1, self.moment2, grads):
+        for i, (p, m, v, g) in enumerate(zip(self.parameters, self.moment1, self.moment2, grads)):
+            if i in self._map_state:
+                if not isinstance(g, RowTensor) or not self.lazy:
+                    raise TypeError("a MapParameter takes a RowTensor gradient and LazyAdam (wide_and_deep.py:415-422)")
+                w, m, v = self._rows(p, self._map_state[i])
+                ops.sparse_lazy_adam(w, m, v, self.hyper, g.values, g.mask, self._dedup(p, g))
+                continue
             if isinstance(g, RowTensor):
                 uq = self._dedup(p, g)
                 if self.lazy:
@@ -192,11 +230,24 @@ class FTRL(_Optimizer):
         if l1 < 0 or l2 < 0:
             raise ValueError("l1/l2 must be >= 0")
         self.hyper = ops.ftrl_hyper(learning_rate, l1, l2, lr_power, loss_scale, device=self.device)
-        self.accum = [torch.full_like(p.data, float(initial_accum)) for p in self.parameters]
-        self.linear = [torch.zeros_like(p.data) for p in self.parameters]
+        self.accum, self.linear, self._map_state = [], [], {}
+        for i, p in enumerate(self.parameters):
+            if _is_map(p):          # new keys: accum = initial_accum, linear = 0
+                self._map_state[i] = self._state_arenas(p, (float(initial_accum), 0.0))
+                self.accum.append(None)
+                self.linear.append(None)
+            else:
+                self.accum.append(torch.full_like(p.data, float(initial_accum)))
+                self.linear.append(torch.zeros_like(p.data))
 
     def step(self, grads):
-        for p, a, l, g in zip(self.parameters, self.accum, self.linear, grads):
+        for i, (p, a, l, g) in enumerate(zip(self.parameters, self.accum, self.linear, grads)):
+            if i in self._map_state:
+                if not isinstance(g, RowTensor):
+                    raise TypeError("a MapParameter takes a RowTensor gradient")
+                w, a, l = self._rows(p, self._map_state[i])
+                ops.sparse_ftrl(w, a, l, self.hyper, g.values, g.mask, self._dedup(p, g))
+                continue
             if isinstance(g, RowTensor):
                 ops.sparse_ftrl(p.data, a, l, self.hyper, g.values, g.mask, self._dedup(p, g))
             else:

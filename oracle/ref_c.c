@@ -25,6 +25,18 @@ int mrec_ref_threads(void) {
 #endif
 }
 
+/* Pin the OpenMP team size (bench.py: torchrun exports OMP_NUM_THREADS=1, which would otherwise shrink the CPU arm
+ * to one core); returns the team size now in force. */
+int mrec_ref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 /* models/wide_deep/src/wide_and_deep.py:302,308-309: deep_in = table[ids] * mask -> [B, F*D] */
 void mrec_ref_gather_masked(const float *table, int64_t vocab, int dim, const int32_t *ids,
                             const float *mask, int64_t n, float *out) {

@@ -56,6 +56,22 @@ def threads():
     return lib().mrec_ref_threads()
 
 
+def use_all_cores():
+    """Run the port (OpenMP loops AND numpy's BLAS) on every host core whatever OMP_NUM_THREADS says (torchrun sets
+    it to 1).  Returns the thread count in force."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    L = lib()
+    L.mrec_ref_set_threads.argtypes = [_int]
+    L.mrec_ref_set_threads.restype = _int
+    got = L.mrec_ref_set_threads(n)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return got
+
+
 def gather_masked(table, ids, mask):
     n = ids.size
     dim = table.shape[1]

@@ -41,7 +41,7 @@ def test_lookup_dedup_and_updates_against_fixture(cuda):
     ww, acc, lin = wide.clone(), torch.ones_like(wide), torch.zeros_like(wide)
     ops.sparse_ftrl(ww, acc, lin, ops.ftrl_hyper(5e-2, 1e-8, 1e-8, loss_scale=1024.0, device=cuda),
                     _d(z["gw"], cuda), wts.reshape(-1), uq)
-    np.testing.assert_allclose(ww.cpu().numpy(), z["ftrl_w"], rtol=2e-5, atol=1e-8)
+    np.testing.assert_allclose(ww.cpu().numpy(), z["ftrl_w"], rtol=1e-5, atol=1e-6 * np.abs(z["ftrl_w"]).max())
     np.testing.assert_allclose(acc.cpu().numpy(), z["ftrl_acc"], rtol=1e-5)
 
 

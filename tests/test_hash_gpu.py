@@ -151,6 +151,32 @@ def test_lazy_adam_on_map_parameter_by_slot(cuda):
     assert torch.equal(mp.values[mp.capacity], w0[mp.capacity])   # default row untouched
 
 
+def test_optimizer_never_moves_the_default_row(cuda):
+    """with permit_filter_value > 1 (or a full table) lookups return slot C, the shared default row.  An
+    optimizer driven through as_parameter() must leave row C of the values and of every moment arena alone."""
+    dim = 8
+    mp = H.MapParameter(key_dtype=torch.int64, value_shape=dim, default_value="ones", permit_filter_value=2,
+                        capacity=64, device=cuda)
+    m, v = mp.add_arena(0.0), mp.add_arena(0.0)
+    keys = torch.arange(300, dtype=torch.int64, device=cuda) * 7 + 1
+    hyper = ops.adam_hyper(1e-2, device=cuda)
+    p = mp.as_parameter()
+    assert p.data.shape[0] == mp.capacity
+    for it in range(3):                                # first pass: nothing admitted; later: table overflows
+        slots = mp.lookup_slots(keys).clone()
+        assert bool((slots == mp.capacity).any())
+        g = torch.ones((keys.numel(), dim), device=cuda)
+        uq = ops.unique(slots, table_like=p.data)
+        ops.adam_begin_step(hyper)
+        ops.sparse_lazy_adam(p.data, mp.arena_rows(m), mp.arena_rows(v), hyper, g, None, uq)
+    assert mp.overflowed
+    c = mp.capacity
+    assert torch.equal(mp.values[c], torch.ones(dim, device=cuda))
+    assert torch.equal(m[c], torch.zeros(dim, device=cuda)) and torch.equal(v[c], torch.zeros(dim, device=cuda))
+    touched = torch.unique(slots[slots < c]).long()
+    assert touched.numel() == c and bool((mp.values[touched] != 1.0).all())
+
+
 def _sorted_data(mp):
     k, v = mp.get_data()
     order = torch.argsort(k)
