@@ -42,6 +42,11 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--vocab-scale", type=float, default=1.0, help="shrink the Kaggle cardinalities (debug)")
     ap.add_argument("--alpha", type=float, default=1.05)
+    ap.add_argument("--layout", default=os.environ.get("MREC_BENCH_LAYOUT", "interleaved"), choices=["interleaved", "split"],
+                    help="deep table of the single-GPU step: w|m|v records [V,3,D] (one DRAM burst per row update) or "
+                         "three [V,D] arrays")
+    ap.add_argument("--c5-rows-per-gpu", type=int, default=96_000_000,
+                    help="config 5: rows of the dim-128 table per GPU (w + LazyAdam m, v in fp32 = 1.5 KB per row)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config-3 / config-4 / config-5 blocks")
     ap.add_argument("--exchange", default=os.environ.get("MREC_BENCH_EXCHANGE", "device"), choices=["nccl", "device"],
@@ -223,8 +228,9 @@ def measure_dominant_op(step, batches, b, reps=10):
     from mindrec_b200 import ops
     model = step.model
     d = model.emb_dim
-    table = model.embedding_table.data
-    m, v = step.optimizer_d.moment1[0], step.optimizer_d.moment2[0]
+    packed = model.embedding_table.packed is not None      # w | m | v interleaved per row ([V,3,D])
+    table = model.embedding_table.kernel_arg
+    m, v = (None, None) if packed else (step.optimizer_d.moment1[0], step.optimizer_d.moment2[0])
     hyper = step.optimizer_d.hyper
     sets, alg, us = [], 0, []
     for ids, wts, _ in batches:
@@ -267,6 +273,7 @@ def measure_dominant_op(step, batches, b, reps=10):
             pass
     return {"kernel": "mrec_sparse_lazy_adam = segsum_stage_kernel<__half> + "
                       "rows_update_kernel<F8,LazyAdamSink> (256-bit rows; 2 launches, timed as one op)",
+            "table_layout": "interleaved w|m|v records [V,3,D]" if packed else "split w[V,D], m[V,D], v[V,D]",
             "bound": "hbm", "achieved": round(gbs, 1), "peak": peak,
             "peak_source": "MEASURED_PEAKS.json (measured)" if how == "measured" else "fallback 6650",
             "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": traffic, "algorithmic_bytes": alg,
@@ -326,7 +333,7 @@ def measure_gather(table, zipf_ids):
     import torch
     from mindrec_b200 import ops
     dev = table.device
-    v, d = table.shape
+    v, d = table.shape[0], table.shape[-1]
     n = zipf_ids[0].numel()
     outs = [torch.empty((n, d), dtype=torch.float32, device=dev) for _ in range(2)]
     gen = torch.Generator(device=dev)
@@ -419,6 +426,83 @@ def measure_c4(args, dev, steps):
             "fm_bwd": _roof("fm_bwd_kernel", 2 * vol + b * 4, bwd, "fm_bwd")}
 
 
+def measure_c5(args, world, rank, dev, group_one):
+    """BASELINE configs[4]: the multitable model's emb128 table (dim 128, + its dim-1 wide vector) row-sharded over the
+    ranks with rows-per-GPU fixed, plus a hash-sharded MapParameter (int64 Zipf keys over 2^40, admission on the second
+    sighting, eviction of keys unseen for 8 steps) in the same step; 5 x 1024 DenseLayers data parallel; batch 16384 x
+    (26 table fields + 26 dynamic-feature fields) per GPU; row-sparse LazyAdam / FTRL (mindrec_b200.multitable_sharded).
+    Returns the block for the bench line (rank 0) — every rank must call it."""
+    import torch
+    import torch.distributed as dist
+    from mindrec_b200 import multitable_sharded as M
+    from tools import sharded_parity
+    b, ft, fh = 16384, 26, 26
+    out = {}
+    # parity first (small table): G ranks vs the same step on a one-rank group fed the concatenated batch
+    out["parity_check"] = {"fp32": sharded_parity.multitable(world, rank, dev, b, mixed=False, group_one=group_one,
+                                                             n_table_fields=ft, n_hash_fields=fh, evict_filter_value=1,
+                                                             evict_every=2, hash_capacity=1 << 22),
+                           "fp16": sharded_parity.multitable(world, rank, dev, b, mixed=True, group_one=group_one,
+                                                             n_table_fields=ft, n_hash_fields=fh, evict_filter_value=1,
+                                                             evict_every=2, hash_capacity=1 << 22)}
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info(dev)
+    row_bytes = (128 + 1) * 4 * 3                       # w, m, v (+ the wide vector's w, accum, linear)
+    rows = min(args.c5_rows_per_gpu, int((free - (28 << 30)) // row_bytes))
+    t = torch.tensor([rows], device=dev, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    rows = int(t.item())
+    if rows < (1 << 20):
+        return dict(out, skipped="not enough free HBM for the config-5 table (%d rows per GPU)" % rows)
+    rows_total = rows * world
+    step = M.ShardedMultitableStep(b, rows_total, dev, n_table_fields=ft, n_hash_fields=fh, hash_capacity=1 << 23, seed=1)
+    host = sharded_parity.c5_batches(b, ft, fh, rows_total, 40, 20260105, rank, 4, alpha=args.alpha)
+    ring = [tuple(torch.from_numpy(x).to(dev) for x in hb) for hb in host]
+    step.capture(*ring[0], warmup=2)
+    k = max(3, min(args.steps, 20))
+    for i in range(3):
+        step.replay(*ring[i % 4])
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3, 3 + k):
+        loss = step.replay(*ring[i % 4])[0]
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    tt = torch.tensor([ms], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    st = step.exchange_stats()
+    flags = step.error_flags()
+    agg = torch.tensor([float(st["nvlink_bytes_out"]), float(st["table"]["unique_keys"]), float(st["table"]["rows_owned"]),
+                        float(st["hash"]["unique_keys"]), float(st["hash"]["rows_owned"]), float(flags),
+                        float(len(step.hash.rk.table)), float(loss)], device=dev)
+    mx = agg.clone()
+    dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    a = (agg / world).tolist()
+    out.update({
+        "workload": "BASELINE config 5: emb128 table (dim 128) + wide vector row-sharded, %d rows per GPU = %d rows on %d "
+                    "GPUs (fp32 w + LazyAdam m, v resident), MapParameter hash-sharded (int64 Zipf keys over 2^40, "
+                    "permit 2, evict 8), batch 16384 x (26 + 26) fields per GPU, DenseLayers 6656-1024x5-1 fp16 data "
+                    "parallel, row-sparse LazyAdam / FTRL" % (rows, rows_total, world),
+        "samples_per_s": b * world / (ms * 1e-3), "ms_per_step": ms, "steps": k, "rows_per_gpu": rows,
+        "rows_total": rows_total, "gpu_launches_per_step": step.launches_per_step,
+        "exchange": {"nvlink_bytes_out_per_rank_per_step": int(a[0]), "table_unique_keys_per_rank": int(a[1]),
+                     "table_rows_owned_per_rank": int(a[2]), "hash_unique_keys_per_rank": int(a[3]),
+                     "hash_rows_owned_per_rank": int(a[4]),
+                     "avg_gbs_per_direction_over_step": round(a[0] / (ms * 1e-3) / 1e9, 1),
+                     "nvlink_peak_gbs_per_direction": 900, "nvlink_frac": round(a[0] / (ms * 1e-3) / 1e9 / 900, 4)},
+        "error_flags": int(mx[5].item()), "hash_resident_keys_per_rank": int(a[6]), "final_loss": a[7]})
+    step.close()
+    del step
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
@@ -446,7 +530,8 @@ def run_ours(args):
     b = args.batch
     if world == 1:
         cfg = cells.WideDeepConfig(batch_size=b, field_size=FIELDS, vocab_size=vocab, emb_dim=EMB,
-                                   deep_layer_dim=HIDDEN, use_mixed_precision=True, sparse=True, seed=1)
+                                   deep_layer_dim=HIDDEN, use_mixed_precision=True, sparse=True, seed=1,
+                                   interleave_adam_state=(args.layout == "interleaved"))
         model = cells.WideDeepModel(cfg, device=dev)
         step = cells.TrainStepWrap(cells.NetWithLossClass(model, cfg), sens=1024.0, sparse=True, lazy_adam=True)
     else:
@@ -566,7 +651,7 @@ def run_ours(args):
     roofline_gather, configs = None, {}
     if world == 1:
         roofline = measure_dominant_op(step, devb[:4], b)
-        roofline_gather = measure_gather(step.model.embedding_table.data, [x[0] for x in devb[:4]])
+        roofline_gather = measure_gather(step.model.embedding_table.kernel_arg, [x[0] for x in devb[:4]])
 
     exchange = None
     if world > 1 and hasattr(step.tables, "rk"):
@@ -595,6 +680,25 @@ def run_ours(args):
         if exch_err:
             raise SystemExit("bench.py: sharded exchange raised error flags %d (1 = wait time-out, 2 = inbox overflow)" % exch_err)
 
+    parity = None
+    if world > 1 and hasattr(step.tables, "rk") and not args.no_extra_configs:
+        # multi-GPU parity of the benchmarked exchange + BASELINE config 5 (every rank takes part)
+        from tools import sharded_parity
+        step.tables.close()
+        del step
+        torch.cuda.empty_cache()
+        group_one = dist.new_group([0])
+        parity = {"fp32": sharded_parity.wide_deep(world, rank, dev, b, FIELDS, EMB, HIDDEN, mixed=False, alpha=args.alpha),
+                  "fp16": sharded_parity.wide_deep(world, rank, dev, b, FIELDS, EMB, HIDDEN, mixed=True, alpha=args.alpha)}
+        parity["ok"] = parity["fp32"]["ok"] and parity["fp16"]["ok"]
+        configs["c5"] = measure_c5(args, world, rank, dev, group_one)
+        c5p = configs["c5"].get("parity_check", {})
+        bad = (not parity["ok"]) or any(not v.get("ok", False) for v in c5p.values()) or configs["c5"].get("error_flags", 0)
+        if bad:
+            if rank == 0:
+                print(json.dumps({"parity_check": parity, "c5": configs["c5"]}), file=sys.stderr, flush=True)
+            raise SystemExit("bench.py: multi-GPU parity check FAILED (see stderr)")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -622,7 +726,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(per_step_launches * args.steps),
         "gpu_launches_per_step": int(per_step_launches),
-        "roofline": roofline, "roofline_gather": roofline_gather, "configs": configs, "cpu_baseline": cb, "breakdown_ms": breakdown, "exchange": exchange, "final_loss": final_loss,
+        "roofline": roofline, "roofline_gather": roofline_gather, "configs": configs, "parity_check": parity,
+        "cpu_baseline": cb, "breakdown_ms": breakdown, "exchange": exchange, "final_loss": final_loss,
         "lib": _lib.version(),
     }
     print(json.dumps(line), flush=True)

@@ -49,7 +49,7 @@ class WideDeepConfig:
                  deep_layer_dim=(1024, 512, 256, 128), deep_layer_act="relu", keep_prob=1.0,
                  dropout_flag=False, l2_coef=8e-5, emb_init="normal", weight_bias_init=("normal", "normal"),
                  use_mixed_precision=True, sparse=False, dynamic_embedding=False, parameter_server=False,
-                 vocab_cache_size=0, seed=1, hash_capacity=1 << 20, hash_auto_grow=True):
+                 vocab_cache_size=0, seed=1, hash_capacity=1 << 20, hash_auto_grow=True, interleave_adam_state=False):
         self.batch_size = batch_size
         self.field_size = field_size
         self.vocab_size = vocab_size
@@ -70,6 +70,8 @@ class WideDeepConfig:
         # dynamic_embedding only: initial slot count of the two MapParameters and whether they grow by themselves
         self.hash_capacity = hash_capacity
         self.hash_auto_grow = hash_auto_grow
+        # deep table stored as one [V,3,D] array of w | m | v records (LazyAdam only): see nn.EmbeddingLookup
+        self.interleave_adam_state = interleave_adam_state
 
 
 class WideDeepModel:
@@ -105,7 +107,8 @@ class WideDeepModel:
             self.deep_embeddinglookup = EmbeddingLookup(config.vocab_size, config.emb_dim,
                                                         param_init=config.emb_init, sparse=config.sparse,
                                                         device=self.device,
-                                                        name="deep_embeddinglookup.embedding_table", generator=gen)
+                                                        name="deep_embeddinglookup.embedding_table", generator=gen,
+                                                        interleave_state=config.interleave_adam_state)
         self.embedding_table = self.deep_embeddinglookup.embedding_table
         dims = [self.field_size * self.emb_dim] + list(config.deep_layer_dim) + [1]
         w_init, b_init = config.weight_bias_init
@@ -160,7 +163,7 @@ class WideDeepModel:
             self.slots_d = dt.embedding_table.lookup_slots(id_hldr).view(b, f)
             ops.gather_masked(dt.embedding_table.values, self.slots_d, wt_hldr, out=self._deep_in)
         else:
-            ops.gather_masked(self.deep_embeddinglookup.embedding_table.data, id_hldr, wt_hldr,
+            ops.gather_masked(self.deep_embeddinglookup.embedding_table.kernel_arg, id_hldr, wt_hldr,
                               out=self._deep_in)
         deep_out = self.dense.forward(self._deep_in)       # :310-314
         main.wait_stream(self._wide_stream)
@@ -277,7 +280,7 @@ class TrainStepWrap:
             self._uq = ops.UniqueResult(n, batch_ids.dtype, batch_ids.device)
         side.wait_stream(main)
         with torch.cuda.stream(side), rng("unique"):
-            uq = ops.unique(batch_ids, table_like=model.embedding_table.data, result=self._uq)
+            uq = ops.unique(batch_ids, table_like=model.embedding_table.kernel_arg, result=self._uq)
         with rng("forward"):
             loss_w, loss_d = self.network(batch_ids, batch_wts, label)
         with rng("dense_backward"):

@@ -51,7 +51,7 @@ template <int CPR, typename IdT, bool MASKED, typename OutT>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids,
                    const float* __restrict__ mask, typename OutChunk<OutT>::type* __restrict__ out, int64_t n_rows,
-                   int64_t vocab, int cpr_rt, int bulk_ok, int* __restrict__ oob) {
+                   int64_t vocab, int cpr_rt, int bulk_ok, int* __restrict__ oob, int64_t pitch /* float4 per table row */) {
   constexpr int TR = tile_rows_for(CPR == 0 ? 16 : CPR);
   const int cpr = (CPR == 0) ? cpr_rt : CPR;
   __shared__ __align__(16) IdT s_ids[2][TR];
@@ -119,7 +119,7 @@ gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
           const int64_t id = (int64_t)s_ids[st][r];
           if (MASKED) mk[k] = s_mask[st][r];
           if ((uint64_t)id < (uint64_t)vocab) {
-            v[k] = ld_stream_f4(table + id * CPR + col);
+            v[k] = ld_stream_f4(table + id * pitch + col);
           } else {
             if (oob) atomicOr(oob, 1);
           }
@@ -149,7 +149,7 @@ gather_rows_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
             const int64_t id = (int64_t)s_ids[st][r];
             if (MASKED) mk[k] = s_mask[st][r];
             if ((uint64_t)id < (uint64_t)vocab) {
-              v[k] = ld_stream_f4(table + id * cpr + col);
+              v[k] = ld_stream_f4(table + id * pitch + col);
             } else {
               if (oob) atomicOr(oob, 1);
             }
@@ -261,9 +261,10 @@ gather_pool_kernel(const float4* __restrict__ table, const IdT* __restrict__ ids
 
 template <typename IdT, bool MASKED, typename OutT>
 static int launch_gather(const float* table, const IdT* ids, const float* mask, OutT* out,
-                         int64_t n_rows, int dim, int64_t vocab, int* oob, cudaStream_t stream) {
+                         int64_t n_rows, int dim, int64_t vocab, int* oob, cudaStream_t stream, int64_t row_floats) {
   if (n_rows == 0) return OK;
   if (dim % 4 != 0) {
+    if (row_floats != dim) return fail(ERR_DIM, "mrec_gather: an interleaved table [V,K,D] needs D %% 4 == 0");
     const int64_t total = n_rows * dim;
     int grid = grid_for(cdiv(total, 256), 16);
     MREC_LAUNCH((gather_scalar_kernel<IdT, MASKED, OutT>), grid, 256, 0, stream, table, ids, mask, out,
@@ -271,6 +272,7 @@ static int launch_gather(const float* table, const IdT* ids, const float* mask, 
     return check_launch("gather_scalar");
   }
   const int cpr = dim / 4;
+  const int64_t pitch = row_floats / 4;
   const int bulk_ok = ((reinterpret_cast<uintptr_t>(ids) % 16) == 0) &&
                       (!MASKED || (reinterpret_cast<uintptr_t>(mask) % 16) == 0);
   const float4* t4 = reinterpret_cast<const float4*>(table);
@@ -280,7 +282,7 @@ static int launch_gather(const float* table, const IdT* ids, const float* mask, 
     constexpr int TR = tile_rows_for(C);                                                      \
     int grid = grid_for(cdiv(n_rows, TR), 8);                     \
     MREC_LAUNCH((gather_rows_kernel<C, IdT, MASKED, OutT>), grid, kGatherThreads, 0, stream, t4, ids, \
-                mask, o4, n_rows, vocab, cpr, bulk_ok, oob);                                  \
+                mask, o4, n_rows, vocab, cpr, bulk_ok, oob, pitch);                           \
   } break;
   switch (cpr) {
     MREC_GATHER_CASE(4)
@@ -292,7 +294,7 @@ static int launch_gather(const float* table, const IdT* ids, const float* mask, 
       constexpr int TR = tile_rows_for(16);
       int grid = grid_for(cdiv(n_rows, TR), 8);
       MREC_LAUNCH((gather_rows_kernel<0, IdT, MASKED, OutT>), grid, kGatherThreads, 0, stream, t4, ids,
-                  mask, o4, n_rows, vocab, cpr, bulk_ok, oob);
+                  mask, o4, n_rows, vocab, cpr, bulk_ok, oob, pitch);
     } break;
   }
 #undef MREC_GATHER_CASE
@@ -312,9 +314,11 @@ static int gather_entry(const Aot& a, bool masked) {
   MREC_REQUIRE(a.is_f32(0) && (a.is_f32(o) || out16), ERR_DTYPE,
                "mrec_gather: table must be float32, out float32 or float16");
   MREC_REQUIRE(a.is_i32(1) || a.is_i64(1), ERR_DTYPE, "mrec_gather: ids must be int32 or int64");
-  MREC_REQUIRE(a.ndims[0] == 2 || a.ndims[0] == 1, ERR_SHAPE, "mrec_gather: table must be [V,D] or [V]");
+  // table[V,K,D]: K interleaved arrays per row (the w | m | v record of mrec_sparse_lazy_adam); array 0 is read
+  MREC_REQUIRE(a.ndims[0] >= 1 && a.ndims[0] <= 3, ERR_SHAPE, "mrec_gather: table must be [V,D], [V] or [V,K,D]");
   const int64_t vocab = a.dim(0, 0);
-  const int dim = a.ndims[0] == 2 ? (int)a.dim(0, 1) : 1;
+  const int dim = a.ndims[0] == 3 ? (int)a.dim(0, 2) : (a.ndims[0] == 2 ? (int)a.dim(0, 1) : 1);
+  const int64_t row_floats = a.ndims[0] == 3 ? a.dim(0, 1) * a.dim(0, 2) : dim;
   const int64_t n = a.numel(1);
   MREC_REQUIRE(dim >= 1, ERR_DIM, "mrec_gather: embedding dim must be >= 1");
   MREC_REQUIRE(a.numel(o) == n * dim, ERR_SHAPE, "mrec_gather: out numel %lld != N*D %lld",
@@ -334,7 +338,7 @@ static int gather_entry(const Aot& a, bool masked) {
   const float* mask = masked ? a.ptr<float>(2) : nullptr;
 #define MREC_GATHER_DISPATCH(IDT, MASKED_, OUTT)                                                   \
   return launch_gather<IDT, MASKED_, OUTT>(a.ptr<float>(0), a.ptr<IDT>(1), mask, a.ptr<OUTT>(o), n, dim, \
-                                           vocab, oob, a.stream)
+                                           vocab, oob, a.stream, row_floats)
   if (a.is_i32(1)) {
     if (masked) { if (out16) MREC_GATHER_DISPATCH(int32_t, true, __half); MREC_GATHER_DISPATCH(int32_t, true, float); }
     if (out16) MREC_GATHER_DISPATCH(int32_t, false, __half);

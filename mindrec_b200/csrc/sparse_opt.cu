@@ -133,6 +133,8 @@ struct LazyAdamSink<float4, IdT> {
   const float* hyper;
   int64_t vocab;
   int cpr;
+  int64_t pitch;   // Vec units between consecutive rows: cpr, or 3 * cpr for the interleaved w|m|v record
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * pitch + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
   __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
   __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = m[o]; s.c = v[o]; }
@@ -151,8 +153,8 @@ struct LazyAdamSink<float4, IdT> {
     const int64_t row = row_of(seg);
     if (!in_range(row)) return;                    // out-of-range ids carry no row
     State s;
-    load(row * cpr + c, s);
-    finish(row * cpr + c, s, gs);
+    load(offset(row, c), s);
+    finish(offset(row, c), s, gs);
   }
 };
 // 32-byte form of the LazyAdam row update: D/8 threads per row, LDG.256 / STG.256 with L2 evict-first on w, m, v
@@ -166,6 +168,8 @@ struct LazyAdamSink<F8, IdT> {
   const float* hyper;
   int64_t vocab;
   int cpr;
+  int64_t pitch;   // Vec units between consecutive rows: cpr, or 3 * cpr for the interleaved w|m|v record
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * pitch + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
   __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
   __device__ __forceinline__ void load(int64_t o, State& s) const {
@@ -190,8 +194,8 @@ struct LazyAdamSink<F8, IdT> {
     const int64_t row = row_of(seg);
     if (!in_range(row)) return;
     State s;
-    load(row * cpr + c, s);
-    finish(row * cpr + c, s, gs);
+    load(offset(row, c), s);
+    finish(offset(row, c), s, gs);
   }
 };
 template <typename IdT>
@@ -203,6 +207,8 @@ struct LazyAdamSink<float, IdT> {
   const float* hyper;
   int64_t vocab;
   int cpr;
+  int64_t pitch;   // Vec units between consecutive rows: cpr, or 3 * cpr for the interleaved w|m|v record
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * pitch + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
   __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
   __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = m[o]; s.c = v[o]; }
@@ -216,8 +222,8 @@ struct LazyAdamSink<float, IdT> {
     const int64_t row = row_of(seg);
     if (!in_range(row)) return;
     State s;
-    load(row * cpr + c, s);
-    finish(row * cpr + c, s, gs);
+    load(offset(row, c), s);
+    finish(offset(row, c), s, gs);
   }
 };
 
@@ -231,6 +237,7 @@ struct FtrlSink<float4, IdT> {
   const float* hyper;
   int64_t vocab;
   int cpr;
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * cpr + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
   __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
   __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = acc[o]; s.c = lin[o]; }
@@ -261,6 +268,7 @@ struct FtrlSink<float, IdT> {
   const float* hyper;
   int64_t vocab;
   int cpr;
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * cpr + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
   __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
   __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = w[o]; s.b = acc[o]; s.c = lin[o]; }
@@ -290,6 +298,7 @@ struct ScatterAddSink {
   const IdT* uniq;
   int64_t vocab;
   int cpr;
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * cpr + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return (int64_t)uniq[seg]; }
   __device__ __forceinline__ bool in_range(int64_t row) const { return (uint64_t)row < (uint64_t)vocab; }
   __device__ __forceinline__ void load(int64_t o, State& s) const { s.a = table[o]; }
@@ -565,7 +574,7 @@ rows_update_kernel(int cpr, const int32_t* __restrict__ seg_of, const int32_t* _
       const int64_t u = u0 + k * n_groups;
       const int uc = (int)min(u, (int64_t)n_seg - 1);
       ok[k] = (u < n_seg) && sink.in_range(row[k]);
-      off[k] = (ok[k] ? row[k] : 0) * cpr + c;
+      off[k] = sink.offset(ok[k] ? row[k] : 0, c);
       if (Sink::kApplyComplete) gs[k] = gsum[(int64_t)uc * cpr + c];
       sink.load(off[k], st[k]);
     }
@@ -598,6 +607,7 @@ struct StoreSink {
   using State = State0;
   Vec* out;
   int cpr;
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * cpr + c; }
   __device__ __forceinline__ int64_t row_of(int seg) const { return seg; }
   __device__ __forceinline__ bool in_range(int64_t) const { return true; }
   __device__ __forceinline__ void load(int64_t, State&) const {}
@@ -717,7 +727,7 @@ static int run_segsum_t(const GT* g, int dim, int div, const float* mask, const 
         using S8 = LazyAdamSink<F8, typename IsLazyAdamF4<Sink>::Id>;
         const int cpr8 = dim / 8, groups8 = kSegThreads / cpr8;
         S8 s8{reinterpret_cast<F8*>(sink.w), reinterpret_cast<F8*>(sink.m), reinterpret_cast<F8*>(sink.v), sink.uniq,
-              sink.hyper, sink.vocab, cpr8};
+              sink.hyper, sink.vocab, cpr8, sink.pitch / 2};
         int rb8 = (int)std::min<int64_t>(cdiv(n, (int64_t)groups8), (int64_t)kNumSMs * (per_sm_env ? per_sm_env : 8));
         if (rb8 < 1) rb8 = 1;
         MREC_LAUNCH((rows_update_kernel<F8, S8, 1>), kChainBlocks + rb8, kSegThreads, 0, stream, cpr8, seg_of, seg_start, n,
@@ -898,9 +908,17 @@ MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_
                "mrec_sparse_lazy_adam: w/m/v/hyper must be float32");
   MREC_REQUIRE(a.numel(3) >= kHyperLen, ERR_SHAPE, "mrec_sparse_lazy_adam: hyper needs %d floats", kHyperLen);
   const int64_t vocab = a.dim(0, 0);
-  const int dim = a.ndims[0] >= 2 ? (int)a.dim(0, 1) : 1;
-  MREC_REQUIRE(a.numel(1) == a.numel(0) && a.numel(2) == a.numel(0), ERR_SHAPE,
-               "mrec_sparse_lazy_adam: m/v shape must equal w shape");
+  // interleaved layout: ONE array wmv[V,3,D] holds each row's w | m | v back to back (a 3*D*4-byte record: one DRAM
+  // burst per row update instead of three); m and v are then passed with numel 0
+  const bool packed = a.ndims[0] == 3 && a.dim(0, 1) == 3 && a.numel(1) == 0 && a.numel(2) == 0;
+  const int dim = packed ? (int)a.dim(0, 2) : (a.ndims[0] >= 2 ? (int)a.dim(0, 1) : 1);
+  MREC_REQUIRE(packed || (a.numel(1) == a.numel(0) && a.numel(2) == a.numel(0)), ERR_SHAPE,
+               "mrec_sparse_lazy_adam: m/v shape must equal w shape (or w = wmv[V,3,D] with empty m, v)");
+  MREC_REQUIRE(!packed || dim % 4 == 0, ERR_DIM, "mrec_sparse_lazy_adam: the interleaved layout needs D % 4 == 0");
+  float* const w_p = a.ptr<float>(0);
+  float* const m_p = packed ? w_p + dim : a.ptr<float>(1);
+  float* const v_p = packed ? w_p + 2 * dim : a.ptr<float>(2);
+  const int64_t rows_pitch = packed ? 3 : 1;      // in units of one row of D floats
   SegArgs s;
   int rc = parse_seg_args(a, 4, dim, true, &s, "mrec_sparse_lazy_adam");
   if (rc) return rc;
@@ -908,27 +926,27 @@ MREC_API int mrec_sparse_lazy_adam(int nparam, void** params, int* ndims, int64_
   void* ws = a.params[ws_i];
   const float* hyper = a.ptr<float>(3);
   if (dim % 4 == 0) {
-    MREC_REQUIRE(a.aligned(0, 16) && a.aligned(1, 16) && a.aligned(2, 16), ERR_ALIGN,
+    MREC_REQUIRE(a.aligned(0, 16) && (packed || (a.aligned(1, 16) && a.aligned(2, 16))), ERR_ALIGN,
                  "mrec_sparse_lazy_adam: w/m/v must be 16-byte aligned");
     const int cpr = dim / 4;
     MREC_REQUIRE(cpr <= kSegThreads, ERR_DIM, "mrec_sparse_lazy_adam: D too large");
     if (s.uniq64) {
-      LazyAdamSink<float4, int64_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
-                                         (const int64_t*)s.uniq, hyper, vocab, cpr};
+      LazyAdamSink<float4, int64_t> sink{(float4*)w_p, (float4*)m_p, (float4*)v_p,
+                                         (const int64_t*)s.uniq, hyper, vocab, cpr, rows_pitch * cpr};
       return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
     }
-    LazyAdamSink<float4, int32_t> sink{a.ptr<float4>(0), a.ptr<float4>(1), a.ptr<float4>(2),
-                                       (const int32_t*)s.uniq, hyper, vocab, cpr};
+    LazyAdamSink<float4, int32_t> sink{(float4*)w_p, (float4*)m_p, (float4*)v_p,
+                                       (const int32_t*)s.uniq, hyper, vocab, cpr, rows_pitch * cpr};
     return run_segsum<float4>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
   }
   MREC_REQUIRE(dim <= kSegThreads, ERR_DIM, "mrec_sparse_lazy_adam: D too large");
   if (s.uniq64) {
-    LazyAdamSink<float, int64_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
-                                      (const int64_t*)s.uniq, hyper, vocab, dim};
+    LazyAdamSink<float, int64_t> sink{w_p, m_p, v_p,
+                                      (const int64_t*)s.uniq, hyper, vocab, dim, (int64_t)dim};
     return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
   }
-  LazyAdamSink<float, int32_t> sink{a.ptr<float>(0), a.ptr<float>(1), a.ptr<float>(2),
-                                    (const int32_t*)s.uniq, hyper, vocab, dim};
+  LazyAdamSink<float, int32_t> sink{w_p, m_p, v_p,
+                                    (const int32_t*)s.uniq, hyper, vocab, dim, (int64_t)dim};
   return run_segsum<float>(s.g, s.g16, dim, s.div, s.mask, s.perm, s.seg_start, s.seg_of, s.n, ws, ws_bytes, sink, a.stream, nullptr, n_valid);
 }
 

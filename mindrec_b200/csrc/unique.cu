@@ -19,6 +19,8 @@
 // never allocates (aot contract).
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
 
 namespace mrec {
 
@@ -357,6 +359,361 @@ seg_emit_kernel(const typename UKeyOf<KeyT>::type* __restrict__ sorted,
   }
 }
 
+// =============================================================================================
+// One-sweep form (round 2): 1 memset + (1 + passes + 1) launches instead of 3 * passes + 3.
+//
+//   onesweep_hist_kernel   digit totals of EVERY pass in one read of the keys (they do not depend on the order)
+//   onesweep_pass_kernel   one launch per digit: a CTA takes the next tile (atomic ticket = tile index, so tile t only
+//                          ever waits for tiles that already run), ranks its keys stably (warp match-any + per-warp
+//                          counters, as the LSD kernels above), publishes its per-digit counts, obtains the counts
+//                          of all earlier tiles by decoupled look-back (per digit: walk back over the published
+//                          aggregates until a tile with an inclusive prefix is met) and scatters
+//   onesweep_seg_kernel    head flags -> segment ids -> uniq / inverse / seg_start / seg_of / count, tile offsets by
+//                          decoupled look-back too (one warp looks at 32 predecessors at a time)
+// The problem is latency bound (N = 624 000 keys = 2.5 MB, everything lives in the L2): tiles are LARGE (16 384 int32
+// keys, 8 192 int64 keys: 39 tiles at N = 624 000) so that the look-back chain is a few batched reads, not hundreds.
+// A look-back word is (flag << 30) | count: flag and payload travel in one 32-bit store, no fence is needed.
+constexpr int OS_THREADS = 512;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr uint32_t LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_MASK = (1u << 30) - 1u;
+constexpr int OS_MAX_PASSES = 8;
+constexpr int kSpinLimit = 1 << 22;   // ~3 s of L2 round trips
+template <typename KeyT> struct OsItems { static constexpr int value = 8; };    // 4096 keys per tile: N = 624 000 -> 153
+template <> struct OsItems<int64_t> { static constexpr int value = 8; };        // tiles, one wave over the 148 SMs
+
+__device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_vol_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ghist[pass][digit] += occurrences; warp-aggregated (match-any) so that the hot digits of a Zipf batch (every key of
+// the 13 dense Criteo fields shares its upper digits) cost one shared-memory atomic per warp, not one per key.
+constexpr int OS_HIST_THREADS = 1024;
+template <typename KeyT>
+__global__ void __launch_bounds__(OS_HIST_THREADS)
+onesweep_hist_kernel(const KeyT* __restrict__ keys, int64_t n, uint64_t bound, int passes, int digit_bits,
+                     uint32_t* __restrict__ ghist, const int32_t* __restrict__ n_valid) {
+  __shared__ uint32_t s_hist[OS_MAX_PASSES * MAX_RADIX];
+  const int radix = 1 << digit_bits;
+  n = eff_n(n, n_valid);
+  for (int d = threadIdx.x; d < passes * radix; d += OS_HIST_THREADS) s_hist[d] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * OS_HIST_THREADS;
+  // whole warps iterate together (match-any needs the full mask)
+  for (int64_t i0 = (int64_t)blockIdx.x * OS_HIST_THREADS + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+    const int64_t i = i0 + lane;
+    const bool ok = i < n;
+    const auto k = ok ? encode_key<KeyT>(keys[i], bound) : (typename UKeyOf<KeyT>::type)0;
+    for (int p = 0; p < passes; ++p) {
+      const uint32_t dig = ok ? ((uint32_t)(k >> (p * digit_bits)) & (radix - 1)) : (uint32_t)radix;
+      const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+      if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * radix + dig], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < passes * radix; d += OS_HIST_THREADS) {
+    const uint32_t c = s_hist[d];
+    if (c) atomicAdd(&ghist[(d / radix) * MAX_RADIX + (d & (radix - 1))], c);
+  }
+}
+
+template <typename KeyT, bool RAW>
+__global__ void __launch_bounds__(OS_THREADS, 1)
+onesweep_pass_kernel(const void* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                     typename UKeyOf<KeyT>::type* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n,
+                     int shift, int radix, uint64_t bound, const uint32_t* __restrict__ ghist /* this pass */,
+                     uint32_t* __restrict__ lookback /* [tiles][radix], zeroed */, uint32_t* __restrict__ ticket,
+                     const int32_t* __restrict__ n_valid) {
+  using U = typename UKeyOf<KeyT>::type;
+  constexpr int ITEMS = OsItems<KeyT>::value;
+  constexpr int TILE = OS_THREADS * ITEMS;
+  // dynamic shared memory: first the per-warp look-back partials [OS_WARPS][radix] u32, later (aliased) the tile's
+  // keys and values in their sorted order
+  extern __shared__ uint4 os_dyn[];
+  uint32_t* s_pref = reinterpret_cast<uint32_t*>(os_dyn);
+  U* s_key = reinterpret_cast<U*>(os_dyn);
+  int32_t* s_val = reinterpret_cast<int32_t*>(s_key + TILE);
+  __shared__ uint16_t s_cnt[OS_WARPS][MAX_RADIX];   // per-warp digit counts (<= 32 * ITEMS), then exclusive over warps
+  __shared__ uint32_t s_goff[MAX_RADIX];            // global position of sorted-tile index 0 of each digit (mod 2^32)
+  __shared__ uint32_t s_dstart[MAX_RADIX];          // first sorted-tile index of each digit
+  __shared__ uint32_t s_wsum[OS_WARPS];
+  __shared__ int s_tile;
+  const int RADIX = radix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  n = eff_n(n, n_valid);
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  for (int d = tid; d < OS_WARPS * MAX_RADIX / 2; d += OS_THREADS) reinterpret_cast<uint32_t*>(&s_cnt[0][0])[d] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t tile0 = (int64_t)tile * TILE;
+  if (tile0 >= n) return;
+  const int tile_n = (int)min((int64_t)TILE, n - tile0);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  U key[ITEMS];
+  int32_t val[ITEMS];
+  uint32_t rk[ITEMS / 2];                           // rank inside (warp, digit), two 16-bit ranks per register
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int li = warp * (ITEMS * 32) + i * 32 + lane;
+    if (li < tile_n) {
+      key[i] = load_key<KeyT, RAW>(keys_in, tile0 + li, bound);
+      val[i] = RAW ? (int32_t)(tile0 + li) : vals_in[tile0 + li];
+    } else {
+      key[i] = 0;
+      val[i] = 0;
+    }
+  }
+  // digit base = exclusive scan of this pass's digit totals (one digit per thread); overlaps the key loads
+  uint32_t base_d = 0;
+  {
+    const uint32_t t0 = tid < RADIX ? ghist[tid] : 0u;
+    uint32_t v = t0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_wsum[warp] = v;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    base_d = off + v - t0;
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int li = warp * (ITEMS * 32) + i * 32 + lane;
+    const uint32_t dig = (li < tile_n) ? ((uint32_t)(key[i] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;   // RADIX = invalid
+    const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader && dig < (uint32_t)RADIX) {
+      old = s_cnt[warp][dig];
+      s_cnt[warp][dig] = (uint16_t)(old + __popc(peers));
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    const uint32_t rank = old + __popc(peers & lt_mask);
+    if (i & 1) rk[i >> 1] |= rank << 16;
+    else rk[i >> 1] = rank;
+    __syncwarp();
+  }
+  __syncthreads();
+  // thread = digit: exclusive prefix over the warps, tile count -> published for the later tiles
+  uint32_t run = 0;
+  if (tid < RADIX) {
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) {
+      const uint32_t c = s_cnt[w][tid];
+      s_cnt[w][tid] = (uint16_t)run;
+      run += c;
+    }
+    st_vol_u32(lookback + (int64_t)tile * RADIX + tid, run | LB_AGG);
+  }
+  // look back: the counts of ALL earlier tiles, summed.  Warp w takes tiles w, w + 16, ...; a lane reads 4 digits
+  // per 16-byte load, every load of the warp's rows is issued before the first is used.  Earlier tiles hold earlier
+  // tickets, so they run and publish without waiting for anyone; the spin bound only turns a bug into wrong output.
+  if ((RADIX & 127) == 0) {
+    const int chunks = RADIX >> 7;                  // 16-byte loads per lane and row (<= 4)
+    uint4 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = make_uint4(0u, 0u, 0u, 0u);
+    constexpr int RB = 4;                           // rows per batch: RB * chunks 16-byte loads in flight per lane
+    for (int t0 = warp; t0 < tile; t0 += RB * OS_WARPS) {
+      uint4 v[RB][4];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int t = t0 + r * OS_WARPS;
+        const uint4* row = reinterpret_cast<const uint4*>(lookback + (int64_t)min(t, tile - 1) * RADIX);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < chunks)
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[r][c].x), "=r"(v[r][c].y), "=r"(v[r][c].z), "=r"(v[r][c].w) : "l"(row + c * 32 + lane) : "memory");
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int t = t0 + r * OS_WARPS;
+        if (t >= tile) break;
+        const uint4* row = reinterpret_cast<const uint4*>(lookback + (int64_t)t * RADIX);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < chunks) {
+            uint4 x = v[r][c];
+            for (int spin = 0; ((x.x & x.y & x.z & x.w) >> 30) == 0u && spin < kSpinLimit; ++spin)
+              asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(row + c * 32 + lane) : "memory");
+            acc[c].x += x.x & LB_MASK; acc[c].y += x.y & LB_MASK; acc[c].z += x.z & LB_MASK; acc[c].w += x.w & LB_MASK;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < chunks) reinterpret_cast<uint4*>(s_pref + warp * RADIX)[c * 32 + lane] = acc[c];
+  } else {
+    for (int d = lane; d < RADIX; d += 32) {
+      uint32_t a = 0;
+      for (int t = warp; t < tile; t += OS_WARPS) {
+        uint32_t v = ld_vol_u32(lookback + (int64_t)t * RADIX + d);
+        for (int spin = 0; (v >> 30) == 0u && spin < kSpinLimit; ++spin) v = ld_vol_u32(lookback + (int64_t)t * RADIX + d);
+        a += v & LB_MASK;
+      }
+      s_pref[warp * RADIX + d] = a;
+    }
+  }
+  // tile-local exclusive scan of the digit counts (first sorted-tile index of each digit)
+  {
+    uint32_t v = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_wsum[warp] = v;
+    __syncthreads();                                // also: s_pref complete
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    if (tid < RADIX) {
+      const uint32_t dstart = off + v - run;
+      uint32_t excl = 0;
+#pragma unroll
+      for (int w = 0; w < OS_WARPS; ++w) excl += s_pref[w * RADIX + tid];
+      s_dstart[tid] = dstart;
+      s_goff[tid] = base_d + excl - dstart;
+    }
+  }
+  __syncthreads();                                  // s_pref is dead: the same memory now takes the sorted tile
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int li = warp * (ITEMS * 32) + i * 32 + lane;
+    if (li < tile_n) {
+      const uint32_t dig = (uint32_t)(key[i] >> shift) & (RADIX - 1);
+      const uint32_t si = s_dstart[dig] + s_cnt[warp][dig] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+      s_key[si] = key[i];
+      s_val[si] = val[i];
+    }
+  }
+  __syncthreads();
+  // write-out: consecutive threads hold consecutive sorted-tile indices = consecutive addresses inside a digit run
+  for (int j = tid; j < tile_n; j += OS_THREADS) {
+    const U k = s_key[j];
+    const uint32_t pos = s_goff[(uint32_t)(k >> shift) & (RADIX - 1)] + (uint32_t)j;
+    keys_out[pos] = k;
+    vals_out[pos] = s_val[j];
+  }
+}
+
+// count + scan + emit in one launch.  Global accesses are striped (thread t touches tile0 + k * 512 + t: coalesced);
+// the position-ordered scan works on a blocked view of the head flags in shared memory.
+constexpr int SEG_ITEMS = 8;
+constexpr int SEG_TILE = OS_THREADS * SEG_ITEMS;   // 4096
+template <typename KeyT>
+__global__ void __launch_bounds__(OS_THREADS)
+onesweep_seg_kernel(const typename UKeyOf<KeyT>::type* __restrict__ sorted, const int32_t* __restrict__ perm, int64_t n,
+                    uint64_t bound, uint32_t* __restrict__ lookback /* [tiles], zeroed */, uint32_t* __restrict__ ticket,
+                    KeyT* __restrict__ uniq, int32_t* __restrict__ inverse, int32_t* __restrict__ count,
+                    int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_of, const int32_t* __restrict__ n_valid) {
+  __shared__ __align__(8) uint8_t s_head[SEG_TILE];
+  __shared__ uint32_t s_seg[SEG_TILE + SEG_TILE / 32];   // padded: the blocked writes of a warp spread over the banks
+  __shared__ uint32_t s_warp[OS_WARPS];
+  __shared__ uint32_t s_excl;
+  __shared__ int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  n = eff_n(n, n_valid);
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t tile0 = (int64_t)tile * SEG_TILE;
+  if (n == 0) {
+    if (tile == 0 && tid == 0) { count[0] = 0; seg_start[0] = 0; }
+    return;
+  }
+  if (tile0 >= n) return;
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    const int li = k * OS_THREADS + tid;
+    const int64_t i = tile0 + li;
+    uint8_t h = 0;
+    if (i < n) h = (i == 0 || sorted[i] != sorted[i - 1]) ? 1 : 0;
+    s_head[li] = h;
+  }
+  __syncthreads();
+  // blocked view: thread t owns positions [8t, 8t + 8)
+  const uint2 hb = reinterpret_cast<const uint2*>(s_head)[tid];
+  const uint32_t c = __popc(hb.x) + __popc(hb.y);
+  uint32_t v = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_warp[warp] = v;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < OS_WARPS; ++w) {
+    const uint32_t x = s_warp[w];
+    if (w < warp) before += x;
+    total += x;
+  }
+  if (warp == 0) {
+    if (lane == 0) st_vol_u32(lookback + tile, total | (tile == 0 ? LB_INC : LB_AGG));
+    uint32_t excl = 0;
+    for (int t = tile - 1; t >= 0; t -= 32) {
+      const int tq = t - lane;
+      uint32_t x = (tq >= 0) ? ld_vol_u32(lookback + tq) : LB_INC;
+      for (int spin = 0; __any_sync(0xffffffffu, (x >> 30) == 0u) && spin < kSpinLimit; ++spin)
+        if ((x >> 30) == 0u) x = ld_vol_u32(lookback + tq);
+      const uint32_t inc_mask = __ballot_sync(0xffffffffu, (x & LB_INC) != 0u);
+      const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+      uint32_t part = (lane <= first_inc) ? (x & LB_MASK) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      excl += part;
+      if (inc_mask) break;
+    }
+    if (lane == 0) {
+      if (tile != 0) st_vol_u32(lookback + tile, (excl + total) | LB_INC);
+      s_excl = excl;
+      if (tile0 + SEG_TILE >= n) {                   // the tile that holds the last key closes the outputs
+        count[0] = (int32_t)(excl + total);
+        seg_start[excl + total] = (int32_t)n;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    uint32_t seg = s_excl + before + v - c;          // heads strictly before this thread's first position
+    const uint64_t bits = (uint64_t)hb.x | ((uint64_t)hb.y << 32);
+#pragma unroll
+    for (int j = 0; j < SEG_ITEMS; ++j) {
+      seg += (uint32_t)((bits >> (8 * j)) & 1u);
+      const int li = tid * SEG_ITEMS + j;
+      s_seg[li + (li >> 5)] = seg - 1u;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    const int li = k * OS_THREADS + tid;
+    const int64_t i = tile0 + li;
+    if (i < n) {
+      const int32_t sgi = (int32_t)s_seg[li + (li >> 5)];
+      seg_of[i] = sgi;
+      inverse[perm[i]] = sgi;
+      if (s_head[li]) {
+        uniq[sgi] = decode_key<KeyT>(sorted[i], bound);
+        seg_start[sgi] = (int32_t)i;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -364,6 +721,9 @@ struct SortPlan {
   int64_t n;
   int n_tiles, n_blocks, tiles_per_block, passes, digit_bits;
   size_t off_keys_a, off_keys_b, off_vals_tmp, off_hist, off_hist2, off_tiles, total;
+  // one-sweep control region (zeroed by one memset per call): digit totals, tickets, look-back words
+  int os_tiles, seg_tiles;
+  size_t off_ctrl, ctrl_bytes, off_ghist, off_ticket, off_lb_seg, off_lb;
 };
 
 static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
@@ -383,6 +743,20 @@ static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
   p.off_hist = o; o = align_up(o + (size_t)(p.n_blocks + 1) * MAX_RADIX * 4, 256);
   p.off_hist2 = o; o = align_up(o + (size_t)(p.n_blocks + 1) * MAX_RADIX * 4, 256);
   p.off_tiles = o; o = align_up(o + (size_t)(p.n_tiles + 1) * 4, 256);
+  {
+    const int os_tile = OS_THREADS * (key_bytes == 8 ? OsItems<int64_t>::value : OsItems<int32_t>::value);
+    p.os_tiles = (int)cdiv(n > 0 ? n : 1, os_tile);
+    p.seg_tiles = (int)cdiv(n > 0 ? n : 1, SEG_TILE);
+    p.off_ctrl = o;
+    p.off_ghist = o; o += (size_t)OS_MAX_PASSES * MAX_RADIX * 4;
+    p.off_ticket = o; o += 64;
+    p.off_lb_seg = o; o = align_up(o + (size_t)p.seg_tiles * 4, 256);
+    // the look-back area is sized for the widest sort of this key type (the workspace is requested without knowing
+    // the bound); one call zeroes only the passes * tiles * radix words it uses
+    p.off_lb = o;
+    p.ctrl_bytes = o + (size_t)p.passes * p.os_tiles * ((size_t)1 << p.digit_bits) * 4 - p.off_ctrl;
+    o = align_up(o + (size_t)cdiv(8 * key_bytes, MAX_RADIX_BITS) * p.os_tiles * MAX_RADIX * 4, 256);
+  }
   p.total = o;
   return p;
 }
@@ -421,9 +795,48 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
   uint32_t* hist = reinterpret_cast<uint32_t*>(w + p.off_hist);
   uint32_t* tiles = reinterpret_cast<uint32_t*>(w + p.off_tiles);
 
+  const int radix = 1 << p.digit_bits;
+  static const bool use_lsd = [] { const char* e = getenv("MREC_UNIQUE_LSD"); return e && atoi(e) != 0; }();
+  if (!use_lsd && n < ((int64_t)1 << 30) && p.passes <= OS_MAX_PASSES) {
+    uint32_t* ghist = reinterpret_cast<uint32_t*>(w + p.off_ghist);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(w + p.off_ticket);
+    uint32_t* lb_seg = reinterpret_cast<uint32_t*>(w + p.off_lb_seg);
+    uint32_t* lb = reinterpret_cast<uint32_t*>(w + p.off_lb);
+    cudaMemsetAsync(w + p.off_ctrl, 0, p.ctrl_bytes, stream);
+    // sorted tile (keys + values) or the look-back partials, whichever is larger; > 48 KB needs the opt-in
+    constexpr size_t os_smem = (size_t)OS_THREADS * OsItems<KeyT>::value * (sizeof(U) + 4) > (size_t)OS_WARPS * MAX_RADIX * 4
+                                   ? (size_t)OS_THREADS * OsItems<KeyT>::value * (sizeof(U) + 4) : (size_t)OS_WARPS * MAX_RADIX * 4;
+    static const bool attr_ok = [] {
+      return cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_smem) == cudaSuccess &&
+             cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_smem) == cudaSuccess;
+    }();
+    if (!attr_ok) return fail(ERR_CUDA, "mrec_unique: cannot reserve %zu bytes of dynamic shared memory", os_smem);
+    // few CTAs: the 6 KB of digit totals live in 48 cache lines, and every CTA ends with ~1500 global atomics on them
+    const int hist_grid = (int)std::min<int64_t>(cdiv(n, 16 * OS_HIST_THREADS), kNumSMs);
+    MREC_LAUNCH(onesweep_hist_kernel<KeyT>, hist_grid, OS_HIST_THREADS, 0, stream, ids, n, bound, p.passes, p.digit_bits,
+                ghist, n_valid);
+    const void* kin = ids;
+    const int32_t* vin = nullptr;
+    for (int pass = 0; pass < p.passes; ++pass) {
+      U* kout = kbuf[pass & 1];
+      int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vtmp;    // the last pass lands in `perm`
+      uint32_t* lbp = lb + (size_t)pass * p.os_tiles * radix;
+      if (pass == 0) {
+        MREC_LAUNCH((onesweep_pass_kernel<KeyT, true>), p.os_tiles, OS_THREADS, os_smem, stream, kin, vin, kout, vout, n,
+                    pass * p.digit_bits, radix, bound, ghist + pass * MAX_RADIX, lbp, ticket + pass, n_valid);
+      } else {
+        MREC_LAUNCH((onesweep_pass_kernel<KeyT, false>), p.os_tiles, OS_THREADS, os_smem, stream, kin, vin, kout, vout, n,
+                    pass * p.digit_bits, radix, bound, ghist + pass * MAX_RADIX, lbp, ticket + pass, n_valid);
+      }
+      kin = kout;
+      vin = vout;
+    }
+    MREC_LAUNCH(onesweep_seg_kernel<KeyT>, p.seg_tiles, OS_THREADS, 0, stream, reinterpret_cast<const U*>(kin), perm, n,
+                bound, lb_seg, ticket + OS_MAX_PASSES, uniq, inverse, count, seg_start, seg_of, n_valid);
+    return check_launch("unique_sorted");
+  }
   const void* kin = ids;
   const int32_t* vin = nullptr;
-  const int radix = 1 << p.digit_bits;
   const int scan_grid = (int)cdiv(radix, 32);
   uint32_t* hbuf[2] = {hist, reinterpret_cast<uint32_t*>(w + p.off_hist2)};
   const size_t hist_bytes = (size_t)(p.n_blocks + 1) * radix * sizeof(uint32_t);

@@ -20,10 +20,18 @@ from . import ops
 class Parameter:
     """A named device buffer (mindspore.Parameter stand-in)."""
 
-    def __init__(self, data, name, requires_grad=True):
+    def __init__(self, data, name, requires_grad=True, packed=None):
         self.data = data
         self.name = name
         self.requires_grad = requires_grad
+        # interleaved layout (EmbeddingLookup(interleave_state=True)): `packed` is wmv[V,3,D], each row's weights |
+        # Adam m | Adam v back to back; `data` is then the strided view packed[:, 0, :]
+        self.packed = packed
+
+    @property
+    def kernel_arg(self):
+        """What the aot kernels are handed: the contiguous table, or the interleaved record array."""
+        return self.packed if self.packed is not None else self.data
 
     @property
     def shape(self):
@@ -77,7 +85,7 @@ class EmbeddingLookup:
 
     def __init__(self, vocab_size, embedding_size, param_init="normal", target="DEVICE",
                  slice_mode="batch_slice", manual_shapes=None, max_norm=None, sparse=True,
-                 vocab_cache_size=0, device="cuda", name="embedding_table", generator=None):
+                 vocab_cache_size=0, device="cuda", name="embedding_table", generator=None, interleave_state=False):
         if not isinstance(vocab_size, int) or vocab_size <= 0:
             raise ValueError("For 'EmbeddingLookup', 'vocab_size' must be a positive int, got %r" % (vocab_size,))
         if not isinstance(embedding_size, int) or embedding_size <= 0:
@@ -94,14 +102,24 @@ class EmbeddingLookup:
         self.embedding_size = embedding_size
         self.sparse = sparse
         self.max_norm = max_norm
-        self.embedding_table = Parameter(_init_table((vocab_size, embedding_size), param_init, device, generator),
-                                         name=name)
+        if interleave_state:
+            # one [V, 3, D] array: w | m | v of a row are one 3*D*4-byte record, so the LazyAdam row update is one
+            # random DRAM access per row instead of three (mrec_sparse_lazy_adam's interleaved form); the gathers read
+            # array 0 at the record pitch.  m, v start at zero.
+            if embedding_size % 4:
+                raise ValueError("interleave_state needs embedding_size % 4 == 0")
+            packed = torch.zeros((vocab_size, 3, embedding_size), dtype=torch.float32, device=device)
+            packed[:, 0, :] = _init_table((vocab_size, embedding_size), param_init, device, generator)
+            self.embedding_table = Parameter(packed[:, 0, :], name=name, packed=packed)
+        else:
+            self.embedding_table = Parameter(_init_table((vocab_size, embedding_size), param_init, device, generator),
+                                             name=name)
 
     def __call__(self, indices):
         return self.construct(indices)
 
     def construct(self, indices):
-        out = ops.gather(self.embedding_table.data, indices)
+        out = ops.gather(self.embedding_table.kernel_arg, indices)
         if self.max_norm is not None:
             norm = out.norm(dim=-1, keepdim=True).clamp_min(1e-12)
             out = out * torch.clamp(self.max_norm / norm, max=1.0)
@@ -146,7 +164,7 @@ class _Optimizer:
 
     def _dedup(self, p, g):
         if g.uq is None:
-            g.uq = ops.unique(g.indices, table_like=p.values[:p.capacity] if _is_map(p) else p.data)
+            g.uq = ops.unique(g.indices, table_like=p.values[:p.capacity] if _is_map(p) else p.kernel_arg)
         return g.uq
 
     def __call__(self, grads):
@@ -178,6 +196,11 @@ class Adam(_Optimizer):
                 self._map_state[i] = self._state_arenas(p, (0.0, 0.0))
                 self.moment1.append(None)
                 self.moment2.append(None)
+            elif getattr(p, "packed", None) is not None:      # interleaved record: the moments are views of it
+                if not self.lazy:
+                    raise ValueError("an interleaved table (interleave_state=True) is updated by LazyAdam only")
+                self.moment1.append(p.packed[:, 1, :])
+                self.moment2.append(p.packed[:, 2, :])
             else:
                 self.moment1.append(torch.zeros_like(p.data))
                 self.moment2.append(torch.zeros_like(p.data))
@@ -200,7 +223,9 @@ class Adam(_Optimizer):
                 continue
             if isinstance(g, RowTensor):
                 uq = self._dedup(p, g)
-                if self.lazy:
+                if self.lazy and getattr(p, "packed", None) is not None:
+                    ops.sparse_lazy_adam(p.packed, None, None, self.hyper, g.values, g.mask, uq)
+                elif self.lazy:
                     ops.sparse_lazy_adam(p.data, m, v, self.hyper, g.values, g.mask, uq)
                 else:
                     ops.adam_rowsparse_dense_equiv(p.data, m, v, self.hyper, g.values, g.mask, uq,

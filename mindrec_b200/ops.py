@@ -43,8 +43,9 @@ def _size_fn(name):
 # K1 gather
 # ------------------------------------------------------------------------------------------------
 def gather(table, ids, out=None, oob_flag=None):
-    """out[..., :] = table[ids[...], :]  (mrec_gather; nn.EmbeddingLookup / P.Gather axis 0)."""
-    dim = table.shape[1] if table.dim() == 2 else 1
+    """out[..., :] = table[ids[...], :]  (mrec_gather; nn.EmbeddingLookup / P.Gather axis 0).  A [V,K,D] table is the
+    interleaved record layout: array 0 of every row is read."""
+    dim = table.shape[-1] if table.dim() >= 2 else 1
     if out is None:
         out = torch.empty(tuple(ids.shape) + (dim,), dtype=torch.float32, device=table.device)
     args = [table, ids, out] + ([oob_flag] if oob_flag is not None else [])
@@ -55,7 +56,7 @@ def gather(table, ids, out=None, oob_flag=None):
 def gather_masked(table, ids, mask, out=None, oob_flag=None, out_dtype=torch.float32):
     """out[b, f*D:(f+1)*D] = table[ids[b,f]] * mask[b,f]  (gather + Mul + Reshape fused).
     A float16 `out` additionally fuses the Cast at the head of a mixed-precision DenseLayer."""
-    dim = table.shape[1] if table.dim() == 2 else 1
+    dim = table.shape[-1] if table.dim() >= 2 else 1
     if out is None:
         out = torch.empty((ids.shape[0], ids.numel() // ids.shape[0] * dim), dtype=out_dtype,
                           device=table.device)
@@ -206,8 +207,13 @@ def segment_sum_scatter_add(table, g, mask, uq):
 
 def sparse_lazy_adam(w, m, v, hyper, g, mask, uq, n_valid=None):
     """Fused segment-sum + LazyAdam row update on the rows named by uq.uniq (in place).
-    n_valid (device int32[1]): only the first n_valid sorted positions are real (static inbox)."""
-    dim = w.shape[1] if w.dim() == 2 else 1
+    n_valid (device int32[1]): only the first n_valid sorted positions are real (static inbox).
+    m = v = None: `w` is the interleaved record array wmv[V,3,D] (weights | m | v of a row back to back)."""
+    dim = w.shape[-1] if w.dim() >= 2 else 1
+    if m is None:
+        if not (w.dim() == 3 and w.shape[1] == 3):
+            raise ValueError("sparse_lazy_adam without m, v needs the interleaved array wmv[V,3,D]")
+        m = v = _empty_mask(w.device)
     mask = _empty_mask(w.device) if mask is None else mask.reshape(-1)
     nv = [] if n_valid is None else [n_valid]
     _lib.aot_call("mrec_sparse_lazy_adam", [w, m, v, hyper, g, mask, uq.uniq, uq.perm, uq.seg_start,

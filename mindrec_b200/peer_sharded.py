@@ -36,26 +36,35 @@ class PeerRank:
     """State and phases of one rank.  `alloc(name, shape, dtype)` returns the rank's peer-writable buffers."""
 
     def __init__(self, rank, world, vocab_size, emb_dim, n_lookups, device, alloc, seed=1, sens=1024.0,
-                 init_std=0.01, cap_rows=None):
+                 init_std=0.01, cap_rows=None, adam=(3.5e-4, 1e-8), ftrl=(5e-2, 1e-8, 1e-8, 1.0)):
+        """adam = (lr, eps) of the LazyAdam on the deep shard, ftrl = (lr, l1, l2, initial_accum) of the FTRL on the
+        dim-1 shard: wide_and_deep.py:420-430 by default; the multitable model passes its own (:525-535)."""
         self.rank, self.world = rank, world
         self.plan = ShardPlan(vocab_size, world)
         self.dim, self.n = emb_dim, n_lookups
         self.device = torch.device(device)
         g, r, dev = world, self.plan.rows_per_rank, self.device
-        self.cap = int(cap_rows or n_lookups)          # rows an inbox / landing buffer can hold
+        # Rows an inbox can hold.  A requester never has more than N unique keys (the landing buffers are N rows), but
+        # an OWNER receives the keys of all G ranks: up to min(G * N, R) rows when no two lookups repeat a key and every
+        # rank asks for this owner's rows only.  Default: 2 N rows — the whole worst case for G <= 2; for G > 2 it
+        # covers twice the load of G ranks with N distinct keys each spread evenly over the owners (N rows), which a
+        # key-mod-G owner function only exceeds under an adversarial key set.  An overflow is never silent: the push
+        # kernel drops the row and raises err bit 1, which poisons the step's loss with NaN
+        # (PeerShardedWideDeepStep._a2).  cap_rows = G * N removes the possibility altogether.
+        self.cap = int(cap_rows or min(g * n_lookups, max(r, n_lookups), 2 * n_lookups))
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 1000 + rank)
         self.wide = torch.empty((r, 1), dtype=torch.float32, device=dev).normal_(0, init_std, generator=gen)
         self.deep = torch.empty((r, emb_dim), dtype=torch.float32, device=dev).normal_(0, init_std, generator=gen)
-        self.acc, self.lin = torch.ones_like(self.wide), torch.zeros_like(self.wide)
+        self.acc, self.lin = torch.full_like(self.wide, float(ftrl[3])), torch.zeros_like(self.wide)
         self.m, self.v = torch.zeros_like(self.deep), torch.zeros_like(self.deep)
-        self.adam_hyper = ops.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * world, device=dev)
-        self.ftrl_hyper = ops.ftrl_hyper(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens * world, device=dev)
+        self.adam_hyper = ops.adam_hyper(adam[0], eps=adam[1], loss_scale=sens * world, device=dev)
+        self.ftrl_hyper = ops.ftrl_hyper(ftrl[0], l1=ftrl[1], l2=ftrl[2], loss_scale=sens * world, device=dev)
         # peer-writable buffers
         i32, f32 = torch.int32, torch.float32
         self.buf = {
             "ball": alloc("ball", (g * (g + 1),), i32), "keys_in": alloc("keys_in", (self.cap,), i32),
-            "land_deep": alloc("land_deep", (self.cap, emb_dim), f32), "land_wide": alloc("land_wide", (self.cap, 1), f32),
+            "land_deep": alloc("land_deep", (n_lookups, emb_dim), f32), "land_wide": alloc("land_wide", (n_lookups, 1), f32),
             "grad_in": alloc("grad_in", (self.cap, emb_dim), f32), "gwide_in": alloc("gwide_in", (self.cap, 1), f32),
             "flags": alloc("flags", (N_PHASES * g,), i32),
         }
@@ -239,7 +248,8 @@ class PeerHashRank:
     reserved key -1 so that it cannot touch the table."""
 
     def __init__(self, rank, world, emb_dim, n_lookups, device, alloc, key_bits=40, capacity=1 << 16, seed=0,
-                 learning_rate=1e-3, loss_scale=1.0, permit_filter_value=1, evict_filter_value=None, cap_rows=None):
+                 learning_rate=1e-3, loss_scale=1.0, permit_filter_value=1, evict_filter_value=None, cap_rows=None,
+                 eps=1e-8):
         from . import hash as _hash
         self.rank, self.world, self.dim, self.n = rank, world, emb_dim, n_lookups
         self.bits = int(key_bits)
@@ -247,16 +257,16 @@ class PeerHashRank:
             raise ValueError("key_bits + log2(world) must stay below 62")
         self.device = torch.device(device)
         dev, g = self.device, world
-        self.cap = int(cap_rows or n_lookups)
+        self.cap = int(cap_rows or min(g * n_lookups, 2 * n_lookups))     # see PeerRank: inbox rows, overflow -> err bit 1
         self.table = _hash.MapParameter(key_dtype=torch.int64, value_shape=emb_dim, default_value="normal",
                                         permit_filter_value=permit_filter_value,
                                         evict_filter_value=evict_filter_value or _hash.MAX_SIZE, capacity=capacity,
                                         device=dev, seed=seed)
         self.m, self.v = self.table.add_arena(0.0), self.table.add_arena(0.0)
-        self.hyper = ops.adam_hyper(learning_rate, loss_scale=loss_scale, device=dev)
+        self.hyper = ops.adam_hyper(learning_rate, eps=eps, loss_scale=loss_scale, device=dev)
         i32, i64, f32 = torch.int32, torch.int64, torch.float32
         self.buf = {"ball": alloc("ball", (g * (g + 1),), i32), "keys_in": alloc("keys_in", (self.cap,), i64),
-                    "land": alloc("land", (self.cap, emb_dim), f32), "grad_in": alloc("grad_in", (self.cap, emb_dim), f32),
+                    "land": alloc("land", (n_lookups, emb_dim), f32), "grad_in": alloc("grad_in", (self.cap, emb_dim), f32),
                     "flags": alloc("flags", (N_PHASES * g,), i32)}
         self.buf["ball"].zero_()
         self.buf["flags"].zero_()
@@ -381,11 +391,15 @@ class PeerShardedHashEmbedding:
 
     def __init__(self, emb_dim, n_lookups, device, group=None, **kw):
         self.group = group
-        arena = _IpcArena(group)
+        arena = self._arena = _IpcArena(group)
         self.rk = _connect_collectively(
             lambda: PeerHashRank(dist.get_rank(group), dist.get_world_size(group), emb_dim, n_lookups, device,
                                  arena.alloc(device), **kw), arena, group, torch.device(device))
         self.dim = emb_dim
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective: every rank of the group calls it)."""
+        self._arena.close()
 
     def lookup(self, keys, out=None):
         rk = self.rk
@@ -454,7 +468,10 @@ class _IpcArena:
         self.lib.mrec_ipc_open_handle.restype = ctypes.c_void_p
         self.lib.mrec_ipc_open_handle.argtypes = [ctypes.c_char_p]
         self.lib.mrec_ipc_get_handle.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        self.lib.mrec_ipc_close_handle.argtypes = [ctypes.c_void_p]
+        self.lib.mrec_peer_free.argtypes = [ctypes.c_void_p]
         self.local = {}
+        self.opened = []
 
     def alloc(self, device):
         def _alloc(name, shape, dtype):
@@ -487,16 +504,28 @@ class _IpcArena:
                     p = self.lib.mrec_ipc_open_handle(gathered[r][name])
                     if not p:
                         raise RuntimeError("mrec_ipc_open_handle failed: " + _lib.last_error())
+                    self.opened.append(p)
                     lst.append(p)
             base[name] = lst
         return base
+
+    def close(self):
+        """Every rank first unmaps what it opened, then (after a barrier) frees what it owns."""
+        torch.cuda.synchronize()
+        for p in self.opened:
+            self.lib.mrec_ipc_close_handle(ctypes.c_void_p(p))
+        self.opened = []
+        dist.barrier(group=self.group)
+        for ptr, _ in self.local.values():
+            self.lib.mrec_peer_free(ctypes.c_void_p(ptr))
+        self.local = {}
 
 
 class PeerShardedTables:
     """Multi-process form: drop-in for sharded.ShardedWideDeepTables inside sharded.ShardedWideDeepStep
     (`plan_batch` / `lookup` / `update` / `gather_full`), with nothing read back to the host."""
 
-    def __init__(self, vocab_size, emb_dim, n_lookups, device, group=None, seed=1, sens=1024.0):
+    def __init__(self, vocab_size, emb_dim, n_lookups, device, group=None, seed=1, sens=1024.0, cap_rows=None, **rank_kw):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -505,10 +534,10 @@ class PeerShardedTables:
         self.plan_stream = None
         self.owner_stream = torch.cuda.Stream(device=self.device)
         self._side_open = False
-        arena = _IpcArena(group)
+        arena = self._arena = _IpcArena(group)
         self.rk = _connect_collectively(
             lambda: PeerRank(self.rank, self.world, vocab_size, emb_dim, n_lookups, device, arena.alloc(device),
-                             seed=seed, sens=sens), arena, group, self.device)
+                             seed=seed, sens=sens, cap_rows=cap_rows, **rank_kw), arena, group, self.device)
         self.plan = self.rk.plan
         self.dim = emb_dim
         self._ids = None
@@ -572,6 +601,10 @@ class PeerShardedTables:
         """bit 0: a peer wait timed out; bit 1: an inbox overflowed (host read — call outside the hot loop)."""
         return int(self.rk.err.item())
 
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective: every rank of the group calls it)."""
+        self._arena.close()
+
     def gather_full(self):
         g, r, v = self.world, self.plan.rows_per_rank, self.plan.vocab_size
         wl = [torch.empty_like(self.rk.wide) for _ in range(g)]
@@ -596,11 +629,13 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
     time."""
 
     def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
-                 use_mixed_precision=True, group=None, graph=True):
+                 use_mixed_precision=True, group=None, graph=True, cap_rows=None):
         super().__init__(batch_size, vocab_size, emb_dim, hidden, device, seed=seed, sens=sens, fields=fields,
                          use_mixed_precision=use_mixed_precision, group=group, graph_dense=False,
                          tables_factory=lambda: PeerShardedTables(vocab_size, emb_dim, batch_size * fields, device,
-                                                                  group=group, seed=seed, sens=sens))
+                                                                  group=group, seed=seed, sens=sens, cap_rows=cap_rows))
+        self._nan = torch.tensor(float("nan"), dtype=torch.float32, device=self.device)
+        self._zero = torch.zeros((), dtype=torch.float32, device=self.device)
         self._graph_step = graph
         self._graphs = None
         self._loss = None
@@ -634,7 +669,9 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         loss, delta, gx = self._dense_segment()
         main.wait_stream(self._plan_stream)
         self._bwd = (delta, gx)
-        return loss
+        # an exchange error (a wait that timed out, an inbox that overflowed) must not train on silently: the loss
+        # the caller reads turns NaN from the step after the one that raised the bit
+        return loss + torch.where(self.tables.rk.err[0] != 0, self._nan, self._zero)
 
     def _b(self):
         self.tables.update(*self._bwd)

@@ -205,3 +205,33 @@ def test_fp16_gradient_rows_equal_cast_then_fp32(cuda, dim, b, use_mask):
         ops.sparse_lazy_adam(w, m, v, hyper, g, mask, uq)
         res.append(w)
     assert torch.equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("dim", [80, 128, 12])
+@pytest.mark.parametrize("half", [False, True])
+def test_interleaved_records_equal_split_arrays(cuda, dim, half):
+    """The interleaved layout wmv[V,3,D] (one w | m | v record per row) is a storage choice: two LazyAdam steps leave
+    bit-identical weights and moments, and the gathers read the same rows, as with three [V,D] arrays."""
+    rng = np.random.default_rng(50 + dim)
+    vocab, b, f = 5000, 700, 39
+    w0 = torch.from_numpy((rng.standard_normal((vocab, dim)) * 0.01).astype(np.float32)).to(cuda)
+    w, m, v = w0.clone(), torch.zeros_like(w0), torch.zeros_like(w0)
+    wmv = torch.zeros((vocab, 3, dim), device=cuda)
+    wmv[:, 0, :] = w0
+    h1, h2 = ops.adam_hyper(1e-3, loss_scale=8.0, device=cuda), ops.adam_hyper(1e-3, loss_scale=8.0, device=cuda)
+    for step in range(2):
+        ids = torch.from_numpy(_zipf_ids(rng, b, f, vocab + 20)).to(cuda)
+        g = torch.from_numpy(rng.standard_normal((b * f, dim)).astype(np.float32)).to(cuda)
+        g = g.half() if half else g
+        mask = torch.from_numpy(rng.random(b * f).astype(np.float32)).to(cuda)
+        uq = ops.unique(ids, table_like=w)
+        ops.adam_begin_step(h1)
+        ops.sparse_lazy_adam(w, m, v, h1, g, mask, uq)
+        ops.adam_begin_step(h2)
+        ops.sparse_lazy_adam(wmv, None, None, h2, g, mask, ops.unique(ids, table_like=wmv))
+        assert torch.equal(wmv[:, 0, :], w) and torch.equal(wmv[:, 1, :], m) and torch.equal(wmv[:, 2, :], v)
+        wts = mask.view(b, f)
+        assert torch.equal(ops.gather(wmv, ids), ops.gather(w, ids))
+        assert torch.equal(ops.gather_masked(wmv, ids, wts), ops.gather_masked(w, ids, wts))
+        assert torch.equal(ops.gather_masked(wmv, ids, wts, out_dtype=torch.float16),
+                           ops.gather_masked(w, ids, wts, out_dtype=torch.float16))

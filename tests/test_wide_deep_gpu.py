@@ -146,3 +146,28 @@ def test_replay_with_staged_next_batch_equals_plain_replay(cuda):
     torch.cuda.synchronize()
     assert torch.equal(model.embedding_table.data, model2.embedding_table.data)
     assert torch.equal(model.dense.flat, model2.dense.flat)
+
+
+def test_interleaved_adam_state_step_is_bit_identical(cuda):
+    """WideDeepConfig(interleave_adam_state=True) changes where the deep table's w, m, v live, not what a step does."""
+    outs = []
+    for inter in (False, True):
+        cfg = cells.WideDeepConfig(batch_size=257, vocab_size=3000, emb_dim=16, deep_layer_dim=(64, 32),
+                                   use_mixed_precision=False, sparse=True, seed=7, interleave_adam_state=inter)
+        model = cells.WideDeepModel(cfg, device=cuda)
+        step = cells.TrainStepWrap(cells.NetWithLossClass(model, cfg), sens=1024.0, sparse=True, lazy_adam=True)
+        gen = synth.CriteoSynth(cfg.batch_size, cards=[50] * 26, vocab_pad=cfg.vocab_size, seed=3)
+        losses = []
+        for it in range(3):
+            ids, wts, label = gen.next()
+            losses.append(float(step(torch.from_numpy(ids).to(cuda), torch.from_numpy(wts).to(cuda),
+                                     torch.from_numpy(label).to(cuda))[0]))
+        outs.append((losses, model.embedding_table.data.clone(), step.optimizer_d.moment1[0].clone(),
+                     step.optimizer_d.moment2[0].clone(), model.dense.flat.clone()))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError, match="LazyAdam"):
+        cfg = cells.WideDeepConfig(batch_size=8, vocab_size=100, emb_dim=8, deep_layer_dim=(8,), sparse=True,
+                                   interleave_adam_state=True)
+        cells.TrainStepWrap(cells.NetWithLossClass(cells.WideDeepModel(cfg, device=cuda), cfg), sparse=True)
