@@ -51,7 +51,7 @@ class PeerRank:
         # key-mod-G owner function only exceeds under an adversarial key set.  An overflow is never silent: the push
         # kernel drops the row and raises err bit 1, which poisons the step's loss with NaN
         # (PeerShardedWideDeepStep._a2).  cap_rows = G * N removes the possibility altogether.
-        self.cap = int(cap_rows or min(g * n_lookups, max(r, n_lookups), 2 * n_lookups))
+        self.cap = (int(cap_rows or min(g * n_lookups, max(r, n_lookups), 2 * n_lookups)) + 3) // 4 * 4
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 1000 + rank)
         self.wide = torch.empty((r, 1), dtype=torch.float32, device=dev).normal_(0, init_std, generator=gen)
@@ -60,10 +60,12 @@ class PeerRank:
         self.m, self.v = torch.zeros_like(self.deep), torch.zeros_like(self.deep)
         self.adam_hyper = ops.adam_hyper(adam[0], eps=adam[1], loss_scale=sens * world, device=dev)
         self.ftrl_hyper = ops.ftrl_hyper(ftrl[0], l1=ftrl[1], l2=ftrl[2], loss_scale=sens * world, device=dev)
-        # peer-writable buffers
+        # peer-writable buffers.  The KEY phase (bounds matrix, key inbox) exists twice: while step t runs on set
+        # t & 1, the key phase of batch t + 1 (plan, publish, key push, owner dedup) runs one step ahead on the other
+        # set underneath step t's DenseLayers, so that only serve -> expand stays in front of them.
         i32, f32 = torch.int32, torch.float32
         self.buf = {
-            "ball": alloc("ball", (g * (g + 1),), i32), "keys_in": alloc("keys_in", (self.cap,), i32),
+            "ball": alloc("ball", (2 * g * (g + 1),), i32), "keys_in": alloc("keys_in", (2 * self.cap,), i32),
             "land_deep": alloc("land_deep", (n_lookups, emb_dim), f32), "land_wide": alloc("land_wide", (n_lookups, 1), f32),
             "grad_in": alloc("grad_in", (self.cap, emb_dim), f32), "gwide_in": alloc("gwide_in", (self.cap, 1), f32),
             "flags": alloc("flags", (N_PHASES * g,), i32),
@@ -75,19 +77,20 @@ class PeerRank:
         self.ctrl = torch.tensor([rank, world], dtype=i32, device=dev)
         self.epoch = [torch.zeros(1, dtype=i32, device=dev) for _ in range(N_PHASES)]
         self.err = torch.zeros(1, dtype=i32, device=dev)
-        self.bounds = torch.zeros(g + 1, dtype=i32, device=dev)
-        self.dst_off = torch.zeros(g, dtype=i32, device=dev)
-        self.src_off = torch.zeros(g + 1, dtype=i32, device=dev)
-        self.inbox_off = torch.zeros(g, dtype=i32, device=dev)
-        self.n_r = torch.zeros(1, dtype=i32, device=dev)
         self.edges = (torch.arange(g + 1, device=dev, dtype=i32) * r)
-        self.key = torch.empty(n_lookups, dtype=i32, device=dev)
-        self.uq = ops.UniqueResult(n_lookups, i32, dev, packed=True)
-        # the NEXT batch's local plan (remap + dedup + bounds), computed one step ahead under the DenseLayers
-        self.key_n = torch.empty(n_lookups, dtype=i32, device=dev)
-        self.uq_n = ops.UniqueResult(n_lookups, i32, dev, packed=True)
-        self.bounds_n = torch.zeros(g + 1, dtype=i32, device=dev)
-        self.uq_owner = ops.UniqueResult(self.cap, i32, dev)
+        self._sets = []
+        for si in range(2):
+            st = {
+                "ball": self.buf["ball"][si * g * (g + 1):(si + 1) * g * (g + 1)],
+                "keys_in": self.buf["keys_in"][si * self.cap:(si + 1) * self.cap],
+                "bounds": torch.zeros(g + 1, dtype=i32, device=dev), "dst_off": torch.zeros(g, dtype=i32, device=dev),
+                "src_off": torch.zeros(g + 1, dtype=i32, device=dev), "inbox_off": torch.zeros(g, dtype=i32, device=dev),
+                "n_r": torch.zeros(1, dtype=i32, device=dev), "key": torch.empty(n_lookups, dtype=i32, device=dev),
+                "uq": ops.UniqueResult(n_lookups, i32, dev, packed=True), "uq_owner": ops.UniqueResult(self.cap, i32, dev),
+                "tag": "unique_peer_plan%d" % si, "owner_tag": "unique_peer_owner%d" % si,
+            }
+            self._sets.append(st)
+        self.cur = 0
         self.gs_deep = torch.empty((n_lookups, emb_dim), dtype=f32, device=dev)
         self.gs_wide = torch.empty((n_lookups, 1), dtype=f32, device=dev)
         self._bound_like = torch.empty((g * r, 0), device=dev)
@@ -101,13 +104,32 @@ class PeerRank:
         self.ptrs = None
         self._wts = None
 
+    # the CURRENT set's state under the names the phases (and the tests) use
+    def _s(self, nxt=False):
+        return self._sets[self.cur ^ 1 if nxt else self.cur]
+
+    key = property(lambda self: self._s()["key"])
+    uq = property(lambda self: self._s()["uq"])
+    bounds = property(lambda self: self._s()["bounds"])
+    dst_off = property(lambda self: self._s()["dst_off"])
+    src_off = property(lambda self: self._s()["src_off"])
+    inbox_off = property(lambda self: self._s()["inbox_off"])
+    n_r = property(lambda self: self._s()["n_r"])
+    uq_owner = property(lambda self: self._s()["uq_owner"])
+    keys_in = property(lambda self: self._s()["keys_in"])
+
+    def use_set(self, i):
+        self.cur = int(i) & 1
+
     def connect(self, base_ptrs):
         """base_ptrs[name][s] = address of rank s's buffer `name` as mapped in THIS process."""
         g, me, dev = self.world, self.rank, self.device
         t = lambda lst: torch.tensor(lst, dtype=torch.int64, device=dev)
+        for si, st in enumerate(self._sets):
+            st["p_ball_row"] = t([base_ptrs["ball"][s] + (si * g * (g + 1) + me * (g + 1)) * 4 for s in range(g)])
+            st["p_keys_in"] = t([base_ptrs["keys_in"][s] + si * self.cap * 4 for s in range(g)])
         self.ptrs = {
-            "ball_row": t([base_ptrs["ball"][s] + me * (g + 1) * 4 for s in range(g)]),
-            "keys_in": t(base_ptrs["keys_in"]), "land_deep": t(base_ptrs["land_deep"]),
+            "land_deep": t(base_ptrs["land_deep"]),
             "land_wide": t(base_ptrs["land_wide"]), "grad_in": t(base_ptrs["grad_in"]),
             "gwide_in": t(base_ptrs["gwide_in"]),
             "flag": [t([base_ptrs["flags"][s] + (ph * g + me) * 4 for s in range(g)]) for ph in range(N_PHASES)],
@@ -125,33 +147,46 @@ class PeerRank:
 
     # ---- phases --------------------------------------------------------------------------------------
     def p_plan_local(self, ids, nxt=False):
-        """The rank-local part of the plan: owner-major remap, dedup, bucket bounds.  nxt=True writes the look-ahead
-        buffers (p_adopt moves them in at the start of the next step)."""
-        key, uq, bounds = (self.key_n, self.uq_n, self.bounds_n) if nxt else (self.key, self.uq, self.bounds)
-        ops.shard_remap(ids.reshape(-1), self._vocab_like, self._owners_like, out=key)
-        ops.unique(key, table_like=self._bound_like, result=uq, ws_tag="unique_peer_plan_next" if nxt else "unique_peer_plan")
-        ops.shard_bounds(uq.uniq, uq.count, self.edges, out=bounds)
+        """The rank-local part of the plan: owner-major remap, dedup, bucket bounds.  nxt=True works on the OTHER set
+        (the next batch, one step ahead); p_adopt makes that set the current one."""
+        st = self._s(nxt)
+        ops.shard_remap(ids.reshape(-1), self._vocab_like, self._owners_like, out=st["key"])
+        ops.unique(st["key"], table_like=self._bound_like, result=st["uq"], ws_tag=st["tag"])
+        ops.shard_bounds(st["uq"].uniq, st["uq"].count, self.edges, out=st["bounds"])
 
     def p_adopt(self):
-        self.uq.copy_from(self.uq_n)
-        self.bounds.copy_(self.bounds_n)
+        """The set prepared one step ahead becomes the current one (no copy: the two sets swap roles)."""
+        self.cur ^= 1
 
-    def p_publish(self):
-        self.signal(0, self.bounds, self.ptrs["ball_row"])
+    def p_publish(self, nxt=False):
+        st = self._s(nxt)
+        self.signal(0, st["bounds"], st["p_ball_row"])
 
     def p_plan_publish(self, ids):
         self.p_plan_local(ids)
         self.p_publish()
 
-    def p_keys(self):
-        ops.shard_offsets(self.buf["ball"], self.ctrl, self.dst_off, self.src_off, self.inbox_off, self.n_r)
-        ops.push_rows_to_peers(self.uq.uniq, self.bounds, self.inbox_off, self.ptrs["keys_in"], self._cap_like,
+    def p_keys(self, nxt=False):
+        st = self._s(nxt)
+        ops.shard_offsets(st["ball"], self.ctrl, st["dst_off"], st["src_off"], st["inbox_off"], st["n_r"])
+        ops.push_rows_to_peers(st["uq"].uniq, st["bounds"], st["inbox_off"], st["p_keys_in"], self._cap_like,
                                self._mod_rows, self.err)
         self.signal(1)
 
+    def p_key_phase(self, ids, nxt=False):
+        """Everything of a batch that does not depend on the table's values: plan, publish, key push, owner dedup.
+        With nxt=True it runs for the NEXT batch on the other set (callers put it on a forked branch underneath the
+        current step's DenseLayers); its waits only depend on the peers' key phases."""
+        self.p_plan_local(ids, nxt)
+        self.p_publish(nxt)
+        self.wait(0)
+        self.p_keys(nxt)
+        self.wait(1)
+        self.p_owner_dedup(nxt)
+
     def p_serve(self):
-        ops.gather_to_peers(self.deep, self.buf["keys_in"], self.ptrs["land_deep"], self.dst_off, self.src_off)
-        ops.gather_to_peers(self.wide, self.buf["keys_in"], self.ptrs["land_wide"], self.dst_off, self.src_off)
+        ops.gather_to_peers(self.deep, self.keys_in, self.ptrs["land_deep"], self.dst_off, self.src_off)
+        ops.gather_to_peers(self.wide, self.keys_in, self.ptrs["land_wide"], self.dst_off, self.src_off)
         self.signal(2)
 
     def p_expand(self, ids_shape, wts, wide_bias, deep_out, wide_out):
@@ -170,11 +205,11 @@ class PeerRank:
                                self._mod_none, self.err)
         self.signal(3)
 
-    def p_owner_dedup(self):
+    def p_owner_dedup(self, nxt=False):
         """The same row can be asked for by several ranks: dedup the key inbox (needs only the keys, so callers
         run it on a side stream underneath the DenseLayer segment).  Work follows n_r, not the capacity."""
-        ops.unique(self.buf["keys_in"], table_like=self.deep, result=self.uq_owner, ws_tag="unique_peer_owner",
-                   n_valid=self.n_r)
+        st = self._s(nxt)
+        ops.unique(st["keys_in"], table_like=self.deep, result=st["uq_owner"], ws_tag=st["owner_tag"], n_valid=st["n_r"])
 
     def p_update_wide(self):
         ops.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, self.buf["gwide_in"], None, self.uq_owner,
@@ -544,25 +579,18 @@ class PeerShardedTables:
 
     # sharded.ShardedWideDeepStep drives these three; the "plan" is implicit in device state
     def plan_batch(self, ids, ahead=False, adopt=False):
-        """adopt=True: the local plan of this batch was computed one step ahead (plan_next_local)."""
+        """The key phase of the batch.  adopt=True: it already ran one step ahead (key_phase_next) on the other set,
+        which now becomes the current one."""
         rk = self.rk
         if adopt:
             rk.p_adopt()
-            rk.p_publish()
         else:
-            rk.p_plan_publish(ids)
-        rk.wait(0)
-        rk.p_keys()
-        rk.wait(1)
-        # owner-side dedup of the key inbox: forked (a parallel branch when captured) under serve / DenseLayers
-        self.owner_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.owner_stream):
-            rk.p_owner_dedup()
-        self._side_open = True
+            rk.p_key_phase(ids)
         return _DevicePlan(ids)
 
-    def plan_next_local(self, ids):
-        self.rk.p_plan_local(ids, nxt=True)
+    def key_phase_next(self, ids):
+        """Key phase of the NEXT batch on the other set (call it on a forked branch underneath the DenseLayers)."""
+        self.rk.p_key_phase(ids, nxt=True)
 
     def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
         rk = self.rk
@@ -576,7 +604,6 @@ class PeerShardedTables:
         rk.p_grads(delta, gx)
         rk.wait(3)
         main = torch.cuda.current_stream()
-        self.join_side()
         self.owner_stream.wait_stream(main)
         with torch.cuda.stream(self.owner_stream):       # latency-bound FTRL beside the LazyAdam rows
             rk.p_update_wide()
@@ -646,28 +673,31 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         self._stage = None
         self._staged_for = None
 
-    # The step in three fixed-shape pieces:
-    #   A1  plan (inline, or adopted from the look-ahead buffers) -> key / row exchange -> expand
-    #   A2  DenseLayers forward / loss / backward, with the NEXT batch's local plan (remap + dedup + bounds) on a
-    #       forked branch underneath — the plan never sits on the critical path in steady state
-    #   B   gradient exchange -> fused row updates
-    # Between A1 and A2 the host makes the stream wait for the staged copy of the next batch (it overlaps A1);
-    # between A2 and B it launches the DenseLayer mean all-reduce + Adam on a side stream (they overlap B).
-    def _a1(self, adopt):
-        ids, wts, _ = self._slots[0]
-        t = self.tables
-        plan = t.plan_batch(ids, adopt=adopt)
-        t.lookup(plan, wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
-        t.join_side()
+    # The step in fixed-shape pieces, each captured once per key-phase set (the two sets alternate step by step):
+    #   pre  key phase of the current batch in line (first step, or no look-ahead was given)
+    #   a1   serve -> wait -> expand: the only exchange work in front of the DenseLayers in steady state
+    #   a2   DenseLayers forward / loss / backward, with the NEXT batch's whole key phase (plan, publish, key push,
+    #        owner dedup) on a forked branch underneath (a2_plain: without it)
+    #   b    gradient exchange -> fused row updates
+    # Between a1 and a2 the host makes the stream wait for the staged copy of the next batch (it overlaps a1);
+    # between a2 and b it launches the DenseLayer mean all-reduce + Adam on a side stream (they overlap b).
+    def _pre(self):
+        self.tables.plan_batch(self._slots[0][0])
 
-    def _a2(self):
+    def _a1(self):
+        ids, wts, _ = self._slots[0]
+        self.tables.lookup(_DevicePlan(ids), wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
+
+    def _a2(self, ahead=True):
         main = torch.cuda.current_stream()
-        self._plan_stream.wait_stream(main)
-        with torch.cuda.stream(self._plan_stream):
-            self.tables.plan_next_local(self._stage[0])
+        if ahead:
+            self._plan_stream.wait_stream(main)
+            with torch.cuda.stream(self._plan_stream):
+                self.tables.key_phase_next(self._stage[0])
         self._io["label"].copy_(self._slots[0][2])
         loss, delta, gx = self._dense_segment()
-        main.wait_stream(self._plan_stream)
+        if ahead:
+            main.wait_stream(self._plan_stream)
         self._bwd = (delta, gx)
         # an exchange error (a wait that timed out, an inbox that overflowed) must not train on silently: the loss
         # the caller reads turns NaN from the step after the one that raised the bit
@@ -676,26 +706,25 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
     def _b(self):
         self.tables.update(*self._bwd)
 
-    def _one_step(self, adopt=False):
+    def _one_step(self, adopt=False, ahead=True):
         main = torch.cuda.current_stream()
-        g = self._graphs
+        rk = self.tables.rk
         main.wait_stream(self._dense_stream)                 # last step's dense Adam wrote the weights
+        if adopt:
+            rk.p_adopt()                                     # the set whose key phase ran under the previous step
+        g = self._graphs[rk.cur] if self._graphs is not None else None
+        if not adopt:
+            g["pre"].replay() if g is not None else self._pre()
+        g["a1"].replay() if g is not None else self._a1()
+        main.wait_stream(self._stage_stream)                 # the next batch is on the device (copied under a1)
         if g is not None:
-            g["a1_adopt" if adopt else "a1_inline"].replay()
+            g["a2" if ahead else "a2_plain"].replay()
         else:
-            self._a1(adopt)
-        main.wait_stream(self._stage_stream)                 # the next batch is on the device (copied under A1)
-        if g is not None:
-            g["a2"].replay()
-        else:
-            self._loss = self._a2()
+            self._loss = self._a2(ahead)
         self._dense_stream.wait_stream(main)
         with torch.cuda.stream(self._dense_stream):          # NCCL + dense Adam under the gradient exchange
             self._dense_update()
-        if g is not None:
-            g["b"].replay()
-        else:
-            self._b()
+        g["b"].replay() if g is not None else self._b()
         return self._loss
 
     def capture(self, ids, wts, label, warmup=3):
@@ -703,26 +732,33 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         self._stage = tuple(t.clone() for t in self._slots[0])
         self._ensure_io(ids)
         for _ in range(warmup):
-            self._one_step()
+            self._one_step(ahead=False)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         if self._graph_step:
             # capture executes nothing: the pieces are recorded back to back, real steps are replayed afterwards
-            graphs, pool = {}, None
+            rk = self.tables.rk
+            cur0 = rk.cur
+            sets, pool = [], None
             self.launches_per_step = 2                       # the eager dense Adam pair (begin_step + adam_dense)
-            for name, fn in (("a1_inline", lambda: self._a1(False)), ("a1_adopt", lambda: self._a1(True)),
-                             ("a2", self._a2), ("b", self._b)):
-                gr = torch.cuda.CUDAGraph()
-                n0 = _lib.launch_count()
-                with torch.cuda.graph(gr, pool=pool):
-                    out = fn()
-                if name != "a1_inline":                      # steady state replays a1_adopt + a2 + b
-                    self.launches_per_step += _lib.launch_count() - n0
-                if name == "a2":
-                    self._loss = out
-                pool = pool or gr.pool()
-                graphs[name] = gr
-            self._graphs = graphs
+            for si in range(2):
+                rk.use_set(si)
+                graphs = {}
+                for name, fn in (("pre", self._pre), ("a1", self._a1), ("a2", lambda: self._a2(True)),
+                                 ("a2_plain", lambda: self._a2(False)), ("b", self._b)):
+                    gr = torch.cuda.CUDAGraph()
+                    n0 = _lib.launch_count()
+                    with torch.cuda.graph(gr, pool=pool):
+                        out = fn()
+                    if si == 0 and name in ("a1", "a2", "b"):        # steady state replays a1 + a2 + b
+                        self.launches_per_step += _lib.launch_count() - n0
+                    if name in ("a2", "a2_plain"):
+                        graphs[name + "_loss"] = out
+                    pool = pool or gr.pool()
+                    graphs[name] = gr
+                sets.append(graphs)
+            rk.use_set(cur0)
+            self._graphs = sets
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
         self._staged_for = None
@@ -730,20 +766,22 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
 
     def replay(self, ids=None, wts=None, label=None, next_batch=None):
         """One step on (ids, wts, label).  next_batch (host-pinned or device tensors): staged on a copy stream during
-        this step AND planned (dedup + bucket bounds) underneath this step's DenseLayers; pass the same tensors as
-        the next call's batch to use both."""
+        this step AND taken through its key phase (dedup, bucket bounds, key exchange, owner dedup) underneath this
+        step's DenseLayers; pass the same tensors as the next call's batch to use both.  Every rank must make the same
+        choice (the key phase is a collective of the group)."""
         main = torch.cuda.current_stream()
         adopt = False
         if ids is not None:
             if self._staged_for is not None and self._staged_for is ids:
-                for d, s in zip(self._slots[0], self._stage):        # staged (and planned) one step ahead
+                for d, s in zip(self._slots[0], self._stage):        # staged (and keyed) one step ahead
                     d.copy_(s, non_blocking=True)
                 adopt = True
             else:
                 for d, s in zip(self._slots[0], (ids, wts, label)):
                     d.copy_(s, non_blocking=True)
         self._staged_for = None
-        if next_batch is not None:
+        ahead = next_batch is not None
+        if ahead:
             ev = torch.cuda.Event()
             ev.record(main)                                  # the staging buffers have been consumed
             self._stage_stream.wait_event(ev)
@@ -751,5 +789,7 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
                 for d, s in zip(self._stage, next_batch):
                     d.copy_(s, non_blocking=True)
             self._staged_for = next_batch[0]
-        loss = self._one_step(adopt)
+        loss = self._one_step(adopt, ahead)
+        if self._graphs is not None:
+            loss = self._graphs[self.tables.rk.cur]["a2_loss" if ahead else "a2_plain_loss"]
         return loss, loss
