@@ -257,6 +257,23 @@ int mrec_hash_export(MREC_AOT_ARGS);
 int mrec_hash_rehash(MREC_AOT_ARGS);
 int mrec_hash_move_rows(MREC_AOT_ARGS);
 
+/* ---- input pipeline, host side (not aot, no GPU): TFRecord framing + tf.train.Example decoding -------------------
+ * Replaces MindSpore's C++ dataset engine behind ds.TFRecordDataset for the reference's Criteo files
+ * (models/wide_deep/src/datasets.py:272-326: columns feat_ids int32, feat_vals float32, label float32, one record =
+ * line_per_sample = 1000 samples; writer datasets/criteo_1tb/process_data.py:203-283).  The Python loader
+ * (mindrec_b200/data.py) maps the files, decodes into pinned host buffers and copies to the device on a copy stream.
+ *   mrec_tfrecord_index  scan a file image: offsets / lengths of the record payloads; returns the record count or
+ *                        -(byte position + 1) of the first framing / CRC error
+ *   mrec_tfrecord_parse  decode feature `name` of one serialized Example; kind 0: Int64List -> int32, 1: FloatList -> float
+ *   mrec_crc32c(_masked) CRC-32C of a buffer (the masked form is what TFRecord stores); mrec_varint_pack: writer side */
+int64_t mrec_tfrecord_index(const uint8_t *buf, int64_t n, int64_t *offsets, int64_t *lengths, int64_t max_records,
+                            int check_crc);
+int mrec_tfrecord_parse(const uint8_t *rec, int64_t len, const char *name, int kind, void *out, int64_t cap,
+                        int64_t *count);
+uint32_t mrec_crc32c(const void *data, size_t n);
+uint32_t mrec_crc32c_masked(const void *data, size_t n);
+int64_t mrec_varint_pack(const int32_t *v, int64_t n, uint8_t *out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,9 +88,21 @@ class WideDeepModel:
         self.emb_dim = config.emb_dim
         self.device = torch.device(device)
         self.dynamic = bool(config.dynamic_embedding)
+        self.cached = (not self.dynamic) and int(config.vocab_cache_size) > 0
         gen = torch.Generator(device=self.device)
         gen.manual_seed(config.seed)
-        if self.dynamic:
+        if self.cached:
+            # embedding-cache mode (wide_and_deep.py:176-230 with vocab_cache_size > 0): the tables live in pinned host
+            # memory, the device holds vocab_cache_size rows behind an id -> slot map (mindrec_b200.cache); from here
+            # on the model addresses rows by slot exactly as in dynamic-embedding mode
+            from .cache import CachedEmbeddingLookup
+            kw = dict(param_init=config.emb_init, sparse=config.sparse, device=self.device, generator=gen)
+            self.wide_embeddinglookup = CachedEmbeddingLookup(config.vocab_size, 1, config.vocab_cache_size,
+                                                              name="wide_embeddinglookup.embedding_table", **kw)
+            self.deep_embeddinglookup = CachedEmbeddingLookup(config.vocab_size, config.emb_dim, config.vocab_cache_size,
+                                                              name="deep_embeddinglookup.embedding_table", **kw)
+            self.dynamic = True
+        elif self.dynamic:
             # wide_and_deep.py:268-274: HashEmbeddingLookup(embedding_size=emb_dim) + HashEmbeddingLookup(embedding_size=1)
             # over two MapParameters (int32 keys, admitted on first sight, never evicted: the constructor defaults)
             from .hash import HashEmbeddingLookup
@@ -230,8 +242,11 @@ class TrainStepWrap:
         network.sens_t.fill_(self.sens)
         self.sparse = sparse
         self.dynamic = bool(getattr(model, "dynamic", False))
-        if self.dynamic and not dynamic_embedding:
-            raise ValueError("the model was built with dynamic_embedding=True: pass dynamic_embedding=True here too")
+        if self.dynamic and not (dynamic_embedding or (cache_enable and getattr(model, "cached", False))):
+            raise ValueError("the model was built with dynamic_embedding=True (or vocab_cache_size > 0): pass "
+                             "dynamic_embedding=True (cache_enable=True) here too")
+        if getattr(model, "cached", False):
+            dynamic_embedding = True            # rows are addressed by cache slot: the MapParameter optimizer path
         if self.dynamic and not network.no_l2loss:
             # the reference's launcher pairs --dynamic_embedding=True with --sparse=True
             # (scripts/run_dynamic_embed_standalone_train_for_gpu.sh:24-30): no dense l2 gradient on a MapParameter
