@@ -265,7 +265,7 @@ def measure_dominant_op(step, batches, b, reps=10):
     peak, how = hbm_peak()
     gbs = alg / ms / 1e6
     # dram__bytes_read + dram__bytes_write of the op's two kernels, from this round's ncu --set full capture
-    traffic = _traffic("sparse_lazy_adam")
+    traffic = _traffic("sparse_lazy_adam" if packed else "sparse_lazy_adam_split")
     if traffic is None:
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic_bytes_per_launch"]

@@ -239,14 +239,32 @@ class EmulatedPeerGroup:
         for rk in self.ranks:
             rk.connect(base)
 
-    def forward(self, ids_list, wts_list, bias, deep_outs, wide_outs):
+    def key_phase_next(self, ids_list):
+        """The NEXT batch's key phase on the other buffer set, phase-major (what a2's forked branch does per rank)."""
         for rk, ids in zip(self.ranks, ids_list):
-            rk.p_plan_publish(ids)
+            rk.p_plan_local(ids, nxt=True)
+            rk.p_publish(nxt=True)
         for rk in self.ranks:
             rk.wait(0)
-            rk.p_keys()
+            rk.p_keys(nxt=True)
         for rk in self.ranks:
             rk.wait(1)
+            rk.p_owner_dedup(nxt=True)
+
+    def forward(self, ids_list, wts_list, bias, deep_outs, wide_outs, planned=False):
+        """planned=True: the batch went through key_phase_next during the previous step; adopt that set."""
+        if planned:
+            for rk in self.ranks:
+                rk.p_adopt()
+        else:
+            for rk, ids in zip(self.ranks, ids_list):
+                rk.p_plan_publish(ids)
+            for rk in self.ranks:
+                rk.wait(0)
+                rk.p_keys()
+        for rk in self.ranks:
+            if not planned:
+                rk.wait(1)
             rk.p_serve()
         for rk, ids, wts, do, wo in zip(self.ranks, ids_list, wts_list, deep_outs, wide_outs):
             rk.wait(2)

@@ -62,6 +62,41 @@ def test_emulated_ranks_on_cpu_match_oracle_on_full_tables(cpu_ops, world, vocab
         np.testing.assert_allclose(wide1, wide0, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_key_phase_one_step_ahead_on_the_second_buffer_set(cpu_ops, world):
+    """Steady state of the graphed step: while step t still has its backward to do, the key phase of batch t + 1
+    (plan, publish, key push, owner dedup) runs on the OTHER buffer set; step t + 1 adopts it and starts at serve.
+    Two ranks groups run the same four batches, one planning in line, one a step ahead: identical tables."""
+    vocab, b, f, dim = 211, 10, 4, 8
+    rng = np.random.default_rng(3)
+    def batch():
+        ids = [torch.from_numpy(rng.integers(0, vocab, size=(b, f)).astype(np.int32)) for _ in range(world)]
+        wts = [torch.from_numpy((rng.random((b, f)) < 0.9).astype(np.float32)) for _ in range(world)]
+        delta = [torch.from_numpy(rng.standard_normal((b, 1)).astype(np.float32)) for _ in range(world)]
+        gx = [torch.from_numpy(rng.standard_normal((b, f * dim)).astype(np.float32)) for _ in range(world)]
+        return ids, wts, delta, gx
+    batches = [batch() for _ in range(4)]
+    bias = torch.tensor([0.1])
+    inline = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, "cpu", seed=5)
+    ahead = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, "cpu", seed=5)
+    outs = lambda: ([torch.empty((b, f * dim)) for _ in range(world)], [torch.empty((b, 1)) for _ in range(world)])
+    for t, (ids, wts, delta, gx) in enumerate(batches):
+        di, wi = outs()
+        da, wa = outs()
+        inline.forward(ids, wts, bias, di, wi)
+        ahead.forward(ids, wts, bias, da, wa, planned=t > 0)
+        for r in range(world):
+            assert torch.equal(di[r], da[r]) and torch.equal(wi[r], wa[r])
+        if t + 1 < len(batches):
+            ahead.key_phase_next(batches[t + 1][0])                    # under step t's DenseLayers
+        inline.backward(delta, gx)
+        ahead.backward(delta, gx)
+        for a_, b_ in zip(inline.full_tables(), ahead.full_tables()):
+            assert torch.equal(a_, b_)
+    for rk in ahead.ranks:
+        assert int(rk.err) == 0 and rk.cur == 1                        # three adoptions: the sets alternated
+
+
 def test_look_ahead_plan_equals_inline_plan_on_cpu(cpu_ops):
     """p_plan_local(nxt=True) + p_adopt leaves exactly the state of an inline p_plan_local."""
     vocab, n = 300, 40

@@ -220,3 +220,40 @@ def test_shard_remap_hash_and_fill_tail(cuda):
     buf = torch.arange(10, dtype=torch.int64, device=cuda)
     ops.fill_tail(buf, torch.tensor([4], dtype=torch.int32, device=cuda), torch.tensor([-1], dtype=torch.int64, device=cuda))
     assert buf.tolist() == [0, 1, 2, 3] + [-1] * 6
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_key_phase_one_step_ahead_on_the_second_buffer_set(cuda, world):
+    """The graphed step's steady state on the real kernels: batch t + 1's key phase (plan, publish, key push, owner
+    dedup) runs on the other buffer set while step t still has its backward to do; step t + 1 adopts it and starts at
+    serve.  Same four batches through an in-line group and a one-step-ahead group: bit-identical tables."""
+    vocab, b, f, dim = 2003, 40, 6, 16
+    rng = np.random.default_rng(3)
+
+    def batch():
+        t = lambda a: torch.from_numpy(a).to(cuda)
+        ids = [t(rng.integers(0, vocab, size=(b, f)).astype(np.int32)) for _ in range(world)]
+        wts = [t((rng.random((b, f)) < 0.9).astype(np.float32)) for _ in range(world)]
+        delta = [t(rng.standard_normal((b, 1)).astype(np.float32)) for _ in range(world)]
+        gx = [t(rng.standard_normal((b, f * dim)).astype(np.float32)) for _ in range(world)]
+        return ids, wts, delta, gx
+    batches = [batch() for _ in range(4)]
+    bias = torch.tensor([0.1], device=cuda)
+    inline = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, cuda, seed=5)
+    ahead = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, cuda, seed=5)
+    outs = lambda: ([torch.empty((b, f * dim), device=cuda) for _ in range(world)],
+                    [torch.empty((b, 1), device=cuda) for _ in range(world)])
+    for t, (ids, wts, delta, gx) in enumerate(batches):
+        (di, wi), (da, wa) = outs(), outs()
+        inline.forward(ids, wts, bias, di, wi)
+        ahead.forward(ids, wts, bias, da, wa, planned=t > 0)
+        for r in range(world):
+            assert torch.equal(di[r], da[r]) and torch.equal(wi[r], wa[r])
+        if t + 1 < len(batches):
+            ahead.key_phase_next(batches[t + 1][0])
+        inline.backward(delta, gx)
+        ahead.backward(delta, gx)
+        for a_, b_ in zip(inline.full_tables(), ahead.full_tables()):
+            assert torch.equal(a_, b_)
+    for rk in ahead.ranks:
+        assert int(rk.err.item()) == 0 and rk.cur == 1
