@@ -153,6 +153,14 @@ int mrec_segment_sum(MREC_AOT_ARGS);
  *   in : g[N/div,D] f32|f16, mask[N|0], uniq[N], perm[N], seg_start[N+1], seg_of[N]
  *   out: table[V,D] f32 with table[uniq[u]] += segment sum (accumulates over calls; no atomics), workspace */
 int mrec_segment_sum_scatter_add(MREC_AOT_ARGS);
+/* Fused UnsortedSegmentSum + gradient push of row-sharded tables (the backward all-to-all of SURVEY 8e): the sum of
+ * segment u is stored straight into the inbox of the rank that owns u's key, through its peer-mapped pointer — no local
+ * gsum buffer, no second pass.  With keys owner-major, segment u belongs to owner o = #{r >= 1 : u >= my_bounds[r]} and
+ * lands at row inbox_off[o] + u - my_bounds[o] (segments >= my_bounds[G], i.e. out-of-range ids, are dropped).
+ *   in : g[N/div,D] f32|f16 (D % 4 == 0), mask[N|0], perm[N], seg_start[N+1], seg_of[N], my_bounds[G+1] i32,
+ *        inbox_off[G] i32, peer_ptrs[G] i64, cap_like[cap_rows,..]
+ *   out: err[1] i32 (bit 1: an inbox overflowed; the row is dropped), workspace[mrec_segment_sum_workspace_bytes(N, D)] */
+int mrec_segment_sum_to_peers(MREC_AOT_ARGS);
 /* nn.Adam (not Lazy) with a RowTensor gradient = dense-equivalent update of the WHOLE table (every
  * row's moments decay; wide_and_deep.py:435-437 when sparse=True on one device):
  *   in : w m v hyper[16] g mask uniq perm seg_start seg_of row_flags[V] u8 (zero on entry and exit)

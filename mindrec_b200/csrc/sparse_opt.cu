@@ -397,6 +397,31 @@ segsum_tiles_kernel(const GT* __restrict__ g, int cpr, int div, const float* __r
 // in flight), (3) the segmented sums are then walked out of shared memory, one thread per (32-position tile,
 // float4 chunk), in exactly the order and with exactly the outputs of segsum_tiles_kernel (bit-identical).
 // Many small CTAs per SM overlap one CTA's walk with the others' loads.
+// Fused gradient push of the row-sharded path (backward all-to-all): a segment sum is not parked in a
+// local gsum[U, D] buffer and copied again, it is stored straight into the inbox of the rank that OWNS the segment's
+// key, through the peer-mapped pointer (NVLink).  With keys owner-major, segment `seg` of my sorted unique keys
+// belongs to owner o = #{r >= 1 : seg >= bounds[r]} and lands at inbox row inbox_off[o] + seg - bounds[o].
+struct PeerDest {
+  const int32_t* bounds;      // [G+1] start of every owner's bucket among my sorted unique keys (bounds[G] = valid keys)
+  const int32_t* inbox_off;   // [G]   row of my bucket's first key inside owner o's inbox
+  const int64_t* peer_ptrs;   // [G]   base address of owner o's inbox as mapped in this process
+  int world;
+  int64_t cap;                // rows an inbox holds
+  int32_t* err;               // bit 1 is raised when a row does not fit (it is dropped)
+};
+template <typename Vec>
+__device__ __forceinline__ Vec* peer_row(const PeerDest& pd, int seg, int cpr) {
+  if (seg >= pd.bounds[pd.world]) return nullptr;          // the segment of out-of-range ids carries no row
+  int o = 0;
+  for (int r = 1; r < pd.world; ++r) o += (seg >= pd.bounds[r]) ? 1 : 0;
+  const int64_t slot = (int64_t)pd.inbox_off[o] + (seg - pd.bounds[o]);
+  if (slot >= pd.cap) {
+    atomicOr(pd.err, 2);
+    return nullptr;
+  }
+  return reinterpret_cast<Vec*>(pd.peer_ptrs[o]) + slot * cpr;
+}
+
 template <typename GT>
 __device__ __forceinline__ float4 seg_smem_f4(const GT* row, int c);
 template <>
@@ -411,13 +436,13 @@ __device__ __forceinline__ float4 seg_smem_f4<__half>(const __half* row, int c) 
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <typename GT, bool HAS_MASK>
+template <typename GT, bool HAS_MASK, bool PEER = false>
 __global__ void __launch_bounds__(kSegThreads)
 segsum_stage_kernel(const GT* __restrict__ g, int dim, int div, const float* __restrict__ mask,
                     const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
                     const int32_t* __restrict__ seg_start, int64_t n64, int P, float4* __restrict__ part,
                     float4* __restrict__ gsum, int32_t* __restrict__ long_list, int32_t* __restrict__ long_count,
-                    const int32_t* __restrict__ n_valid) {
+                    const int32_t* __restrict__ n_valid, PeerDest pd = PeerDest{}) {
   extern __shared__ uint4 seg_smem[];
   int n = (int)n64;
   if (n_valid) n = min(n, n_valid[0]);
@@ -452,6 +477,15 @@ segsum_stage_kernel(const GT* __restrict__ g, int dim, int div, const float* __r
   __syncthreads();
 
   const int cpr = dim >> 2;
+  // a complete segment sum goes to the local gsum row, or (PEER) straight into its owner's inbox
+  auto store_sum = [&](int seg, int c, const float4& a) {
+    if constexpr (PEER) {
+      float4* r = peer_row<float4>(pd, seg, cpr);
+      if (r) r[c] = a;
+    } else {
+      gsum[(int64_t)seg * cpr + c] = a;
+    }
+  };
   const int tiles = (cnt + kSegTile - 1) / kSegTile;
   for (int t = tid; t < tiles * cpr; t += kSegThreads) {
     const int tl = t / cpr;
@@ -469,7 +503,7 @@ segsum_stage_kernel(const GT* __restrict__ g, int dim, int div, const float* __r
       const int sg = s_seg[l];
       if (sg != cur) {
         if (enters) part[(int64_t)(j * 2 + 0) * cpr + c] = acc;
-        else gsum[(int64_t)cur * cpr + c] = acc;
+        else store_sum(cur, c, acc);
         cur = sg;
         enters = false;
         acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -488,7 +522,7 @@ segsum_stage_kernel(const GT* __restrict__ g, int dim, int div, const float* __r
         if (j_last - j > kLongChain) long_list[atomicAdd(long_count, 1)] = cur;
       }
     } else {
-      gsum[(int64_t)cur * cpr + c] = acc;
+      store_sum(cur, c, acc);
     }
   }
 }
@@ -614,6 +648,28 @@ struct StoreSink {
   __device__ __forceinline__ void fence(State&) const {}
   __device__ __forceinline__ void finish(int64_t o, State&, const Vec& gs) const { out[o] = gs; }
   __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const { out[(int64_t)seg * cpr + c] = gs; }
+};
+
+// chain totals of the fused gradient push: rows_update_kernel hands every multi-tile segment's sum to this sink
+template <typename Vec>
+struct PeerStoreSink {
+  static constexpr bool kApplyComplete = false;
+  using State = State0;
+  PeerDest pd;
+  int cpr;
+  __device__ __forceinline__ int64_t offset(int64_t row, int c) const { return row * cpr + c; }
+  __device__ __forceinline__ int64_t row_of(int seg) const { return seg; }
+  __device__ __forceinline__ bool in_range(int64_t seg) const { return seg < pd.bounds[pd.world]; }
+  __device__ __forceinline__ void load(int64_t, State&) const {}
+  __device__ __forceinline__ void fence(State&) const {}
+  __device__ __forceinline__ void finish(int64_t o, State&, const Vec& gs) const {
+    const int seg = (int)(o / cpr);
+    apply(seg, (int)(o - (int64_t)seg * cpr), gs);
+  }
+  __device__ __forceinline__ void apply(int seg, int c, const Vec& gs) const {
+    Vec* r = peer_row<Vec>(pd, seg, cpr);
+    if (r) r[c] = gs;
+  }
 };
 
 struct SegWorkspace {
@@ -1144,4 +1200,60 @@ MREC_API int mrec_ftrl_dense(int nparam, void** params, int* ndims, int64_t** sh
   MREC_LAUNCH(ftrl_dense_kernel, grid_for(cdiv(n, 256), 8), 256, 0, a.stream, a.ptr<float>(0),
               a.ptr<float>(1), a.ptr<float>(2), a.ptr<float>(4), a.ptr<float>(3), n);
   return check_launch("ftrl_dense");
+}
+
+// Fused UnsortedSegmentSum + gradient push (backward all-to-all of row-sharded tables): segment u of the local dedup
+// is summed and stored directly into the inbox of the rank that owns its key (see PeerDest).
+// inputs : g[N/div,D] f32|f16 (D % 4 == 0), mask[N|0], perm[N], seg_start[N+1], seg_of[N], my_bounds[G+1] i32,
+//          inbox_off[G] i32, peer_ptrs[G] i64, cap_like[cap_rows, ..]
+// outputs: err[1] i32 (bit 1: an inbox overflowed), workspace[mrec_segment_sum_workspace_bytes(N, D)]
+MREC_API int mrec_segment_sum_to_peers(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                       void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  MREC_CHECK_NPARAM(a, 11);
+  const int dim = (int)a.last(0);
+  MREC_REQUIRE(dim >= 4 && dim % 4 == 0 && dim / 4 <= kSegThreads, ERR_DIM, "mrec_segment_sum_to_peers: D must be a multiple of 4");
+  SegArgs s;
+  int rc = parse_seg_args(a, 0, dim, false, &s, "mrec_segment_sum_to_peers");
+  if (rc) return rc;
+  MREC_REQUIRE(a.is_i32(5) && a.is_i32(6) && a.is_i64(7) && a.is_i32(9), ERR_DTYPE,
+               "mrec_segment_sum_to_peers: bounds/inbox_off/err int32, peer_ptrs int64");
+  const int world = (int)a.numel(6);
+  MREC_REQUIRE(world >= 1 && a.numel(5) == world + 1 && a.numel(7) == world && a.numel(9) >= 1, ERR_SHAPE,
+               "mrec_segment_sum_to_peers: bounds[G+1], inbox_off[G], peer_ptrs[G], err[1]");
+  const int64_t n = s.n;
+  if (n == 0) return OK;
+  MREC_REQUIRE(n < ((int64_t)1 << 31), ERR_SHAPE, "mrec_segment_sum_to_peers: N must be < 2^31");
+  const SegWorkspace W = seg_ws(n, dim, false);
+  MREC_REQUIRE((size_t)a.numel(10) >= W.total, ERR_WORKSPACE, "mrec_segment_sum_to_peers: workspace %lld < %zu",
+               (long long)a.numel(10), W.total);
+  MREC_REQUIRE(a.aligned(10, 16), ERR_ALIGN, "mrec_segment_sum_to_peers: workspace must be 16-byte aligned");
+  char* w = a.ptr<char>(10);
+  float4* part = reinterpret_cast<float4*>(w + W.off_part);
+  int32_t* long_list = reinterpret_cast<int32_t*>(w + W.off_list);
+  int32_t* long_count = reinterpret_cast<int32_t*>(w + W.off_count);
+  const PeerDest pd{a.ptr<int32_t>(5), a.ptr<int32_t>(6), a.ptr<int64_t>(7), world, a.dim(8, 0), a.ptr<int32_t>(9)};
+  const int row_bytes = dim * (s.g16 ? 2 : 4);
+  int stage_p = 128;
+  while (stage_p > 32 && (size_t)stage_p * (row_bytes + 12) > 40 * 1024) stage_p >>= 1;
+  MREC_REQUIRE((size_t)stage_p * (row_bytes + 12) <= 40 * 1024, ERR_DIM, "mrec_segment_sum_to_peers: D too large");
+  const size_t smem = (size_t)stage_p * (row_bytes + 12);
+  const int grid_s = (int)cdiv(n, stage_p);
+  cudaMemsetAsync(long_count, 0, sizeof(int32_t), a.stream);
+#define MREC_STAGE_PEER(GT, HM)                                                                                        \
+  MREC_LAUNCH((segsum_stage_kernel<GT, HM, true>), grid_s, kSegThreads, smem, a.stream, reinterpret_cast<const GT*>(s.g), \
+              dim, s.div, s.mask, s.perm, s.seg_of, s.seg_start, n, stage_p, part, (float4*)nullptr, long_list, long_count, \
+              (const int32_t*)nullptr, pd)
+  if (s.g16) { if (s.mask) MREC_STAGE_PEER(__half, true); else MREC_STAGE_PEER(__half, false); }
+  else { if (s.mask) MREC_STAGE_PEER(float, true); else MREC_STAGE_PEER(float, false); }
+#undef MREC_STAGE_PEER
+  const int cpr = dim / 4;
+  const int groups = kSegThreads / cpr;
+  if (cdiv(n, kSegTile) > 1) {
+    PeerStoreSink<float4> sink{pd, cpr};
+    const int row_blocks = grid_for(cdiv(n, groups), 8);
+    MREC_LAUNCH((rows_update_kernel<float4, PeerStoreSink<float4>, 1>), kChainBlocks + row_blocks, kSegThreads, 0, a.stream,
+                cpr, s.seg_of, s.seg_start, n, (const float4*)nullptr, part, long_list, long_count, sink, (const int32_t*)nullptr);
+  }
+  return check_launch("segment_sum_to_peers");
 }

@@ -196,6 +196,16 @@ def segment_sum(g, mask, uq, dim=None, out=None):
     return out
 
 
+def segment_sum_to_peers(g, mask, uq, my_bounds, inbox_off, peer_ptrs, cap_like, err, dim=None):
+    """Fused segment-sum + gradient push: the sum of segment u goes straight into the inbox of the rank that owns u's
+    key (peer-mapped pointers), without a local gsum buffer (mrec_segment_sum_to_peers)."""
+    dim = dim if dim is not None else g.shape[-1]
+    mask = _empty_mask(g.device) if mask is None else mask.reshape(-1)
+    nbytes = _size_fn("mrec_segment_sum_workspace_bytes")(uq.n, dim)
+    _lib.aot_call("mrec_segment_sum_to_peers", [g, mask, uq.perm, uq.seg_start, uq.seg_of, my_bounds, inbox_off, peer_ptrs,
+                                                cap_like, err, _ws("segsum_peers_%d" % dim, nbytes, g.device)])
+
+
 def segment_sum_scatter_add(table, g, mask, uq):
     """table[uq.uniq[u]] += segment sum u (dense gradient of a non-sparse Gather; accumulates over calls)."""
     dim = table.shape[1] if table.dim() == 2 else 1

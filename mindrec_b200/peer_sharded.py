@@ -91,7 +91,6 @@ class PeerRank:
             }
             self._sets.append(st)
         self.cur = 0
-        self.gs_deep = torch.empty((n_lookups, emb_dim), dtype=f32, device=dev)
         self.gs_wide = torch.empty((n_lookups, 1), dtype=f32, device=dev)
         self._bound_like = torch.empty((g * r, 0), device=dev)
         self._vocab_like = torch.empty((vocab_size, 0), device=dev)
@@ -197,10 +196,10 @@ class PeerRank:
 
     def p_grads(self, delta, gx):
         mask = self._wts.reshape(-1)
-        ops.segment_sum(gx.view(self.n, self.dim), mask, self.uq, dim=self.dim, out=self.gs_deep)
+        # deep rows: the segment sums are stored straight into the owners' gradient inboxes (no local gsum pass)
+        ops.segment_sum_to_peers(gx.view(self.n, self.dim), mask, self.uq, self.bounds, self.inbox_off,
+                                 self.ptrs["grad_in"], self._cap_like, self.err, dim=self.dim)
         ops.segment_sum(delta, mask, self.uq, dim=1, out=self.gs_wide)
-        ops.push_rows_to_peers(self.gs_deep, self.bounds, self.inbox_off, self.ptrs["grad_in"], self._cap_like,
-                               self._mod_none, self.err)
         ops.push_rows_to_peers(self.gs_wide, self.bounds, self.inbox_off, self.ptrs["gwide_in"], self._cap_like,
                                self._mod_none, self.err)
         self.signal(3)
@@ -384,9 +383,13 @@ class PeerHashRank:
         ops.gather(self.buf["land"], self.uq.inverse, out=out.view(self.n, self.dim))
 
     def p_grads(self, g_out):
-        ops.segment_sum(g_out.reshape(self.n, self.dim), None, self.uq, dim=self.dim, out=self.gs)
-        ops.push_rows_to_peers(self.gs, self.bounds, self.inbox_off, self.ptrs["grad_in"], self._cap_like,
-                               self._mod_none, self.err)
+        if self.dim % 4 == 0:      # fused: segment sums go straight into the owners' gradient inboxes
+            ops.segment_sum_to_peers(g_out.reshape(self.n, self.dim), None, self.uq, self.bounds, self.inbox_off,
+                                     self.ptrs["grad_in"], self._cap_like, self.err, dim=self.dim)
+        else:
+            ops.segment_sum(g_out.reshape(self.n, self.dim), None, self.uq, dim=self.dim, out=self.gs)
+            ops.push_rows_to_peers(self.gs, self.bounds, self.inbox_off, self.ptrs["grad_in"], self._cap_like,
+                                   self._mod_none, self.err)
         self.signal(3)
 
     def p_update(self):

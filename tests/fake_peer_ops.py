@@ -98,6 +98,14 @@ def push_rows_to_peers(rows, my_bounds, inbox_off, peer_ptrs, cap_like, mod_like
             dst[:] = seg[j]
 
 
+def segment_sum_to_peers(g, mask, uq, my_bounds, inbox_off, peer_ptrs, cap_like, err, dim=None):
+    """Stand-in of the fused kernel: segment sums, then the rows of the valid segments through the real addresses."""
+    dim = dim if dim is not None else g.shape[-1]
+    gs = torch.zeros((uq.n, dim), dtype=torch.float32)
+    segment_sum(g, mask, uq, dim=dim, out=gs)
+    push_rows_to_peers(gs, my_bounds, inbox_off, peer_ptrs, cap_like, torch.empty((0, 0)), err)
+
+
 def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
     t = _np(table)
     d = t.shape[1]
