@@ -282,6 +282,35 @@ uint32_t mrec_crc32c(const void *data, size_t n);
 uint32_t mrec_crc32c_masked(const void *data, size_t n);
 int64_t mrec_varint_pack(const int32_t *v, int64_t n, uint8_t *out, int64_t cap);
 
+/* ---- host runtime (not aot): what the Python host code needs to drive the aot kernels without PyTorch ---------------
+ * (mindrec_b200/runtime.py binds these with ctypes; under MindSpore the framework owns memory and streams instead).
+ * Memory and copies: kind 1 = host -> device, 2 = device -> host, 3 = device -> device, asynchronous on `stream`.
+ * Graph: mrec_rt_graph_begin(stream) ... enqueue aot calls on that stream ... mrec_rt_graph_end(stream) -> executable. */
+int mrec_rt_device_count(void);
+int mrec_rt_set_device(int index);
+int mrec_rt_mem_info(size_t *free_bytes, size_t *total_bytes);
+void *mrec_rt_malloc(size_t bytes);
+int mrec_rt_free(void *p);
+void *mrec_rt_malloc_host(size_t bytes);
+int mrec_rt_free_host(void *p);
+int mrec_rt_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream);
+int mrec_rt_memset(void *p, int byte, size_t bytes, void *stream);
+int mrec_rt_fill32(void *p, uint32_t pattern, int64_t n, void *stream);
+void *mrec_rt_stream_create(void);
+int mrec_rt_stream_destroy(void *stream);
+int mrec_rt_stream_sync(void *stream);
+int mrec_rt_device_sync(void);
+void *mrec_rt_event_create(int timing);
+int mrec_rt_event_record(void *event, void *stream);
+int mrec_rt_event_sync(void *event);
+int mrec_rt_stream_wait_event(void *stream, void *event);
+float mrec_rt_event_elapsed_ms(void *start, void *stop);
+int mrec_rt_event_destroy(void *event);
+int mrec_rt_graph_begin(void *stream);
+void *mrec_rt_graph_end(void *stream);
+int mrec_rt_graph_launch(void *graph_exec, void *stream);
+int mrec_rt_graph_destroy(void *graph_exec);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,8 +7,8 @@ Every kernel of the product path is reached through the MindSpore
           const char **dtypes, void *stream, void *extra)
 
 Under MindSpore the framework builds that argument pack; in this repository the same symbols are driven
-through ctypes with device buffers owned by torch (plumbing only: memory + streams).  There is no CPU
-fallback: a missing library raises.
+through ctypes with device buffers owned either by torch or by mindrec_b200.runtime (plain CUDA allocations: no
+torch in the process) — plumbing only: memory + streams.  There is no CPU fallback: a missing library raises.
 """
 import ctypes
 import os
@@ -62,14 +62,24 @@ def launch_count():
 
 
 def _dtype_name(t):
-    if not _DTYPE_NAMES:
-        import torch
-        _DTYPE_NAMES.update({
-            torch.float32: b"float32", torch.float16: b"float16", torch.bfloat16: b"bfloat16",
-            torch.int32: b"int32", torch.int64: b"int64", torch.uint8: b"uint8", torch.int8: b"int8",
-            torch.float64: b"float64", torch.bool: b"bool",
-        })
-    return _DTYPE_NAMES[t.dtype]
+    """MindSpore dtype string of a buffer: torch tensors ('torch.float32') and mindrec_b200.runtime buffers
+    ('float32') both spell it in their dtype."""
+    d = t.dtype
+    name = _DTYPE_NAMES.get(d)
+    if name is None:
+        name = (d if isinstance(d, str) else str(d).replace("torch.", "")).encode()
+        _DTYPE_NAMES[d] = name
+    return name
+
+
+def _current_stream(tensors):
+    """The stream the kernels go to when the caller names none: the current stream of whoever owns the buffers."""
+    for t in tensors:
+        dev = getattr(t, "device", None)
+        if getattr(dev, "__mrec_rt__", False):
+            return dev.current_stream_handle()
+    import torch
+    return torch.cuda.current_stream().cuda_stream
 
 
 _AOT_SIG = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
@@ -128,7 +138,6 @@ def aot_call(symbol, tensors, stream=None, check_device=True):
     The marshalled argument pack is cached per (symbol, buffer addresses, shapes, dtypes): a training step
     calls the same entry points on the same preallocated buffers, so the steady-state host cost of a call
     is one dictionary lookup (this matters for the eager, launch-bound multi-GPU step)."""
-    import torch
     # key: buffers, dtypes and ranks; extents are refreshed in place (they vary per step on the sharded path)
     key = (symbol, tuple((t.data_ptr(), t.dtype, t.dim()) for t in tensors))
     pack = _pack_cache.get(key)
@@ -150,7 +159,7 @@ def aot_call(symbol, tensors, stream=None, check_device=True):
                 off += 1
     n, params, ndims, shapes, dtypes, _ = pack
     if stream is None:
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _current_stream(tensors)
     rc = _fn(symbol)(n, params, ndims, shapes, dtypes, ctypes.c_void_p(stream), None)
     if rc != 0:
         raise MindrecKernelError(symbol, rc, last_error())

@@ -6,19 +6,41 @@ Each wrapper only allocates outputs / workspaces (torch is the allocator here, M
 """
 import ctypes
 
-import torch
-
 from . import _lib
 
 _ws_cache = {}
 HYPER_LEN = 16
 
 
+# ---- allocation: the wrappers only ever allocate OUTPUTS and WORKSPACES next to their inputs.  The allocator is picked
+# from the input's device: a mindrec_b200.runtime.Device (plain CUDA allocations, no torch in the process) or a torch
+# device (tests, bench, the model cells).  Nothing below imports torch unless it is handed a torch tensor.
+def _dt(dtype):
+    """Canonical dtype name ('float32', 'int32', ...) of a torch dtype or a name."""
+    return dtype if isinstance(dtype, str) else str(dtype).replace("torch.", "")
+
+
+def _alloc(device, shape, dtype="float32", zero=False):
+    shape = tuple(shape) if isinstance(shape, (tuple, list)) else (int(shape),)
+    if getattr(device, "__mrec_rt__", False):
+        return device.zeros(shape, _dt(dtype)) if zero else device.empty(shape, _dt(dtype))
+    import torch
+    td = getattr(torch, _dt(dtype))
+    return torch.zeros(shape, dtype=td, device=device) if zero else torch.empty(shape, dtype=td, device=device)
+
+
+def _from_list(device, values, dtype="float32"):
+    if getattr(device, "__mrec_rt__", False):
+        return device.tensor(values, dtype)
+    import torch
+    return torch.tensor(values, dtype=getattr(torch, dtype), device=device)
+
+
 def _ws(tag, nbytes, device):
     key = (tag, device)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        buf = _alloc(device, max(int(nbytes), 256), "uint8")
         _ws_cache[key] = buf
     return buf
 
@@ -27,7 +49,7 @@ def _dummy(device):
     key = ("dummy", device)
     buf = _ws_cache.get(key)
     if buf is None:
-        buf = torch.zeros(1, dtype=torch.int32, device=device)
+        buf = _alloc(device, 1, "int32", zero=True)
         _ws_cache[key] = buf
     return buf
 
@@ -47,19 +69,18 @@ def gather(table, ids, out=None, oob_flag=None):
     interleaved record layout: array 0 of every row is read."""
     dim = table.shape[-1] if table.dim() >= 2 else 1
     if out is None:
-        out = torch.empty(tuple(ids.shape) + (dim,), dtype=torch.float32, device=table.device)
+        out = _alloc(table.device, tuple(ids.shape) + (dim,), "float32")
     args = [table, ids, out] + ([oob_flag] if oob_flag is not None else [])
     _lib.aot_call("mrec_gather", args)
     return out
 
 
-def gather_masked(table, ids, mask, out=None, oob_flag=None, out_dtype=torch.float32):
+def gather_masked(table, ids, mask, out=None, oob_flag=None, out_dtype="float32"):
     """out[b, f*D:(f+1)*D] = table[ids[b,f]] * mask[b,f]  (gather + Mul + Reshape fused).
     A float16 `out` additionally fuses the Cast at the head of a mixed-precision DenseLayer."""
     dim = table.shape[-1] if table.dim() >= 2 else 1
     if out is None:
-        out = torch.empty((ids.shape[0], ids.numel() // ids.shape[0] * dim), dtype=out_dtype,
-                          device=table.device)
+        out = _alloc(table.device, (ids.shape[0], ids.numel() // ids.shape[0] * dim), out_dtype)
     args = [table, ids, mask, out] + ([oob_flag] if oob_flag is not None else [])
     _lib.aot_call("mrec_gather_masked", args)
     return out
@@ -68,7 +89,7 @@ def gather_masked(table, ids, mask, out=None, oob_flag=None, out_dtype=torch.flo
 def gather_reduce(table, ids, mask, bias, out=None, oob_flag=None):
     """out[b] = sum_f table[ids[b,f]] * mask[b,f] + bias  for a dim-1 table (wide / linear term)."""
     if out is None:
-        out = torch.empty((ids.shape[0], 1), dtype=torch.float32, device=table.device)
+        out = _alloc(table.device, (ids.shape[0], 1), "float32")
     args = [table, ids, mask, bias, out] + ([oob_flag] if oob_flag is not None else [])
     _lib.aot_call("mrec_gather_reduce", args)
     return out
@@ -77,7 +98,7 @@ def gather_reduce(table, ids, mask, bias, out=None, oob_flag=None):
 def gather_pool(table, ids, mask, out=None, oob_flag=None):
     """out[b] = mean over the S slots of table[ids[b,s]] * mask[b,s]  (multi-hot fields of the multitable model)."""
     if out is None:
-        out = torch.empty((ids.shape[0], table.shape[1]), dtype=torch.float32, device=table.device)
+        out = _alloc(table.device, (ids.shape[0], table.shape[1]), "float32")
     args = [table, ids, mask, out] + ([oob_flag] if oob_flag is not None else [])
     _lib.aot_call("mrec_gather_pool", args)
     return out
@@ -94,21 +115,21 @@ class UniqueResult:
     def __init__(self, n, dtype, device, packed=False):
         self.n = n
         self.flat = None
-        if packed and dtype == torch.int32:
+        if packed and _dt(dtype) == "int32":
             a = (n + 3) // 4 * 4                              # every field starts 16-byte aligned
             b = (n + 1 + 3) // 4 * 4
-            self.flat = torch.zeros(4 * a + b + 4, dtype=torch.int32, device=device)
+            self.flat = _alloc(device, 4 * a + b + 4, "int32", zero=True)
             f = self.flat
             self.uniq, self.inverse, self.perm, self.seg_of = f[0:n], f[a:a + n], f[2 * a:2 * a + n], f[3 * a:3 * a + n]
             self.seg_start = f[4 * a:4 * a + n + 1]
             self.count = f[4 * a + b:4 * a + b + 1]
             return
-        self.uniq = torch.empty(n, dtype=dtype, device=device)
-        self.inverse = torch.empty(n, dtype=torch.int32, device=device)
-        self.count = torch.zeros(1, dtype=torch.int32, device=device)
-        self.perm = torch.empty(n, dtype=torch.int32, device=device)
-        self.seg_start = torch.empty(n + 1, dtype=torch.int32, device=device)
-        self.seg_of = torch.empty(n, dtype=torch.int32, device=device)
+        self.uniq = _alloc(device, n, dtype)
+        self.inverse = _alloc(device, n, "int32")
+        self.count = _alloc(device, 1, "int32", zero=True)
+        self.perm = _alloc(device, n, "int32")
+        self.seg_start = _alloc(device, n + 1, "int32")
+        self.seg_of = _alloc(device, n, "int32")
 
     def copy_from(self, other):
         if self.flat is not None and other.flat is not None and self.flat.numel() == other.flat.numel():
@@ -156,9 +177,9 @@ def unique_first(ids):
     """First-occurrence-order unique (the order of upstream's CPU Unique): (uniq[N], inverse[N], count[1])."""
     flat = ids.reshape(-1)
     n = flat.numel()
-    uniq = torch.empty(n, dtype=flat.dtype, device=flat.device)
-    inverse = torch.empty(n, dtype=torch.int32, device=flat.device)
-    count = torch.zeros(1, dtype=torch.int32, device=flat.device)
+    uniq = _alloc(flat.device, n, flat.dtype)
+    inverse = _alloc(flat.device, n, "int32")
+    count = _alloc(flat.device, 1, "int32", zero=True)
     nbytes = _size_fn("mrec_unique_first_workspace_bytes")(n, flat.element_size())
     ws = _ws("unique_first", nbytes, flat.device)
     _lib.aot_call("mrec_unique_first", [flat, uniq, inverse, count, ws])
@@ -174,7 +195,7 @@ _EMPTY = {}
 def _empty_mask(device):
     m = _EMPTY.get(device)
     if m is None:
-        m = torch.empty(0, dtype=torch.float32, device=device)
+        m = _alloc(device, 0, "float32")
         _EMPTY[device] = m
     return m
 
@@ -189,7 +210,7 @@ def segment_sum(g, mask, uq, dim=None, out=None):
     """gsum[u] = sum over positions n of segment u of mask[n] * g[n // div]  (sorted order, no atomics)."""
     dim = dim if dim is not None else (g.shape[-1] if g.dim() >= 2 else 1)
     if out is None:
-        out = torch.zeros((uq.n, dim), dtype=torch.float32, device=g.device)
+        out = _alloc(g.device, (uq.n, dim), "float32", zero=True)
     mask = _empty_mask(g.device) if mask is None else mask.reshape(-1)
     _lib.aot_call("mrec_segment_sum", [g, mask, uq.perm, uq.seg_start, uq.seg_of, out,
                                        _opt_ws(uq.n, dim, g.device)])
@@ -250,14 +271,12 @@ def sparse_ftrl(w, accum, linear, hyper, g, mask, uq, n_valid=None):
 
 def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, loss_scale=1.0, l2=0.0, device="cuda"):
     """Device hyper block for Adam / LazyAdam: [lr, b1, b2, eps, b1^t, b2^t, lr_t, 1/loss_scale, l2, 0...]."""
-    return torch.tensor([lr, beta1, beta2, eps, 1.0, 1.0, 0.0, 1.0 / loss_scale, l2] + [0.0] * 7,
-                        dtype=torch.float32, device=device)
+    return _from_list(device, [lr, beta1, beta2, eps, 1.0, 1.0, 0.0, 1.0 / loss_scale, l2] + [0.0] * 7)
 
 
 def ftrl_hyper(lr, l1=0.0, l2=0.0, lr_power=-0.5, loss_scale=1.0, device="cuda"):
     """Device hyper block for FTRL: [lr, l1, l2, lr_power, 1/loss_scale, 0...]."""
-    return torch.tensor([lr, l1, l2, lr_power, 1.0 / loss_scale] + [0.0] * 11,
-                        dtype=torch.float32, device=device)
+    return _from_list(device, [lr, l1, l2, lr_power, 1.0 / loss_scale] + [0.0] * 11)
 
 
 def adam_begin_step(hyper):
@@ -278,7 +297,7 @@ def ftrl_dense(w, accum, linear, hyper, g):
 def fm_fwd(vx, out=None):
     """fm[b] = 0.5 * sum_d[(sum_f vx)^2 - sum_f vx^2]; vx is [B,F,D] (already masked)."""
     if out is None:
-        out = torch.empty((vx.shape[0], 1), dtype=torch.float32, device=vx.device)
+        out = _alloc(vx.device, (vx.shape[0], 1), "float32")
     _lib.aot_call("mrec_fm_fwd", [vx, out])
     return out
 
@@ -286,7 +305,7 @@ def fm_fwd(vx, out=None):
 def fm_bwd(vx, gout, out=None, addend=None):
     """dvx[b,f,d] = gout[b] * (S[b,d] - vx[b,f,d]) (+ addend[b,f,d], fp32 or fp16, fused into the store)."""
     if out is None:
-        out = torch.empty_like(vx)
+        out = _alloc(vx.device, vx.shape, vx.dtype)
     _lib.aot_call("mrec_fm_bwd", [vx, gout] + ([addend] if addend is not None else []) + [out])
     return out
 
@@ -302,9 +321,9 @@ def cross_fwd(x0, w, b, y=None, p=None):
     """The whole cross stack: y = x_L, p[B,L] = saved dots x0.w_l (needed by cross_bwd).  w, b: [L, D']."""
     layers = w.numel() // x0.shape[1]
     if y is None:
-        y = torch.empty_like(x0)
+        y = _alloc(x0.device, x0.shape, x0.dtype)
     if p is None:
-        p = torch.empty((x0.shape[0], layers), dtype=torch.float32, device=x0.device)
+        p = _alloc(x0.device, (x0.shape[0], layers), "float32")
     _lib.aot_call("mrec_cross_fwd", [x0, w, b, y, p, _cross_ws(layers, x0.shape[1], x0.device)])
     return y, p
 
@@ -312,9 +331,9 @@ def cross_fwd(x0, w, b, y=None, p=None):
 def cross_bwd(x0, dy, w, b, p, dx=None, dw=None, db=None):
     """Backward of the cross stack: (dx0 total, dw[L,D'], db[L,D'])."""
     layers = w.numel() // x0.shape[1]
-    dx = torch.empty_like(x0) if dx is None else dx
-    dw = torch.empty((layers, x0.shape[1]), dtype=torch.float32, device=x0.device) if dw is None else dw
-    db = torch.empty((layers, x0.shape[1]), dtype=torch.float32, device=x0.device) if db is None else db
+    dx = _alloc(x0.device, x0.shape, x0.dtype) if dx is None else dx
+    dw = _alloc(x0.device, (layers, x0.shape[1]), "float32") if dw is None else dw
+    db = _alloc(x0.device, (layers, x0.shape[1]), "float32") if db is None else db
     _lib.aot_call("mrec_cross_bwd", [x0, dy, w, b, p, dx, dw, db, _cross_ws(layers, x0.shape[1], x0.device)])
     return dx, dw, db
 
@@ -322,7 +341,7 @@ def cross_bwd(x0, dy, w, b, p, dx=None, dw=None, db=None):
 def shard_bounds(uniq, count, edges, out=None):
     """bounds[r] = #{i < count : uniq[i] < edges[r]} (device-side lower_bound, no host sync)."""
     if out is None:
-        out = torch.empty(edges.numel(), dtype=torch.int32, device=uniq.device)
+        out = _alloc(uniq.device, edges.numel(), "int32")
     _lib.aot_call("mrec_shard_bounds", [uniq, count, edges, out])
     return out
 
@@ -330,7 +349,7 @@ def shard_bounds(uniq, count, edges, out=None):
 def shard_remap(ids, table_like, owners_like, out=None):
     """key -> (key mod G) * R + key div G with G, R = owners_like.shape (out-of-range keys -> G * R)."""
     if out is None:
-        out = torch.empty_like(ids)
+        out = _alloc(ids.device, ids.shape, ids.dtype)
     _lib.aot_call("mrec_shard_remap", [ids, table_like, owners_like, out])
     return out
 
@@ -341,10 +360,10 @@ def sigmoid_xent(a, b, label, sens, out=None, half=False):
     n = a.numel()
     dev = a.device
     if out is None:
-        out = (torch.empty((n, 1), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.float32, device=dev),
-               torch.empty((n, 1), dtype=torch.float32, device=dev),
-               torch.empty((n, 1) if half else (0,), dtype=torch.float16, device=dev),
-               torch.empty(1, dtype=torch.float32, device=dev))
+        out = (_alloc(dev, (n, 1), "float32"), _alloc(dev, 1, "float32"),
+               _alloc(dev, (n, 1), "float32"),
+               _alloc(dev, (n, 1) if half else (0,), "float16"),
+               _alloc(dev, 1, "float32"))
     b = _empty_mask(dev) if b is None else b
     _lib.aot_call("mrec_sigmoid_xent", [a, b, label, sens, out[0], out[1], out[2], out[3], out[4]])
     return out
@@ -365,7 +384,7 @@ def relu_bwd_bias(g, y, gb, out=None):
         lib = _lib.lib()
         lib.mrec_relu_bwd_bias_workspace_bytes.restype = ctypes.c_size_t
         lib.mrec_relu_bwd_bias_workspace_bytes.argtypes = [ctypes.c_int64]
-        ws = _dense_ws[key] = torch.zeros(lib.mrec_relu_bwd_bias_workspace_bytes(n_cols), dtype=torch.uint8, device=g.device)
+        ws = _dense_ws[key] = _alloc(g.device, lib.mrec_relu_bwd_bias_workspace_bytes(n_cols), "uint8", zero=True)
     gz = g if out is None else out
     if y is None:
         _lib.aot_call("mrec_relu_bwd_bias", [g, _empty_like_dtype(g), _empty_like_dtype(g), gb, ws])
@@ -377,7 +396,7 @@ def relu_bwd_bias(g, y, gb, out=None):
 def dense_head_fwd(h, w, bias, out=None):
     """out[b] = sum_k h[b,k] * w[k] + bias  (the one-unit output DenseLayer; fp32 accumulate and result)."""
     if out is None:
-        out = torch.empty((h.shape[0], 1), dtype=torch.float32, device=h.device)
+        out = _alloc(h.device, (h.shape[0], 1), "float32")
     _lib.aot_call("mrec_dense_head_fwd", [h, w, bias, out])
     return out
 
@@ -395,9 +414,9 @@ def dense_head_bwd(delta, h, w, masked, gw, gb_head, gb_prev=None, out=None):
         lib = _lib.lib()
         lib.mrec_dense_head_workspace_bytes.restype = ctypes.c_size_t
         lib.mrec_dense_head_workspace_bytes.argtypes = [ctypes.c_int64]
-        ws = _head_ws[key] = torch.zeros(lib.mrec_dense_head_workspace_bytes(k), dtype=torch.uint8, device=h.device)
+        ws = _head_ws[key] = _alloc(h.device, lib.mrec_dense_head_workspace_bytes(k), "uint8", zero=True)
     if out is None:
-        out = torch.empty_like(h)
+        out = _alloc(h.device, h.shape, h.dtype)
     flag = _relu_flag(h.device) if masked else _empty_mask(h.device)
     _lib.aot_call("mrec_dense_head_bwd", [delta, h, w, flag, out, gw, gb_head,
                                           gb_prev if gb_prev is not None else _empty_mask(h.device), ws])
@@ -410,7 +429,7 @@ _relu_flags = {}
 def _relu_flag(device):
     f = _relu_flags.get(device)
     if f is None:
-        f = _relu_flags[device] = torch.ones(1, dtype=torch.float32, device=device)
+        f = _relu_flags[device] = _from_list(device, [1.0])
     return f
 
 
@@ -421,7 +440,7 @@ def _empty_like_dtype(t):
     key = (t.device, t.dtype)
     e = _empties.get(key)
     if e is None:
-        e = _empties[key] = torch.empty((0, 0), dtype=t.dtype, device=t.device)
+        e = _empties[key] = _alloc(t.device, (0, 0), t.dtype)
     return e
 
 
@@ -437,7 +456,7 @@ def shard_offsets(bounds_all, ctrl, dst_off, src_off, inbox_off, n_r):
 def shard_remap_hash(keys, owners_like, bits_like, out=None):
     """key -> (owner << B) | key with owner = hash(key) mod G (G, B = dim 0 of the two shape carriers)."""
     if out is None:
-        out = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+        out = _alloc(keys.device, keys.shape, "int64")
     _lib.aot_call("mrec_shard_remap_hash", [keys, owners_like, bits_like, out])
     return out
 
@@ -461,5 +480,5 @@ def peer_wait(flags, epoch, err, max_cycles_log2=None):
     if max_cycles_log2 is None:
         _lib.aot_call("mrec_peer_wait", [flags, epoch, err])
     else:
-        lim = torch.tensor([max_cycles_log2], dtype=torch.int32, device=flags.device)
+        lim = _from_list(flags.device, [max_cycles_log2], "int32")
         _lib.aot_call("mrec_peer_wait", [flags, epoch, lim, err])

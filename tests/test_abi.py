@@ -84,7 +84,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 def test_every_aot_entry_rejects_an_empty_argument_pack(built_lib):
     """Every aot symbol of the header validates nparam before touching CUDA (error 1), never crashes."""
     helpers = ("_workspace_bytes", "mrec_version", "mrec_last_error", "mrec_launch_count", "mrec_peer_alloc",
-               "mrec_peer_free", "mrec_ipc_", "mrec_tfrecord_", "mrec_crc32c", "mrec_varint_pack")
+               "mrec_peer_free", "mrec_ipc_", "mrec_tfrecord_", "mrec_crc32c", "mrec_varint_pack", "mrec_rt_")
     for sym in _declared_symbols():
         if any(h in sym for h in helpers):
             continue
