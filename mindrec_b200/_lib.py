@@ -14,7 +14,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmindrec_b200.so")
+# MREC_LIB_PATH: an experimental build of the same library (kernel tuning A/B runs); the product path is the default
+LIB_PATH = os.environ.get("MREC_LIB_PATH") or os.path.join(_HERE, "libmindrec_b200.so")
 
 ERROR_NAMES = {
     0: "OK", 1: "ERR_NPARAM", 2: "ERR_DTYPE", 3: "ERR_SHAPE", 4: "ERR_ALIGN",

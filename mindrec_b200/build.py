@@ -12,15 +12,19 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libmindrec_b200.so")
+# MREC_BUILD_SUFFIX / MREC_BUILD_DEFINES: an experimental variant next to the product library, e.g.
+#   MREC_BUILD_SUFFIX=_t16 MREC_BUILD_DEFINES=-DMREC_SEG_TILE=16 python -m mindrec_b200.build
+# (run it with MREC_LIB_PATH=mindrec_b200/libmindrec_b200_t16.so); without them this is the product build.
+_SUFFIX = os.environ.get("MREC_BUILD_SUFFIX", "")
+OBJ = os.path.join(HERE, "build" + _SUFFIX)
+LIB = os.path.join(HERE, "libmindrec_b200%s.so" % _SUFFIX)
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("MREC_BUILD_DEFINES", "").split()
 
 
 def _nvcc():

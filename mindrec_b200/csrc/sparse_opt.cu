@@ -32,7 +32,10 @@
 
 namespace mrec {
 
-constexpr int kSegTile = 32;      // sorted positions per tile
+#ifndef MREC_SEG_TILE
+#define MREC_SEG_TILE 32
+#endif
+constexpr int kSegTile = MREC_SEG_TILE;  // sorted positions per tile
 constexpr int kSegBatch = 8;      // independent row loads in flight per thread
 constexpr int kLongChain = 16;    // partial chains longer than this go to the CTA kernel
 constexpr int kSegThreads = 256;

@@ -390,8 +390,9 @@ __device__ __forceinline__ void st_vol_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// ghist[pass][digit] += occurrences; warp-aggregated (match-any) so that the hot digits of a Zipf batch (every key of
-// the 13 dense Criteo fields shares its upper digits) cost one shared-memory atomic per warp, not one per key.
+// ghist[pass][digit] += occurrences, through a shared-memory histogram per CTA.  (A warp-aggregated form built on
+// MATCH.ANY was measured 10x slower here, r2d: 45 us — the instruction's cost grows with the number of DISTINCT values in
+// the warp, and random digits are all distinct.)
 constexpr int OS_HIST_THREADS = 1024;
 template <typename KeyT>
 __global__ void __launch_bounds__(OS_HIST_THREADS)
@@ -402,24 +403,28 @@ onesweep_hist_kernel(const KeyT* __restrict__ keys, int64_t n, uint64_t bound, i
   n = eff_n(n, n_valid);
   for (int d = threadIdx.x; d < passes * radix; d += OS_HIST_THREADS) s_hist[d] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * OS_HIST_THREADS;
-  // whole warps iterate together (match-any needs the full mask)
-  for (int64_t i0 = (int64_t)blockIdx.x * OS_HIST_THREADS + (threadIdx.x & ~31); i0 < n; i0 += stride) {
-    const int64_t i = i0 + lane;
-    const bool ok = i < n;
-    const auto k = ok ? encode_key<KeyT>(keys[i], bound) : (typename UKeyOf<KeyT>::type)0;
-    for (int p = 0; p < passes; ++p) {
-      const uint32_t dig = ok ? ((uint32_t)(k >> (p * digit_bits)) & (radix - 1)) : (uint32_t)radix;
-      const uint32_t peers = __match_any_sync(0xffffffffu, dig);
-      if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * radix + dig], (uint32_t)__popc(peers));
-    }
+  for (int64_t i = (int64_t)blockIdx.x * OS_HIST_THREADS + threadIdx.x; i < n; i += stride) {
+    const auto k = encode_key<KeyT>(keys[i], bound);
+    for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * radix + ((uint32_t)(k >> (p * digit_bits)) & (radix - 1))], 1u);
   }
   __syncthreads();
   for (int d = threadIdx.x; d < passes * radix; d += OS_HIST_THREADS) {
     const uint32_t c = s_hist[d];
     if (c) atomicAdd(&ghist[(d / radix) * MAX_RADIX + (d & (radix - 1))], c);
   }
+}
+
+// Lanes of the warp that hold the same digit, from one ballot per digit bit: constant cost, whereas MATCH.ANY iterates
+// over the distinct values of the warp (32 for random digits; measured r2d: 18-24 us per pass with it).
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t dig, int bits) {
+  uint32_t peers = 0xffffffffu;
+  for (int b = 0; b < bits; ++b) {
+    const bool one = (dig >> b) & 1u;
+    const uint32_t vote = __ballot_sync(0xffffffffu, one);
+    peers &= one ? vote : ~vote;
+  }
+  return peers;
 }
 
 template <typename KeyT, bool RAW>
@@ -454,6 +459,7 @@ onesweep_pass_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
   if (tile0 >= n) return;
   const int tile_n = (int)min((int64_t)TILE, n - tile0);
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const int digit_bits1 = __ffs(RADIX);                 // log2(RADIX) + 1: the extra bit tells the invalid marker apart
 
   U key[ITEMS];
   int32_t val[ITEMS];
@@ -489,7 +495,7 @@ onesweep_pass_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
   for (int i = 0; i < ITEMS; ++i) {
     const int li = warp * (ITEMS * 32) + i * 32 + lane;
     const uint32_t dig = (li < tile_n) ? ((uint32_t)(key[i] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;   // RADIX = invalid
-    const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+    const uint32_t peers = same_digit_lanes(dig, digit_bits1);
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (lane == leader && dig < (uint32_t)RADIX) {
@@ -812,7 +818,7 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
     }();
     if (!attr_ok) return fail(ERR_CUDA, "mrec_unique: cannot reserve %zu bytes of dynamic shared memory", os_smem);
     // few CTAs: the 6 KB of digit totals live in 48 cache lines, and every CTA ends with ~1500 global atomics on them
-    const int hist_grid = (int)std::min<int64_t>(cdiv(n, 16 * OS_HIST_THREADS), kNumSMs);
+    const int hist_grid = (int)std::min<int64_t>(cdiv(n, 4 * OS_HIST_THREADS), kNumSMs);
     MREC_LAUNCH(onesweep_hist_kernel<KeyT>, hist_grid, OS_HIST_THREADS, 0, stream, ids, n, bound, p.passes, p.digit_bits,
                 ghist, n_valid);
     const void* kin = ids;
