@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--layout", default=os.environ.get("MREC_BENCH_LAYOUT", "interleaved"), choices=["interleaved", "split"],
                     help="deep table of the single-GPU step: w|m|v records [V,3,D] (one DRAM burst per row update) or "
                          "three [V,D] arrays")
-    ap.add_argument("--c5-rows-per-gpu", type=int, default=96_000_000,
+    ap.add_argument("--c5-rows-per-gpu", type=int, default=88_000_000,
                     help="config 5: rows of the dim-128 table per GPU (w + LazyAdam m, v in fp32 = 1.5 KB per row)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config-3 / config-4 / config-5 blocks")
@@ -448,7 +448,7 @@ def measure_c5(args, world, rank, dev, group_one):
     torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info(dev)
     row_bytes = (128 + 1) * 4 * 3                       # w, m, v (+ the wide vector's w, accum, linear)
-    rows = min(args.c5_rows_per_gpu, int((free - (28 << 30)) // row_bytes))
+    rows = min(args.c5_rows_per_gpu, int((free - (40 << 30)) // row_bytes))
     t = torch.tensor([rows], device=dev, dtype=torch.int64)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     rows = int(t.item())
@@ -520,7 +520,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     _lib.lib()  # fail loudly if the CUDA extension is missing
 
     if world > 1 and args.vocab_scale == 1.0:

@@ -10,7 +10,10 @@ __all__ = ["EmbeddingLookup", "HashEmbeddingLookup", "MapParameter", "Adam", "La
 
 
 def __getattr__(name):
-    # torch-backed modules are imported lazily so `import mindrec_b200` stays cheap
+    # the torch-backed cells are imported lazily, and only for the names they export: `from mindrec_b200 import ops,
+    # runtime` (the torch-free layer) must not drag them in
+    if name not in __all__:
+        raise AttributeError("module 'mindrec_b200' has no attribute %r" % name)
     import importlib
     for mod in ("nn", "cells", "hash", "interaction"):
         try:

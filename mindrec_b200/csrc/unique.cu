@@ -378,8 +378,14 @@ constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr uint32_t LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_MASK = (1u << 30) - 1u;
 constexpr int OS_MAX_PASSES = 8;
 constexpr int kSpinLimit = 1 << 22;   // ~3 s of L2 round trips
-template <typename KeyT> struct OsItems { static constexpr int value = 8; };    // 4096 keys per tile: N = 624 000 -> 153
-template <> struct OsItems<int64_t> { static constexpr int value = 8; };        // tiles, one wave over the 148 SMs
+// Keys per thread of a pass tile: 8, 12 or 16 (4096 / 6144 / 8192 keys per tile), the smallest that fits the sort into
+// ONE wave of CTAs (one CTA per SM: 148 tiles) — a 149th tile would wait for a free SM and double the pass.
+constexpr int OS_MAX_ITEMS = 16;
+static int os_items_for(int64_t n) {
+  for (int it = 8; it < OS_MAX_ITEMS; it += 4)
+    if (cdiv(n > 0 ? n : 1, (int64_t)OS_THREADS * it) <= kNumSMs) return it;
+  return OS_MAX_ITEMS;
+}
 
 __device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t* p) {
   uint32_t v;
@@ -427,7 +433,7 @@ __device__ __forceinline__ uint32_t same_digit_lanes(uint32_t dig, int bits) {
   return peers;
 }
 
-template <typename KeyT, bool RAW>
+template <typename KeyT, bool RAW, int ITEMS>
 __global__ void __launch_bounds__(OS_THREADS, 1)
 onesweep_pass_kernel(const void* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      typename UKeyOf<KeyT>::type* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n,
@@ -435,7 +441,6 @@ onesweep_pass_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
                      uint32_t* __restrict__ lookback /* [tiles][radix], zeroed */, uint32_t* __restrict__ ticket,
                      const int32_t* __restrict__ n_valid) {
   using U = typename UKeyOf<KeyT>::type;
-  constexpr int ITEMS = OsItems<KeyT>::value;
   constexpr int TILE = OS_THREADS * ITEMS;
   // dynamic shared memory: first the per-warp look-back partials [OS_WARPS][radix] u32, later (aliased) the tile's
   // keys and values in their sorted order
@@ -528,7 +533,7 @@ onesweep_pass_kernel(const void* __restrict__ keys_in, const int32_t* __restrict
     uint4 acc[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[c] = make_uint4(0u, 0u, 0u, 0u);
-    constexpr int RB = 4;                           // rows per batch: RB * chunks 16-byte loads in flight per lane
+    constexpr int RB = ITEMS >= 16 ? 2 : 4;         // rows per batch: RB * chunks 16-byte loads in flight per lane
     for (int t0 = warp; t0 < tile; t0 += RB * OS_WARPS) {
       uint4 v[RB][4];
 #pragma unroll
@@ -728,7 +733,7 @@ struct SortPlan {
   int n_tiles, n_blocks, tiles_per_block, passes, digit_bits;
   size_t off_keys_a, off_keys_b, off_vals_tmp, off_hist, off_hist2, off_tiles, total;
   // one-sweep control region (zeroed by one memset per call): digit totals, tickets, look-back words
-  int os_tiles, seg_tiles;
+  int os_tiles, os_items, seg_tiles;
   size_t off_ctrl, ctrl_bytes, off_ghist, off_ticket, off_lb_seg, off_lb;
 };
 
@@ -750,8 +755,8 @@ static SortPlan make_plan(int64_t n, int key_bytes, int key_bits) {
   p.off_hist2 = o; o = align_up(o + (size_t)(p.n_blocks + 1) * MAX_RADIX * 4, 256);
   p.off_tiles = o; o = align_up(o + (size_t)(p.n_tiles + 1) * 4, 256);
   {
-    const int os_tile = OS_THREADS * (key_bytes == 8 ? OsItems<int64_t>::value : OsItems<int32_t>::value);
-    p.os_tiles = (int)cdiv(n > 0 ? n : 1, os_tile);
+    p.os_items = os_items_for(n);
+    p.os_tiles = (int)cdiv(n > 0 ? n : 1, (int64_t)OS_THREADS * p.os_items);
     p.seg_tiles = (int)cdiv(n > 0 ? n : 1, SEG_TILE);
     p.off_ctrl = o;
     p.off_ghist = o; o += (size_t)OS_MAX_PASSES * MAX_RADIX * 4;
@@ -809,15 +814,20 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
     uint32_t* lb_seg = reinterpret_cast<uint32_t*>(w + p.off_lb_seg);
     uint32_t* lb = reinterpret_cast<uint32_t*>(w + p.off_lb);
     cudaMemsetAsync(w + p.off_ctrl, 0, p.ctrl_bytes, stream);
-    // sorted tile (keys + values) or the look-back partials, whichever is larger; > 48 KB needs the opt-in
-    constexpr size_t os_smem = (size_t)OS_THREADS * OsItems<KeyT>::value * (sizeof(U) + 4) > (size_t)OS_WARPS * MAX_RADIX * 4
-                                   ? (size_t)OS_THREADS * OsItems<KeyT>::value * (sizeof(U) + 4) : (size_t)OS_WARPS * MAX_RADIX * 4;
+    // dynamic shared memory: the sorted tile (keys + values) or the look-back partials, whichever is larger (opt-in
+    // above 48 KB, set once per instantiation)
+    constexpr size_t os_smem_max = (size_t)OS_THREADS * OS_MAX_ITEMS * (sizeof(U) + 4);
     static const bool attr_ok = [] {
-      return cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_smem) == cudaSuccess &&
-             cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_smem) == cudaSuccess;
+      bool ok = true;
+#define MREC_OS_ATTR(IT)                                                                                                       \
+  ok = ok && cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, true, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_smem_max) == cudaSuccess && \
+       cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, false, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_smem_max) == cudaSuccess;
+      MREC_OS_ATTR(8) MREC_OS_ATTR(12) MREC_OS_ATTR(16)
+#undef MREC_OS_ATTR
+      return ok;
     }();
-    if (!attr_ok) return fail(ERR_CUDA, "mrec_unique: cannot reserve %zu bytes of dynamic shared memory", os_smem);
-    // few CTAs: the 6 KB of digit totals live in 48 cache lines, and every CTA ends with ~1500 global atomics on them
+    if (!attr_ok) return fail(ERR_CUDA, "mrec_unique: cannot reserve %zu bytes of dynamic shared memory", os_smem_max);
+    const size_t os_smem = std::max((size_t)OS_THREADS * p.os_items * (sizeof(U) + 4), (size_t)OS_WARPS * MAX_RADIX * 4);
     const int hist_grid = (int)std::min<int64_t>(cdiv(n, 4 * OS_HIST_THREADS), kNumSMs);
     MREC_LAUNCH(onesweep_hist_kernel<KeyT>, hist_grid, OS_HIST_THREADS, 0, stream, ids, n, bound, p.passes, p.digit_bits,
                 ghist, n_valid);
@@ -827,13 +837,15 @@ int unique_sorted(const KeyT* ids, int64_t n, uint64_t bound, KeyT* uniq, int32_
       U* kout = kbuf[pass & 1];
       int32_t* vout = (((p.passes - 1 - pass) & 1) == 0) ? perm : vtmp;    // the last pass lands in `perm`
       uint32_t* lbp = lb + (size_t)pass * p.os_tiles * radix;
+#define MREC_OS_PASS(RAW_, IT)                                                                                          \
+  MREC_LAUNCH((onesweep_pass_kernel<KeyT, RAW_, IT>), p.os_tiles, OS_THREADS, os_smem, stream, kin, vin, kout, vout, n, \
+              pass * p.digit_bits, radix, bound, ghist + pass * MAX_RADIX, lbp, ticket + pass, n_valid)
       if (pass == 0) {
-        MREC_LAUNCH((onesweep_pass_kernel<KeyT, true>), p.os_tiles, OS_THREADS, os_smem, stream, kin, vin, kout, vout, n,
-                    pass * p.digit_bits, radix, bound, ghist + pass * MAX_RADIX, lbp, ticket + pass, n_valid);
+        if (p.os_items == 8) MREC_OS_PASS(true, 8); else if (p.os_items == 12) MREC_OS_PASS(true, 12); else MREC_OS_PASS(true, 16);
       } else {
-        MREC_LAUNCH((onesweep_pass_kernel<KeyT, false>), p.os_tiles, OS_THREADS, os_smem, stream, kin, vin, kout, vout, n,
-                    pass * p.digit_bits, radix, bound, ghist + pass * MAX_RADIX, lbp, ticket + pass, n_valid);
+        if (p.os_items == 8) MREC_OS_PASS(false, 8); else if (p.os_items == 12) MREC_OS_PASS(false, 12); else MREC_OS_PASS(false, 16);
       }
+#undef MREC_OS_PASS
       kin = kout;
       vin = vout;
     }

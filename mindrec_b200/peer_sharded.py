@@ -699,7 +699,7 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
     #   a1   serve -> wait -> expand: the only exchange work in front of the DenseLayers in steady state
     #   a2   DenseLayers forward / loss / backward, with the NEXT batch's whole key phase (plan, publish, key push,
     #        owner dedup) on a forked branch underneath (a2_plain: without it)
-    #   b    gradient exchange -> fused row updates
+    #   b    gradient exchange -> fused row updates (one per a2 variant: it reads that variant's gradient buffers)
     # Between a1 and a2 the host makes the stream wait for the staged copy of the next batch (it overlaps a1);
     # between a2 and b it launches the DenseLayer mean all-reduce + Adam on a side stream (they overlap b).
     def _pre(self):
@@ -745,7 +745,10 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         self._dense_stream.wait_stream(main)
         with torch.cuda.stream(self._dense_stream):          # NCCL + dense Adam under the gradient exchange
             self._dense_update()
-        g["b"].replay() if g is not None else self._b()
+        if g is not None:
+            g["b" if ahead else "b_plain"].replay()
+        else:
+            self._b()
         return self._loss
 
     def capture(self, ids, wts, label, warmup=3):
@@ -765,8 +768,9 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
             for si in range(2):
                 rk.use_set(si)
                 graphs = {}
-                for name, fn in (("pre", self._pre), ("a1", self._a1), ("a2", lambda: self._a2(True)),
-                                 ("a2_plain", lambda: self._a2(False)), ("b", self._b)):
+                # `b` consumes the gradient tensors its `a2` produced: every a2 variant is followed by its own b
+                for name, fn in (("pre", self._pre), ("a1", self._a1), ("a2", lambda: self._a2(True)), ("b", self._b),
+                                 ("a2_plain", lambda: self._a2(False)), ("b_plain", self._b)):
                     gr = torch.cuda.CUDAGraph()
                     n0 = _lib.launch_count()
                     with torch.cuda.graph(gr, pool=pool):
@@ -775,6 +779,7 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
                         self.launches_per_step += _lib.launch_count() - n0
                     if name in ("a2", "a2_plain"):
                         graphs[name + "_loss"] = out
+                        graphs[name + "_bwd"] = self._bwd            # kept alive: the next graph reads these buffers
                     pool = pool or gr.pool()
                     graphs[name] = gr
                 sets.append(graphs)

@@ -13,6 +13,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCRIPT = textwrap.dedent('''
     import sys
+    import traceback
+
+
+    class NoTorch:                                   # any attempt to import torch fails loudly, with the culprit's stack
+        def find_spec(self, name, path=None, target=None):
+            if name == "torch" or name.startswith("torch."):
+                traceback.print_stack()
+                raise ImportError("the torch-free path tried to import " + name)
+            return None
+
+
+    sys.meta_path.insert(0, NoTorch())
     import numpy as np
     from mindrec_b200 import _lib, ops, runtime, synth
     from oracle import ref_numpy as R
@@ -101,7 +113,7 @@ SCRIPT = textwrap.dedent('''
     dev.stream.wait_event(ev)
     np.testing.assert_array_equal(ops.gather(d_w, staged).numpy(), R.gather(w, ids[::-1]))
 
-    assert _lib.launch_count() - before > 30
+    assert _lib.launch_count() - before > 20
     assert "torch" not in sys.modules, "the runtime path imported torch"
     print("RUNTIME_OK", _lib.launch_count() - before)
 ''')

@@ -97,3 +97,26 @@ def test_unique_first_docs_example(cuda):
     assert uniq[:int(count.item())].tolist() == [1, 2, 5] and inverse.tolist() == [0, 1, 2, 1]
     uq = ops.unique(ids)
     assert uq.uniq[:int(uq.count.item())].tolist() == [1, 2, 5] and uq.inverse.tolist() == [0, 1, 2, 1]
+
+
+@pytest.mark.parametrize("n,bits", [(1_300_000, 21), (1_300_000, 26), (800_000, 22), (2_500_000, 24)])
+def test_unique_large_tiles_and_waves(cuda, n, bits):
+    """The pass kernels pick 8, 12 or 16 keys per thread from N (one wave of 148 tiles when possible, several waves
+    beyond 1.2 M keys); every variant against the oracle, with and without a device-side valid count."""
+    rng = np.random.default_rng(n + bits)
+    vocab = (1 << bits) - 77
+    ids = (rng.zipf(1.05, size=n) % vocab).astype(np.int32)
+    ids[::7] = rng.integers(0, vocab, size=ids[::7].size)
+    table_like = torch.empty((vocab, 0), device=cuda)
+    d_ids = torch.from_numpy(ids).to(cuda)
+    _check(ops.unique(d_ids, table_like=table_like), ids, bound=vocab)
+    for nv in (n // 5, n - 3):                           # static inbox, device-side count (owner-side dedup)
+        n_valid = torch.tensor([nv], dtype=torch.int32, device=cuda)
+        uq = ops.unique(d_ids, table_like=table_like, n_valid=n_valid)
+        uniq, inverse, perm, seg_start = R.unique_sorted(ids[:nv], vocab)
+        u = int(uq.count.item())
+        assert u == uniq.size
+        np.testing.assert_array_equal(uq.uniq[:u].cpu().numpy(), uniq)
+        np.testing.assert_array_equal(uq.inverse[:nv].cpu().numpy(), inverse)
+        np.testing.assert_array_equal(uq.perm[:nv].cpu().numpy(), perm)
+        np.testing.assert_array_equal(uq.seg_start[:u + 1].cpu().numpy(), seg_start)

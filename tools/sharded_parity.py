@@ -23,20 +23,26 @@ TOL_SCALE = 2e-5
 
 
 def _cmp(name, got, want, out, l2_tol):
+    """fp32 DenseLayers (l2_tol 1e-5): at most 1e-6 of the elements beyond 2e-5 of the scale.  fp16 DenseLayers
+    (l2_tol 1e-3): the two runs call GEMMs of different M (B vs G * B rows), whose fp16 outputs differ in the last bit
+    on their own — the outlier allowance is 1 % there and the relative L2 error carries the verdict."""
     d = (got.double() - want.double())
     scale = float(want.abs().max())
     n_out = int((d.abs() > TOL_SCALE * scale).sum())
     rel_l2 = float(d.norm() / max(float(want.double().norm()), 1e-30))
     out[name] = {"max_abs_diff": float(d.abs().max()), "scale": scale, "outliers": n_out, "numel": got.numel(),
                  "rel_l2": rel_l2}
-    return n_out <= max(1e-6 * got.numel(), 0) + (2 if got.numel() > 1e6 else 0) and rel_l2 <= l2_tol
+    frac = 1e-6 if l2_tol <= 1e-5 else 1e-2
+    return n_out <= frac * got.numel() + 3 and rel_l2 <= l2_tol
 
 
-def wide_deep(world, rank, dev, batch, fields, emb, hidden, rows_per_rank=2_000_003, steps=3, mixed=False, alpha=1.05):
+def wide_deep(world, rank, dev, batch, fields, emb, hidden, rows_per_rank=2_000_003, steps=3, mixed=False, alpha=1.05,
+              graph=True, ahead=True):
+    """graph / ahead = False run the same step eagerly / without the one-step-ahead key phase (bisection aids)."""
     from mindrec_b200 import cells, peer_sharded, synth
     vocab = rows_per_rank * world
     step = peer_sharded.PeerShardedWideDeepStep(batch, vocab, emb, hidden, dev, seed=3, use_mixed_precision=mixed,
-                                                fields=fields)
+                                                fields=fields, graph=graph)
     wide0, deep0 = step.tables.gather_full()
     flat0 = step.dense.flat.clone()
     scale = vocab / synth.vocab_size(synth.CARD_KAGGLE)
@@ -47,7 +53,7 @@ def wide_deep(world, rank, dev, batch, fields, emb, hidden, rows_per_rank=2_000_
     step.capture(*mine[0], warmup=2)                                     # trains 2 steps on batch 0
     losses = []
     for s in range(1, steps + 1):
-        nxt = mine[s + 1] if s + 1 <= steps else None
+        nxt = mine[s + 1] if (ahead and s + 1 <= steps) else None
         losses.append(step.replay(*mine[s], next_batch=nxt)[0].reshape(1).clone())
     torch.cuda.synchronize()
     flags = step.tables.error_flags()
@@ -170,7 +176,7 @@ def multitable(world, rank, dev, batch, rows_per_rank=1_000_003, steps=3, mixed=
         ok &= _cmp("emb128", deep, ref.tables.rk.deep[:v], res, l2)
         ok &= _cmp("wide_emb128", wide, ref.tables.rk.wide[:v], res, l2)
         ok &= _cmp("dense", step.dense.flat, ref.dense.flat, res, l2)
-        ok &= _cmp("wide_bias", step.wide_bias, ref.wide_bias, res, 1e-3 if mixed else 1e-5)
+        ok &= _cmp("wide_bias", step.wide_bias, ref.wide_bias, res, l2)
         rk, rv = ref.hash.rk.table.get_data()
         same_keys = rk.numel() == hk.numel() and bool(torch.equal(rk, hk))
         res["hash_keys_equal"] = same_keys
