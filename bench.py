@@ -22,6 +22,8 @@ import sys
 import tempfile
 import time
 
+_OUT = sys.stdout
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -143,7 +145,7 @@ def run_reference(args):
         "config1": c1,
         "note": "reference's CPU path as restated in oracle/ (C/OpenMP + numpy BLAS); MindSpore is not installable here",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def workload_config(args, n_gpus):
@@ -167,17 +169,64 @@ def workload_config(args, n_gpus):
 # clocks
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  In-process NVML polling (a thread, one sample every
+    2 ms: a 20-step region of ~15 ms still gets several samples); `nvidia-smi -lms` is the fallback when the NVML
+    binding is missing.  start() / stop() bracket the timed region; samples outside it are dropped."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p = self.f = self.thread = None
+        self.samples, self.run = [], False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:                                      # CUDA_VISIBLE_DEVICES may renumber: match by PCI bus id
+                import torch
+                bus = torch.cuda.get_device_properties(index).pci_bus_id
+                dom = torch.cuda.get_device_properties(index).pci_domain_id
+                dev = torch.cuda.get_device_properties(index).pci_device_id
+                uuid = "%08X:%02X:%02X.0" % (dom, bus, dev)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._one()                               # prove the calls work before relying on them
+            self.samples = []
+        except Exception:
+            self.nvml = None
+
+    def _one(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            why = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.samples.append((mhz, why))
+
+    def _poll(self):
+        while self.run:
+            try:
+                self._one()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "20", "-i", str(self.index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
@@ -185,6 +234,18 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.nvml is not None:
+            try:
+                self._one()                           # at least one sample taken before the region's closing sync returns
+            except Exception:
+                pass
+            self.run = False
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            sm = [m for m, _ in self.samples]
+            reasons = sorted({name for _, why in self.samples for name, bit in self.BITS if why & bit})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -209,7 +270,7 @@ class ClockSampler:
                 if val.strip().lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -731,13 +792,19 @@ def run_ours(args):
         "cpu_baseline": cb, "breakdown_ms": breakdown, "exchange": exchange, "final_loss": final_loss,
         "lib": _lib.version(),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner) are sent to
+    # stderr by pointing fd 1 at fd 2 for the run; the line goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,2 +1,3 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/diag_parity.py > gpurun_out/r2i_diag.log 2>&1; echo "rc=$?" >> gpurun_out/r2i_diag.log
-grep -v "^W\|^\[rank" gpurun_out/r2i_diag.log | tail -20
+N=${N:-2}
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/r2l_bench$N.json 2> gpurun_out/r2l_bench$N.err; echo "bench rc=$?" >> gpurun_out/r2l_bench$N.err
+grep -v "^W\|^\[rank" gpurun_out/r2l_bench$N.err | tail -5
