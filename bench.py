@@ -746,7 +746,7 @@ def run_ours(args):
     if world > 1 and hasattr(step.tables, "rk") and not args.no_extra_configs:
         # multi-GPU parity of the benchmarked exchange + BASELINE config 5 (every rank takes part)
         from tools import sharded_parity
-        step.tables.close()
+        step.close()
         del step
         torch.cuda.empty_cache()
         group_one = dist.new_group([0])

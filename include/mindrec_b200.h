@@ -119,6 +119,13 @@ int mrec_fill_tail(MREC_AOT_ARGS);
 int mrec_push_rows_to_peers(MREC_AOT_ARGS);
 int mrec_peer_signal(MREC_AOT_ARGS);
 int mrec_peer_wait(MREC_AOT_ARGS);
+/* Sum of the G ranks' buffers over peer memory, delivered to every rank: the mean all-reduce of the data-parallel
+ * DenseLayer gradients (DistributedGradReducer, wide_and_deep.py:455-470; the 1/G is folded into the optimizer's
+ * gradient scale) as a node of the step's CUDA graph.  Rank r sums the r-th slice in rank order (deterministic,
+ * replicas bit-identical) and stores it into all G destinations; callers bracket it with signal / wait pairs.
+ *   in : src_ptrs[G] i64, dst_ptrs[G] i64 (every rank's [n] f32 buffers as mapped here), ctrl[2] i32 {rank, G}
+ *   out: dst[n] f32 (this rank's destination buffer) */
+int mrec_peer_allreduce(MREC_AOT_ARGS);
 /* CUDA-IPC plumbing for the peer buffers (host only, set-up time, not aot) */
 void *mrec_peer_alloc(size_t bytes);
 int mrec_peer_free(void *p);

@@ -118,6 +118,15 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
                : "l"(p));
   return r;
 }
+// peer-mapped data written by ANOTHER GPU: system-scope relaxed load (never served from a non-coherent cache)
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)

@@ -274,6 +274,61 @@ __global__ void peer_wait_kernel(const int32_t* __restrict__ flags, int world, c
   __threadfence_system();
 }
 
+
+// Sum of the G ranks' buffers over peer memory, result delivered to every rank (the DenseLayer gradient all-reduce of
+// the data-parallel step, inside the step's CUDA graph): rank r owns the r-th slice; for every 16-byte chunk of it the
+// G sources are loaded (G - 1 of them over NVLink), added in RANK ORDER — the same order on every rank, so the
+// replicas stay bit-identical and the result does not depend on timing — and the sum is stored into all G
+// destination buffers.  Callers bracket it with signal / wait pairs: sources complete before, sums delivered after.
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(const int64_t* __restrict__ src_ptrs, const int64_t* __restrict__ dst_ptrs,
+                      const int32_t* __restrict__ ctrl, int64_t n) {
+  __shared__ const float* s_src[kPeerMaxRanks];
+  __shared__ float* s_dst[kPeerMaxRanks];
+  const int me = ctrl[0], g = ctrl[1];
+  if (threadIdx.x < g) {
+    s_src[threadIdx.x] = reinterpret_cast<const float*>(src_ptrs[threadIdx.x]);
+    s_dst[threadIdx.x] = reinterpret_cast<float*>(dst_ptrs[threadIdx.x]);
+  }
+  __syncthreads();
+  const int64_t n4 = n / 4;
+  const int64_t per = (n4 + g - 1) / g;
+  const int64_t lo = min(n4, (int64_t)me * per), hi = min(n4, lo + per);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < hi; i0 += UNROLL * stride) {
+    float4 acc[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < g; ++s) {                    // rank order; the UNROLL loads of a source are in flight together
+      float4 v[UNROLL];
+#pragma unroll
+      for (int k = 0; k < UNROLL; ++k) {
+        const int64_t i = i0 + k * stride;
+        v[k] = i < hi ? ld_volatile_f4(reinterpret_cast<const float4*>(s_src[s]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < UNROLL; ++k) {
+        acc[k].x += v[k].x; acc[k].y += v[k].y; acc[k].z += v[k].z; acc[k].w += v[k].w;
+      }
+    }
+    for (int s = 0; s < g; ++s) {
+#pragma unroll
+      for (int k = 0; k < UNROLL; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < hi) reinterpret_cast<float4*>(s_dst[s])[i] = acc[k];
+      }
+    }
+  }
+  // the n % 4 tail: the last rank, scalar
+  if (me == g - 1 && blockIdx.x == 0 && threadIdx.x < (int)(n - n4 * 4)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    float acc = 0.f;
+    for (int s = 0; s < g; ++s) acc += *reinterpret_cast<const volatile float*>(s_src[s] + i);
+    for (int s = 0; s < g; ++s) s_dst[s][i] = acc;
+  }
+}
+
 }  // namespace mrec
 
 // in : bounds_all[G*(G+1)] i32, ctrl[2] i32 {rank, world}     out: dst_off[G], src_off[G+1], inbox_off[G], n_r[1] (i32)
@@ -325,6 +380,27 @@ MREC_API int mrec_push_rows_to_peers(int nparam, void** params, int* ndims, int6
                 width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, (int64_t)0, cap_rows, a.ptr<int32_t>(6));
   }
   return check_launch("push_rows_to_peers");
+}
+
+// in : src_ptrs[G] i64 (every rank's source buffer [n] f32 as mapped in THIS process), dst_ptrs[G] i64 (every rank's
+//      destination buffer [n] f32), ctrl[2] i32 {rank, world}          out: dst[n] f32 (this rank's destination: carries n)
+// Every rank calls it between a signal / wait pair (sources complete) and another (sums delivered).
+MREC_API int mrec_peer_allreduce(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                 void* stream, void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 4) return fail(ERR_NPARAM, "mrec_peer_allreduce: expected 4 params, got %d", a.nparam);
+  MREC_REQUIRE(a.is_i64(0) && a.is_i64(1) && a.is_i32(2) && a.is_f32(3), ERR_DTYPE,
+               "mrec_peer_allreduce: src_ptrs/dst_ptrs i64, ctrl i32, dst f32");
+  const int world = (int)a.numel(0);
+  MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks && a.numel(1) == world && a.numel(2) >= 2, ERR_SHAPE,
+               "mrec_peer_allreduce: 1 <= G <= %d, dst_ptrs[G], ctrl[2]", kPeerMaxRanks);
+  MREC_REQUIRE(a.aligned(3, 16), ERR_ALIGN, "mrec_peer_allreduce: buffers must be 16-byte aligned");
+  const int64_t n = a.numel(3);
+  if (n == 0) return OK;
+  const int64_t per = cdiv(cdiv(n, 4), world);
+  MREC_LAUNCH(peer_allreduce_kernel<4>, grid_for(cdiv(per, 1024), 4), 256, 0, a.stream, a.ptr<int64_t>(0), a.ptr<int64_t>(1),
+              a.ptr<int32_t>(2), n);
+  return check_launch("peer_allreduce");
 }
 
 // in : payload[K] i32 (K may be 0), payload_ptrs[G] i64, flag_ptrs[G] i64, epoch[1] i32 (incremented)   out: dummy[1]

@@ -17,15 +17,15 @@ models/wide_deep/src/wide_and_deep.py:415-430): only looked-up rows and their mo
 
 Exchange: the device-driven protocol of mindrec_b200.peer_sharded for both lookups — owner = key mod G for the table,
 owner = hash(key) mod G for the MapParameter; keys, rows and gradients travel as NVLink peer stores into CUDA-IPC
-inboxes at offsets computed on the device; nothing is read back to the host, so the step is three CUDA graphs with the
-NCCL mean all-reduce of the DenseLayer gradients between them.
+inboxes at offsets computed on the device, and the mean all-reduce of the DenseLayer gradients is a kernel over peer
+memory too (peer_sharded.PeerAllReduce); nothing is read back to the host, so the whole step is ONE CUDA graph.
 """
 import torch
 import torch.distributed as dist
 
 from . import _lib, ops
 from .nn import DenseStack
-from .peer_sharded import PeerShardedHashEmbedding, PeerShardedTables
+from .peer_sharded import PeerAllReduce, PeerShardedHashEmbedding, PeerShardedTables
 
 EMB128 = 128
 
@@ -65,8 +65,10 @@ class ShardedMultitableStep:
         self.in_dim = (n_table_fields + n_hash_fields) * EMB128
         dims = [self.in_dim] + list(deep_dim_list) + [1]
         n_dense = DenseStack.numel(dims)
-        # the DenseLayer gradients and the wide_bias gradient share one buffer: one all-reduce per step
-        self._reduce = torch.zeros(n_dense + 4, dtype=torch.float32, device=dev)
+        # the DenseLayer gradients and the wide_bias gradient share one peer-memory buffer: one all-reduce per step,
+        # `_reduce` is this rank's contribution, `_reduced` the sum over the ranks
+        self._ar = PeerAllReduce(n_dense + 4, dev, group)
+        self._reduce, self._reduced = self._ar.src, self._ar.dst
         self.dense = DenseStack(dims, use_mixed_precision, dev, generator=gen, weight_init="normal", bias_init="normal",
                                 storage=(torch.zeros(n_dense, dtype=torch.float32, device=dev), self._reduce[:n_dense]))
         self.dense_hyper = ops.adam_hyper(adam_lr, eps=1e-6, loss_scale=sens * g, device=dev)
@@ -84,10 +86,7 @@ class ShardedMultitableStep:
             ones=torch.ones((b, n_table_fields), dtype=torch.float32, device=dev),
             x_table=torch.empty((b, n_table_fields * EMB128), dtype=f16, device=dev),
             x_hash=torch.empty((b, n_hash_fields * EMB128), dtype=f16, device=dev),
-            deep_in=torch.empty((b, self.in_dim), dtype=f16, device=dev),
             wide_out=torch.empty((b, 1), dtype=torch.float32, device=dev),
-            g_table=torch.empty((b, n_table_fields * EMB128), dtype=f16, device=dev),
-            g_hash=torch.empty((b, n_hash_fields * EMB128), dtype=f16, device=dev),
             loss_out=(torch.empty((b, 1), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.float32, device=dev),
                       torch.empty((b, 1), dtype=torch.float32, device=dev),
                       torch.empty((b, 1) if use_mixed_precision else (0,), dtype=torch.float16, device=dev),
@@ -95,21 +94,24 @@ class ShardedMultitableStep:
         self._sens_t = torch.tensor([self.sens], dtype=torch.float32, device=dev)
         self._nan = torch.tensor(float("nan"), dtype=torch.float32, device=dev)
         self._zero = torch.zeros((), dtype=torch.float32, device=dev)
+        self._main_stream = torch.cuda.Stream(device=dev, priority=-1)       # see PeerShardedWideDeepStep
         self._dense_stream = torch.cuda.Stream(device=dev)
         self._graphs = None
-        self._loss = None
-        self._bwd = None
+        self._loss = torch.zeros((), dtype=torch.float32, device=dev)
         self._steps = 0
+        self._last = None
         self.launches_per_step = None
 
-    # ---- the step in three fixed-shape pieces (same cut as PeerShardedWideDeepStep) -------------------------------
-    def _a1(self):
+    # ---- the step (one CUDA graph) -----------------------------------------------------------------------------
+    def _forward_exchange(self):
         """plan -> key exchange -> row exchange -> expand.  The table (T) and the MapParameter (H) go through the four
         phases in lock step ON ONE STREAM, always T before H: every rank issues its signals and its waits in the same
         order, so a wait can only ever be held up by a peer's earlier work, never by the peer's other lookup waiting
-        on us (two forked branches would leave that order to the scheduler)."""
+        on us (two forked branches would leave that order to the scheduler).  The dim-1 twins of the table's kernels
+        (wide vector) and the owner-side dedup run on a forked branch: they contain no waits."""
         io, t, h = self._io, self.tables.rk, self.hash.rk
         main = torch.cuda.current_stream()
+        side = self.tables.owner_stream
         t.p_plan_publish(io["ids"])
         h.p_plan_publish(io["keys"])
         t.wait(0)
@@ -117,53 +119,49 @@ class ShardedMultitableStep:
         h.wait(0)
         h.p_keys()
         t.wait(1)
-        side = self.tables.owner_stream                      # owner-side dedup of the key inbox: no waits inside,
-        side.wait_stream(main)                               # forked under serve / expand / DenseLayers
-        with torch.cuda.stream(side):
+        side.wait_stream(main)
+        with torch.cuda.stream(side):                        # under serve / expand / DenseLayers
             t.p_owner_dedup()
-        t.p_serve()
+        t.p_serve(side=side)
         h.wait(1)
         h.p_serve()
         t.wait(2)
-        t.p_expand(io["ids"].shape, io["ones"], self.wide_bias, io["x_table"], io["wide_out"])
+        t.p_expand(io["ids"].shape, io["ones"], self.wide_bias, io["x_table"], io["wide_out"], side=side)
         h.wait(2)
         h.p_expand(io["x_hash"])
-        ft = self.ft * EMB128
-        io["deep_in"][:, :ft].copy_(io["x_table"])
-        io["deep_in"][:, ft:].copy_(io["x_hash"])
         main.wait_stream(side)
 
-    def _a2(self):
-        io = self._io
-        deep_out = self.dense.forward(io["deep_in"])
-        _, loss, delta, delta16, dsum = ops.sigmoid_xent(io["wide_out"], deep_out, io["label"], self._sens_t,
-                                                         out=io["loss_out"])
-        gx = self.dense.backward(delta16 if delta16.numel() else delta)
-        ft = self.ft * EMB128
-        io["g_table"].copy_(gx[:, :ft])
-        io["g_hash"].copy_(gx[:, ft:])
-        n = self.dense.flat.numel()
-        self._reduce[n:n + 1].copy_(dsum)                    # d loss / d wide_bias = sum(delta)
-        self._bwd = delta
-        err = self.tables.rk.err[0] | self.hash.rk.err[0]
-        return loss[0] + torch.where(err != 0, self._nan, self._zero)
-
     def _dense_update(self):
+        """All-reduce over peer memory (DistributedGradReducer(mean): the 1/G is in the loss scale) -> dense Adam ->
+        FTRL on wide_bias."""
         n = self.dense.flat.numel()
-        if self.world > 1:                                   # DistributedGradReducer(mean): the 1/G is in the loss scale
-            dist.all_reduce(self._reduce, group=self.group)
+        self._ar.run(self.tables.rk.err)
         ops.adam_begin_step(self.dense_hyper)
-        ops.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self._reduce[:n])
-        ops.ftrl_dense(self.wide_bias, self.bias_acc, self.bias_lin, self.bias_hyper, self._reduce[n:n + 1])
+        ops.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self._reduced[:n])
+        ops.ftrl_dense(self.wide_bias, self.bias_acc, self.bias_lin, self.bias_hyper, self._reduced[n:n + 1])
 
-    def _b(self):
-        """gradient exchange -> fused row updates (same lock-step order as _a1)."""
+    def _body(self):
         io, t, h = self._io, self.tables.rk, self.hash.rk
         main = torch.cuda.current_stream()
-        t.p_grads(self._bwd, io["g_table"])
-        h.p_grads(io["g_hash"])
-        t.wait(3)
         side = self.tables.owner_stream
+        self._forward_exchange()
+        # DenseLayers: the two lookups' outputs feed layer 0 as column blocks (no concatenation, no split of gx)
+        deep_out = self.dense.forward((io["x_table"], io["x_hash"]))
+        _, loss, delta, delta16, dsum = ops.sigmoid_xent(io["wide_out"], deep_out, io["label"], self._sens_t,
+                                                         out=io["loss_out"])
+        g_table, g_hash = self.dense.backward(delta16 if delta16.numel() else delta)
+        n = self.dense.flat.numel()
+        self._reduce[n:n + 1].copy_(dsum)                    # d loss / d wide_bias = sum(delta)
+        self._last = {"delta": delta, "g_table": g_table, "g_hash": g_hash}      # inspection (eager calls, tests)
+        # gradient exchange (same lock-step order), the all-reduce branch forked after the pushes were issued
+        t.p_grads(delta, g_table, side=side)
+        h.p_grads(g_hash)
+        self._dense_stream.wait_stream(main)
+        with torch.cuda.stream(self._dense_stream):
+            self._dense_update()
+            err = t.err[0] | h.err[0]                        # an exchange error poisons the loss the caller reads
+            torch.add(loss[0], torch.where(err != 0, self._nan, self._zero), out=self._loss)
+        t.wait(3)
         side.wait_stream(main)
         with torch.cuda.stream(side):                        # latency-bound FTRL beside the LazyAdam rows
             t.p_update_wide()
@@ -171,24 +169,14 @@ class ShardedMultitableStep:
         h.wait(3)
         h.p_update()
         main.wait_stream(side)
+        main.wait_stream(self._dense_stream)
+        return self._loss
 
     def _one_step(self):
-        main = torch.cuda.current_stream()
-        g = self._graphs
-        main.wait_stream(self._dense_stream)                 # last step's dense Adam wrote the weights
-        if g is not None:
-            g["a1"].replay()
-            g["a2"].replay()
+        if self._graphs is not None:
+            self._graphs.replay()
         else:
-            self._a1()
-            self._loss = self._a2()
-        self._dense_stream.wait_stream(main)
-        with torch.cuda.stream(self._dense_stream):          # NCCL + dense Adam under the gradient exchange
-            self._dense_update()
-        if g is not None:
-            g["b"].replay()
-        else:
-            self._b()
+            self._body()
         self._steps += 1
         if self.evict_every and self._steps % self.evict_every == 0:
             self.hash.rk.table.evict()                       # eviction sweep of this rank's MapParameter (eager)
@@ -212,19 +200,12 @@ class ShardedMultitableStep:
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         if graph:
-            graphs, pool = {}, None
-            self.launches_per_step = 3                       # the eager dense Adam triple
-            for name, fn in (("a1", self._a1), ("a2", self._a2), ("b", self._b)):
-                gr = torch.cuda.CUDAGraph()
-                n0 = _lib.launch_count()
-                with torch.cuda.graph(gr, pool=pool):
-                    out = fn()
-                self.launches_per_step += _lib.launch_count() - n0
-                if name == "a2":
-                    self._loss = out
-                pool = pool or gr.pool()
-                graphs[name] = gr
-            self._graphs = graphs
+            gr = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(gr, stream=self._main_stream):
+                self._body()
+            self.launches_per_step = _lib.launch_count() - n0
+            self._graphs = gr
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
 
@@ -256,3 +237,4 @@ class ShardedMultitableStep:
     def close(self):
         self.tables.close()
         self.hash.close()
+        self._ar.close()

@@ -323,14 +323,8 @@ class DenseStack:
                 b.normal_(0.0, 0.01, generator=generator)
         self._acts = None
         self._flat16 = None
-        self._ones = None
         self._mm_f32 = None
         self._head = False
-
-    def _ones16(self, b):
-        if self._ones is None or self._ones.shape[1] != b:
-            self._ones = torch.ones((1, b), dtype=torch.float16, device=self.flat.device)
-        return self._ones
 
     def _wgrad(self, h_in, g, out):
         """gw = h_in^T g for fp16 operands, fp32 accumulate.  With out_dtype the GEMM writes fp32 straight into the
@@ -360,20 +354,40 @@ class DenseStack:
                 self.b16.append(self._flat16[o:o + m]); o += m
         self._flat16.copy_(self.flat)
 
+    def _first_layer_parts(self, xs, w, b, relu):
+        """Layer 0 on an input given as column blocks [B, k_j] (sum k_j = dims[0]) WITHOUT concatenating them: the
+        blocks meet row blocks of the weight matrix, out = relu(b + sum_j x_j @ W[o_j : o_j + k_j])."""
+        o, h = 0, None
+        for x in xs:
+            k = x.shape[1]
+            h = torch.addmm(b, x, w[o:o + k]) if h is None else h.addmm_(x, w[o:o + k])
+            o += k
+        assert o == self.dims[0], "input blocks do not add up to the first layer's width"
+        return torch.relu_(h) if relu else h
+
     def forward(self, x):
-        """x: [B, dims[0]] fp32, or fp16 when convert_dtype (mrec_gather_masked can emit it directly).
+        """x: [B, dims[0]] fp32, or fp16 when convert_dtype (mrec_gather_masked can emit it directly) — or a tuple of
+        column blocks of it (two lookups feeding one tower: no concatenation copy; backward then returns a tuple).
         Returns the stack output in fp32."""
         nl = len(self.weights)
+        parts = isinstance(x, (tuple, list))
+        if parts and (nl < 2 or (self.dims[-1] == 1 and nl == 1)):
+            raise ValueError("an input in column blocks needs at least one hidden layer")
         acts = [x]
         # a one-unit output layer without activation runs as mrec_dense_head_fwd / _bwd instead of skinny GEMMs
-        head = x.is_cuda and self.dims[-1] == 1 and not self.last_activation
+        head = self.dims[-1] == 1 and not self.last_activation
         self._head = head
         if self.convert_dtype:
             self.refresh_half()
-            h = x if x.dtype == torch.float16 else x.half()
-            acts[0] = h
+            if parts:
+                h = acts[0] = tuple(t if t.dtype == torch.float16 else t.half() for t in x)
+            else:
+                h = x if x.dtype == torch.float16 else x.half()
+                acts[0] = h
             for i in range(nl):
-                if i + 1 < nl or self.last_activation:
+                if i == 0 and parts:
+                    h = self._first_layer_parts(h, self.w16[0], self.b16[0], True)
+                elif i + 1 < nl or self.last_activation:
                     h = torch._addmm_activation(self.b16[i], h, self.w16[i], use_gelu=False)
                 elif head:
                     h = ops.dense_head_fwd(h, self.w16[i].view(-1), self.b16[i])
@@ -384,7 +398,9 @@ class DenseStack:
             return h if head else h.float()
         h = x
         for i, (w, b) in enumerate(zip(self.weights, self.biases)):
-            if head and i + 1 == nl:
+            if i == 0 and parts:
+                a = self._first_layer_parts(h, w, b, False)
+            elif head and i + 1 == nl:
                 a = ops.dense_head_fwd(h, w.view(-1), b)
             else:
                 a = torch.addmm(b, h, w)
@@ -401,11 +417,10 @@ class DenseStack:
         acts = self._acts
         nl = len(self.weights)
         g = g_out.half() if (self.convert_dtype and g_out.dtype != torch.float16) else g_out
-        fused = g.is_cuda          # CUDA: ReluGrad + BiasAddGrad in one mrec_relu_bwd_bias pass, fp32 sums in place
         premasked = False
         for i in range(nl - 1, -1, -1):
             h_in, h_out = acts[i], acts[i + 1]
-            if fused and self._head and i + 1 == nl:
+            if self._head and i + 1 == nl:
                 # output unit: rank-1 input gradient, weight / bias gradients and the previous layer's
                 # ReluGrad + BiasAddGrad in one kernel
                 w = self.w16[i] if self.convert_dtype else self.weights[i]
@@ -416,18 +431,24 @@ class DenseStack:
             masked = i + 1 < nl or self.last_activation
             if premasked:
                 premasked = False
-            elif fused:
+            else:                  # ReluGrad + BiasAddGrad in one mrec_relu_bwd_bias pass, fp32 sums in place
                 g = ops.relu_bwd_bias(g, h_out if masked else None, self.gb[i])
-            elif masked:
-                g = torch.ops.aten.threshold_backward(g, h_out, 0)
-            if self.convert_dtype:
+            w = self.w16[i] if self.convert_dtype else self.weights[i]
+            if isinstance(h_in, tuple):              # layer 0 fed in column blocks: row blocks of gw / w, one gx each
+                o, gxs = 0, []
+                for x in h_in:
+                    k = x.shape[1]
+                    if self.convert_dtype:
+                        self._wgrad(x, g, self.gw[i][o:o + k])
+                    else:
+                        torch.mm(x.t(), g, out=self.gw[i][o:o + k])
+                    gxs.append(torch.mm(g, w[o:o + k].t()))
+                    o += k
+                g = tuple(gxs)
+            elif self.convert_dtype:
                 self._wgrad(h_in, g, self.gw[i])
-                if not fused:
-                    self.gb[i].copy_(torch.mm(self._ones16(g.shape[0]), g).view(-1))
-                g = torch.mm(g, self.w16[i].t())
+                g = torch.mm(g, w.t())
             else:
                 torch.mm(h_in.t(), g, out=self.gw[i])
-                if not fused:
-                    torch.sum(g, 0, out=self.gb[i])
-                g = torch.mm(g, self.weights[i].t())
+                g = torch.mm(g, w.t())
         return g

@@ -475,6 +475,11 @@ def peer_signal(payload, payload_ptrs, flag_ptrs, epoch):
     _lib.aot_call("mrec_peer_signal", [payload, payload_ptrs, flag_ptrs, epoch, _dummy(epoch.device)])
 
 
+def peer_allreduce(src_ptrs, dst_ptrs, ctrl, dst):
+    """dst (on every rank) = sum over ranks of the source buffers, added in rank order by the slice owners."""
+    _lib.aot_call("mrec_peer_allreduce", [src_ptrs, dst_ptrs, ctrl, dst])
+
+
 def peer_wait(flags, epoch, err, max_cycles_log2=None):
     """Spin (bounded) until every flag slot reached epoch; a time-out sets bit 0 of err instead of hanging."""
     if max_cycles_log2 is None:

@@ -21,6 +21,7 @@ GPU in phase-major order (tests: all of the offset / inbox logic without a multi
 sharded.ShardedWideDeepStep.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -29,7 +30,35 @@ from . import _lib, ops
 from .sharded import ShardPlan, ShardedWideDeepStep, _RawCuda
 
 N_PHASES = 4
+# bisection switches (diagnostics only): keep the dim-1 twins / the dense update in line on the main stream
+_NO_WIDE_FORK = os.environ.get("MREC_PEER_NO_WIDE_FORK", "0") == "1"
+_NO_DENSE_FORK = os.environ.get("MREC_PEER_NO_DENSE_FORK", "0") == "1"
 _PEER_BUFFERS = ("ball", "keys_in", "land_deep", "land_wide", "grad_in", "gwide_in", "flags")
+
+
+class _Fork:
+    """`with _Fork(side):` runs the body on `side` after everything queued on the current stream so far; `_join(side)`
+    makes the current stream wait for it.  side=None: the body runs in line."""
+
+    def __init__(self, side):
+        self.side = side
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _join(side):
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
 
 
 class PeerRank:
@@ -183,25 +212,33 @@ class PeerRank:
         self.wait(1)
         self.p_owner_dedup(nxt)
 
-    def p_serve(self):
+    # `side` (a stream, optional) in the next three: the dim-1 work of the wide vector runs there, beside the
+    # bandwidth-bound deep rows (forked from / joined back into the current stream — a parallel branch when captured)
+    def p_serve(self, side=None):
+        with _Fork(side):
+            ops.gather_to_peers(self.wide, self.keys_in, self.ptrs["land_wide"], self.dst_off, self.src_off)
         ops.gather_to_peers(self.deep, self.keys_in, self.ptrs["land_deep"], self.dst_off, self.src_off)
-        ops.gather_to_peers(self.wide, self.keys_in, self.ptrs["land_wide"], self.dst_off, self.src_off)
+        _join(side)
         self.signal(2)
 
-    def p_expand(self, ids_shape, wts, wide_bias, deep_out, wide_out):
+    def p_expand(self, ids_shape, wts, wide_bias, deep_out, wide_out, side=None):
         inverse = self.uq.inverse.view(ids_shape)
+        with _Fork(side):
+            ops.gather_reduce(self.buf["land_wide"], inverse, wts, wide_bias, out=wide_out)
         ops.gather_masked(self.buf["land_deep"], inverse, wts, out=deep_out)
-        ops.gather_reduce(self.buf["land_wide"], inverse, wts, wide_bias, out=wide_out)
+        _join(side)
         self._wts = wts
 
-    def p_grads(self, delta, gx):
+    def p_grads(self, delta, gx, side=None):
         mask = self._wts.reshape(-1)
+        with _Fork(side):
+            ops.segment_sum(delta, mask, self.uq, dim=1, out=self.gs_wide)
+            ops.push_rows_to_peers(self.gs_wide, self.bounds, self.inbox_off, self.ptrs["gwide_in"], self._cap_like,
+                                   self._mod_none, self.err)
         # deep rows: the segment sums are stored straight into the owners' gradient inboxes (no local gsum pass)
         ops.segment_sum_to_peers(gx.view(self.n, self.dim), mask, self.uq, self.bounds, self.inbox_off,
                                  self.ptrs["grad_in"], self._cap_like, self.err, dim=self.dim)
-        ops.segment_sum(delta, mask, self.uq, dim=1, out=self.gs_wide)
-        ops.push_rows_to_peers(self.gs_wide, self.bounds, self.inbox_off, self.ptrs["gwide_in"], self._cap_like,
-                               self._mod_none, self.err)
+        _join(side)
         self.signal(3)
 
     def p_owner_dedup(self, nxt=False):
@@ -577,6 +614,60 @@ class _IpcArena:
         self.local = {}
 
 
+class PeerAllReduce:
+    """Sum of a flat fp32 buffer over the ranks through CUDA-IPC peer memory, capturable in a CUDA graph (NCCL inside a
+    captured graph hung on this stack, and an eager collective cuts the step into several graphs): `src` is this
+    rank's contribution (write it in place — e.g. make it the DenseLayers' flat gradient buffer), `run()` leaves the
+    sum of all ranks in `dst` on every rank.  signal 0 / wait 0: every rank's src is complete; mrec_peer_allreduce:
+    rank r adds the r-th slice of the G sources in rank order and stores it into all G dst buffers; signal 1 / wait 1:
+    every slice has arrived.  The replicas' sums are bit-identical.  Re-use is safe without a third barrier: a peer
+    reads my src only before its signal 1, which I wait for before anything can overwrite src; a peer overwrites my
+    dst only after wait 0 of the NEXT round, which needs my next signal 0 — issued after I consumed dst."""
+
+    def __init__(self, n, device, group=None):
+        self.group = group
+        g, me = dist.get_world_size(group), dist.get_rank(group)
+        self.device = dev = torch.device(device)
+        arena = self._arena = _IpcArena(group)
+        holder = {}
+
+        def make():
+            alloc = arena.alloc(dev)
+            holder["src"] = alloc("ar_src", (n,), torch.float32)
+            holder["dst"] = alloc("ar_dst", (n,), torch.float32)
+            holder["flags"] = alloc("ar_flags", (2 * g,), torch.int32)
+            for t in holder.values():
+                t.zero_()
+            return self
+
+        self._base = None
+        _connect_collectively(make, arena, group, dev)
+        self.src, self.dst, self.flags = holder["src"], holder["dst"], holder["flags"]
+        base = self._base
+        t = lambda lst: torch.tensor(lst, dtype=torch.int64, device=dev)
+        self.p_src, self.p_dst = t(base["ar_src"]), t(base["ar_dst"])
+        self.p_flag = [t([base["ar_flags"][s] + (ph * g + me) * 4 for s in range(g)]) for ph in range(2)]
+        self.flag_views = [self.flags[ph * g:(ph + 1) * g] for ph in range(2)]
+        self.epoch = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.ctrl = torch.tensor([me, g], dtype=torch.int32, device=dev)
+        self._none = t([0] * g)
+        self._no_payload = torch.empty(0, dtype=torch.int32, device=dev)
+
+    def connect(self, base):                                 # called by _connect_collectively
+        self._base = base
+
+    def run(self, err):
+        """On the current stream.  err[1] int32: bit 0 is raised when a wait times out."""
+        for ph in range(2):
+            ops.peer_signal(self._no_payload, self._none, self.p_flag[ph], self.epoch[ph])
+            ops.peer_wait(self.flag_views[ph], self.epoch[ph], err)
+            if ph == 0:
+                ops.peer_allreduce(self.p_src, self.p_dst, self.ctrl, self.dst)
+
+    def close(self):
+        self._arena.close()
+
+
 class PeerShardedTables:
     """Multi-process form: drop-in for sharded.ShardedWideDeepTables inside sharded.ShardedWideDeepStep
     (`plan_batch` / `lookup` / `update` / `gather_full`), with nothing read back to the host."""
@@ -586,9 +677,8 @@ class PeerShardedTables:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
-        self.cuda = True
         self.plan_stream = None
-        self.owner_stream = torch.cuda.Stream(device=self.device)
+        self.owner_stream = torch.cuda.Stream(device=self.device, priority=-1)       # exchange kernels: see main_stream
         self._side_open = False
         arena = self._arena = _IpcArena(group)
         self.rk = _connect_collectively(
@@ -615,14 +705,23 @@ class PeerShardedTables:
 
     def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
         rk = self.rk
-        rk.p_serve()
+        side = None if _NO_WIDE_FORK else self.owner_stream
+        rk.p_serve(side=side)
         rk.wait(2)
-        rk.p_expand(plan.ids.shape, wts, wide_bias, deep_out, wide_out)
+        rk.p_expand(plan.ids.shape, wts, wide_bias, deep_out, wide_out, side=side)
         return wide_out, deep_out
 
     def update(self, delta, gx):
+        self.push_grads(delta, gx)
+        self.apply_grads()
+
+    def push_grads(self, delta, gx):
+        """Segment sums of this rank's gradients into the owners' inboxes (NVLink stores), then signal 3."""
+        self.rk.p_grads(delta, gx, side=None if _NO_WIDE_FORK else self.owner_stream)
+
+    def apply_grads(self):
+        """wait 3, then the fused row updates of the rows this rank owns."""
         rk = self.rk
-        rk.p_grads(delta, gx)
         rk.wait(3)
         main = torch.cuda.current_stream()
         self.owner_stream.wait_stream(main)
@@ -670,91 +769,106 @@ class _DevicePlan:
 
 
 class PeerShardedWideDeepStep(ShardedWideDeepStep):
-    """Wide&Deep step over PeerShardedTables.  Nothing in the step depends on a host-side size, so `capture`
-    records plan -> exchange -> DenseLayers -> gradient exchange -> fused row updates as three CUDA graphs; the mean
-    all-reduce of the DenseLayer gradients and the dense Adam stay eager between them (NCCL in a captured graph
-    hung on this stack), i.e. a step costs three graph launches + one collective + two kernel launches of host
-    time."""
+    """Wide&Deep step over PeerShardedTables.  Nothing in the step depends on a host-side size and the DenseLayer
+    gradient all-reduce is a kernel over peer memory (PeerAllReduce), so `capture` records the WHOLE step — forward
+    exchange, DenseLayers, gradient exchange, fused row updates, all-reduce, dense Adam, and the next batch's key phase
+    underneath the DenseLayers — as ONE CUDA graph per key-phase buffer set: a step costs one graph launch of host
+    time.  Branches of the graph (forked streams while capturing):
+
+        main    serve -> signal/wait 2 -> expand -> DenseLayers fwd / loss / bwd -> segment sums into the owners'
+                inboxes -> signal/wait 3 -> LazyAdam on the owned rows
+        wide    the dim-1 twin of every exchange kernel (serve, reduce, gradient push, FTRL) beside the deep one
+        plan    after expand: wait for the staged copy of the NEXT batch (an external event, so the copy itself stays
+                outside the graph and overlaps the forward exchange), then its whole key phase on the other buffer set
+        dense   after the DenseLayer backward: all-reduce over peer memory -> dense Adam -> loss poison, beside the
+                gradient exchange
+
+    The input batch is double-buffered too: set s reads slots[s]; the next batch is copied (H2D from pinned memory, or
+    D2D) straight into slots[s ^ 1] on a copy stream, so no input copy sits on the step's critical path."""
 
     def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
                  use_mixed_precision=True, group=None, graph=True, cap_rows=None):
+        self._ar = None
+
+        def storage(n):
+            self._ar = PeerAllReduce(n, device, group)
+            return torch.zeros(n, dtype=torch.float32, device=device), self._ar.src
+
         super().__init__(batch_size, vocab_size, emb_dim, hidden, device, seed=seed, sens=sens, fields=fields,
                          use_mixed_precision=use_mixed_precision, group=group, graph_dense=False,
                          tables_factory=lambda: PeerShardedTables(vocab_size, emb_dim, batch_size * fields, device,
-                                                                  group=group, seed=seed, sens=sens, cap_rows=cap_rows))
+                                                                  group=group, seed=seed, sens=sens, cap_rows=cap_rows),
+                         dense_storage=storage)
         self._nan = torch.tensor(float("nan"), dtype=torch.float32, device=self.device)
         self._zero = torch.zeros((), dtype=torch.float32, device=self.device)
         self._graph_step = graph
         self._graphs = None
-        self._loss = None
-        self._bwd = None
+        self._loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        # Priorities (captured into the graph's kernel nodes): the step's critical path — exchange kernels, DenseLayers,
+        # row updates — is recorded on high-priority streams; the all-reduce + dense Adam branch and the next batch's
+        # key phase only have to finish somewhere under it, so their CTAs queue behind the critical ones.
+        self._main_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._dense_stream = torch.cuda.Stream(device=self.device)
         self._stage_stream = torch.cuda.Stream(device=self.device)
         self._plan_stream = torch.cuda.Stream(device=self.device)
-        self._stage = None
+        self._staged_ev = torch.cuda.Event(external=True)    # a wait NODE in the graph: the copy stays outside
         self._staged_for = None
 
-    # The step in fixed-shape pieces, each captured once per key-phase set (the two sets alternate step by step):
-    #   pre  key phase of the current batch in line (first step, or no look-ahead was given)
-    #   a1   serve -> wait -> expand: the only exchange work in front of the DenseLayers in steady state
-    #   a2   DenseLayers forward / loss / backward, with the NEXT batch's whole key phase (plan, publish, key push,
-    #        owner dedup) on a forked branch underneath (a2_plain: without it)
-    #   b    gradient exchange -> fused row updates (one per a2 variant: it reads that variant's gradient buffers)
-    # Between a1 and a2 the host makes the stream wait for the staged copy of the next batch (it overlaps a1);
-    # between a2 and b it launches the DenseLayer mean all-reduce + Adam on a side stream (they overlap b).
+    def _dense_update(self):
+        """All-reduce over peer memory + dense Adam (capturable; replaces the NCCL collective of the base class)."""
+        self._ar.run(self.tables.rk.err)
+        ops.adam_begin_step(self.dense_hyper)
+        ops.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self._ar.dst)
+
     def _pre(self):
-        self.tables.plan_batch(self._slots[0][0])
+        """Key phase of the current batch in line (first step, or no look-ahead was given)."""
+        self.tables.plan_batch(self._slots[self.tables.rk.cur][0])
 
-    def _a1(self):
-        ids, wts, _ = self._slots[0]
-        self.tables.lookup(_DevicePlan(ids), wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
-
-    def _a2(self, ahead=True):
+    def _body(self, ahead=True):
         main = torch.cuda.current_stream()
+        rk = self.tables.rk
+        ids, wts, label = self._slots[rk.cur]
+        self.tables.lookup(_DevicePlan(ids), wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
         if ahead:
             self._plan_stream.wait_stream(main)
             with torch.cuda.stream(self._plan_stream):
-                self.tables.key_phase_next(self._stage[0])
-        self._io["label"].copy_(self._slots[0][2])
-        loss, delta, gx = self._dense_segment()
+                self._plan_stream.wait_event(self._staged_ev)            # the next batch is on the device
+                self.tables.key_phase_next(self._slots[rk.cur ^ 1][0])
+        loss, delta, gx = self._dense_segment(label)
+        # the all-reduce shares the NVLink ports with the gradient push, which is on the critical path: the dense
+        # branch forks AFTER the push has been issued and runs beside the owners' row updates (HBM-bound, local)
+        self.tables.push_grads(delta, gx)
+        dense_stream = main if _NO_DENSE_FORK else self._dense_stream
+        dense_stream.wait_stream(main)
+        with torch.cuda.stream(dense_stream):
+            self._dense_update()
+            # an exchange error (a wait that timed out, an inbox that overflowed) must not train on silently: the loss
+            # the caller reads turns NaN from the step after the one that raised the bit
+            torch.add(loss, torch.where(rk.err[0] != 0, self._nan, self._zero), out=self._loss)
+        self.tables.apply_grads()
+        main.wait_stream(self._dense_stream)
         if ahead:
             main.wait_stream(self._plan_stream)
-        self._bwd = (delta, gx)
-        # an exchange error (a wait that timed out, an inbox that overflowed) must not train on silently: the loss
-        # the caller reads turns NaN from the step after the one that raised the bit
-        return loss + torch.where(self.tables.rk.err[0] != 0, self._nan, self._zero)
-
-    def _b(self):
-        self.tables.update(*self._bwd)
+        return self._loss
 
     def _one_step(self, adopt=False, ahead=True):
-        main = torch.cuda.current_stream()
         rk = self.tables.rk
-        main.wait_stream(self._dense_stream)                 # last step's dense Adam wrote the weights
         if adopt:
             rk.p_adopt()                                     # the set whose key phase ran under the previous step
         g = self._graphs[rk.cur] if self._graphs is not None else None
         if not adopt:
             g["pre"].replay() if g is not None else self._pre()
-        g["a1"].replay() if g is not None else self._a1()
-        main.wait_stream(self._stage_stream)                 # the next batch is on the device (copied under a1)
         if g is not None:
-            g["a2" if ahead else "a2_plain"].replay()
+            g["step" if ahead else "step_plain"].replay()
         else:
-            self._loss = self._a2(ahead)
-        self._dense_stream.wait_stream(main)
-        with torch.cuda.stream(self._dense_stream):          # NCCL + dense Adam under the gradient exchange
-            self._dense_update()
-        if g is not None:
-            g["b" if ahead else "b_plain"].replay()
-        else:
-            self._b()
+            self._body(ahead)
         return self._loss
 
     def capture(self, ids, wts, label, warmup=3):
-        self._slots = [tuple(t.clone() for t in (ids, wts, label))]
-        self._stage = tuple(t.clone() for t in self._slots[0])
+        self._slots = [tuple(t.clone() for t in (ids, wts, label)) for _ in range(2)]
         self._ensure_io(ids)
+        with torch.cuda.stream(self._stage_stream):
+            self._staged_ev.record()
         for _ in range(warmup):
             self._one_step(ahead=False)
         torch.cuda.synchronize()
@@ -764,22 +878,18 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
             rk = self.tables.rk
             cur0 = rk.cur
             sets, pool = [], None
-            self.launches_per_step = 2                       # the eager dense Adam pair (begin_step + adam_dense)
+            self.launches_per_step = 0
             for si in range(2):
                 rk.use_set(si)
                 graphs = {}
-                # `b` consumes the gradient tensors its `a2` produced: every a2 variant is followed by its own b
-                for name, fn in (("pre", self._pre), ("a1", self._a1), ("a2", lambda: self._a2(True)), ("b", self._b),
-                                 ("a2_plain", lambda: self._a2(False)), ("b_plain", self._b)):
+                for name, fn in (("pre", self._pre), ("step", lambda: self._body(True)),
+                                 ("step_plain", lambda: self._body(False))):
                     gr = torch.cuda.CUDAGraph()
                     n0 = _lib.launch_count()
-                    with torch.cuda.graph(gr, pool=pool):
-                        out = fn()
-                    if si == 0 and name in ("a1", "a2", "b"):        # steady state replays a1 + a2 + b
-                        self.launches_per_step += _lib.launch_count() - n0
-                    if name in ("a2", "a2_plain"):
-                        graphs[name + "_loss"] = out
-                        graphs[name + "_bwd"] = self._bwd            # kept alive: the next graph reads these buffers
+                    with torch.cuda.graph(gr, pool=pool, stream=self._main_stream):
+                        fn()
+                    if si == 0 and name == "step":                   # steady state replays `step` only
+                        self.launches_per_step = _lib.launch_count() - n0
                     pool = pool or gr.pool()
                     graphs[name] = gr
                 sets.append(graphs)
@@ -788,34 +898,34 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
         self._staged_for = None
-        return self._slots[0]
+        return self._slots[self.tables.rk.cur]
 
     def replay(self, ids=None, wts=None, label=None, next_batch=None):
-        """One step on (ids, wts, label).  next_batch (host-pinned or device tensors): staged on a copy stream during
-        this step AND taken through its key phase (dedup, bucket bounds, key exchange, owner dedup) underneath this
-        step's DenseLayers; pass the same tensors as the next call's batch to use both.  Every rank must make the same
-        choice (the key phase is a collective of the group)."""
+        """One step on (ids, wts, label).  next_batch (host-pinned or device tensors): copied into the other input
+        slot on a copy stream during this step AND taken through its key phase (dedup, bucket bounds, key exchange,
+        owner dedup) underneath this step's DenseLayers; pass the same tensors as the next call's batch to use both.
+        Every rank must make the same choice (the key phase is a collective of the group)."""
         main = torch.cuda.current_stream()
-        adopt = False
-        if ids is not None:
-            if self._staged_for is not None and self._staged_for is ids:
-                for d, s in zip(self._slots[0], self._stage):        # staged (and keyed) one step ahead
-                    d.copy_(s, non_blocking=True)
-                adopt = True
-            else:
-                for d, s in zip(self._slots[0], (ids, wts, label)):
-                    d.copy_(s, non_blocking=True)
+        rk = self.tables.rk
+        adopt = ids is not None and self._staged_for is not None and self._staged_for is ids
+        if ids is not None and not adopt:
+            for d, s in zip(self._slots[rk.cur], (ids, wts, label)):
+                d.copy_(s, non_blocking=True)
         self._staged_for = None
         ahead = next_batch is not None
         if ahead:
+            nxt = rk.cur if adopt else rk.cur ^ 1            # the slot of the set the next step will run on
             ev = torch.cuda.Event()
-            ev.record(main)                                  # the staging buffers have been consumed
+            ev.record(main)                                  # its last reader (the step before this one) is enqueued
             self._stage_stream.wait_event(ev)
             with torch.cuda.stream(self._stage_stream):
-                for d, s in zip(self._stage, next_batch):
+                for d, s in zip(self._slots[nxt], next_batch):
                     d.copy_(s, non_blocking=True)
+                self._staged_ev.record()
             self._staged_for = next_batch[0]
         loss = self._one_step(adopt, ahead)
-        if self._graphs is not None:
-            loss = self._graphs[self.tables.rk.cur]["a2_loss" if ahead else "a2_plain_loss"]
         return loss, loss
+
+    def close(self):
+        self.tables.close()
+        self._ar.close()

@@ -19,7 +19,16 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import ops as _cuda_ops
+from . import ops
+
+# The device runtime the streams / events / pinned buffers come from.  There is one path (CUDA); the gloo CPU tests of
+# the exchange logic substitute stand-ins for `ops` and `_cu` from the test side (tests/oracle_kernels.py,
+# tests/fake_cuda.py), like tests/fake_peer_ops.py does for the peer protocol.
+_cu = torch.cuda
+
+
+def _pinned(t):
+    return t.pin_memory()
 
 # MREC_SHARDED_GRAPH=0 keeps the DenseLayer segment eager; MREC_SHARDED_AHEAD=0 plans every batch in line.
 _ENV_GRAPH = os.environ.get("MREC_SHARDED_GRAPH", "1") != "0"
@@ -130,25 +139,19 @@ class BatchPlan:
 
 
 class ShardedWideDeepTables:
-    """The wide (dim 1) and deep (dim D) tables of Wide&Deep, row-sharded, with their FTRL / LazyAdam state.
+    """The wide (dim 1) and deep (dim D) tables of Wide&Deep, row-sharded, with their FTRL / LazyAdam state."""
 
-    `kernels` is the module providing gather / unique / segment_sum / sparse_* — mindrec_b200.ops (CUDA) in
-    production; the gloo CPU tests of the exchange logic inject the oracle."""
-
-    def __init__(self, vocab_size, emb_dim, device, group=None, seed=1, sens=1024.0, kernels=_cuda_ops,
-                 init_std=0.01):
+    def __init__(self, vocab_size, emb_dim, device, group=None, seed=1, sens=1024.0, init_std=0.01):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         # planning runs on a side stream: it needs its own communicator (NCCL serialises per communicator)
         self.plan_group = dist.new_group() if (dist.is_initialized() and self.world > 1) else None
         self.plan = ShardPlan(vocab_size, self.world)
-        self.k = kernels
         self.dim = emb_dim
         self.device = torch.device(device)
-        self.cuda = self.device.type == "cuda"
-        self.plan_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
-        self.owner_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.plan_stream = _cu.Stream(device=self.device)
+        self.owner_stream = _cu.Stream(device=self.device)
         r = self.plan.rows_per_rank
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + self.rank)
@@ -159,8 +162,8 @@ class ShardedWideDeepTables:
         self.m = torch.zeros_like(self.deep)
         self.v = torch.zeros_like(self.deep)
         # gradients_mean=True: the owner sums contributions of all ranks, each already divided by G
-        self.adam_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=self.device)
-        self.ftrl_hyper = kernels.ftrl_hyper(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens * self.world, device=self.device)
+        self.adam_hyper = ops.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=self.device)
+        self.ftrl_hyper = ops.ftrl_hyper(5e-2, l1=1e-8, l2=1e-8, loss_scale=sens * self.world, device=self.device)
         self._bound_like = torch.empty((self.world * r, 0), device=self.device)
         self._vocab_like = torch.empty((vocab_size, 0), device=self.device)
         self._owners_like = torch.empty((self.world, r, 0), device=self.device)   # shape carrier: G, R
@@ -172,21 +175,19 @@ class ShardedWideDeepTables:
         self._bufs = {}
         self.peer = None
         self._peer_tried = False
-        self._bar = torch.zeros(1, dtype=torch.float32, device=self.device) if self.cuda else None
+        self._bar = torch.zeros(1, dtype=torch.float32, device=self.device)
         n_b = self.world * (self.world + 1)
-        self._pinned = [torch.empty(n_b, dtype=torch.int32).pin_memory() for _ in range(2)] if self.cuda else None
+        self._pinned = [_pinned(torch.empty(n_b, dtype=torch.int32)) for _ in range(2)]
 
     def _unique(self, key, table_like, tag):
         """mrec_unique into cached, geometrically grown output buffers (no per-step allocation)."""
         n = key.numel()
-        if not hasattr(self.k, "UniqueResult"):
-            return self.k.unique(key, table_like=table_like)
         base = self._uq.get(tag)
         if base is None or base.n < n:
-            base = self.k.UniqueResult(max(n, int(1.5 * base.n) if base else n), key.dtype, key.device)
+            base = ops.UniqueResult(max(n, int(1.5 * base.n) if base else n), key.dtype, key.device)
             self._uq[tag] = base
-        return self.k.unique(key, table_like=table_like, result=base if base.n == n else base.sliced(n),
-                             ws_tag="unique_" + tag)
+        return ops.unique(key, table_like=table_like, result=base if base.n == n else base.sliced(n),
+                          ws_tag="unique_" + tag)
 
     def _buf(self, tag, rows, cols, dtype=torch.float32):
         """Grow-only [rows, cols] scratch buffer (variable per-step sizes without reallocation)."""
@@ -201,15 +202,15 @@ class ShardedWideDeepTables:
     def plan_batch(self, ids, ahead=False):
         """Dedup + bucket the batch's keys and exchange the bucket bounds.  With ahead=True the work is queued
         on the side stream (double-buffered outputs) and the caller keeps enqueuing the current step."""
-        k, g = self.k, self.world
+        k, g = ops, self.world
         plan = BatchPlan()
         plan.ids, plan.send = ids, None
         slot = self._slot
         self._slot ^= 1
-        side = self.plan_stream if (ahead and self.cuda) else None
+        side = self.plan_stream if ahead else None
         if side is not None:
-            side.wait_stream(torch.cuda.current_stream())
-        ctx = torch.cuda.stream(side) if side is not None else _Null()
+            side.wait_stream(_cu.current_stream())
+        ctx = _cu.stream(side) if side is not None else _Null()
         with ctx:
             key = k.shard_remap(ids, self._vocab_like, self._owners_like)
             plan.uq = self._unique(key, self._bound_like, "plan%d" % slot)
@@ -233,22 +234,18 @@ class ShardedWideDeepTables:
                 plan.src_off[1:] = torch.cumsum(ab[:, self.rank + 1] - ab[:, self.rank], 0)
             else:
                 plan.dst_off = plan.src_off = None
-            if self.cuda:
-                plan.bounds_host = self._pinned[slot]
-                plan.bounds_host.copy_(allb, non_blocking=True)
-                plan.event = torch.cuda.Event()
-                plan.event.record()
-            else:
-                plan.bounds_host, plan.event = allb.clone(), None
+            plan.bounds_host = self._pinned[slot]
+            plan.bounds_host.copy_(allb, non_blocking=True)
+            plan.event = _cu.Event()
+            plan.event.record()
         return plan
 
     # ---- forward ----------------------------------------------------------------------------------
     def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
         """Fill deep_out [B, F*D] (fp32 | fp16) and wide_out [B,1] for the planned batch."""
-        k, g = self.k, self.world
+        k, g = ops, self.world
         plan.finalize(self.rank, g)                                   # the step's one host read-back
-        if plan.event is not None:
-            torch.cuda.current_stream().wait_event(plan.event)
+        _cu.current_stream().wait_event(plan.event)
         uq, n_u, n_r, send, recv = plan.uq, plan.n_u, plan.n_r, plan.send, plan.recv
         b, f = plan.ids.shape
         local_rows_send = (uq.uniq[:n_u] % self.plan.rows_per_rank).contiguous()
@@ -258,7 +255,7 @@ class ShardedWideDeepTables:
         else:
             rows_recv.copy_(local_rows_send)
         # owner side: return the requested rows of both tables
-        if g > 1 and self.cuda and _ENV_PEER and not self._peer_tried:
+        if g > 1 and _ENV_PEER and not self._peer_tried:
             self._peer_tried = True
             try:                                   # landing buffers sized for the worst case U = N
                 self.peer = PeerLanding(uq.n, (self.dim, 1), self.device, self.group)
@@ -292,21 +289,18 @@ class ShardedWideDeepTables:
         # underneath the DenseLayer segment (the same row can arrive from several ranks)
         uq2, ev = None, None
         if n_r > 0:
-            if self.cuda:
-                self.owner_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self.owner_stream):
-                    uq2 = self._unique(rows_recv, self.deep, "owner")
-                    ev = torch.cuda.Event()
-                    ev.record()
-            else:
+            self.owner_stream.wait_stream(_cu.current_stream())
+            with _cu.stream(self.owner_stream):
                 uq2 = self._unique(rows_recv, self.deep, "owner")
+                ev = _cu.Event()
+                ev.record()
         self._ctx = (plan, rows_recv, wts, uq2, ev)
         return wide_out, deep_out
 
     # ---- backward + update ------------------------------------------------------------------------
     def update(self, delta, gx):
         """delta: [B,1] logit gradient (x sens), gx: [B, F*D] deep-input gradient (x sens, fp32 or fp16)."""
-        k, g = self.k, self.world
+        k, g = ops, self.world
         plan, rows_recv, wts, uq2, ev = self._ctx
         uq, n_u, n_r, send, recv = plan.uq, plan.n_u, plan.n_r, plan.send, plan.recv
         n = uq.n
@@ -326,17 +320,13 @@ class ShardedWideDeepTables:
             return
         # owner side: fused row updates over the (already deduplicated) received rows; the latency-bound FTRL
         # update of the wide shard runs on the side stream beside the LazyAdam update of the deep shard
-        if ev is not None:
-            main = torch.cuda.current_stream()
-            main.wait_event(ev)
-            self.owner_stream.wait_stream(main)
-            with torch.cuda.stream(self.owner_stream):
-                k.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, rg_wide[:n_r], None, uq2)
-            k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
-            main.wait_stream(self.owner_stream)
-        else:
+        main = _cu.current_stream()
+        main.wait_event(ev)
+        self.owner_stream.wait_stream(main)
+        with _cu.stream(self.owner_stream):
             k.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_hyper, rg_wide[:n_r], None, uq2)
-            k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
+        k.sparse_lazy_adam(self.deep, self.m, self.v, self.adam_hyper, rg_deep[:n_r], None, uq2)
+        main.wait_stream(self.owner_stream)
 
     # ---- test / checkpoint helper -----------------------------------------------------------------
     def gather_full(self):
@@ -371,9 +361,10 @@ class ShardedWideDeepStep:
     is already resident when it is needed and the launch pipeline never drains."""
 
     def __init__(self, batch_size, vocab_size, emb_dim, hidden, device, seed=1, sens=1024.0, fields=39,
-                 use_mixed_precision=True, group=None, kernels=_cuda_ops, graph_dense=True, tables_factory=None):
+                 use_mixed_precision=True, group=None, graph_dense=True, tables_factory=None, dense_storage=None):
+        """dense_storage(n) -> (flat, flat_grad): where the DenseLayers' flat parameter / gradient buffers live (the
+        peer-memory step puts the gradients into an IPC buffer its in-graph all-reduce reads)."""
         from .nn import DenseStack
-        self.k = kernels
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = torch.device(device)
@@ -381,21 +372,21 @@ class ShardedWideDeepStep:
         self.fields, self.emb_dim = fields, emb_dim
         self.mixed = use_mixed_precision
         self.tables = (tables_factory() if tables_factory is not None else
-                       ShardedWideDeepTables(vocab_size, emb_dim, device, group=group, seed=seed, sens=sens,
-                                             kernels=kernels))
+                       ShardedWideDeepTables(vocab_size, emb_dim, device, group=group, seed=seed, sens=sens))
         gen = torch.Generator(device=device)
         gen.manual_seed(seed)                      # identical DenseLayer replicas on every rank
         dims = [fields * emb_dim] + list(hidden) + [1]
         self.dense = DenseStack(dims, use_mixed_precision, device, generator=gen, weight_init="normal",
-                                bias_init="normal", extra=1)
+                                bias_init="normal", extra=1,
+                                storage=dense_storage(DenseStack.numel(dims, 1)) if dense_storage is not None else None)
         self.wide_b = self.dense.extra
         self.wide_b.normal_(0.0, 0.01, generator=gen)
         # the mean of DistributedGradReducer is folded into the gradient scale: 1 / (sens * G)
-        self.dense_hyper = kernels.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=device)
+        self.dense_hyper = ops.adam_hyper(3.5e-4, eps=1e-8, loss_scale=sens * self.world, device=device)
         self.dense_m = torch.zeros_like(self.dense.flat)
         self.dense_v = torch.zeros_like(self.dense.flat)
         self._sens_t = torch.tensor([self.sens], dtype=torch.float32, device=device)
-        self._use_graph = graph_dense and _ENV_GRAPH and self.device.type == "cuda"
+        self._use_graph = graph_dense and _ENV_GRAPH
         self._graph = None
         self._calls = 0
         self._io = None
@@ -404,9 +395,10 @@ class ShardedWideDeepStep:
         self.profile = None          # cells.StepProfile: per-phase CUDA-event timing of eager calls
 
     # ---- fixed-shape segment -----------------------------------------------------------------------
-    def _dense_segment(self):
-        k = self.k
-        deep_in, wide_out, label = self._io["deep_in"], self._io["wide_out"], self._io["label"]
+    def _dense_segment(self, label=None):
+        k = ops
+        deep_in, wide_out = self._io["deep_in"], self._io["wide_out"]
+        label = self._io["label"] if label is None else label
         deep_out = self.dense.forward(deep_in)
         _, loss, delta, delta16, dsum = k.sigmoid_xent(wide_out, deep_out, label, self._sens_t, out=self._io["loss_out"])
         gx = self.dense.backward(delta16 if delta16.numel() else delta)
@@ -414,7 +406,7 @@ class ShardedWideDeepStep:
         return loss[0], delta, gx
 
     def _dense_update(self):
-        k = self.k
+        k = ops
         if self.world > 1:                          # DistributedGradReducer(mean): wide_and_deep.py:455-470
             dist.all_reduce(self.dense.flat_grad, group=self.group)   # eager: capturing it in the graph hangs
         k.adam_begin_step(self.dense_hyper)
@@ -427,14 +419,14 @@ class ShardedWideDeepStep:
             if self._calls < 3:                      # eager warm-up (cuBLAS handles, NCCL channels)
                 return self._dense_segment()
             try:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                _cu.synchronize()
+                g = _cu.CUDAGraph()
+                with _cu.graph(g):
                     self._graph_out = self._dense_segment()
                 self._graph = g
             except Exception:                        # capture refused: stay eager
                 self._use_graph = False
-                torch.cuda.synchronize()
+                _cu.synchronize()
                 return self._dense_segment()
         self._graph.replay()
         return self._graph_out
@@ -500,11 +492,11 @@ class ShardedWideDeepStep:
             nxt = self._slots[self._cur ^ 1]
             side = self.tables.plan_stream
             if side is not None:
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
+                side.wait_stream(_cu.current_stream())
+                with _cu.stream(side):
                     for d, s in zip(nxt, next_batch):
                         d.copy_(s, non_blocking=True)
-            else:
+            else:                                    # peer tables: the key phase is part of the step's graphs
                 for d, s in zip(nxt, next_batch):
                     d.copy_(s)
             self._pending = self.tables.plan_batch(nxt[0], ahead=True)

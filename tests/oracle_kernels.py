@@ -13,6 +13,16 @@ class _Uq:
     pass
 
 
+class UniqueResult:
+    """Shape-compatible with ops.UniqueResult as far as sharded.py uses it (a capacity and a slice)."""
+
+    def __init__(self, n, dtype=None, device=None, packed=False):
+        self.n = n
+
+    def sliced(self, n):
+        return UniqueResult(n)
+
+
 def _np(t):
     return t.detach().cpu().numpy()
 
@@ -26,6 +36,7 @@ def ftrl_hyper(lr, l1=0.0, l2=0.0, lr_power=-0.5, loss_scale=1.0, device="cpu"):
 
 
 def unique(ids, table_like=None, result=None, ws_tag=None):
+    assert result is None or result.n == ids.numel()
     flat = _np(ids).reshape(-1)
     bound = table_like.shape[0] if table_like is not None else None
     uniq, inverse, perm, seg_start = R.unique_sorted(flat, bound)
@@ -132,3 +143,24 @@ def sigmoid_xent(a, b, label, sens, out=None, half=False):
                 o.copy_(r.reshape(o.shape))
         return out
     return res
+
+
+def dense_head_fwd(h, w, bias, out=None):
+    return (h.double() @ w.double().view(-1, 1) + bias.double()).float()
+
+
+def dense_head_bwd(delta, h, w, masked, gw, gb_head, gb_prev=None, out=None):
+    gh = delta.double() @ w.double().view(1, -1)
+    if masked:
+        gh = gh * (h > 0)
+    gw.copy_((delta.double().t() @ h.double()).view(-1).float())
+    gb_head.copy_(delta.double().sum().reshape(gb_head.shape).float())
+    if gb_prev is not None:
+        gb_prev.copy_(gh.sum(0).float())
+    return gh.to(h.dtype)
+
+
+def relu_bwd_bias(g, y, gb, out=None):
+    gz = g if y is None else g * (y > 0)
+    gb.copy_(gz.double().sum(0).float())
+    return gz

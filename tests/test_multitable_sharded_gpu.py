@@ -73,13 +73,13 @@ def test_step_matches_oracle_on_one_rank(cuda, one_rank_group):
         _, first, kinv0 = np.unique(keys.reshape(-1), return_index=True, return_inverse=True)
         np.testing.assert_array_equal(got_h, got_h[first[kinv0]])       # every copy of a key reads the same row
         # ---- backward: LazyAdam / FTRL rows from the step's own DenseLayer gradient ----
-        g_t = io["g_table"].cpu().numpy().reshape(-1, D)
-        delta = step._bwd.cpu().numpy()
+        g_t = step._last["g_table"].cpu().numpy().reshape(-1, D)
+        delta = step._last["delta"].cpu().numpy()
         uniq, inverse, _, _ = R.unique_sorted(ids, bound=rows)
         adam.begin_step()
         R.lazy_adam_sparse(deep, m, v, uniq, R.segment_sum(g_t, inverse, uniq.size), adam)
         R.ftrl_sparse(wide, acc, lin, uniq, R.segment_sum(delta, inverse, uniq.size, div=ft), ftrl)
-        g_h = io["g_hash"].cpu().numpy().reshape(-1, D)
+        g_h = step._last["g_hash"].cpu().numpy().reshape(-1, D)
         hadam.begin_step()
         ku, kinv = np.unique(keys.reshape(-1), return_inverse=True)
         gs = R.segment_sum(g_h, kinv, ku.size)

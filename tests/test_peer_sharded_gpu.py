@@ -257,3 +257,23 @@ def test_key_phase_one_step_ahead_on_the_second_buffer_set(cuda, world):
             assert torch.equal(a_, b_)
     for rk in ahead.ranks:
         assert int(rk.err.item()) == 0 and rk.cur == 1
+
+
+@pytest.mark.parametrize("world,n", [(1, 1000), (2, 4099), (4, 1 << 20), (8, 3_885_058), (3, 7)])
+def test_peer_allreduce_sums_in_rank_order_on_every_rank(cuda, world, n):
+    """mrec_peer_allreduce with G emulated ranks on one GPU (every rank's call; pointer tables as in PeerAllReduce):
+    every destination holds the fp32 sum added in rank order — bit-exact, identical on all ranks — incl. an n that is
+    not a multiple of 4, a slice boundary inside the buffer and the DenseLayer gradient size of the benchmark."""
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(n + world)
+    src = [torch.randn(n, device=cuda, generator=gen) * (10.0 ** (r % 3)) for r in range(world)]
+    dst = [torch.full((n,), float("nan"), device=cuda) for _ in range(world)]
+    p_src = torch.tensor([t.data_ptr() for t in src], dtype=torch.int64, device=cuda)
+    p_dst = torch.tensor([t.data_ptr() for t in dst], dtype=torch.int64, device=cuda)
+    for r in range(world):
+        ops.peer_allreduce(p_src, p_dst, torch.tensor([r, world], dtype=torch.int32, device=cuda), dst[r])
+    want = torch.zeros(n, device=cuda)
+    for r in range(world):
+        want = want + src[r]                    # 0 + s0 + s1 + ... in fp32, the kernel's order
+    for r in range(world):
+        assert torch.equal(dst[r], want)

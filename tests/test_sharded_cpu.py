@@ -13,11 +13,20 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mindrec_b200 import sharded, synth
+from mindrec_b200 import nn, sharded, synth
 from oracle import ref_numpy as R
-from tests import oracle_kernels as OK
+from tests import fake_cuda, oracle_kernels as OK
 
 VOCAB, DIM, B, HIDDEN = 701, 8, 24, (16, 8)
+
+
+def _patch():
+    """The product modules have ONE path (CUDA).  The exchange logic is run on the CPU by replacing, from the test
+    side, the kernel layer with the oracle and the stream objects with synchronous stand-ins."""
+    sharded.ops = OK
+    sharded._cu = fake_cuda
+    sharded._pinned = lambda t: t
+    nn.ops = OK
 
 
 def _free_port():
@@ -41,8 +50,9 @@ def _worker(rank, world, port, steps, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.manual_seed(0)
+        _patch()
         step = sharded.ShardedWideDeepStep(B, VOCAB, DIM, HIDDEN, "cpu", seed=3, use_mixed_precision=False,
-                                           kernels=OK)
+                                           graph_dense=False)
         wide0, deep0 = step.tables.gather_full()
         init = dict(wide=wide0.numpy().copy(), deep=deep0.numpy().copy(),
                     w=[w.numpy().copy() for w in step.dense.weights],
@@ -96,9 +106,14 @@ def test_shard_plan_remap_round_trip():
         sharded.ShardPlan(2 ** 31, 2)
 
 
-def test_single_rank_sharded_step_equals_oracle():
+def test_single_rank_sharded_step_equals_oracle(monkeypatch):
     """world_size 1 path (no process group): same exchange code, degenerate splits."""
-    step = sharded.ShardedWideDeepStep(B, VOCAB, DIM, HIDDEN, "cpu", seed=5, use_mixed_precision=False, kernels=OK)
+    monkeypatch.setattr(sharded, "ops", OK)
+    monkeypatch.setattr(sharded, "_cu", fake_cuda)
+    monkeypatch.setattr(sharded, "_pinned", lambda t: t)
+    monkeypatch.setattr(nn, "ops", OK)
+    step = sharded.ShardedWideDeepStep(B, VOCAB, DIM, HIDDEN, "cpu", seed=5, use_mixed_precision=False,
+                                       graph_dense=False)
     wide0, deep0 = step.tables.gather_full()
     orc = R.WideDeepOracle(wide0.numpy(), deep0.numpy(), [w.numpy() for w in step.dense.weights],
                            [b.numpy() for b in step.dense.biases], step.wide_b.numpy(), mode="lazy")

@@ -89,7 +89,7 @@ def wide_deep(world, rank, dev, batch, fields, emb, hidden, rows_per_rank=2_000_
         ok &= _cmp("dense", step.dense.flat, model.dense.flat, res, l2)
         del ref, model
     del wide, deep
-    step.tables.close()
+    step.close()
     del step
     torch.cuda.empty_cache()
     okt = torch.tensor([1 if ok else 0], device=dev)
