@@ -582,7 +582,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
     _lib.lib()  # fail loudly if the CUDA extension is missing
 
     if world > 1 and args.vocab_scale == 1.0:

@@ -126,6 +126,9 @@ int mrec_peer_wait(MREC_AOT_ARGS);
  *   in : src_ptrs[G] i64, dst_ptrs[G] i64 (every rank's [n] f32 buffers as mapped here), ctrl[2] i32 {rank, G}
  *   out: dst[n] f32 (this rank's destination buffer) */
 int mrec_peer_allreduce(MREC_AOT_ARGS);
+/* buf[idx[0], :] = 0 when the index lies inside buf (the landing-buffer row that out-of-range ids expand from: they read
+ * the zero row, as nn.EmbeddingLookup's gather returns for them).   in : idx[1] i32   out: buf[R,W] f32 */
+int mrec_zero_row(MREC_AOT_ARGS);
 /* CUDA-IPC plumbing for the peer buffers (host only, set-up time, not aot) */
 void *mrec_peer_alloc(size_t bytes);
 int mrec_peer_free(void *p);

@@ -298,11 +298,24 @@ class TrainStepWrap:
             uq = ops.unique(batch_ids, table_like=model.embedding_table.kernel_arg, result=self._uq)
         with rng("forward"):
             loss_w, loss_d = self.network(batch_ids, batch_wts, label)
+        # (mixed precision only: the input-gradient GEMM then reads the fp16 shadow of the weights, so the dense Adam may
+        # rewrite the fp32 masters underneath it)
+        fork_dense = self.overlap and self.lazy_adam and bool(model.dense.convert_dtype)
+
+        def dense_update():
+            # every DenseLayer gradient has been issued: the dense Adam runs on a forked branch underneath the
+            # input-gradient GEMM of layer 0 instead of after the sparse update
+            side2 = self._side_stream(1)
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                self.optimizer_d.begin_step()
+                self.optimizer_d.apply(1, model.dense.flat_grad)
+
         with rng("dense_backward"):
             delta = self.network.delta                                            # sens*(sigmoid-y)/B, [B,1]
             seed = self.network.delta16 if self.network.delta16.numel() else delta
-            gx = model.dense.backward(seed)                                       # [B, F*D]
             model.dense.extra_grad.copy_(self.network.delta_sum)                  # Wide_b gradient
+            gx = model.dense.backward(seed, on_weight_grads=dense_update if fork_dense else None)    # [B, F*D]
         mask = batch_wts.reshape(-1)
         grads_w = [RowTensor(batch_ids, delta, mask, uq)]
         grads_d = [RowTensor(batch_ids, gx.view(n, model.emb_dim), mask, uq), model.dense.flat_grad]
@@ -311,7 +324,11 @@ class TrainStepWrap:
         with torch.cuda.stream(side), rng("ftrl_wide"):
             self.optimizer_w(grads_w)
         with rng("adam_deep"):
-            self.optimizer_d(grads_d)
+            if fork_dense:
+                main.wait_stream(self._side_stream(1))                            # begin_step (and the dense Adam) done
+                self.optimizer_d.apply(0, grads_d[0])
+            else:
+                self.optimizer_d(grads_d)
         main.wait_stream(side)
         return loss_w, loss_d
 
@@ -349,10 +366,10 @@ class TrainStepWrap:
         main.wait_stream(side)
         return loss_w, loss_d
 
-    def _side_stream(self):
+    def _side_stream(self, i=0):
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.model.device)
-        return self._side
+            self._side = [torch.cuda.Stream(device=self.model.device) for _ in range(2)]
+        return self._side[i]
 
     # ---- CUDA-graph replay of the whole step -------------------------------------------------------
     def capture(self, batch_ids, batch_wts, label, warmup=3):

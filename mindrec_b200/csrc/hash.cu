@@ -28,6 +28,11 @@ namespace mrec {
 constexpr long long kEmpty = -1;
 constexpr long long kErased = -2;
 constexpr int kHashThreads = 256;
+// A probe sequence is at most this many 8-slot groups long, for finds, inserts and the rebuild alike: a key therefore
+// always sits within kMaxProbeGroups groups of its home group, and a miss on a FULL table costs 64 KB of key reads
+// instead of the whole table (a table driven past its capacity raises the overflow flag; it must not also stall
+// every lookup for seconds).  At the load factors the table is run at (growth at 0.6) chains are a few groups long.
+constexpr int64_t kMaxProbeGroups = 1024;
 enum { ST_SIZE = 0, ST_STEP = 1, ST_TOMB = 2, ST_OVERFLOW = 3, ST_OCC = 4, ST_LOGN = 5, ST_LOGOVF = 6, ST_LEN = 8 };
 
 // Erase log (incremental export): every key removed by erase / evict is appended to a
@@ -91,6 +96,7 @@ hash_probe_kernel(const KeyT* __restrict__ keys_in, int64_t n, long long* __rest
   const int lt = lane & 7;      // lane in tile
   const int tbase = lane & ~7;  // first lane of my tile == bit offset of my tile inside a warp ballot
   const int64_t n_groups = capacity >> 3;
+  const int64_t probe_cap = n_groups < kMaxProbeGroups ? n_groups : kMaxProbeGroups;
   const int step = state[ST_STEP];
   const int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~(int64_t)7;  // tile's first item
   const int64_t mine = base + lt;
@@ -124,7 +130,7 @@ hash_probe_kernel(const KeyT* __restrict__ keys_in, int64_t n, long long* __rest
             first_free_val = ((be >> fl) & 1u) ? kEmpty : kErased;
           }
           ++probes;
-          if (be || probes >= n_groups) {  // end of the probe chain: the key is not in the table
+          if (be || probes >= probe_cap) {  // end of the probe chain: the key is not in the table
             if ((MODE == 1 || MODE == 2) && first_free >= 0) {
               want_cas = true;
             } else {
@@ -322,7 +328,8 @@ hash_rehash_kernel(const long long* __restrict__ keys_old, const unsigned long l
     }
     int64_t g = (int64_t)(mix64((uint64_t)k) & (uint64_t)(n_groups - 1));
     int32_t placed = -1;
-    for (int64_t probes = 0; probes < n_groups && placed < 0; ++probes) {
+    const int64_t probe_cap = n_groups < kMaxProbeGroups ? n_groups : kMaxProbeGroups;
+    for (int64_t probes = 0; probes < probe_cap && placed < 0; ++probes) {
       for (int j = 0; j < 8; ++j) {
         const int64_t slot = g * 8 + j;
         if (*reinterpret_cast<volatile long long*>(&keys_new[slot]) != kEmpty) continue;

@@ -329,6 +329,16 @@ peer_allreduce_kernel(const int64_t* __restrict__ src_ptrs, const int64_t* __res
   }
 }
 
+
+// buf[idx[0], :] = 0 when 0 <= idx[0] < rows.  The bounded dedup gives every out-of-range id the inverse index U (the
+// unique count): zeroing row U of the landing buffers makes those lookups read the zero row the unsharded gather
+// returns for them, whatever an earlier step left there.
+__global__ void zero_row_kernel(float* __restrict__ buf, int64_t rows, int64_t width, const int32_t* __restrict__ idx) {
+  const int64_t r = idx[0];
+  if (r < 0 || r >= rows) return;
+  for (int64_t c = threadIdx.x; c < width; c += blockDim.x) buf[r * width + c] = 0.f;
+}
+
 }  // namespace mrec
 
 // in : bounds_all[G*(G+1)] i32, ctrl[2] i32 {rank, world}     out: dst_off[G], src_off[G+1], inbox_off[G], n_r[1] (i32)
@@ -380,6 +390,19 @@ MREC_API int mrec_push_rows_to_peers(int nparam, void** params, int* ndims, int6
                 width, a.ptr<int32_t>(1), a.ptr<int32_t>(2), a.ptr<int64_t>(3), world, (int64_t)0, cap_rows, a.ptr<int32_t>(6));
   }
   return check_launch("push_rows_to_peers");
+}
+
+// in : idx[1] i32        out: buf[R, W] f32 — row idx[0] is zeroed when it lies inside the buffer
+MREC_API int mrec_zero_row(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                           void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 2) return fail(ERR_NPARAM, "mrec_zero_row: expected 2 params, got %d", a.nparam);
+  MREC_REQUIRE(a.is_i32(0) && a.is_f32(1) && a.numel(0) >= 1 && a.ndims[1] >= 1, ERR_DTYPE, "mrec_zero_row: idx[1] i32, buf[R,W] f32");
+  const int64_t rows = a.dim(1, 0);
+  if (rows == 0) return OK;
+  const int64_t width = a.numel(1) / rows;
+  MREC_LAUNCH(zero_row_kernel, 1, 128, 0, a.stream, a.ptr<float>(1), rows, width, a.ptr<int32_t>(0));
+  return check_launch("zero_row");
 }
 
 // in : src_ptrs[G] i64 (every rank's source buffer [n] f32 as mapped in THIS process), dst_ptrs[G] i64 (every rank's

@@ -134,8 +134,11 @@ class ShardedMultitableStep:
     def _dense_update(self):
         """All-reduce over peer memory (DistributedGradReducer(mean): the 1/G is in the loss scale) -> dense Adam ->
         FTRL on wide_bias."""
-        n = self.dense.flat.numel()
         self._ar.run(self.tables.rk.err)
+        self._dense_adam()
+
+    def _dense_adam(self):
+        n = self.dense.flat.numel()
         ops.adam_begin_step(self.dense_hyper)
         ops.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self._reduced[:n])
         ops.ftrl_dense(self.wide_bias, self.bias_acc, self.bias_lin, self.bias_hyper, self._reduced[n:n + 1])
@@ -149,18 +152,24 @@ class ShardedMultitableStep:
         deep_out = self.dense.forward((io["x_table"], io["x_hash"]))
         _, loss, delta, delta16, dsum = ops.sigmoid_xent(io["wide_out"], deep_out, io["label"], self._sens_t,
                                                          out=io["loss_out"])
-        g_table, g_hash = self.dense.backward(delta16 if delta16.numel() else delta)
         n = self.dense.flat.numel()
         self._reduce[n:n + 1].copy_(dsum)                    # d loss / d wide_bias = sum(delta)
-        self._last = {"delta": delta, "g_table": g_table, "g_hash": g_hash}      # inspection (eager calls, tests)
-        # gradient exchange (same lock-step order), the all-reduce branch forked after the pushes were issued
-        t.p_grads(delta, g_table, side=side)
-        h.p_grads(g_hash)
-        self._dense_stream.wait_stream(main)
+
+        def fork_allreduce():                                # under the input-gradient GEMMs of layer 0
+            self._dense_stream.wait_stream(main)
+            with torch.cuda.stream(self._dense_stream):
+                self._ar.run(t.err)
+
+        g_table, g_hash = self.dense.backward(delta16 if delta16.numel() else delta, on_weight_grads=fork_allreduce)
+        self._dense_stream.wait_stream(main)                 # those GEMMs were the last readers of the weights
         with torch.cuda.stream(self._dense_stream):
-            self._dense_update()
+            self._dense_adam()
             err = t.err[0] | h.err[0]                        # an exchange error poisons the loss the caller reads
             torch.add(loss[0], torch.where(err != 0, self._nan, self._zero), out=self._loss)
+        self._last = {"delta": delta, "g_table": g_table, "g_hash": g_hash}      # inspection (eager calls, tests)
+        # gradient exchange (same lock-step order as the forward)
+        t.p_grads(delta, g_table, side=side)
+        h.p_grads(g_hash)
         t.wait(3)
         side.wait_stream(main)
         with torch.cuda.stream(side):                        # latency-bound FTRL beside the LazyAdam rows

@@ -213,25 +213,34 @@ class Adam(_Optimizer):
         return flags
 
     def step(self, grads):
+        self.begin_step()
+        for i, g in enumerate(grads):
+            self.apply(i, g)
+
+    def begin_step(self):
+        """Advance the step count / bias-corrected learning rate (device side).  `step` = begin_step + apply(i, g) for
+        every parameter; callers that overlap the updates of different parameters on forked streams call the two
+        halves themselves."""
         ops.adam_begin_step(self.hyper)
-        for i, (p, m, v, g) in enumerate(zip(self.parameters, self.moment1, self.moment2, grads)):
-            if i in self._map_state:
-                if not isinstance(g, RowTensor) or not self.lazy:
-                    raise TypeError("a MapParameter takes a RowTensor gradient and LazyAdam (wide_and_deep.py:415-422)")
-                w, m, v = self._rows(p, self._map_state[i])
-                ops.sparse_lazy_adam(w, m, v, self.hyper, g.values, g.mask, self._dedup(p, g))
-                continue
-            if isinstance(g, RowTensor):
-                uq = self._dedup(p, g)
-                if self.lazy and getattr(p, "packed", None) is not None:
-                    ops.sparse_lazy_adam(p.packed, None, None, self.hyper, g.values, g.mask, uq)
-                elif self.lazy:
-                    ops.sparse_lazy_adam(p.data, m, v, self.hyper, g.values, g.mask, uq)
-                else:
-                    ops.adam_rowsparse_dense_equiv(p.data, m, v, self.hyper, g.values, g.mask, uq,
-                                                   self._row_flags(p))
+
+    def apply(self, i, g):
+        p, m, v = self.parameters[i], self.moment1[i], self.moment2[i]
+        if i in self._map_state:
+            if not isinstance(g, RowTensor) or not self.lazy:
+                raise TypeError("a MapParameter takes a RowTensor gradient and LazyAdam (wide_and_deep.py:415-422)")
+            w, m, v = self._rows(p, self._map_state[i])
+            ops.sparse_lazy_adam(w, m, v, self.hyper, g.values, g.mask, self._dedup(p, g))
+        elif isinstance(g, RowTensor):
+            uq = self._dedup(p, g)
+            if self.lazy and getattr(p, "packed", None) is not None:
+                ops.sparse_lazy_adam(p.packed, None, None, self.hyper, g.values, g.mask, uq)
+            elif self.lazy:
+                ops.sparse_lazy_adam(p.data, m, v, self.hyper, g.values, g.mask, uq)
             else:
-                ops.adam_dense(p.data, m, v, self.hyper, g)
+                ops.adam_rowsparse_dense_equiv(p.data, m, v, self.hyper, g.values, g.mask, uq,
+                                               self._row_flags(p))
+        else:
+            ops.adam_dense(p.data, m, v, self.hyper, g)
 
 
 class LazyAdam(Adam):
@@ -411,9 +420,11 @@ class DenseStack:
         self._acts = acts
         return h
 
-    def backward(self, g_out, input_grad_dtype=None):
+    def backward(self, g_out, input_grad_dtype=None, on_weight_grads=None):
         """g_out: gradient wrt the stack output.  Fills flat_grad (fp32) and returns the gradient wrt the
-        input — fp16 when convert_dtype (the sparse optimizers read fp16 rows directly)."""
+        input — fp16 when convert_dtype (the sparse optimizers read fp16 rows directly).  on_weight_grads(): called
+        once every weight / bias gradient has been issued, BEFORE the input-gradient GEMM of layer 0 — a data-parallel
+        caller forks its gradient all-reduce there, underneath that GEMM."""
         acts = self._acts
         nl = len(self.weights)
         g = g_out.half() if (self.convert_dtype and g_out.dtype != torch.float16) else g_out
@@ -434,21 +445,21 @@ class DenseStack:
             else:                  # ReluGrad + BiasAddGrad in one mrec_relu_bwd_bias pass, fp32 sums in place
                 g = ops.relu_bwd_bias(g, h_out if masked else None, self.gb[i])
             w = self.w16[i] if self.convert_dtype else self.weights[i]
-            if isinstance(h_in, tuple):              # layer 0 fed in column blocks: row blocks of gw / w, one gx each
-                o, gxs = 0, []
-                for x in h_in:
-                    k = x.shape[1]
-                    if self.convert_dtype:
-                        self._wgrad(x, g, self.gw[i][o:o + k])
-                    else:
-                        torch.mm(x.t(), g, out=self.gw[i][o:o + k])
-                    gxs.append(torch.mm(g, w[o:o + k].t()))
-                    o += k
-                g = tuple(gxs)
-            elif self.convert_dtype:
-                self._wgrad(h_in, g, self.gw[i])
-                g = torch.mm(g, w.t())
-            else:
-                torch.mm(h_in.t(), g, out=self.gw[i])
-                g = torch.mm(g, w.t())
+            xs = h_in if isinstance(h_in, tuple) else (h_in,)      # layer 0 may be fed in column blocks
+            o = 0
+            for x in xs:                             # weight gradients: row blocks of gw
+                k = x.shape[1]
+                if self.convert_dtype:
+                    self._wgrad(x, g, self.gw[i][o:o + k])
+                else:
+                    torch.mm(x.t(), g, out=self.gw[i][o:o + k])
+                o += k
+            if i == 0 and on_weight_grads is not None:
+                on_weight_grads()
+            o, gxs = 0, []
+            for x in xs:                             # input gradients: row blocks of w, one per block
+                k = x.shape[1]
+                gxs.append(torch.mm(g, w[o:o + k].t()))
+                o += k
+            g = tuple(gxs) if isinstance(h_in, tuple) else gxs[0]
         return g

@@ -475,6 +475,11 @@ def peer_signal(payload, payload_ptrs, flag_ptrs, epoch):
     _lib.aot_call("mrec_peer_signal", [payload, payload_ptrs, flag_ptrs, epoch, _dummy(epoch.device)])
 
 
+def zero_row(buf, idx):
+    """buf[idx[0]] = 0 (device-side index; a no-op when it lies outside buf)."""
+    _lib.aot_call("mrec_zero_row", [idx, buf])
+
+
 def peer_allreduce(src_ptrs, dst_ptrs, ctrl, dst):
     """dst (on every rank) = sum over ranks of the source buffers, added in rank order by the slice owners."""
     _lib.aot_call("mrec_peer_allreduce", [src_ptrs, dst_ptrs, ctrl, dst])

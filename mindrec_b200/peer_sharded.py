@@ -223,8 +223,13 @@ class PeerRank:
 
     def p_expand(self, ids_shape, wts, wide_bias, deep_out, wide_out, side=None):
         inverse = self.uq.inverse.view(ids_shape)
+        # ids outside [0, V) collapse onto ONE extra unique entry behind the valid ones (index bounds[G]), which no
+        # owner serves: make that landing row the zero row, what the unsharded gather returns for such ids
+        n_valid_keys = self.bounds[self.world:self.world + 1]
         with _Fork(side):
+            ops.zero_row(self.buf["land_wide"], n_valid_keys)
             ops.gather_reduce(self.buf["land_wide"], inverse, wts, wide_bias, out=wide_out)
+        ops.zero_row(self.buf["land_deep"], n_valid_keys)
         ops.gather_masked(self.buf["land_deep"], inverse, wts, out=deep_out)
         _join(side)
         self._wts = wts
@@ -817,6 +822,9 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
     def _dense_update(self):
         """All-reduce over peer memory + dense Adam (capturable; replaces the NCCL collective of the base class)."""
         self._ar.run(self.tables.rk.err)
+        self._dense_adam()
+
+    def _dense_adam(self):
         ops.adam_begin_step(self.dense_hyper)
         ops.adam_dense(self.dense.flat, self.dense_m, self.dense_v, self.dense_hyper, self._ar.dst)
 
@@ -834,17 +842,25 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
             with torch.cuda.stream(self._plan_stream):
                 self._plan_stream.wait_event(self._staged_ev)            # the next batch is on the device
                 self.tables.key_phase_next(self._slots[rk.cur ^ 1][0])
-        loss, delta, gx = self._dense_segment(label)
-        # the all-reduce shares the NVLink ports with the gradient push, which is on the critical path: the dense
-        # branch forks AFTER the push has been issued and runs beside the owners' row updates (HBM-bound, local)
-        self.tables.push_grads(delta, gx)
+        # The all-reduce branch forks as soon as the last weight gradient has been issued, underneath the
+        # input-gradient GEMM of layer 0 (compute-bound, no NVLink traffic), so that most of it is over when the
+        # gradient push — which shares the NVLink ports and IS on the critical path — starts.  The dense Adam follows
+        # on the same branch once that GEMM, the last reader of the weights, has been issued.
         dense_stream = main if _NO_DENSE_FORK else self._dense_stream
+
+        def fork_allreduce():
+            dense_stream.wait_stream(main)
+            with torch.cuda.stream(dense_stream):
+                self._ar.run(rk.err)
+
+        loss, delta, gx = self._dense_segment(label, on_weight_grads=fork_allreduce)
         dense_stream.wait_stream(main)
         with torch.cuda.stream(dense_stream):
-            self._dense_update()
+            self._dense_adam()
             # an exchange error (a wait that timed out, an inbox that overflowed) must not train on silently: the loss
             # the caller reads turns NaN from the step after the one that raised the bit
             torch.add(loss, torch.where(rk.err[0] != 0, self._nan, self._zero), out=self._loss)
+        self.tables.push_grads(delta, gx)
         self.tables.apply_grads()
         main.wait_stream(self._dense_stream)
         if ahead:

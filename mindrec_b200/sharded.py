@@ -395,14 +395,14 @@ class ShardedWideDeepStep:
         self.profile = None          # cells.StepProfile: per-phase CUDA-event timing of eager calls
 
     # ---- fixed-shape segment -----------------------------------------------------------------------
-    def _dense_segment(self, label=None):
+    def _dense_segment(self, label=None, on_weight_grads=None):
         k = ops
         deep_in, wide_out = self._io["deep_in"], self._io["wide_out"]
         label = self._io["label"] if label is None else label
         deep_out = self.dense.forward(deep_in)
         _, loss, delta, delta16, dsum = k.sigmoid_xent(wide_out, deep_out, label, self._sens_t, out=self._io["loss_out"])
-        gx = self.dense.backward(delta16 if delta16.numel() else delta)
-        self.dense.extra_grad.copy_(dsum)
+        self.dense.extra_grad.copy_(dsum)            # Wide_b's gradient rides in the DenseLayers' flat buffer
+        gx = self.dense.backward(delta16 if delta16.numel() else delta, on_weight_grads=on_weight_grads)
         return loss[0], delta, gx
 
     def _dense_update(self):

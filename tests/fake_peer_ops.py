@@ -269,3 +269,9 @@ class FakeMapParameter:
 
     def __len__(self):
         return len(self.slot_of)
+
+
+def zero_row(buf, idx):
+    r = int(idx[0])
+    if 0 <= r < buf.shape[0]:
+        buf[r].zero_()

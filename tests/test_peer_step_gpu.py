@@ -39,7 +39,11 @@ SCRIPT = textwrap.dedent('''
     cards = [max(3, int(c * scale * 0.9)) for c in synth.CARD_KAGGLE]      # every id in range
     assert synth.vocab_size(cards) <= vocab
     gen = synth.CriteoSynth(b, cards=cards, vocab_pad=vocab, seed=4)
-    host = [tuple(torch.from_numpy(x).pin_memory() for x in gen.next()) for _ in range(7)]
+    raw = [gen.next() for _ in range(7)]
+    for j in (2, 3, 5):                                      # ids outside [0, V): the zero row forward, no update
+        raw[j][0][::37, 3] = vocab + 11
+        raw[j][0][5::41, 30] = -7
+    host = [tuple(torch.from_numpy(x).pin_memory() for x in hb) for hb in raw]
     batches = [tuple(x.to(dev) for x in hb) for hb in host]
     n0 = _lib.launch_count()
     step.capture(*batches[0], warmup=2)                      # trains 2 steps on batch 0

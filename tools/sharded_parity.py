@@ -159,7 +159,10 @@ def multitable(world, rank, dev, batch, rows_per_rank=1_000_003, steps=3, mixed=
            "exchange_flags": flags, "hash_resident_keys": int(hk.numel())}
     ok = flags == 0
     if rank == 0:
-        ref = M.ShardedMultitableStep(batch * world, rows, dev, group=group_one, use_mixed_precision=mixed, seed=5, **kw)
+        # the one-rank reference holds the keys of ALL ranks in one MapParameter: G times the slots (a table that fills
+        # up makes every find-or-insert probe its whole length)
+        kw_ref = dict(kw, hash_capacity=kw.get("hash_capacity", 1 << 22) * world)
+        ref = M.ShardedMultitableStep(batch * world, rows, dev, group=group_one, use_mixed_precision=mixed, seed=5, **kw_ref)
         ref.tables.rk.wide.copy_(wide0[:ref.tables.rk.wide.shape[0]])
         ref.tables.rk.deep.copy_(deep0[:ref.tables.rk.deep.shape[0]])
         ref.dense.flat.copy_(flat0)
