@@ -25,7 +25,7 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from .nn import DenseStack
-from .peer_sharded import PeerAllReduce, PeerShardedHashEmbedding, PeerShardedTables
+from .peer_sharded import PeerAllReduce, PeerShardedHashEmbedding, PeerShardedTables, _Fork, _join
 
 EMB128 = 128
 
@@ -96,6 +96,7 @@ class ShardedMultitableStep:
         self._zero = torch.zeros((), dtype=torch.float32, device=dev)
         self._main_stream = torch.cuda.Stream(device=dev, priority=-1)       # see PeerShardedWideDeepStep
         self._dense_stream = torch.cuda.Stream(device=dev)
+        self._t_stream = torch.cuda.Stream(device=dev, priority=-1)          # the table's branch beside the MapParameter's
         self._graphs = None
         self._loss = torch.zeros((), dtype=torch.float32, device=dev)
         self._steps = 0
@@ -105,10 +106,11 @@ class ShardedMultitableStep:
     # ---- the step (one CUDA graph) -----------------------------------------------------------------------------
     def _forward_exchange(self):
         """plan -> key exchange -> row exchange -> expand.  The table (T) and the MapParameter (H) go through the four
-        phases in lock step ON ONE STREAM, always T before H: every rank issues its signals and its waits in the same
-        order, so a wait can only ever be held up by a peer's earlier work, never by the peer's other lookup waiting
-        on us (two forked branches would leave that order to the scheduler).  The dim-1 twins of the table's kernels
-        (wide vector) and the owner-side dedup run on a forked branch: they contain no waits."""
+        phases in lock step, always T before H, with every SIGNAL issued on one stream: every rank signals in the same
+        order, so a wait can only ever be held up by a peer's earlier work.  What follows a wait of T and is local
+        (expand; in the backward the row updates) runs on a forked branch next to H's NVLink phases — those waits depend
+        only on signals the peers issue BEFORE their H work.  The dim-1 twins of the table's kernels (wide vector) and
+        the owner-side dedup run on another forked branch: they contain no waits."""
         io, t, h = self._io, self.tables.rk, self.hash.rk
         main = torch.cuda.current_stream()
         side = self.tables.owner_stream
@@ -123,12 +125,18 @@ class ShardedMultitableStep:
         with torch.cuda.stream(side):                        # under serve / expand / DenseLayers
             t.p_owner_dedup()
         t.p_serve(side=side)
+        # the table's expand (HBM / L2 bound) runs on a forked branch while the MapParameter's rows are still crossing
+        # NVLink: T's wait 2 only depends on the peers' T serves, issued before their H serves
+        tb = self._t_stream
+        tb.wait_stream(main)
+        with torch.cuda.stream(tb):
+            t.wait(2)
+            t.p_expand(io["ids"].shape, io["ones"], self.wide_bias, io["x_table"], io["wide_out"], side=side)
         h.wait(1)
         h.p_serve()
-        t.wait(2)
-        t.p_expand(io["ids"].shape, io["ones"], self.wide_bias, io["x_table"], io["wide_out"], side=side)
         h.wait(2)
         h.p_expand(io["x_hash"])
+        main.wait_stream(tb)
         main.wait_stream(side)
 
     def _dense_update(self):
@@ -167,17 +175,21 @@ class ShardedMultitableStep:
             err = t.err[0] | h.err[0]                        # an exchange error poisons the loss the caller reads
             torch.add(loss[0], torch.where(err != 0, self._nan, self._zero), out=self._loss)
         self._last = {"delta": delta, "g_table": g_table, "g_hash": g_hash}      # inspection (eager calls, tests)
-        # gradient exchange (same lock-step order as the forward)
+        # gradient exchange (same lock-step order as the forward); the table's row updates — HBM bound — run on a forked
+        # branch while the MapParameter's gradients are still crossing NVLink
         t.p_grads(delta, g_table, side=side)
+        tb = self._t_stream
+        tb.wait_stream(main)
+        with torch.cuda.stream(tb):
+            t.wait(3)
+            with _Fork(side):                                # latency-bound FTRL beside the LazyAdam rows
+                t.p_update_wide()
+            t.p_update_deep()
+            _join(side)
         h.p_grads(g_hash)
-        t.wait(3)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):                        # latency-bound FTRL beside the LazyAdam rows
-            t.p_update_wide()
-        t.p_update_deep()
         h.wait(3)
         h.p_update()
-        main.wait_stream(side)
+        main.wait_stream(tb)
         main.wait_stream(self._dense_stream)
         return self._loss
 

@@ -36,10 +36,24 @@ def _from_list(device, values, dtype="float32"):
     return torch.tensor(values, dtype=getattr(torch, dtype), device=device)
 
 
+_ws_retired = []
+
+
 def _ws(tag, nbytes, device):
-    key = (tag, device)
+    """Cached workspace for (tag, device, CURRENT STREAM).  Keyed by the stream because two calls that share a tag may
+    run concurrently on forked streams (parallel branches of a captured graph): calls on one stream are ordered, calls
+    on different streams get different buffers.  A buffer that has to grow is replaced, and the old one is kept alive
+    for the life of the process: captured CUDA graphs and kernels still queued hold raw pointers to it."""
+    if getattr(device, "__mrec_rt__", False):
+        stream = device.current_stream_handle()
+    else:
+        import torch
+        stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+    key = (tag, device, stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
         buf = _alloc(device, max(int(nbytes), 256), "uint8")
         _ws_cache[key] = buf
     return buf
