@@ -487,6 +487,36 @@ def measure_c4(args, dev, steps):
             "fm_bwd": _roof("fm_bwd_kernel", 2 * vol + b * 4, bwd, "fm_bwd")}
 
 
+def measure_torch_free(args, cards, host_batches, steps):
+    """BASELINE config 2 through the torch-free host path (mindrec_b200.rt_wide_deep.WideDeepRT: runtime buffers and
+    streams, aot kernels, cuBLASLt through mrec_rt_gemm, one CUDA graph per step) — the same step as the headline, driven
+    without a torch tensor, allocator, stream or GEMM.  (This process has torch loaded for the other blocks;
+    tests/test_rt_wide_deep_gpu.py runs the class with the torch import blocked.)"""
+    from mindrec_b200 import runtime, synth
+    from mindrec_b200.rt_wide_deep import WideDeepRT
+    dev = runtime.Device(int(os.environ.get("LOCAL_RANK", "0")))
+    step = WideDeepRT(dev, args.batch, FIELDS, synth.vocab_size(cards), EMB, HIDDEN, mixed=True, sens=1024.0, seed=1)
+    ring = [tuple(dev.from_numpy(x.numpy()) for x in hb) for hb in host_batches]
+    step.set_inputs(*ring[0])
+    step.capture(warmup=2)
+    for i in range(5):
+        step.train_step(*ring[i % len(ring)])
+    dev.synchronize()
+    e0, e1 = runtime.Event(timing=True), runtime.Event(timing=True)
+    e0.record(dev.stream)
+    for i in range(steps):
+        step.train_step(*ring[i % len(ring)])
+    e1.record(dev.stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    loss = float(step.loss_out[1].item())
+    out = {"class": "mindrec_b200.rt_wide_deep.WideDeepRT", "ms_per_step": ms, "samples_per_s": args.batch / (ms * 1e-3),
+           "steps": steps, "gpu_launches_per_step": step.launches_per_step, "final_loss": loss,
+           "host": "ctypes over mrec_rt_* + the aot entry points; DenseLayer GEMMs: cuBLASLt via mrec_rt_gemm"}
+    del step, ring
+    return out
+
+
 def measure_c5(args, world, rank, dev, group_one):
     """BASELINE configs[4]: the multitable model's emb128 table (dim 128, + its dim-1 wide vector) row-sharded over the
     ranks with rows-per-GPU fixed, plus a hash-sharded MapParameter (int64 Zipf keys over 2^40, admission on the second
@@ -776,6 +806,9 @@ def run_ours(args):
         del step, model
         torch.cuda.empty_cache()
         n_extra = max(3, min(args.steps, 20))
+        configs["torch_free"] = measure_torch_free(args, cards, host[:4], max(20, min(args.steps, 100)))
+        import gc
+        gc.collect()
         configs["c3"] = measure_c3(args, dev, n_extra)
         configs["c4"] = measure_c4(args, dev, n_extra)
 

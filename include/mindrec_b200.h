@@ -320,6 +320,15 @@ int mrec_rt_graph_begin(void *stream);
 void *mrec_rt_graph_end(void *stream);
 int mrec_rt_graph_launch(void *graph_exec, void *stream);
 int mrec_rt_graph_destroy(void *graph_exec);
+/* DenseLayer GEMM of the torch-free host path (wide_and_deep.py:72-133: MatMul + BiasAdd + ReLU; fp16 storage with fp32
+ * accumulation under use_mixed_precision).  cuBLASLt, bound at run time with dlopen; asynchronous on `stream`, capturable.
+ * Row-major C[M,N] = act(alpha * op(A) op(B) + beta * C + bias[N]); A stored [M,K] (trans_a = 0) or [K,M]; B stored [K,N]
+ * (trans_b = 0) or [N,K]; ab_half / c_half: 1 = fp16, 0 = fp32 storage; epilogue 0 none | 1 bias | 2 relu(bias). */
+int mrec_rt_gemm(const void *a, const void *b, void *c, const void *bias, int64_t m, int64_t n, int64_t k, int trans_a,
+                 int trans_b, int ab_half, int c_half, float alpha, float beta, int epilogue, void *stream);
+/* Cast(weight, float16) of the mixed-precision DenseLayers for the whole flat parameter buffer (aot signature).
+ *   in : src[n] f32      out: dst[n] f16 */
+int mrec_cast_f32_f16(MREC_AOT_ARGS);
 
 #ifdef __cplusplus
 }

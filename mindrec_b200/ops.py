@@ -489,6 +489,14 @@ def peer_signal(payload, payload_ptrs, flag_ptrs, epoch):
     _lib.aot_call("mrec_peer_signal", [payload, payload_ptrs, flag_ptrs, epoch, _dummy(epoch.device)])
 
 
+def cast_f32_f16(src, out=None):
+    """out = fp16(src) for a flat fp32 buffer (the per-step Cast of the mixed-precision DenseLayers' weights)."""
+    if out is None:
+        out = _alloc(src.device, src.shape, "float16")
+    _lib.aot_call("mrec_cast_f32_f16", [src, out])
+    return out
+
+
 def zero_row(buf, idx):
     """buf[idx[0]] = 0 (device-side index; a no-op when it lies outside buf)."""
     _lib.aot_call("mrec_zero_row", [idx, buf])

@@ -46,6 +46,8 @@ def _c():
                 ("mrec_rt_event_elapsed_ms", ctypes.c_float, [vp, vp]), ("mrec_rt_event_destroy", ctypes.c_int, [vp]),
                 ("mrec_rt_graph_begin", ctypes.c_int, [vp]), ("mrec_rt_graph_end", vp, [vp]),
                 ("mrec_rt_graph_launch", ctypes.c_int, [vp, vp]), ("mrec_rt_graph_destroy", ctypes.c_int, [vp]),
+                ("mrec_rt_gemm", ctypes.c_int, [vp, vp, vp, vp, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp]),
                 ("mrec_rt_device_count", ctypes.c_int, []), ("mrec_rt_set_device", ctypes.c_int, [ctypes.c_int]),
                 ("mrec_rt_mem_info", ctypes.c_int, [ctypes.POINTER(sz), ctypes.POINTER(sz)])):
             f = getattr(L, name)
@@ -113,6 +115,27 @@ class Graph:
         _check(_c().mrec_rt_graph_launch(ctypes.c_void_p(self.handle), ctypes.c_void_p(s.handle)), "graph launch")
 
     replay = launch
+
+
+def gemm(a, b, out, bias=None, trans_a=False, trans_b=False, relu=False, alpha=1.0, beta=0.0):
+    """Row-major out[M,N] = act(alpha * op(a) op(b) + beta * out + bias) on the device's current stream (cuBLASLt through
+    mrec_rt_gemm: fp16 or fp32 storage, fp32 accumulation).  op(a) is a or a^T, op(b) likewise; relu needs a bias."""
+    if a.dtype != b.dtype or a.dtype not in ("float16", "float32") or out.dtype not in ("float16", "float32"):
+        raise TypeError("gemm: a, b fp16 or fp32 (same type), out fp16 or fp32")
+    m, k = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    k2, n = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if k != k2 or tuple(out.shape) != (m, n):
+        raise ValueError("gemm: shapes %r x %r -> %r do not match" % (a.shape, b.shape, out.shape))
+    if relu and bias is None:
+        raise ValueError("gemm: the relu epilogue comes with a bias")
+    if bias is not None and (bias.numel() != n or bias.dtype != out.dtype):
+        raise ValueError("gemm: bias must be [N] of out's type")
+    _check(_c().mrec_rt_gemm(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                             ctypes.c_void_p(bias.data_ptr() if bias is not None else 0), m, n, k, int(trans_a), int(trans_b),
+                             int(a.dtype == "float16"), int(out.dtype == "float16"), float(alpha), float(beta),
+                             (2 if relu else 1) if bias is not None else 0,
+                             ctypes.c_void_p(a.device.current_stream_handle())), "gemm")
+    return out
 
 
 class _Allocation:
