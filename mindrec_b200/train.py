@@ -165,3 +165,68 @@ def import_tables(step, state):
         if tuple(state[k].shape) != tuple(t.shape):
             raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(state[k].shape), tuple(t.shape)))
         t.copy_(state[k])
+
+
+# --------------------------------------------------------------------------------------------------
+# row-sharded checkpoints: every rank saves its slice, evaluation merges them (models/wide_deep/eval.py:86-107:
+# load_checkpoint per slice -> merge_sliced_parameter -> load_param_into_net)
+# --------------------------------------------------------------------------------------------------
+_SLICED = ("wide_embeddinglookup.embedding_table", "deep_embeddinglookup.embedding_table", "ftrl.accum", "ftrl.linear",
+           "adam.moment1.table", "adam.moment2.table")
+
+
+def export_sharded_tables(step):
+    """This rank's slice of a row-sharded Wide&Deep step (sharded.ShardedWideDeepStep / peer_sharded.PeerSharded-
+    WideDeepStep): its rows of the two tables and of their optimizer state, the (replicated) DenseLayers, and the
+    sharding it was written under.  One file per rank, like the reference's per-rank checkpoints."""
+    tb = step.tables
+    rk = getattr(tb, "rk", tb)                        # PeerShardedTables keeps the arrays on its PeerRank
+    plan = tb.plan
+    out = {
+        "wide_embeddinglookup.embedding_table": rk.wide, "deep_embeddinglookup.embedding_table": rk.deep,
+        "ftrl.accum": rk.acc, "ftrl.linear": rk.lin, "adam.moment1.table": rk.m, "adam.moment2.table": rk.v,
+        "dense_layers+Wide_b": step.dense.flat, "adam.moment1.dense": step.dense_m, "adam.moment2.dense": step.dense_v,
+        "adam.hyper": rk.adam_hyper, "ftrl.hyper": rk.ftrl_hyper, "adam.hyper.dense": step.dense_hyper,
+    }
+    state = {k: v.detach().cpu().clone() for k, v in out.items()}
+    state["sharding"] = {"rank": int(tb.rank), "world": int(tb.world), "vocab_size": int(plan.vocab_size),
+                         "rows_per_rank": int(plan.rows_per_rank), "layout": "mod"}
+    return state
+
+
+def merge_sliced_tables(slices, layout=None):
+    """Per-rank slices (export_sharded_tables, any order) -> one state in export_tables' format, loadable into the
+    unsharded cell with import_tables (evaluation, serving, re-sharding to another G).
+
+    layout "mod" (this repository: owner = row mod G, local index = row div G) interleaves the slices; layout
+    "contiguous" (the reference's TABLE_ROW_SLICE: rank r holds rows [r R, (r+1) R), what merge_sliced_parameter
+    concatenates) appends them.  Replicated entries (DenseLayers, their moments) are taken from rank 0 after checking
+    that every rank holds the same values."""
+    import torch
+    if not slices:
+        raise ValueError("merge_sliced_tables: no slices")
+    meta = [s["sharding"] for s in slices]
+    world = meta[0]["world"]
+    if sorted(m["rank"] for m in meta) != list(range(world)) or any(m["world"] != world for m in meta):
+        raise ValueError("merge_sliced_tables: need exactly one slice of every rank 0..%d" % (world - 1))
+    layout = layout or meta[0].get("layout", "mod")
+    if layout not in ("mod", "contiguous"):
+        raise ValueError("layout must be 'mod' or 'contiguous'")
+    by_rank = sorted(slices, key=lambda s: s["sharding"]["rank"])
+    vocab, rows = meta[0]["vocab_size"], meta[0]["rows_per_rank"]
+    out = {}
+    for key in _SLICED:
+        parts = [s[key] for s in by_rank]
+        if any(p.shape[0] != rows for p in parts):
+            raise ValueError("slice of %s does not have rows_per_rank = %d rows" % (key, rows))
+        full = torch.stack(parts, 1).reshape(rows * world, -1) if layout == "mod" else torch.cat(parts, 0)
+        out[key] = full[:vocab].contiguous()
+    for key in ("dense_layers+Wide_b", "adam.moment1.dense", "adam.moment2.dense", "ftrl.hyper"):
+        ref = by_rank[0][key]
+        for s in by_rank[1:]:
+            if not torch.equal(s[key], ref):
+                raise ValueError("replicated entry %s differs between ranks" % key)
+        out[key] = ref.clone()
+    # the unsharded cell keeps one Adam hyper block for the table and the DenseLayers (same step count on both)
+    out["adam.hyper"] = by_rank[0]["adam.hyper"].clone()
+    return out

@@ -64,3 +64,32 @@ def test_online_train_runs_until_stopped_and_fires_hooks_in_order():
     assert net.calls == 3 and params.cur_step_num == 3 and params.cur_epoch_num == 1
     assert events == ["begin", "epoch_begin"] + ["step_begin", "step_end"] * 3 + ["epoch_end", "end"]
     assert float(params.net_outputs) == 3900.0
+
+
+def test_merge_sliced_tables_mod_and_contiguous_layouts():
+    """Per-rank slices of a row-sharded checkpoint merge back into the full tables (models/wide_deep/eval.py:86-107) for
+    the owner = row mod G layout of this repository and for the reference's contiguous TABLE_ROW_SLICE split."""
+    import torch
+    from mindrec_b200 import train
+    torch.manual_seed(0)
+    vocab, dim, world = 103, 4, 4
+    rows = (vocab + world - 1) // world
+    full = {k: torch.randn(rows * world, 1 if "wide" in k or "ftrl" in k else dim) for k in train._SLICED}
+    dense = {"dense_layers+Wide_b": torch.randn(37), "adam.moment1.dense": torch.randn(37), "adam.moment2.dense": torch.randn(37),
+             "ftrl.hyper": torch.randn(16), "adam.hyper": torch.randn(16), "adam.hyper.dense": torch.randn(16)}
+    for layout in ("mod", "contiguous"):
+        slices = []
+        for r in range(world):
+            s = {k: (v[r::world] if layout == "mod" else v[r * rows:(r + 1) * rows]).clone() for k, v in full.items()}
+            s.update({k: v.clone() for k, v in dense.items()})
+            s["sharding"] = {"rank": r, "world": world, "vocab_size": vocab, "rows_per_rank": rows, "layout": layout}
+            slices.append(s)
+        merged = train.merge_sliced_tables(slices[::-1])
+        for k, v in full.items():
+            assert torch.equal(merged[k], v[:vocab])
+        assert torch.equal(merged["dense_layers+Wide_b"], dense["dense_layers+Wide_b"])
+    slices[1]["dense_layers+Wide_b"][0] += 1.0
+    with pytest.raises(ValueError, match="differs between ranks"):
+        train.merge_sliced_tables(slices)
+    with pytest.raises(ValueError, match="one slice of every rank"):
+        train.merge_sliced_tables(slices[:-1])

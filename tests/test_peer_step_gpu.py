@@ -72,6 +72,18 @@ SCRIPT = textwrap.dedent('''
     torch.testing.assert_close(deep, model.embedding_table.data, **tol)
     torch.testing.assert_close(wide, model.wide_embeddinglookup.embedding_table.data, **tol)
     torch.testing.assert_close(step.dense.flat, model.dense.flat, **tol)
+    # sharded checkpoint: this rank's slice -> merged state -> a fresh unsharded cell continues identically
+    from mindrec_b200 import train
+    merged = train.merge_sliced_tables([train.export_sharded_tables(step)])
+    model2 = cells.WideDeepModel(cfg, device=dev)
+    ref2 = cells.TrainStepWrap(cells.NetWithLossClass(model2, cfg), sparse=True, lazy_adam=True)
+    train.import_tables(ref2, merged)
+    l_sh = float(step.replay(*batches[1])[0])
+    l_un = float(ref2(*batches[1])[0])
+    np.testing.assert_allclose(l_sh, l_un, rtol=1e-3 if mixed else 1e-6)
+    wide, deep = step.tables.gather_full()
+    torch.testing.assert_close(deep, model2.embedding_table.data, **tol)
+    torch.testing.assert_close(step.dense.flat, model2.dense.flat, **tol)
     step.close()
     dist.destroy_process_group()
     print("PEER_STEP_OK", step.launches_per_step)
