@@ -97,6 +97,11 @@ int mrec_shard_remap(MREC_AOT_ARGS);
  *        peer_ptrs[G] i64 (landing-buffer base of every rank as mapped in this process), dst_off[G] i32,
  *        src_off[G+1] i32                                                                      out: dummy[1] */
 int mrec_gather_to_peers(MREC_AOT_ARGS);
+/* Split serve: with two more inputs — dirty[ceil(R/32)] i32 (bit r set = row r is rewritten by the current step's update,
+ * filled by mrec_bitmap_set from the owner-side dedup) and mode_like[mode,..] — mrec_gather_to_peers serves only the clean
+ * rows (mode 1: one step early, underneath the DenseLayers) or only the dirty rows (mode 2: after the update).
+ *   mrec_bitmap_set   in : rows[N] i32, count[1] i32        out: bitmap[W] i32 (bits OR-ed in; the caller clears) */
+int mrec_bitmap_set(MREC_AOT_ARGS);
 /* Device-driven exchange (no host-side sizes; the whole sharded step can be one CUDA graph).  With
  * B[s][o] = start of rank s's bucket for owner o among its sorted unique keys (B[s][G] = U_s):
  *   mrec_shard_offsets       in : bounds_all[G*(G+1)] i32, ctrl[2] i32 {rank, G}

@@ -22,11 +22,15 @@ struct PeerTable {
   int32_t src_off[kPeerMaxRanks + 1];
 };
 
+// `dirty` (optional): one bit per local table row, set for the rows the CURRENT step's update rewrites.  mode 1 serves
+// only the rows whose bit is clear (early, underneath the current step's DenseLayers: their values cannot change any
+// more before the next step reads them), mode 2 only the rows whose bit is set (after the update); mode 0 all rows.
 template <typename Vec>
 __global__ void __launch_bounds__(256)
 gather_to_peers_kernel(const float* __restrict__ table, const int32_t* __restrict__ rows, int64_t n_rows, int cpr,
                        int64_t vocab, int world, const int64_t* __restrict__ peer_ptrs,
-                       const int32_t* __restrict__ dst_off, const int32_t* __restrict__ src_off) {
+                       const int32_t* __restrict__ dst_off, const int32_t* __restrict__ src_off,
+                       const uint32_t* __restrict__ dirty, int mode) {
   __shared__ PeerTable s_t;
   if (threadIdx.x < world) {
     s_t.ptr[threadIdx.x] = reinterpret_cast<float*>(peer_ptrs[threadIdx.x]);
@@ -48,16 +52,31 @@ gather_to_peers_kernel(const float* __restrict__ table, const int32_t* __restric
       if (e < total) {
         const int64_t i = e / cpr;
         const int c = (int)(e - i * cpr);
-        int s = 0;
-        while (s + 1 < world && i >= s_t.src_off[s + 1]) ++s;   // G <= 16: a short scan of the bucket edges
         const int64_t row = rows[i];
-        dst[k] = reinterpret_cast<Vec*>(s_t.ptr[s]) + ((int64_t)s_t.dst_off[s] + (i - s_t.src_off[s])) * cpr + c;
-        if ((uint64_t)row < (uint64_t)vocab) v[k] = reinterpret_cast<const Vec*>(table)[row * cpr + c];
+        const bool in_range = (uint64_t)row < (uint64_t)vocab;
+        bool take = true;
+        if (mode != 0 && in_range) take = (((dirty[row >> 5] >> (row & 31)) & 1u) != 0u) == (mode == 2);
+        if (take) {
+          int s = 0;
+          while (s + 1 < world && i >= s_t.src_off[s + 1]) ++s;   // G <= 16: a short scan of the bucket edges
+          dst[k] = reinterpret_cast<Vec*>(s_t.ptr[s]) + ((int64_t)s_t.dst_off[s] + (i - s_t.src_off[s])) * cpr + c;
+          if (in_range) v[k] = reinterpret_cast<const Vec*>(table)[row * cpr + c];
+        }
       }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (dst[k]) *dst[k] = v[k];   // st.global on a peer-mapped address: goes out over NVLink
+  }
+}
+
+// bitmap[r >> 5] |= 1 << (r & 31) for the first count[0] entries of rows
+__global__ void bitmap_set_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ count, int64_t n,
+                                  uint32_t* __restrict__ bitmap, int64_t n_bits) {
+  const int64_t m = min(n, (int64_t)count[0]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = rows[i];
+    if ((uint64_t)r < (uint64_t)n_bits) atomicOr(&bitmap[r >> 5], 1u << (r & 31));
   }
 }
 
@@ -109,11 +128,13 @@ MREC_API int mrec_peer_free(void* p) { return cudaFree(p) == cudaSuccess ? OK : 
 //      peer_ptrs[G] i64 (base address of every rank's landing buffer [cap, D], as mapped in THIS process),
 //      dst_off[G] i32 (row offset inside rank s's landing buffer = s's bucket start for this owner),
 //      src_off[G+1] i32 (rows of source s are rows[src_off[s] : src_off[s+1]])
+//      optional: dirty[ceil(R/32)] i32 (one bit per local row), mode_like[mode, ..] (shape carrier: 1 = serve rows whose bit
+//      is clear, 2 = rows whose bit is set, 0 = all)
 // out: dummy[1] i32
 MREC_API int mrec_gather_to_peers(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
                                   void* stream, void* /*extra*/) {
   Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
-  MREC_CHECK_NPARAM(a, 6);
+  if (a.nparam != 6 && a.nparam != 8) return fail(ERR_NPARAM, "mrec_gather_to_peers: expected 6 or 8 params, got %d", a.nparam);
   MREC_REQUIRE(a.is_f32(0) && a.is_i32(1) && a.is_i64(2) && a.is_i32(3) && a.is_i32(4), ERR_DTYPE,
                "mrec_gather_to_peers: table f32, rows i32, peer_ptrs i64, dst_off/src_off i32");
   const int64_t vocab = a.dim(0, 0);
@@ -121,18 +142,41 @@ MREC_API int mrec_gather_to_peers(int nparam, void** params, int* ndims, int64_t
   const int world = (int)a.numel(2);
   MREC_REQUIRE(world >= 1 && world <= kPeerMaxRanks, ERR_SHAPE, "mrec_gather_to_peers: 1 <= G <= %d", kPeerMaxRanks);
   MREC_REQUIRE(a.numel(3) >= world && a.numel(4) >= world + 1, ERR_SHAPE, "mrec_gather_to_peers: dst_off[G], src_off[G+1]");
+  const uint32_t* dirty = nullptr;
+  int mode = 0;
+  if (a.nparam == 8) {                                // dirty[ceil(R / 32)] i32, mode_like[mode, ..] (1: clean rows, 2: dirty rows)
+    MREC_REQUIRE(a.is_i32(5), ERR_DTYPE, "mrec_gather_to_peers: the dirty bitmap is int32");
+    mode = (int)a.dim(6, 0);
+    MREC_REQUIRE(mode >= 0 && mode <= 2 && a.numel(5) * 32 >= vocab, ERR_SHAPE,
+                 "mrec_gather_to_peers: mode in {0,1,2}, one bitmap bit per table row");
+    dirty = reinterpret_cast<const uint32_t*>(a.params[5]);
+    if (mode != 0 && !dirty) return fail(ERR_NULL, "mrec_gather_to_peers: null bitmap");
+  }
   const int64_t n = a.numel(1);
   if (n == 0) return OK;
   if (dim % 4 == 0) {
     MREC_REQUIRE(a.aligned(0, 16), ERR_ALIGN, "mrec_gather_to_peers: table must be 16-byte aligned");
     const int cpr = dim / 4;
     MREC_LAUNCH(gather_to_peers_kernel<float4>, grid_for(cdiv(n * cpr, 1024), 8), 256, 0, a.stream, a.ptr<float>(0),
-                a.ptr<int32_t>(1), n, cpr, vocab, world, a.ptr<int64_t>(2), a.ptr<int32_t>(3), a.ptr<int32_t>(4));
+                a.ptr<int32_t>(1), n, cpr, vocab, world, a.ptr<int64_t>(2), a.ptr<int32_t>(3), a.ptr<int32_t>(4), dirty, mode);
   } else {
     MREC_LAUNCH(gather_to_peers_kernel<float>, grid_for(cdiv(n * dim, 1024), 8), 256, 0, a.stream, a.ptr<float>(0),
-                a.ptr<int32_t>(1), n, dim, vocab, world, a.ptr<int64_t>(2), a.ptr<int32_t>(3), a.ptr<int32_t>(4));
+                a.ptr<int32_t>(1), n, dim, vocab, world, a.ptr<int64_t>(2), a.ptr<int32_t>(3), a.ptr<int32_t>(4), dirty, mode);
   }
   return check_launch("gather_to_peers");
+}
+
+// in : rows[N] i32, count[1] i32 (only the first count rows are read)      out: bitmap[W] i32 — bit r is set for every row r
+MREC_API int mrec_bitmap_set(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                             void* /*extra*/) {
+  Aot a{nparam, params, ndims, shapes, dtypes, (cudaStream_t)stream};
+  if (a.nparam != 3) return fail(ERR_NPARAM, "mrec_bitmap_set: expected 3 params, got %d", a.nparam);
+  MREC_REQUIRE(a.is_i32(0) && a.is_i32(1) && a.is_i32(2) && a.numel(1) >= 1, ERR_DTYPE, "mrec_bitmap_set: rows, count, bitmap int32");
+  const int64_t n = a.numel(0);
+  if (n == 0 || a.numel(2) == 0) return OK;
+  MREC_LAUNCH(bitmap_set_kernel, grid_for(cdiv(n, 256), 4), 256, 0, a.stream, a.ptr<int32_t>(0), a.ptr<int32_t>(1), n,
+              reinterpret_cast<uint32_t*>(a.params[2]), a.numel(2) * 32);
+  return check_launch("bitmap_set");
 }
 
 // =================================================================================================

@@ -458,9 +458,25 @@ def _empty_like_dtype(t):
     return e
 
 
-def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
-    """Owner-side gather fused with the NVLink peer store of every row into its requester's landing buffer."""
-    _lib.aot_call("mrec_gather_to_peers", [table, rows, peer_ptrs, dst_off, src_off, _dummy(table.device)])
+_mode_like = {}
+
+
+def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off, dirty=None, mode=0):
+    """Owner-side gather fused with the NVLink peer store of every row into its requester's landing buffer.
+    dirty (int32 bitmap, one bit per table row) + mode: 1 = only rows whose bit is clear, 2 = only rows whose bit is set."""
+    if dirty is None or mode == 0:
+        _lib.aot_call("mrec_gather_to_peers", [table, rows, peer_ptrs, dst_off, src_off, _dummy(table.device)])
+        return
+    key = (table.device, mode)
+    ml = _mode_like.get(key)
+    if ml is None:
+        ml = _mode_like[key] = _alloc(table.device, (mode, 0), "float32")
+    _lib.aot_call("mrec_gather_to_peers", [table, rows, peer_ptrs, dst_off, src_off, dirty, ml, _dummy(table.device)])
+
+
+def bitmap_set(rows, count, bitmap):
+    """bitmap bit r |= 1 for r in rows[:count] (device-side count)."""
+    _lib.aot_call("mrec_bitmap_set", [rows, count, bitmap])
 
 
 def shard_offsets(bounds_all, ctrl, dst_off, src_off, inbox_off, n_r):

@@ -33,6 +33,7 @@ N_PHASES = 4
 # bisection switches (diagnostics only): keep the dim-1 twins / the dense update in line on the main stream
 _NO_WIDE_FORK = os.environ.get("MREC_PEER_NO_WIDE_FORK", "0") == "1"
 _NO_DENSE_FORK = os.environ.get("MREC_PEER_NO_DENSE_FORK", "0") == "1"
+_NO_EARLY_SERVE = os.environ.get("MREC_PEER_NO_EARLY_SERVE", "0") == "1"    # every row is served after the update
 _PEER_BUFFERS = ("ball", "keys_in", "land_deep", "land_wide", "grad_in", "gwide_in", "flags")
 
 
@@ -120,6 +121,10 @@ class PeerRank:
             }
             self._sets.append(st)
         self.cur = 0
+        # one bit per owned row: set for the rows the CURRENT step's update rewrites (its owner-side dedup names them).
+        # Rows of the NEXT batch whose bit is clear are served one step early, underneath the DenseLayers (p_serve_early);
+        # only the others — the Zipf head both batches share — wait for the update (p_serve(late=True)).
+        self.dirty = torch.zeros((r + 31) // 32, dtype=i32, device=dev)
         self.gs_wide = torch.empty((n_lookups, 1), dtype=f32, device=dev)
         self._bound_like = torch.empty((g * r, 0), device=dev)
         self._vocab_like = torch.empty((vocab_size, 0), device=dev)
@@ -201,25 +206,47 @@ class PeerRank:
                                self._mod_rows, self.err)
         self.signal(1)
 
-    def p_key_phase(self, ids, nxt=False):
+    def p_key_phase(self, ids, nxt=False, early_serve=False):
         """Everything of a batch that does not depend on the table's values: plan, publish, key push, owner dedup.
         With nxt=True it runs for the NEXT batch on the other set (callers put it on a forked branch underneath the
-        current step's DenseLayers); its waits only depend on the peers' key phases."""
+        current step's DenseLayers); its waits only depend on the peers' key phases.  early_serve: additionally serve
+        the requested rows that the current step's update will not touch (p_mark_updates must have run)."""
         self.p_plan_local(ids, nxt)
         self.p_publish(nxt)
         self.wait(0)
         self.p_keys(nxt)
         self.wait(1)
         self.p_owner_dedup(nxt)
+        if early_serve:
+            self.p_serve_early(nxt)
 
-    # `side` (a stream, optional) in the next three: the dim-1 work of the wide vector runs there, beside the
+    # `side` (a stream, optional) in the next ones: the dim-1 work of the wide vector runs there, beside the
     # bandwidth-bound deep rows (forked from / joined back into the current stream — a parallel branch when captured)
-    def p_serve(self, side=None):
+    def _serve(self, st, mode, side):
         with _Fork(side):
-            ops.gather_to_peers(self.wide, self.keys_in, self.ptrs["land_wide"], self.dst_off, self.src_off)
-        ops.gather_to_peers(self.deep, self.keys_in, self.ptrs["land_deep"], self.dst_off, self.src_off)
+            ops.gather_to_peers(self.wide, st["keys_in"], self.ptrs["land_wide"], st["dst_off"], st["src_off"],
+                                dirty=self.dirty, mode=mode)
+        ops.gather_to_peers(self.deep, st["keys_in"], self.ptrs["land_deep"], st["dst_off"], st["src_off"],
+                            dirty=self.dirty, mode=mode)
         _join(side)
+
+    def p_serve(self, side=None, late=False):
+        """Serve the current batch's rows (late=True: only those the previous update rewrote — the rest went out with
+        p_serve_early one step ahead), then signal 2."""
+        self._serve(self._s(), 2 if late else 0, side)
         self.signal(2)
+
+    def p_serve_early(self, nxt=True, side=None):
+        """Rows of the batch on the other set that the CURRENT step's update does not touch: their values are final, so
+        they cross NVLink now.  No signal: the late part of the same serve sends it.  (Every requester has finished
+        expanding its current batch: this runs after wait 1 of the next batch's key phase, and a peer signals 1 after
+        its expand.)"""
+        self._serve(self._s(nxt), 1, side)
+
+    def p_mark_updates(self):
+        """dirty := the rows this step's update rewrites (the current set's owner-side dedup)."""
+        self.dirty.zero_()
+        ops.bitmap_set(self.uq_owner.uniq, self.uq_owner.count, self.dirty)
 
     def p_expand(self, ids_shape, wts, wide_bias, deep_out, wide_out, side=None):
         inverse = self.uq.inverse.view(ids_shape)
@@ -280,8 +307,9 @@ class EmulatedPeerGroup:
         for rk in self.ranks:
             rk.connect(base)
 
-    def key_phase_next(self, ids_list):
-        """The NEXT batch's key phase on the other buffer set, phase-major (what a2's forked branch does per rank)."""
+    def key_phase_next(self, ids_list, early_serve=True):
+        """The NEXT batch's key phase on the other buffer set, phase-major (what the step graph's forked branch does
+        per rank), followed by the early part of its serve."""
         for rk, ids in zip(self.ranks, ids_list):
             rk.p_plan_local(ids, nxt=True)
             rk.p_publish(nxt=True)
@@ -291,25 +319,35 @@ class EmulatedPeerGroup:
         for rk in self.ranks:
             rk.wait(1)
             rk.p_owner_dedup(nxt=True)
+        if early_serve:
+            for rk in self.ranks:
+                rk.p_serve_early(nxt=True)
+        self._early = bool(early_serve)
 
     def forward(self, ids_list, wts_list, bias, deep_outs, wide_outs, planned=False):
-        """planned=True: the batch went through key_phase_next during the previous step; adopt that set."""
+        """planned=True: the batch went through key_phase_next during the previous step; adopt that set (and serve only
+        the rows the previous update rewrote, if the rest went out early)."""
+        late = False
         if planned:
             for rk in self.ranks:
                 rk.p_adopt()
+            late = getattr(self, "_early", False)
         else:
             for rk, ids in zip(self.ranks, ids_list):
                 rk.p_plan_publish(ids)
             for rk in self.ranks:
                 rk.wait(0)
                 rk.p_keys()
+        self._early = False
         for rk in self.ranks:
             if not planned:
                 rk.wait(1)
-            rk.p_serve()
+                rk.p_owner_dedup()
+            rk.p_serve(late=late)
         for rk, ids, wts, do, wo in zip(self.ranks, ids_list, wts_list, deep_outs, wide_outs):
             rk.wait(2)
             rk.p_expand(ids.shape, wts, bias, do, wo)
+            rk.p_mark_updates()
 
     def backward(self, deltas, gxs):
         for rk, d, g in zip(self.ranks, deltas, gxs):
@@ -704,14 +742,21 @@ class PeerShardedTables:
             rk.p_key_phase(ids)
         return _DevicePlan(ids)
 
-    def key_phase_next(self, ids):
-        """Key phase of the NEXT batch on the other set (call it on a forked branch underneath the DenseLayers)."""
-        self.rk.p_key_phase(ids, nxt=True)
+    def key_phase_next(self, ids, early_serve=True):
+        """Key phase of the NEXT batch on the other set, then the early part of its serve: the requested rows this
+        step's update does not touch (call it on a forked branch underneath the DenseLayers, after `lookup`: the bitmap
+        of the rows this step rewrites replaces the previous step's, which `lookup(late=True)` has just used)."""
+        early = early_serve and not _NO_EARLY_SERVE
+        if early:
+            self.rk.p_mark_updates()
+        self.rk.p_key_phase(ids, nxt=True, early_serve=early)
 
-    def lookup(self, plan, wts, wide_bias, deep_out, wide_out):
+    def lookup(self, plan, wts, wide_bias, deep_out, wide_out, late=False):
+        """late=True: the batch's key phase ran one step ahead WITH its early serve, so only the rows the previous update
+        rewrote still have to cross NVLink."""
         rk = self.rk
         side = None if _NO_WIDE_FORK else self.owner_stream
-        rk.p_serve(side=side)
+        rk.p_serve(side=side, late=late and not _NO_EARLY_SERVE)
         rk.wait(2)
         rk.p_expand(plan.ids.shape, wts, wide_bias, deep_out, wide_out, side=side)
         return wide_out, deep_out
@@ -832,11 +877,13 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         """Key phase of the current batch in line (first step, or no look-ahead was given)."""
         self.tables.plan_batch(self._slots[self.tables.rk.cur][0])
 
-    def _body(self, ahead=True):
+    def _body(self, ahead=True, late=False):
+        """ahead: run the next batch's key phase + early serve on the forked branch.  late: this batch went through that
+        one step ago (it is being adopted), so the serve only moves the rows the previous update rewrote."""
         main = torch.cuda.current_stream()
         rk = self.tables.rk
         ids, wts, label = self._slots[rk.cur]
-        self.tables.lookup(_DevicePlan(ids), wts, self.wide_b, self._io["deep_in"], self._io["wide_out"])
+        self.tables.lookup(_DevicePlan(ids), wts, self.wide_b, self._io["deep_in"], self._io["wide_out"], late=late)
         if ahead:
             self._plan_stream.wait_stream(main)
             with torch.cuda.stream(self._plan_stream):
@@ -874,10 +921,11 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
         g = self._graphs[rk.cur] if self._graphs is not None else None
         if not adopt:
             g["pre"].replay() if g is not None else self._pre()
+        # an adopted batch had the clean part of its rows served one step early (late = adopt)
         if g is not None:
-            g["step" if ahead else "step_plain"].replay()
+            g[("step" if ahead else "step_plain") + ("" if adopt else "_full")].replay()
         else:
-            self._body(ahead)
+            self._body(ahead, late=adopt)
         return self._loss
 
     def capture(self, ids, wts, label, warmup=3):
@@ -898,8 +946,10 @@ class PeerShardedWideDeepStep(ShardedWideDeepStep):
             for si in range(2):
                 rk.use_set(si)
                 graphs = {}
-                for name, fn in (("pre", self._pre), ("step", lambda: self._body(True)),
-                                 ("step_plain", lambda: self._body(False))):
+                for name, fn in (("pre", self._pre), ("step", lambda: self._body(True, late=True)),
+                                 ("step_full", lambda: self._body(True, late=False)),
+                                 ("step_plain", lambda: self._body(False, late=True)),
+                                 ("step_plain_full", lambda: self._body(False, late=False))):
                     gr = torch.cuda.CUDAGraph()
                     n0 = _lib.launch_count()
                     with torch.cuda.graph(gr, pool=pool, stream=self._main_stream):

@@ -106,17 +106,28 @@ def segment_sum_to_peers(g, mask, uq, my_bounds, inbox_off, peer_ptrs, cap_like,
     push_rows_to_peers(gs, my_bounds, inbox_off, peer_ptrs, cap_like, torch.empty((0, 0)), err)
 
 
-def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off):
+def gather_to_peers(table, rows, peer_ptrs, dst_off, src_off, dirty=None, mode=0):
     t = _np(table)
     d = t.shape[1]
     g = peer_ptrs.numel()
     r = _np(rows)
+    bits = _np(dirty).view(np.uint32) if dirty is not None else None
     for s in range(g):
         lo, hi = int(src_off[s]), min(int(src_off[s + 1]), r.size)      # like the kernel: never past the inbox
         for j in range(max(0, hi - lo)):
-            dst = _at(int(peer_ptrs[s]) + (int(dst_off[s]) + j) * d * 4, d, ctypes.c_float, np.float32)
             row = int(r[lo + j])
-            dst[:] = t[row] if 0 <= row < t.shape[0] else 0.0
+            ok = 0 <= row < t.shape[0]
+            if mode and ok and bool((int(bits[row >> 5]) >> (row & 31)) & 1) != (mode == 2):
+                continue                                                 # the other half of the split serve moves this row
+            dst = _at(int(peer_ptrs[s]) + (int(dst_off[s]) + j) * d * 4, d, ctypes.c_float, np.float32)
+            dst[:] = t[row] if ok else 0.0
+
+
+def bitmap_set(rows, count, bitmap):
+    b = _np(bitmap).view(np.uint32)
+    for row in _np(rows)[:int(count[0])].tolist():
+        if 0 <= row < b.size * 32:
+            b[row >> 5] |= np.uint32(1 << (row & 31))
 
 
 def peer_signal(payload, payload_ptrs, flag_ptrs, epoch):

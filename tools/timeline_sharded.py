@@ -57,10 +57,11 @@ def main():
         ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
         ev.sort(key=lambda e: e["ts"])
         # cut into steps at the first kernel of graph a1 (gather_to_peers) / of the step
-        marker = "gather_to_peers" if not c5 else ev[0]["name"]
-        starts = [i for i, e in enumerate(ev) if marker in e["name"]]
-        if not c5:
-            starts = starts[::2]                    # two gather_to_peers launches per step (deep, wide)
+        # a step ends with the LazyAdam row update of the (last) table: cut behind it
+        ends = [i for i, e in enumerate(ev) if "LazyAdamSink" in e["name"]]
+        if c5:
+            ends = ends[1::2]                       # two LazyAdam updates per step (table, MapParameter)
+        starts = [i + 1 for i in ends]
         if len(starts) >= 4:
             lo, hi = starts[2], starts[3]
         else:
