@@ -698,6 +698,7 @@ def run_ours(args):
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     if hasattr(step, "_pending"):
         step._pending = None                                        # drop the look-ahead of the resident loop
+        step._pending_src = None
     loss_seen = []
 
     def e2e_step(i):

@@ -722,7 +722,6 @@ class PeerShardedTables:
         self.device = torch.device(device)
         self.plan_stream = None
         self.owner_stream = torch.cuda.Stream(device=self.device, priority=-1)       # exchange kernels: see main_stream
-        self._side_open = False
         arena = self._arena = _IpcArena(group)
         self.rk = _connect_collectively(
             lambda: PeerRank(self.rank, self.world, vocab_size, emb_dim, n_lookups, device, arena.alloc(device),
@@ -779,12 +778,6 @@ class PeerShardedTables:
             rk.p_update_wide()
         rk.p_update_deep()
         main.wait_stream(self.owner_stream)
-
-    def join_side(self):
-        """Join the forked dedup branch (a captured graph must end with every branch joined)."""
-        if self._side_open:
-            torch.cuda.current_stream().wait_stream(self.owner_stream)
-            self._side_open = False
 
     @property
     def wide(self):

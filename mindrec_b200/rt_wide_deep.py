@@ -120,6 +120,13 @@ class WideDeepRT:
             if i != nl - 2:                                  # (the head kernel did layer nl-2's ReluGrad + BiasAddGrad)
                 g = ops.relu_bwd_bias(g, self.acts[i + 1], self.gb[i])
             runtime.gemm(self.acts[i], g, self.gw[i], trans_a=True)                      # weight gradient, fp32 out
+            if i == 0 and mixed:
+                # every DenseLayer gradient has been issued, and the last GEMM reads the fp16 shadow of the weights: the
+                # dense Adam rewrites the fp32 masters on a forked branch underneath it
+                self.side2.wait_stream(main)
+                with dev.use_stream(self.side2):
+                    ops.adam_begin_step(self.adam_dense)
+                    ops.adam_dense(self.flat, self.flat_m, self.flat_v, self.adam_dense, self.flat_grad)
             g = runtime.gemm(g, self.w[i], self.g[i], trans_b=True)                      # input gradient
         gx = g.view(n, self.d)
         mask = self.wts.view(-1)
@@ -130,8 +137,11 @@ class WideDeepRT:
             ops.sparse_ftrl(self.wide, self.acc, self.lin, self.ftrl_wide, delta, mask, self.uq)
         ops.adam_begin_step(self.adam_deep)
         ops.sparse_lazy_adam(self.deep, self.m, self.vv, self.adam_deep, gx, mask, self.uq)
-        ops.adam_begin_step(self.adam_dense)
-        ops.adam_dense(self.flat, self.flat_m, self.flat_v, self.adam_dense, self.flat_grad)
+        if mixed:
+            main.wait_stream(self.side2)
+        else:
+            ops.adam_begin_step(self.adam_dense)
+            ops.adam_dense(self.flat, self.flat_m, self.flat_v, self.adam_dense, self.flat_grad)
         main.wait_stream(self.side)
         return loss
 

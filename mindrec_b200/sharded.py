@@ -392,6 +392,7 @@ class ShardedWideDeepStep:
         self._io = None
         self._slots = None
         self._pending = None
+        self._pending_src = None
         self.profile = None          # cells.StepProfile: per-phase CUDA-event timing of eager calls
 
     # ---- fixed-shape segment -----------------------------------------------------------------------
@@ -486,8 +487,12 @@ class ShardedWideDeepStep:
                     d.copy_(s, non_blocking=True)
             plan = self.tables.plan_batch(cur[0])
         else:
+            if ids is not None and self._pending_src is not None and self._pending_src is not ids:
+                raise ValueError("replay(): the batch passed in is not the one given as next_batch to the previous call "
+                                 "(its dedup was planned one step ahead); pass the same tensors or next_batch=None")
             plan = self._pending
         self._pending = None
+        self._pending_src = None
         if next_batch is not None and _ENV_AHEAD:
             nxt = self._slots[self._cur ^ 1]
             side = self.tables.plan_stream
@@ -500,6 +505,7 @@ class ShardedWideDeepStep:
                 for d, s in zip(nxt, next_batch):
                     d.copy_(s)
             self._pending = self.tables.plan_batch(nxt[0], ahead=True)
+            self._pending_src = next_batch[0]
         out = self._step(plan, cur[1], cur[2])
         if self._pending is not None:
             self._cur ^= 1

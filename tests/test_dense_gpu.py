@@ -102,3 +102,30 @@ def test_dense_stack_backward_matches_autograd(cuda, mixed):
         close("gw%d" % i, stack.gw[i], ws[i].grad)
         close("gb%d" % i, stack.gb[i], bs[i].grad)
     assert all(e < 5e-2 for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_dense_stack_input_in_column_blocks_equals_concatenated_input(cuda, mixed):
+    """DenseStack.forward((x_a, x_b)) — two lookups feeding one tower without a concatenation copy (config 5) — against
+    the same stack on cat(x_a, x_b): outputs, every weight / bias gradient and the per-block input gradients; and
+    on_weight_grads fires once, after the last weight gradient and before the layer-0 input gradient."""
+    dims = [96 + 160, 64, 32, 1]
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(3)
+    a = nn.DenseStack(dims, mixed, cuda, generator=gen, bias_init="normal")
+    b = nn.DenseStack(dims, mixed, cuda, storage=(a.flat.clone(), torch.zeros_like(a.flat_grad)))
+    x = torch.randn((300, dims[0]), device=cuda, generator=gen)
+    if mixed:
+        x = x.half()
+    xa, xb = x[:, :96].contiguous(), x[:, 96:].contiguous()
+    ya, yb = a.forward(x), b.forward((xa, xb))
+    tol = dict(rtol=2e-2, atol=2e-3) if mixed else dict(rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(yb, ya, **tol)
+    go = torch.randn((300, 1), device=cuda, generator=gen) * 0.01
+    calls = []
+    ga = a.backward(go)
+    gb = b.backward(go, on_weight_grads=lambda: calls.append(float(b.gw[0].abs().sum())))
+    assert len(calls) == 1 and calls[0] > 0          # issued after layer 0's weight gradient
+    assert isinstance(gb, tuple) and [g.shape[1] for g in gb] == [96, 160]
+    torch.testing.assert_close(torch.cat(gb, 1).float(), ga.float(), **tol)
+    torch.testing.assert_close(b.flat_grad, a.flat_grad, **(dict(rtol=2e-2, atol=2e-3) if mixed else dict(rtol=1e-4, atol=1e-6)))

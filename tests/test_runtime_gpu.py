@@ -113,6 +113,38 @@ SCRIPT = textwrap.dedent('''
     dev.stream.wait_event(ev)
     np.testing.assert_array_equal(ops.gather(d_w, staged).numpy(), R.gather(w, ids[::-1]))
 
+    # mrec_rt_gemm (cuBLASLt bound with dlopen): every transpose / storage / epilogue combination vs float64 numpy
+    rng2 = np.random.default_rng(5)
+    for (m_, n_, k_) in ((64, 48, 40), (257, 24, 136), (8, 512, 64)):
+        for ta in (False, True):
+            for tb in (False, True):
+                for ab, cd in (("float32", "float32"), ("float16", "float16"), ("float16", "float32")):
+                    a_h = rng2.standard_normal((k_, m_) if ta else (m_, k_)).astype(ab)
+                    b_h = rng2.standard_normal((n_, k_) if tb else (k_, n_)).astype(ab)
+                    want = (a_h.T if ta else a_h).astype(np.float64) @ (b_h.T if tb else b_h).astype(np.float64)
+                    tol = dict(rtol=2e-3, atol=2e-2) if "float16" in (ab, cd) else dict(rtol=1e-5, atol=1e-4)
+                    out = dev.empty((m_, n_), cd)
+                    runtime.gemm(dev.from_numpy(a_h), dev.from_numpy(b_h), out, trans_a=ta, trans_b=tb)
+                    np.testing.assert_allclose(out.numpy().astype(np.float64), want, **tol)
+                    bias_h = rng2.standard_normal(n_).astype(cd)
+                    runtime.gemm(dev.from_numpy(a_h), dev.from_numpy(b_h), out, bias=dev.from_numpy(bias_h), relu=True,
+                                 trans_a=ta, trans_b=tb)
+                    np.testing.assert_allclose(out.numpy().astype(np.float64), np.maximum(want + bias_h.astype(np.float64), 0), **tol)
+    acc = dev.from_numpy(np.ones((64, 48), np.float32))          # beta = 1 accumulates into out
+    a_h, b_h = rng2.standard_normal((64, 40)).astype(np.float32), rng2.standard_normal((40, 48)).astype(np.float32)
+    runtime.gemm(dev.from_numpy(a_h), dev.from_numpy(b_h), acc, alpha=0.5, beta=1.0)
+    np.testing.assert_allclose(acc.numpy(), 1.0 + 0.5 * (a_h.astype(np.float64) @ b_h), rtol=1e-5, atol=1e-4)
+    for bad in (lambda: runtime.gemm(dev.empty((4, 5)), dev.empty((6, 7)), dev.empty((4, 7))),
+                lambda: runtime.gemm(dev.empty((4, 5)), dev.empty((5, 7), "float16"), dev.empty((4, 7))),
+                lambda: runtime.gemm(dev.empty((4, 5)), dev.empty((5, 7)), dev.empty((4, 7)), relu=True)):
+        try:
+            bad()
+            raise SystemExit("gemm accepted inconsistent arguments")
+        except (ValueError, TypeError):
+            pass
+    src = rng2.standard_normal(1003).astype(np.float32)
+    np.testing.assert_array_equal(ops.cast_f32_f16(dev.from_numpy(src)).numpy(), src.astype(np.float16))
+
     assert _lib.launch_count() - before > 20
     assert "torch" not in sys.modules, "the runtime path imported torch"
     print("RUNTIME_OK", _lib.launch_count() - before)
