@@ -1,2 +1,2 @@
-N=${N:-4}
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/r2ae_bench$N.json 2> gpurun_out/r2ae_bench$N.err; echo "bench rc=$?"
+timeout 600 python -m pytest tests/test_dense_gpu.py tests/test_runtime_gpu.py tests/test_rt_wide_deep_gpu.py -m gpu -q --timeout=600 -x -k "column_blocks or torch" > gpurun_out/r2ag_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2ag_pytest.log
+tail -25 gpurun_out/r2ag_pytest.log
