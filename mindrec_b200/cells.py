@@ -271,7 +271,6 @@ class TrainStepWrap:
         self._static = None
         self.profile = None
         self._staged = None
-        self._staging = None
         self.overlap = True          # fork dedup / FTRL onto a side stream (see construct)
         self._side = None
 
@@ -373,12 +372,15 @@ class TrainStepWrap:
 
     # ---- CUDA-graph replay of the whole step -------------------------------------------------------
     def capture(self, batch_ids, batch_wts, label, warmup=3):
-        """Capture construct() on static input buffers.  Afterwards `replay(ids, wts, label)` copies the
-        inputs in and launches the graph."""
+        """Capture construct() on static input buffers.  Afterwards `replay(ids, wts, label)` launches the captured
+        step.  The static inputs exist TWICE (one captured graph each, sharing one memory pool): while a step runs on
+        one slot, the next batch is copied into the other on a copy stream, so no input copy sits on the step's critical
+        path."""
         if self.dynamic and (self.model.wide_embeddinglookup.auto_grow or self.model.deep_embeddinglookup.auto_grow):
             raise RuntimeError("dynamic_embedding with hash_auto_grow=True cannot be captured (growth re-allocates the "
                                "tables): size hash_capacity up front and set hash_auto_grow=False")
-        self._static = (batch_ids.clone(), batch_wts.clone(), label.clone())
+        self._slots = [(batch_ids.clone(), batch_wts.clone(), label.clone()) for _ in range(2)]
+        self._static = self._slots[0]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -386,41 +388,49 @@ class TrainStepWrap:
                 self.construct(*self._static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_out = self.construct(*self._static)
+        self._graphs, self._outs, pool = [], [], None
+        for slot in self._slots:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                out = self.construct(*slot)
+            pool = pool or g.pool()
+            self._graphs.append(g)
+            self._outs.append(out)
+        self._graph, self._static_out = self._graphs[0], self._outs[0]
+        self._cur = 0
+        self._staged = None
+        self._copy_stream = torch.cuda.Stream(device=batch_ids.device)
         return self._static
 
     def replay(self, batch_ids=None, batch_wts=None, label=None, next_batch=None):
-        """Copy the batch into the graph's static inputs and launch the captured step.
+        """Launch the captured step on (batch_ids, batch_wts, label).
 
-        next_batch (optional): the batch the caller will pass next.  It is staged to the device on a copy
-        stream while this step computes, so that its host->device transfer (5 MB over PCIe for 16000 x 39)
-        is off the critical path; the next call then only does a device-to-device copy."""
+        next_batch (optional, pinned-host or device tensors): the batch the caller will pass next.  It is copied into
+        the OTHER input slot on a copy stream while this step computes (5 MB over PCIe for 16000 x 39 from the host);
+        passing the same tensors to the next call then costs no copy at all.  A batch that was not announced is copied
+        into the current slot on the compute stream."""
         main = torch.cuda.current_stream()
+        slot = self._cur
         if batch_ids is not None:
             if self._staged is not None and self._staged[0] is batch_ids:
+                slot = self._staged[2]
                 main.wait_event(self._staged[1])
-                for d, s_ in zip(self._static, self._staging):
-                    d.copy_(s_, non_blocking=True)
             else:
-                self._static[0].copy_(batch_ids, non_blocking=True)
-                self._static[1].copy_(batch_wts, non_blocking=True)
-                self._static[2].copy_(label, non_blocking=True)
+                for d, s_ in zip(self._slots[slot], (batch_ids, batch_wts, label)):
+                    d.copy_(s_, non_blocking=True)
         self._staged = None
-        if next_batch is not None and not next_batch[0].is_cuda:
-            if self._staging is None:
-                self._staging = tuple(torch.empty_like(t) for t in self._static)
-                self._copy_stream = torch.cuda.Stream(device=self._static[0].device)
-            self._copy_stream.wait_stream(main)       # the previous staged batch has been consumed
+        self._cur = slot
+        if next_batch is not None:
+            other = slot ^ 1
+            self._copy_stream.wait_stream(main)       # the last step that read this slot has been enqueued
             with torch.cuda.stream(self._copy_stream):
-                for d, s_ in zip(self._staging, next_batch):
+                for d, s_ in zip(self._slots[other], next_batch):
                     d.copy_(s_, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
-            self._staged = (next_batch[0], ev)
-        self._graph.replay()
-        return self._static_out
+            self._staged = (next_batch[0], ev, other)
+        self._graphs[slot].replay()
+        return self._outs[slot]
 
 
 class PredictWithSigmoid:
