@@ -60,8 +60,9 @@ class WideDeepRT:
             o += m_
         self.wide_b, self.wide_b_grad = self.flat[o:o + 1], self.flat_grad[o:o + 1]
         # ---- static inputs, activations, gradients: nothing is allocated inside a step (graph capture) ------------------
-        self.ids = dev.zeros((b, self.f), id_dtype)
-        self.wts, self.label = dev.zeros((b, self.f)), dev.zeros((b, 1))
+        # two input slots (one captured graph each): while a step runs on one, the next batch is copied into the other
+        self.slots = [(dev.zeros((b, self.f), id_dtype), dev.zeros((b, self.f)), dev.zeros((b, 1))) for _ in range(2)]
+        self.cur = 0
         self.acts = [dev.empty((b, self.dims[0]), act)] + [dev.empty((b, self.dims[i]), act) for i in range(1, nl)]
         self.deep_out, self.wide_out = dev.empty((b, 1)), dev.empty((b, 1))
         self.loss_out = (dev.empty((b, 1)), dev.zeros(1), dev.empty((b, 1)), dev.empty((b, 1) if mixed else (0,), "float16"),
@@ -69,9 +70,14 @@ class WideDeepRT:
         self.g = [dev.empty((b, self.dims[i]), act) for i in range(nl)]      # gradient wrt the input of layer i
         self.sens_t = dev.tensor([self.sens])
         self.uq = ops.UniqueResult(n, id_dtype, dev)
-        self.side, self.side2 = runtime.Stream(), runtime.Stream()
-        self.graph = None
+        self.side, self.side2, self.copy_stream = runtime.Stream(), runtime.Stream(), runtime.Stream()
+        self.graphs = None
+        self._staged = None
         self.launches_per_step = None
+
+    ids = property(lambda self: self.slots[self.cur][0])
+    wts = property(lambda self: self.slots[self.cur][1])
+    label = property(lambda self: self.slots[self.cur][2])
 
     def _init_table(self, t, std, seed):
         """normal(0, std) rows: one random block of 2^16 rows tiled over the table (synthetic weights; tests load theirs)."""
@@ -152,24 +158,46 @@ class WideDeepRT:
         for _ in range(max(1, warmup)):
             self._body()
         self.dev.synchronize()
-        n0 = _lib.launch_count()
-        with self.dev.capture() as g:
-            self._body()
-        self.launches_per_step = _lib.launch_count() - n0
-        self.graph = g
+        keep, graphs = self.cur, []
+        for slot in (0, 1):                                  # the same step, reading the other input slot
+            self.cur = slot
+            n0 = _lib.launch_count()
+            with self.dev.capture() as g:
+                self._body()
+            self.launches_per_step = _lib.launch_count() - n0
+            graphs.append(g)
+        self.cur, self.graphs = keep, graphs
         return self
 
     def set_inputs(self, ids, wts, label):
-        for dst, src in ((self.ids, ids), (self.wts, wts), (self.label, label)):
+        for dst, src in zip(self.slots[self.cur], (ids, wts, label)):
             dst.copy_(src)
 
-    def train_step(self, ids=None, wts=None, label=None):
-        """Copy the batch into the static inputs (numpy arrays — pin them and set dev.async_host_copies for overlap —
-        or DeviceBuffers) and run one step.  Returns the loss as a DeviceBuffer [1] (`.item()` reads it)."""
+    def train_step(self, ids=None, wts=None, label=None, next_batch=None):
+        """One step on (ids, wts, label): numpy arrays (pin them and set dev.async_host_copies for overlap) or
+        DeviceBuffers.  next_batch: the batch the caller will pass next — it is copied into the other input slot on a copy
+        stream while this step runs; passing the same objects to the next call then costs no copy.  Returns the loss as
+        a DeviceBuffer [1] (`.item()` reads it)."""
+        dev = self.dev
+        main = runtime.Stream(dev.current_stream_handle())
         if ids is not None:
-            self.set_inputs(ids, wts, label)
-        if self.graph is not None:
-            self.graph.launch()
+            if self._staged is not None and self._staged[0] is ids:
+                self.cur = self._staged[2]
+                main.wait_event(self._staged[1])
+            else:
+                self.set_inputs(ids, wts, label)
+        self._staged = None
+        if next_batch is not None:
+            other = self.cur ^ 1
+            self.copy_stream.wait_stream(main)               # the last step that read that slot has been enqueued
+            with dev.use_stream(self.copy_stream):
+                for dst, src in zip(self.slots[other], next_batch):
+                    dst.copy_(src)
+            ev = runtime.Event()
+            ev.record(self.copy_stream)
+            self._staged = (next_batch[0], ev, other)
+        if self.graphs is not None:
+            self.graphs[self.cur].launch()
         else:
             self._body()
         return self.loss_out[1]

@@ -88,9 +88,12 @@ SCRIPT = textwrap.dedent('''
     a.capture(warmup=1)
     assert a.launches_per_step >= 15
     e.train_step(*bt[0])
-    for ids, wts, label in bt[1:]:
-        la = a.train_step(ids, wts, label).item()
-        le = e.train_step(ids, wts, label).item()
+    dbt = [tuple(dev.from_numpy(x) for x in b_) for b_ in bt]          # device-resident copies: staged D2D on the copy stream
+    for i in range(1, 4):
+        nxt = (dbt[i + 1] if i % 2 else bt[i + 1]) if i + 1 < 4 else None   # announced from the device / from the host / not
+        cur = dbt[i] if (i - 1) % 2 and i > 1 else bt[i]
+        la = a.train_step(*cur, next_batch=nxt).item()
+        le = e.train_step(*bt[i]).item()
         assert la == le
     for x, y in ((a.deep, e.deep), (a.wide, e.wide), (a.flat, e.flat), (a.m, e.m), (a.acc, e.acc)):
         np.testing.assert_array_equal(x.numpy(), y.numpy())
