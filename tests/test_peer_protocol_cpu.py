@@ -80,6 +80,7 @@ def test_key_phase_one_step_ahead_on_the_second_buffer_set(cpu_ops, world):
     inline = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, "cpu", seed=5)
     ahead = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, "cpu", seed=5)
     outs = lambda: ([torch.empty((b, f * dim)) for _ in range(world)], [torch.empty((b, 1)) for _ in range(world)])
+    split_seen = False
     for t, (ids, wts, delta, gx) in enumerate(batches):
         di, wi = outs()
         da, wa = outs()
@@ -88,11 +89,24 @@ def test_key_phase_one_step_ahead_on_the_second_buffer_set(cpu_ops, world):
         for r in range(world):
             assert torch.equal(di[r], da[r]) and torch.equal(wi[r], wa[r])
         if t + 1 < len(batches):
-            ahead.key_phase_next(batches[t + 1][0])                    # under step t's DenseLayers
+            # split serve: poison the landing buffers (their rows were consumed by the expand above), then the rows the
+            # coming update does not touch go out early (under step t's DenseLayers) and the rest after it — every row of
+            # batch t + 1 must be written by exactly one of the two, or the NaNs show up in the next forward
+            for rk in ahead.ranks:
+                rk.buf["land_deep"].fill_(float("nan"))
+                rk.buf["land_wide"].fill_(float("nan"))
+            ahead.key_phase_next(batches[t + 1][0])
+            early = [int(torch.isfinite(rk.buf["land_wide"]).sum()) for rk in ahead.ranks]
+            n_u = [int(rk._s(nxt=True)["bounds"][world]) for rk in ahead.ranks]
+            dirty = [int(sum(bin(int(w) & 0xffffffff).count("1") for w in rk.dirty.tolist())) for rk in ahead.ranks]
+            assert all(d > 0 for d in dirty)                           # the update of step t names rows
+            assert all(0 < e <= u for e, u in zip(early, n_u))         # part of batch t + 1 went out early ...
+            split_seen = split_seen or any(e < u for e, u in zip(early, n_u))      # ... and part of it had to wait
         inline.backward(delta, gx)
         ahead.backward(delta, gx)
         for a_, b_ in zip(inline.full_tables(), ahead.full_tables()):
             assert torch.equal(a_, b_)
+    assert split_seen
     for rk in ahead.ranks:
         assert int(rk.err) == 0 and rk.cur == 1                        # three adoptions: the sets alternated
 

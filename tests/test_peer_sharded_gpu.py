@@ -243,6 +243,7 @@ def test_key_phase_one_step_ahead_on_the_second_buffer_set(cuda, world):
     ahead = peer_sharded.EmulatedPeerGroup(world, vocab, dim, b * f, cuda, seed=5)
     outs = lambda: ([torch.empty((b, f * dim), device=cuda) for _ in range(world)],
                     [torch.empty((b, 1), device=cuda) for _ in range(world)])
+    split_seen = False
     for t, (ids, wts, delta, gx) in enumerate(batches):
         (di, wi), (da, wa) = outs(), outs()
         inline.forward(ids, wts, bias, di, wi)
@@ -250,11 +251,21 @@ def test_key_phase_one_step_ahead_on_the_second_buffer_set(cuda, world):
         for r in range(world):
             assert torch.equal(di[r], da[r]) and torch.equal(wi[r], wa[r])
         if t + 1 < len(batches):
+            # split serve on the real kernels: the landing buffers are poisoned, the rows the coming update does not
+            # touch go out now (mode 1), the rest after the update (mode 2): a row written by neither shows up as NaN
+            for rk in ahead.ranks:
+                rk.buf["land_deep"].fill_(float("nan"))
+                rk.buf["land_wide"].fill_(float("nan"))
             ahead.key_phase_next(batches[t + 1][0])
+            early = [int(torch.isfinite(rk.buf["land_wide"]).sum()) for rk in ahead.ranks]
+            n_u = [int(rk._s(nxt=True)["bounds"][world]) for rk in ahead.ranks]
+            assert all(0 < e <= u for e, u in zip(early, n_u))
+            split_seen = split_seen or any(e < u for e, u in zip(early, n_u))
         inline.backward(delta, gx)
         ahead.backward(delta, gx)
         for a_, b_ in zip(inline.full_tables(), ahead.full_tables()):
             assert torch.equal(a_, b_)
+    assert split_seen
     for rk in ahead.ranks:
         assert int(rk.err.item()) == 0 and rk.cur == 1
 
