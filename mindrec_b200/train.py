@@ -230,3 +230,34 @@ def merge_sliced_tables(slices, layout=None):
     # the unsharded cell keeps one Adam hyper block for the table and the DenseLayers (same step count on both)
     out["adam.hyper"] = by_rank[0]["adam.hyper"].clone()
     return out
+
+
+def split_tables(state, world, layout="mod"):
+    """Inverse of merge_sliced_tables: a full-table state (export_tables / merge_sliced_tables) -> `world` per-rank
+    slices in export_sharded_tables' format, e.g. to re-shard a checkpoint written on G GPUs for G' GPUs, or to hand a
+    single-GPU checkpoint to a row-sharded job.  Rows beyond the vocabulary (padding of the last rank) are zero, with
+    FTRL's accumulator padded by its own initial value so that a later merge round-trips."""
+    import torch
+    if layout not in ("mod", "contiguous"):
+        raise ValueError("layout must be 'mod' or 'contiguous'")
+    world = int(world)
+    vocab = state["deep_embeddinglookup.embedding_table"].shape[0]
+    rows = (vocab + world - 1) // world
+    pad = rows * world - vocab
+    out = []
+    full = {}
+    for key in _SLICED:
+        t = state[key]
+        t = t.reshape(vocab, -1)
+        fill = 1.0 if key == "ftrl.accum" else 0.0
+        full[key] = torch.cat([t, torch.full((pad, t.shape[1]), fill, dtype=t.dtype)], 0) if pad else t
+    for r in range(world):
+        s = {}
+        for key in _SLICED:
+            s[key] = (full[key][r::world] if layout == "mod" else full[key][r * rows:(r + 1) * rows]).contiguous().clone()
+        for key in ("dense_layers+Wide_b", "adam.moment1.dense", "adam.moment2.dense", "ftrl.hyper", "adam.hyper"):
+            s[key] = state[key].clone()
+        s["adam.hyper.dense"] = state.get("adam.hyper.dense", state["adam.hyper"]).clone()
+        s["sharding"] = {"rank": r, "world": world, "vocab_size": int(vocab), "rows_per_rank": int(rows), "layout": layout}
+        out.append(s)
+    return out

@@ -88,6 +88,11 @@ def test_merge_sliced_tables_mod_and_contiguous_layouts():
         for k, v in full.items():
             assert torch.equal(merged[k], v[:vocab])
         assert torch.equal(merged["dense_layers+Wide_b"], dense["dense_layers+Wide_b"])
+        # re-sharding: merged state -> slices for another world size -> merged again
+        for g2 in (1, 3, 8):
+            again = train.merge_sliced_tables(train.split_tables(merged, g2, layout=layout))
+            for k in train._SLICED + ("dense_layers+Wide_b", "adam.hyper"):
+                assert torch.equal(again[k], merged[k])
     slices[1]["dense_layers+Wide_b"][0] += 1.0
     with pytest.raises(ValueError, match="differs between ranks"):
         train.merge_sliced_tables(slices)
